@@ -1,0 +1,161 @@
+"""Pins the CPU oracle (oracle/sd_oracle.c) against golden vectors produced by the unmodified
+reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL_FP32, assert_close, golden_scene_arrays, rel_err
+from oracle import oracle as O
+
+
+def _w2c(c2w):
+    # the reference inverts poses with torch.inverse in fp32 (models/bts.py:125-126)
+    return torch.inverse(torch.from_numpy(np.ascontiguousarray(c2w))).numpy()
+
+
+def _scene(g, feat, imgs, b=None, **kw):
+    K = g["K"] if b is None else g["K"][b]
+    c2w = g["c2w"] if b is None else g["c2w"][b]
+    w2c = _w2c(c2w)
+    i = 0 if b is None else b
+    return O.Scene(feat=feat[i:i + 1], K_f=K[:1], w2c_f=w2c[:1], rgb=imgs[i], K_c=K, w2c_c=w2c, **kw)
+
+
+def _mlp(g):
+    return O.Mlp(g["w_in"], g["b_in"], g["w_out"], g["b_out"])
+
+
+def test_projection_and_mask_bit_exact(golden):
+    g = golden("query")
+    w2c = _w2c(g["c2w"])
+    xy, z, inv = O.project(g["K"][0], w2c[0], g["points"])
+    assert np.array_equal(inv, g["frustum_invalid"])          # bit-exact mask (a-9)
+    assert np.array_equal(xy, g["xy"]) and np.array_equal(z, g["z"])
+    assert 0.15 < inv.mean() < 0.6 and (g["z"] <= 1e-3).sum() >= 3   # the case is non-trivial
+
+
+@pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
+def test_query_points(golden, tag, learn_empty):
+    g = golden("query")
+    feat, imgs = golden_scene_arrays(g)
+    sc = _scene(g, feat, imgs, learn_empty=learn_empty,
+                empty_feature=g["empty_feature"] if learn_empty else None)
+    sf, sinv = O.sample_features(sc, g["points"])
+    assert np.array_equal(sinv[:, 0], g["sample_invalid" + tag])
+    n = g["sample_features" + tag].shape[0]
+    assert np.array_equal(sf[:n, 0, :256], g["sample_features" + tag][:, :256])   # gather (a-12/13)
+    assert_close(sf[:n, 0, 256:], g["sample_features" + tag][:, 256:], 1e-6, "xyz code")  # a-10/11
+    q = O.query_points(sc, _mlp(g), g["points"], want_raw=True)
+    assert_close(q["raw"], g["mlp_raw" + tag], TOL_FP32, "mlp output")            # a-15
+    assert_close(q["sigma"], g["sigma" + tag], TOL_FP32, "sigma")                 # a-16
+    assert_close(q["dino"], g["dino" + tag], TOL_FP32, "dino")
+    assert np.array_equal(q["rgb"], g["rgb" + tag])                               # a-17
+    assert np.array_equal(q["invalid"], g["invalid" + tag])                       # a-18
+    assert np.array_equal(q["invalid_features"], g["invalid_features" + tag])
+    ex = O.expand_dim(g["dino" + tag][:256], g["e_w1"], g["e_b1"], g["e_w2"], g["e_b2"])
+    assert_close(ex, g["dino_full" + tag], TOL_FP32, "expand_dim")                # 8f-1
+
+
+def _check_pass(o, g, prefix, tol=TOL_FP32):
+    R = g["rays"].shape[0] * g["rays"].shape[1]
+    K = g[prefix + "z_samps"].shape[-1]
+    assert_close(o["weights"], g[prefix + "weights"].reshape(R, K), tol, prefix + "weights")
+    assert_close(o["alphas"], g[prefix + "alphas"].reshape(R, K), tol, prefix + "alphas")
+    assert_close(o["depth"], g[prefix + "depth"].reshape(R), tol, prefix + "depth")
+    assert_close(o["rgb"], g[prefix + "rgb"].reshape(R, -1), tol, prefix + "rgb")
+    assert_close(o["dino_features"], g[prefix + "dino_features"].reshape(R, -1), tol, prefix + "dino")
+    assert np.array_equal(o["invalid"], g[prefix + "invalid"].reshape(R, K, -1))
+
+
+def test_render_coarse(golden):
+    g = golden("render_coarse")
+    feat, imgs = golden_scene_arrays(g)
+    sc = _scene(g, feat, imgs)
+    rays = g["rays"][0]
+    z = O.sample_coarse(rays, g["u_coarse"], g["lin"], lindisp=True)
+    assert np.array_equal(z, g["coarse.z_samps"][0])                               # a-1 bit-exact
+    o = O.render_pass(sc, _mlp(g), rays, z, hard_alpha_cap=False, want_rgb_samps=True)
+    _check_pass(o, g, "coarse.")
+    # _format_outputs reshapes invalid_features with invalid's last dim (nv_c), nerf.py:564,596:
+    # for nv_c = 2 the reference returns [1, R/2, K, 2]; the flat order is still [R, K].
+    assert g["coarse.invalid_features"].shape == (1, rays.shape[0] // 2, 64, 2)
+    assert np.array_equal(o["invalid_features"].ravel(), g["coarse.invalid_features"].ravel())
+    assert np.array_equal(o["rgb_samps"], g["coarse.rgb_samps"][0])
+    assert np.array_equal(g["coarse.ray_info"][0], rays[:, 8:])
+
+
+@pytest.mark.parametrize("name", ["render_fine", "render_fine_lin"])
+def test_render_fine(golden, name):
+    g = golden(name)
+    feat, imgs = golden_scene_arrays(g)
+    sc = _scene(g, feat, imgs)
+    rays = g["rays"][0]
+    Kc, Kf, Kfd, lindisp, white = [int(v) for v in g["conf"]]
+    out = O.render_rays(sc, _mlp(g), rays, lin=g["lin"], u_coarse=g["u_coarse"], u_fine0=g["u_fine0"],
+                        u_fine1=g["u_fine1"], n_depth=g["n_depth"], depth_std=float(g["depth_std"]),
+                        lindisp=bool(lindisp), hard_alpha_cap=True, white_bkgd=bool(white))
+    assert np.array_equal(out["coarse"]["z_samps"], g["coarse.z_samps"][0])
+    _check_pass(out["coarse"], g, "coarse.")
+    # a-2: importance-sample indices.  The oracle's normaliser is a sequential double sum, torch's a
+    # vectorised fp32 sum, so an index may flip only where u sits within an ulp of a CDF entry.
+    flips = (out["fine_inds"] != g["fine_inds"]).sum()
+    assert flips <= max(1, int(1e-4 * g["fine_inds"].size)), f"{flips} index flips"
+    # sample_fine on the GOLDEN coarse weights must reproduce the golden fine z-samples bit for bit
+    # wherever the index agrees
+    zf, inds = O.sample_fine(rays, g["coarse.weights"][0], g["u_fine0"], g["u_fine1"], bool(lindisp))
+    zd = O.sample_fine_depth(rays, g["coarse.depth"][0], g["n_depth"], float(g["depth_std"]))
+    zall = O.sort_rows(np.concatenate([g["coarse.z_samps"][0], zf, zd], 1))
+    same_rows = (inds == g["fine_inds"]).all(1)
+    assert same_rows.mean() > 0.99
+    assert np.array_equal(zall[same_rows], g["fine.z_samps"][0][same_rows])        # a-2,a-3,a-5
+    o = O.render_pass(sc, _mlp(g), rays, g["fine.z_samps"][0], hard_alpha_cap=True, white_bkgd=bool(white))
+    _check_pass(o, g, "fine.")
+
+
+def test_render_from_dist(golden):
+    g = golden("render_from_dist")
+    feat, imgs = golden_scene_arrays(g)
+    sc = _scene(g, feat, imgs)
+    rays = g["rays"][0]
+    z, inds = O.sample_coarse_from_dist(g["prop_weights"][0], g["prop_z"][0], g["u0"], g["u1"], True)
+    flips = (inds != g["inds"]).sum()
+    assert flips <= 1
+    zs = O.sort_rows(z)
+    same = (inds == g["inds"]).all(1)
+    assert np.array_equal(zs[same], g["coarse.z_samps"][0][same])                  # a-4 bit-exact
+    o = O.render_pass(sc, _mlp(g), rays, g["coarse.z_samps"][0])
+    _check_pass(o, g, "coarse.")
+
+
+def test_render_superbatch(golden):
+    g = golden("render_superbatch")
+    feat, imgs = golden_scene_arrays(g, n=2)
+    u = g["u_coarse"].reshape(2, -1, g["u_coarse"].shape[-1])
+    for b in range(2):
+        sc = _scene(g, feat, imgs, b=b)
+        rays = g["rays"][b]
+        z = O.sample_coarse(rays, u[b], g["lin"], True)
+        assert np.array_equal(z, g["coarse.z_samps"][b])
+        o = O.render_pass(sc, _mlp(g), rays, z, hard_alpha_cap=True)
+        gb = {k: v[b:b + 1] for k, v in g.items() if k.startswith("coarse.")}
+        gb["rays"] = g["rays"][b:b + 1]
+        _check_pass(o, gb, "coarse.")
+
+
+def test_composite_properties():
+    """Size-independent properties of a-19: weights are a sub-partition of unity; hard_alpha_cap
+    makes them sum to one; a delta-function density returns the sample's own depth/feature."""
+    rs = np.random.RandomState(0)
+    R, K, D = 64, 48, 8
+    z = np.sort(rs.uniform(3, 80, (R, K)).astype(np.float32), 1)
+    sigma = rs.uniform(0, 0.3, (R, K)).astype(np.float32)
+    feat = rs.standard_normal((R, K, D)).astype(np.float32)
+    o = O.composite(z, sigma, feat, None, hard_alpha_cap=False)
+    assert (o["weights"] >= 0).all() and (o["weights"].sum(1) <= 1 + 1e-5).all()
+    o = O.composite(z, sigma * 0, feat, None, hard_alpha_cap=True)
+    np.testing.assert_allclose(o["weights"].sum(1), 1.0, rtol=1e-6)
+    np.testing.assert_allclose(o["depth"], z[:, -1], rtol=1e-6)
+    spike = np.zeros_like(sigma); spike[:, 7] = 1e4
+    o = O.composite(z, spike, feat, None)
+    np.testing.assert_allclose(o["depth"], z[:, 7], rtol=1e-5)
+    np.testing.assert_allclose(o["dino"], feat[:, 7], rtol=1e-5, atol=1e-6)
