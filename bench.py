@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the feature-field query-and-render hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+
+Headline workload (BASELINE.json configs[1]): the SSCBench voxel-grid query -- 256 x 256 x 32 voxels
+@ 0.2 m projected into one 192 x 640 view whose DINO ViT-B/8 feature map is 256 x 384 x 1280, MLP head
+295 -> 128 -> 65.  One "step" = one pass of the hot path over the whole grid (2 097 152 voxels):
+sd_query_points -> sigma [N] + 64-d features [N,64] + frustum mask [N].  Synthetic data: seeded random
+feature map and random-init (kaiming) head weights.  The same line also carries a full-image render
+(122 880 rays x 64 samples) as ``render``.
+
+N > 1 (torchrun, one rank per GPU): every rank queries one full grid against its own replica of the
+map (weak scaling: voxel slabs / frames are independent), then all ranks all-gather the density grid
+and the frustum mask over NCCL; time = max over ranks.
+
+``--impl reference``: the CPU restatement of the reference algorithm (oracle/, the reference is pure
+Python and cannot travel to the GPU box) on all host cores, rank 0 only, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from scenedino_b200 import synthetic as syn  # noqa: E402
+
+GRID = (256, 256, 32)
+C_FEAT, HF, WF = 256, 384, 1280          # DINO ViT-B/8 + DPT head at 192 x 640
+D_IN, D_HID, D_OUT = 295, 128, 65
+FLOP_PER_POINT = 2 * (D_IN * D_HID + D_HID * D_OUT)   # 92 160
+RENDER_R, RENDER_K = syn.IMG_H * syn.IMG_W, 64
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ---- nvidia-smi clock sampler ---------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- workload -------------------------------------------------------------------------------------
+def unique_texels(pts, K, Hf, Wf):
+    """Number of distinct feature-map texels the 4-tap footprints of all points touch (for the
+    compulsory-bytes figure of SURVEY.md 8d); fp32 numpy restatement of the projection."""
+    p = pts.astype(np.float32)
+    q = (K.astype(np.float32) @ p.T).T
+    zc = np.maximum(q[:, 2], np.float32(1e-3))
+    x = np.clip(q[:, 0] / zc, -2, 2); y = np.clip(q[:, 1] / zc, -2, 2)
+    ix = np.clip((x + 1) * np.float32(Wf * 0.5) - 0.5, 0, Wf - 1); iy = np.clip((y + 1) * np.float32(Hf * 0.5) - 0.5, 0, Hf - 1)
+    x0 = np.floor(ix).astype(np.int64); y0 = np.floor(iy).astype(np.int64)
+    x1 = np.minimum(x0 + 1, Wf - 1); y1 = np.minimum(y0 + 1, Hf - 1)
+    ids = np.concatenate([y0 * Wf + x0, y0 * Wf + x1, y1 * Wf + x0, y1 * Wf + x1])
+    return int(np.unique(ids).size)
+
+
+def cpu_reference_voxels(feat_nchw, mlp_w, pts, budget_s=12.0):
+    """Times the CPU oracle (OpenMP, all host cores) on a strided sample of the grid."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    O.set_num_threads(cores)
+    K = syn.kitti360_K()[None]; w2c = np.eye(4, dtype=np.float32)[None]
+    sc = O.Scene(feat=feat_nchw, K_f=K, w2c_f=w2c)
+    mlp = O.Mlp(*mlp_w)
+    n = 16384
+    sub = pts[:: max(1, len(pts) // n)][:n]
+    O.query_points(sc, mlp, sub[:1024], want_rgb=False)
+    t0 = time.perf_counter(); O.query_points(sc, mlp, sub, want_rgb=False); dt = time.perf_counter() - t0
+    n2 = int(min(len(pts), max(n, n * budget_s / max(dt, 1e-6))))
+    n2 = max(n, (n2 // 4096) * 4096)
+    sub = pts[:: max(1, len(pts) // n2)][:n2]
+    t0 = time.perf_counter(); O.query_points(sc, mlp, sub, want_rgb=False); dt = time.perf_counter() - t0
+    return dict(value=len(sub) / dt, unit="voxels/s", cores=O.num_threads(), kind="port",
+                sample=f"{len(sub)} voxels strided over the 256x256x32 grid, oracle/sd_oracle.c (OpenMP), {dt:.2f} s")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    feat = syn.make_feature_map(1, C_FEAT, HF, WF)
+    mlp_w = syn.make_mlp(0)
+    pts = syn.ssc_voxel_grid(GRID)
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_voxels(feat, mlp_w, pts, budget_s=max(2.0, 40.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"impl": "reference", "metric": "ssc_voxel_query_throughput", "value": v, "unit": "voxels/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": GRID[0] * GRID[1] * GRID[2] / v * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config("fp32"), "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(precision):
+    return {"workload": "SSC voxel-grid query 256x256x32 @0.2m (51.2 m), DINO ViT-B/8 map 256x384x1280, "
+                        "MLP 295->128->65, outputs sigma+64-d features+mask",
+            "voxels_per_step": GRID[0] * GRID[1] * GRID[2], "feature_map": [C_FEAT, HF, WF],
+            "mlp": [D_IN, D_HID, D_OUT], "precision": precision,
+            "l2": "working set per step (map + 25 MB points + 545 MB outputs) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from scenedino_b200 import _abi, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    prec = ops.BF16 if args.precision == "bf16" else ops.FP32
+    fdt = torch.bfloat16 if args.precision == "bf16" else torch.float32
+
+    # ---- scene: seeded random map (encoder stand-in), camera, head -----------------------------------
+    g = torch.Generator(device=dev).manual_seed(1)
+    feat_nchw = torch.randn((1, C_FEAT, HF, WF), device=dev, generator=g)
+    K = syn.kitti360_K()[None]; w2c = np.eye(4, dtype=np.float32)[None]
+    imgs = syn.make_images(2, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    feat = ops.featmap_pack(feat_nchw, fdt)
+    e1.record(); torch.cuda.synchronize()
+    pack_ms = e0.elapsed_time(e1)
+    scene = ops.Scene(feat=feat[0], K_f=torch.from_numpy(K).to(dev), w2c_f=torch.from_numpy(w2c).to(dev))
+    scene_rgb = ops.Scene(feat=feat[0], K_f=scene.K_f, w2c_f=scene.w2c_f, rgb=torch.from_numpy(imgs).to(dev),
+                          K_c=scene.K_f, w2c_c=scene.w2c_f)
+    mlp_w = syn.make_mlp(0)
+    mlp = ops.Mlp(*mlp_w, device=dev, precision=prec)
+    pts_np = syn.ssc_voxel_grid(GRID)
+    N = len(pts_np)
+    pts_host = torch.from_numpy(pts_np).pin_memory()
+    pts = pts_host.to(dev)
+    out = dict(sigma=torch.empty(N, device=dev), dino=torch.empty((N, D_OUT - 1), device=dev),
+               invalid_features=torch.empty(N, dtype=torch.uint8, device=dev))
+    sig_all = torch.empty((world, N), device=dev) if world > 1 else None
+    inv_all = torch.empty((world, N), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step():
+        ops.query_points(scene, mlp, pts, want_rgb=False, out=out)
+        if world > 1:
+            dist.all_gather_into_tensor(sig_all, out["sigma"])
+            dist.all_gather_into_tensor(inv_all, out["invalid_features"])
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    n0 = _abi.launch_count()
+    with Clocks(local) as clk:
+        fence()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        fence()
+        ms = e0.elapsed_time(e1)
+        # keep the sampler alive long enough to see the load on very short runs
+        t_end = time.time() + max(0.0, 0.6 - ms / 1e3)
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+    launches = _abi.launch_count() - n0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    value = world * N / (ms_step * 1e-3)
+
+    # ---- end to end: pinned host points -> device -> query -> density grid + mask back to the host ------
+    sig_host = torch.empty(N, dtype=torch.float32).pin_memory()
+    inv_host = torch.empty(N, dtype=torch.uint8).pin_memory()
+    pts_dev2 = torch.empty_like(pts)
+
+    def e2e_step():
+        pts_dev2.copy_(pts_host, non_blocking=True)
+        ops.query_points(scene, mlp, pts_dev2, want_rgb=False, out=out)
+        sig_host.copy_(out["sigma"], non_blocking=True)
+        inv_host.copy_(out["invalid_features"], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    fence()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    fence()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * N / (e2e_ms / args.steps * 1e-3)
+
+    line = None
+    if rank == 0:
+        ntex = unique_texels(pts_np, K[0], HF, WF)
+        esize = 2 if args.precision == "bf16" else 4
+        algo_bytes = N * (12 + 4 + 4 * (D_OUT - 1) + 1) + ntex * C_FEAT * esize
+        t_kernel = ms_step * 1e-3
+        hbm_ach = algo_bytes / t_kernel / 1e9
+        tc_ach = N * FLOP_PER_POINT / t_kernel / 1e12
+        roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_ach / pk["hbm"],
+                    "traffic": None, "algorithmic_bytes": algo_bytes, "unique_texels": ntex, "peak_source": pk["src"]}
+        roof_tc = {"bound": "tensor", "achieved": tc_ach, "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                   "frac": tc_ach / pk["tc_burst"], "traffic": None, "algorithmic_flops": N * FLOP_PER_POINT,
+                   "peak_source": pk["src"] + " (burst: kernel timed alone)"}
+        # the binding roof is the one with the lower ceiling for this workload
+        primary = roof_tc if (N * FLOP_PER_POINT / (pk["tc_burst"] * 1e12)) >= (algo_bytes / (pk["hbm"] * 1e9)) else roof_hbm
+        if args.precision == "fp32":
+            primary = roof_hbm   # FFMA head: neither roof binds; report the memory one
+        line = {"metric": "ssc_voxel_query_throughput", "value": value, "unit": "voxels/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic", "config": workload_config(args.precision),
+                "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12,
+                        "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,
+                        "note": "pinned xyz in; density grid + frustum mask out (the 64-d features stay on the "
+                                "device for expand_dim / the SSC head, as in the reference)"},
+                "gpu_launches": int(launches), "clocks": clk.summary(),
+                "roofline": primary, "roofline_hbm": roof_hbm, "roofline_tensor": roof_tc,
+                "featmap_pack_ms": pack_ms}
+
+    # ---- full-image render (122 880 rays x 64 samples), reported in the same line ---------------------
+    if not args.no_render:
+        rays = torch.from_numpy(syn.image_rays(syn.view_pose_c2w(1), K[0])).to(dev)
+        lin = torch.linspace(0, 1 - 1.0 / RENDER_K, RENDER_K, device=dev)
+        u = torch.rand((RENDER_R, RENDER_K), device=dev, generator=g)
+
+        def render_step():
+            z = ops.sample_coarse(rays, u, lin, True)
+            return ops.render_pass(scene_rgb, mlp, rays, z, per_sample=False)
+
+        for _ in range(3):
+            render_step()
+        fence()
+        n_r = max(3, args.steps // 2)
+        e0.record()
+        for _ in range(n_r):
+            render_step()
+        e1.record(); fence()
+        r_ms = e0.elapsed_time(e1) / n_r
+        if line is not None:
+            line["render"] = {"workload": "full 192x640 image from a stereo-offset view, 64 coarse samples/ray, "
+                                          "per-ray outputs depth+64-d+rgb",
+                              "msamples_per_s": RENDER_R * RENDER_K / (r_ms * 1e-3) / 1e6, "ms": r_ms,
+                              "tensor_frac": RENDER_R * RENDER_K * FLOP_PER_POINT / (r_ms * 1e-3) / 1e12 / pk["tc_burst"]}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_voxels(feat_nchw.cpu().numpy(), mlp_w, pts_np)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/*
+ * scenedino_b200.h -- C ABI of the B200-native feature-field query-and-render path.
+ *
+ * The reference (tum-vision/scenedino) is pure Python/PyTorch and has no FFI layer; the "plugin
+ * surface" it exposes for this path is a set of Python methods.  Each entry
+ * point below replaces the body of one of those methods and cites it (paths relative to the
+ * reference root).  The Python shim in scenedino_b200/ binds these symbols with ctypes and keeps the
+ * reference's method names, argument meaning and error behaviour.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers into buffers allocated and owned by the caller
+ *     (PyTorch's caching allocator in the shim).  The library never allocates or frees
+ *     caller-visible memory; scratch space is passed in (see *_workspace_bytes).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; 0 = legacy default).
+ *   - Return value: 0 on success, a negative sd_status otherwise; sd_last_error() returns a
+ *     thread-local message.  Nothing throws, nothing calls exit().
+ *   - Row-major everywhere.  "rays" rows are [origin(3) dir(3) near far ...] with r_dim >= 8 floats
+ *     per ray (common/ray_sampler.py:476-484).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     SD_ERR_CUDA.
+ */
+#ifndef SCENEDINO_B200_H
+#define SCENEDINO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+typedef enum sd_status {
+    SD_OK = 0,
+    SD_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    SD_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA error string) */
+    SD_ERR_WORKSPACE = -3    /* workspace too small */
+} sd_status;
+
+typedef enum sd_dtype { SD_F32 = 0, SD_BF16 = 1 } sd_dtype;
+
+/* MLP arithmetic.  SD_MLP_FP32: fp32 FFMA on CUDA cores (parity mode, rel 1e-4).
+ * SD_MLP_BF16_TC: bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM (rel 2e-2). */
+typedef enum sd_precision { SD_MLP_FP32 = 0, SD_MLP_BF16_TC = 1 } sd_precision;
+
+/* What BTSNet.encode stashes for ONE batch element (models/bts.py:246-257), with the feature map
+ * re-laid out channels-last by sd_featmap_pack. */
+typedef struct sd_scene {
+    const void  *feat;          /* [nv_f, Hf, Wf, C] channels-last, feat_dtype            */
+    int          feat_dtype;    /* sd_dtype                                               */
+    int          nv_f, C, Hf, Wf;
+    const float *K_f;           /* [nv_f,3,3] normalised intrinsics   (bts.py:247)         */
+    const float *w2c_f;         /* [nv_f,4,4] world->camera           (bts.py:248)         */
+    const float *rgb;           /* [nv_c,3,Hc,Wc] fp32 planar, as grid_c_imgs (bts.py:252) */
+    int          nv_c, Hc, Wc;
+    const float *K_c;           /* [nv_c,3,3] (bts.py:253) */
+    const float *w2c_c;         /* [nv_c,4,4] (bts.py:254) */
+    float        d_min, d_max;  /* z_near, z_far of the encoding (bts.py:60)               */
+    int          inv_z;         /* bts.py:64                                               */
+    int          num_freqs;     /* PositionalEncoding (positional_encoding.py:49-66)       */
+    float        freq_factor;
+    int          include_input;
+    int          learn_empty;   /* bts.py:311-319                                          */
+    const float *empty_feature; /* [C] or NULL                                             */
+} sd_scene;
+
+/* ResnetFC head with n_blocks = 0 (models/prediction_heads/resnetfc.py:90-96,162-199).
+ * `packed` is the blob written by sd_mlp_pack (transposed/padded fp32 weights for the CUDA-core
+ * path and bf16 UMMA shared-memory images for the tcgen05 path). */
+typedef struct sd_mlp {
+    const void *packed;
+    int         d_in, d_hidden, d_out;
+    int         precision;      /* sd_precision */
+} sd_mlp;
+
+/* NeRFRenderer options that change arithmetic (renderer/nerf.py:73-119). */
+typedef struct sd_render_cfg {
+    int   lindisp;
+    int   hard_alpha_cap;
+    int   white_bkgd;
+} sd_render_cfg;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int         sd_abi_version(void);
+const char *sd_last_error(void);
+/* SM count of the current device, or a negative sd_status. */
+int         sd_device_sm_count(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+long long   sd_launch_count(void);
+
+/* ---- one-off packing ------------------------------------------------------------------------ */
+/* BTSNet.encode stash (bts.py:214-257): [n_img, C, H, W] fp32 planar -> [n_img, H, W, C]
+ * channels-last in dst_dtype.  Replaces the no-op F.interpolate copy at bts.py:217-222. */
+int    sd_featmap_pack(const float *nchw, int n_img, int C, int H, int W, void *nhwc, int dst_dtype,
+                       void *stream);
+/* Size of / writer for the packed weight blob of an MLP head (nn.Linear layout in, fp32). */
+size_t sd_mlp_pack_bytes(int d_in, int d_hidden, int d_out);
+int    sd_mlp_pack(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
+                   int d_in, int d_hidden, int d_out, void *packed, void *stream);
+
+/* ---- point ops, one per reference function (unfused; for 1:1 parity tests) -------------------- */
+/* pts_into_camera + project_to_image + outside_frustum (common/cameras/pinhole.py:40-112) for one
+ * camera.  xy [N,2] is unclamped; invalid [N] is 0/1. */
+int sd_project_points(const float *K, const float *w2c, const float *xyz, long long N, float *xy,
+                      float *z, unsigned char *invalid, void *stream);
+/* BTSNet.sample_features (bts.py:271-328), nv_f == 1: feat [N, C+code] fp32, invalid [N]. */
+int sd_sample_features(const sd_scene *scene, const float *xyz, long long N, float *feat,
+                       unsigned char *invalid, void *stream);
+/* BTSNet.sample_colors (bts.py:330-358), default options (bilinear, no combine / frame filter /
+ * flow): rgb [N,3*nv_c] (view-major inside a row, as bts.py:559-561 lays it out), invalid [N,nv_c]
+ * 0/1 computed on the clamped coordinates like the reference. */
+int sd_sample_colors(const sd_scene *scene, const float *xyz, long long N, float *rgb,
+                     unsigned char *invalid, void *stream);
+/* ResnetFC.forward (resnetfc.py:135-203): x [N,d_in] -> out [N,d_out]. */
+int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, float *out, void *stream);
+
+/* ---- BTSNet.forward (bts.py:476-595) --------------------------------------------------------- */
+/* sigma [N], dino [N,d_out-1], rgb [N,3*nv_c], invalid [N,nv_c] (fp32 0/1, = invalid_colors |
+ * all(invalid_features), bts.py:566-569), invalid_feat [N] (0/1).  Any output may be NULL. */
+int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                    float *sigma, float *dino, float *rgb, float *invalid,
+                    unsigned char *invalid_feat, void *stream);
+
+/* ---- NeRFRenderer sampling (renderer/nerf.py:121-228) --------------------------------------- */
+/* sample_coarse (nerf.py:121-141).  u [R,Kc] = torch.rand_like draw, lin [Kc] = torch.linspace. */
+int sd_sample_coarse(const float *rays, long long R, int r_dim, const float *u, const float *lin,
+                     int Kc, int lindisp, float *z, void *stream);
+/* sample_fine (nerf.py:181-212).  u0,u1 [R,Kf]; inds [R,Kf] optional (parity). */
+int sd_sample_fine(const float *rays, long long R, int r_dim, const float *weights, int Kc,
+                   const float *u0, const float *u1, int Kf, int lindisp, float *z, int *inds,
+                   void *stream);
+/* sample_fine_depth (nerf.py:214-228).  noise [R,Kfd] = torch.randn_like draw. */
+int sd_sample_fine_depth(const float *rays, long long R, int r_dim, const float *depth,
+                         const float *noise, int Kfd, float depth_std, float *z, void *stream);
+/* sample_coarse_from_dist (nerf.py:143-179), unsorted like the reference. */
+int sd_sample_coarse_from_dist(long long R, const float *weights, const float *z_samp, int Kp,
+                               const float *u0, const float *u1, int Kc, int lindisp, float *z,
+                               int *inds, void *stream);
+/* torch.sort(z, dim=-1) values, in place (nerf.py:490,522).  K <= 1024. */
+int sd_sort_rows(float *z, long long R, int K, void *stream);
+
+/* ---- NeRFRenderer.composite (nerf.py:230-449) ------------------------------------------------ */
+/* Core arithmetic only (nerf.py:246-249,376-405,418-421): z,sigma [R,K]; feat [R,K,D];
+ * rgb [R,K,Crgb] -> weights,alphas [R,K]; depth [R]; dino [R,D]; rgb_out [R,Crgb]. */
+int sd_composite(const float *z, const float *sigma, const float *feat, const float *rgb,
+                 long long R, int K, int D, int Crgb, const sd_render_cfg *cfg, float *weights,
+                 float *alphas, float *depth, float *dino, float *rgb_out, void *stream);
+
+/* One full composite() call for one scene: points along the rays at z [R,K], field query,
+ * compositing.  Per-ray outputs: depth [R], dino [R,D], rgb_out [R,3nv_c].  Per-sample outputs
+ * (any may be NULL): weights, alphas [R,K]; invalid [R,K,nv_c] fp32; invalid_feat [R,K];
+ * rgb_samps [R,K,3nv_c]; sigma [R,K].  With mlp->precision == SD_MLP_BF16_TC and a supported
+ * shape this is ONE fused kernel and needs no workspace. */
+size_t sd_render_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long R, int K);
+int    sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_cfg *cfg,
+                      const float *rays, long long R, int r_dim, const float *z, int K,
+                      float *depth, float *dino, float *rgb_out, float *weights, float *alphas,
+                      float *invalid, unsigned char *invalid_feat, float *rgb_samps, float *sigma,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- section 8f-1: MlpDimReduction.transform_expand (backbones/dino/dim_reduction.py:22-25) --- */
+/* `mlp` packs linear_in / linear_out; out [N,d_out] is L2-normalised per row (F.normalize). */
+int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCENEDINO_B200_H */

@@ -1,0 +1,297 @@
+"""``BTSNet`` -- host-side mirror of the reference field model (scenedino/models/bts.py:22-595).
+
+Same constructor, attribute names (``encoder``, ``code_xyz``, ``heads``, ``empty_feature``: the
+state-dict keys reference checkpoints carry), ``encode`` / ``sample_features`` / ``sample_colors`` /
+``forward`` signatures and return conventions.  The DINO encoder stays a PyTorch module; everything
+per 3-D point (projection, frustum mask, bilinear gather, positional code, MLP head, softplus, colour
+lookup) runs in libscenedino_b200 through the C ABI.  There is no PyTorch fallback for those stages.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .heads import ResnetFC, _f32c, _ptr, _stream, require_cuda
+
+PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "bf16": _abi.SD_MLP_BF16_TC}
+
+
+class BTSNet(nn.Module):
+    def __init__(self, conf, encoder: nn.Module, code_xyz, heads: dict, final_pred_head: str | None = None,
+                 uncertainty_predictor: nn.Module | None = None, ren_nc=None,
+                 downstream_head: nn.Module | None = None):
+        super().__init__()
+        self.encoder = encoder
+        self.code_xyz = code_xyz
+        self.heads = nn.ModuleDict(heads)
+        self.uncertainty_predictor = uncertainty_predictor
+        self.extra_outs = getattr(self.encoder, "extra_outs", 0)
+        self.final_pred_head = final_pred_head if final_pred_head else list(self.heads.keys())[0]
+        self.requires_bottleneck_feats = False
+        self.use_viewdirs = conf.get("use_viewdirs", False)
+        self.d_min, self.d_max = conf.get("z_near", 3), conf.get("z_far", 80)
+        self.learn_empty = conf.get("learn_empty", True)
+        self.empty_empty = conf.get("empty_empty", False)
+        self.inv_z = conf.get("inv_z", True)
+        self.color_interpolation = conf.get("color_interpolation", "bilinear")
+        self.code_mode = conf.get("code_mode", "z")
+        self.flip_augmentation = conf.get("flip_augmentation", False)
+        self.return_sample_depth = conf.get("return_sample_depth", False)
+        self.sample_color = conf.get("sample_color", True)
+        self.predict_dino = conf.get("predict_dino", False)
+
+        d_in = self.encoder.latent_size + self.code_xyz.d_out
+        if self.sample_color and self.predict_dino:
+            d_out = 1 + conf.get("dino_dims", 16)
+        elif self.sample_color:
+            d_out = 1
+        else:
+            d_out = 4
+        self._d_in, self._d_out = d_in, d_out
+
+        # what the fused kernels implement = what every shipped config selects
+        # (configs/model/dino_downsampler.yaml:30-62)
+        if self.code_mode != "z":
+            raise NotImplementedError(f"code_mode={self.code_mode!r}: only 'z' is implemented")
+        if self.use_viewdirs or not self.sample_color or self.color_interpolation != "bilinear":
+            raise NotImplementedError("use_viewdirs / sample_color=False / non-bilinear colours are not implemented")
+        if self.extra_outs:
+            raise NotImplementedError("encoder.extra_outs > 0 is not implemented")
+        head = self.heads[self.final_pred_head]
+        if not isinstance(head, ResnetFC) and not (hasattr(head, "lin_in") and hasattr(head, "lin_out")
+                                                   and getattr(head, "n_blocks", 0) == 0):
+            raise NotImplementedError("the prediction head must be a ResnetFC with n_blocks=0")
+
+        if self.learn_empty:
+            self.empty_feature = nn.Parameter(torch.randn((self.encoder.latent_size,), requires_grad=True))
+        self._scale = 0
+        self.downstream_head = downstream_head
+        self.gt_classes = downstream_head.gt_classes if downstream_head is not None else None
+
+        #: "fp32": CUDA-core FFMA head on the fp32 map (rel 1e-4 parity mode);
+        #: "bf16": tcgen05 head on the bf16 map (rel 2e-2, the throughput mode);
+        #: "auto": bf16 under torch autocast (where the reference runs fp16), fp32 otherwise.
+        self.precision = conf.get("sd_precision", "auto")
+        self.encode_loss_features = True
+        self._packed = {}
+        self._head_packed = None
+        self.grid_f_features = None
+
+    # ---- trivial accessors (bts.py:103-110) ------------------------------------------------------
+    def set_scale(self, scale):
+        self._scale = scale
+
+    def get_scale(self):
+        return self._scale
+
+    def compute_grid_transforms(self, *args, **kwargs):
+        pass
+
+    # ---- encode (bts.py:112-259) -----------------------------------------------------------------
+    def encode(self, images, Ks, poses_c2w, ids_encoder=None, ids_render=None, ids_loss=None, images_alt=None,
+               combine_ids=None, color_frame_filter=None, loss_feature_grid_shift=None):
+        if combine_ids is not None or color_frame_filter is not None:
+            raise NotImplementedError("combine_ids / color_frame_filter are not implemented")
+        if loss_feature_grid_shift is not None and tuple(loss_feature_grid_shift) != (0, 0):
+            raise NotImplementedError("loss_feature_grid_shift is not implemented")
+        if self.flip_augmentation and self.training:
+            raise NotImplementedError("flip_augmentation is a training-time option; not implemented")
+        with torch.autocast(device_type=images.device.type, enabled=False):
+            poses_w2c = torch.inverse(poses_c2w.float())
+
+        if ids_encoder is None:
+            images_encoder, Ks_encoder, poses_w2c_encoder = images, Ks, poses_w2c
+        else:
+            images_encoder, Ks_encoder, poses_w2c_encoder = images[:, ids_encoder], Ks[:, ids_encoder], poses_w2c[:, ids_encoder]
+        images_loss = images if ids_loss is None else images[:, ids_loss]
+        images = images_alt if images_alt is not None else images * 0.5 + 0.5
+        if ids_render is None:
+            images_render, Ks_render, poses_w2c_render = images, Ks, poses_w2c
+        else:
+            images_render, Ks_render, poses_w2c_render = images[:, ids_render], Ks[:, ids_render], poses_w2c[:, ids_render]
+
+        n_, nv_, c_, h_, w_ = images_encoder.shape
+        image_latents_ms = self.encoder(images_encoder.reshape(n_ * nv_, c_, h_, w_))
+        if self.encode_loss_features:
+            nl_, nvl_ = images_loss.shape[:2]
+            loss_ms = self.encoder(images_loss.reshape(nl_ * nvl_, *images_loss.shape[2:]), ground_truth=True)
+            self.grid_l_loss_features = [l.view(nl_, nvl_, -1, *l.shape[-2:]) for l in loss_ms]
+        else:
+            self.grid_l_loss_features = None
+
+        hf, wf = image_latents_ms[0].shape[-2:]
+        for l in image_latents_ms:
+            if tuple(l.shape[-2:]) != (hf, wf):
+                raise NotImplementedError("multi-scale encoder outputs of different sizes are not implemented")
+        # bts.py:217-222 copies every map through F.interpolate(size=same); here the one re-layout
+        # pass (sd_featmap_pack, planar -> channels-last) replaces that copy, lazily per scale/dtype.
+        self.grid_f_features = [l.view(n_, nv_, -1, hf, wf) for l in image_latents_ms]
+        self.grid_f_extra = None
+        self.grid_f_Ks = Ks_encoder
+        self.grid_f_poses_w2c = poses_w2c_encoder
+        self.grid_f_combine = None
+        self.grid_c_imgs = images_render.detach()
+        self.grid_c_Ks = Ks_render
+        self.grid_c_poses_w2c = poses_w2c_render
+        self.grid_c_combine = None
+        self.color_frame_filter = None
+        self._packed = {}
+
+    # ---- C-ABI plumbing ----------------------------------------------------------------------------
+    def _precision(self) -> int:
+        p = self.precision
+        if p == "auto":
+            p = "bf16" if torch.is_autocast_enabled() else "fp32"
+        if p not in PRECISIONS:
+            raise ValueError(f"precision must be one of fp32|bf16|auto, got {self.precision!r}")
+        return PRECISIONS[p]
+
+    def _state(self, precision: int):
+        """Packed, contiguous device state for the current scale: (feat_nhwc, dtype, cams...)."""
+        if self.grid_f_features is None:
+            raise RuntimeError("BTSNet.encode must be called before querying the field")
+        dt = _abi.SD_BF16 if precision == _abi.SD_MLP_BF16_TC else _abi.SD_F32
+        key = (self._scale, dt)
+        st = self._packed.get(key)
+        if st is None:
+            fmap = self.grid_f_features[self._scale]
+            require_cuda(fmap, "the encoder feature map")
+            n, nv, c, hf, wf = fmap.shape
+            if nv != 1:
+                raise NotImplementedError("the default head supports exactly one encoder view (ids_encoder=[0])")
+            src = _f32c(fmap)
+            dst = torch.empty((n, nv, hf, wf, c), device=src.device,
+                              dtype=torch.bfloat16 if dt == _abi.SD_BF16 else torch.float32)
+            _abi.check(_abi.lib().sd_featmap_pack(_ptr(src), n * nv, c, hf, wf, _ptr(dst), dt, _stream()),
+                       "sd_featmap_pack")
+            st = dict(
+                feat=dst, dt=dt, n=n, C=c, Hf=hf, Wf=wf,
+                K_f=_f32c(self.grid_f_Ks).reshape(n, nv, 3, 3).contiguous(),
+                w2c_f=_f32c(self.grid_f_poses_w2c).reshape(n, nv, 4, 4).contiguous(),
+                rgb=_f32c(self.grid_c_imgs),
+                K_c=_f32c(self.grid_c_Ks).contiguous(), w2c_c=_f32c(self.grid_c_poses_w2c).contiguous(),
+            )
+            if st["rgb"].shape[2] != 3:
+                raise NotImplementedError("colour views must have 3 channels")
+            self._packed[key] = st
+        return st
+
+    def _scene(self, st, b: int) -> _abi.SdScene:
+        s = _abi.SdScene()
+        s.feat = st["feat"][b].data_ptr()
+        s.feat_dtype = st["dt"]
+        s.nv_f, s.C, s.Hf, s.Wf = 1, st["C"], st["Hf"], st["Wf"]
+        s.K_f = st["K_f"][b].data_ptr()
+        s.w2c_f = st["w2c_f"][b].data_ptr()
+        rgb = st["rgb"]
+        s.rgb = rgb[b].data_ptr()
+        s.nv_c, s.Hc, s.Wc = rgb.shape[1], rgb.shape[3], rgb.shape[4]
+        s.K_c = st["K_c"][b].data_ptr()
+        s.w2c_c = st["w2c_c"][b].data_ptr()
+        s.d_min, s.d_max, s.inv_z = float(self.d_min), float(self.d_max), int(bool(self.inv_z))
+        s.num_freqs = int(self.code_xyz.num_freqs)
+        s.freq_factor = float(getattr(self.code_xyz, "freq_factor", float(self.code_xyz.freqs[0])))
+        s.include_input = int(bool(self.code_xyz.include_input))
+        s.learn_empty = int(bool(self.learn_empty))
+        if self.learn_empty:
+            self._empty_f32 = _f32c(self.empty_feature)
+            s.empty_feature = self._empty_f32.data_ptr()
+        return s
+
+    def _mlp(self, precision: int) -> _abi.SdMlp:
+        head = self.heads[self.final_pred_head]
+        if isinstance(head, ResnetFC):
+            return head.packed(precision)
+        if self._head_packed is None:
+            from .heads import PackedMlp
+            self._head_packed = PackedMlp()
+        return self._head_packed.get(head.lin_in, head.lin_out, precision)
+
+    def _check_points(self, xyz):
+        require_cuda(xyz, "xyz")
+        if xyz.dim() != 3 or xyz.shape[-1] != 3:
+            raise ValueError(f"xyz must be [n, n_pts, 3], got {tuple(xyz.shape)}")
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError("scenedino_b200 is forward-only: call under torch.no_grad() / .eval()")
+        return _f32c(xyz)
+
+    # ---- BTSNet.sample_features (bts.py:271-328) ---------------------------------------------------
+    def sample_features(self, xyz):
+        xyz = self._check_points(xyz)
+        st = self._state(_abi.SD_MLP_FP32)
+        n, N, _ = xyz.shape
+        d = st["C"] + self.code_xyz.d_out
+        feat = torch.empty((n, N, 1, d), dtype=torch.float32, device=xyz.device)
+        inv = torch.empty((n, N, 1), dtype=torch.uint8, device=xyz.device)
+        lib = _abi.lib()
+        for b in range(n):
+            sc = self._scene(st, b)
+            _abi.check(lib.sd_sample_features(C.byref(sc), _ptr(xyz[b]), N, _ptr(feat[b]), _ptr(inv[b]), _stream()),
+                       "sd_sample_features")
+        return feat, inv.view(torch.bool)
+
+    # ---- BTSNet.sample_colors (bts.py:330-441) -----------------------------------------------------
+    def sample_colors(self, xyz, **kwargs):
+        if kwargs.get("render_flow", False):
+            raise NotImplementedError("render_flow is not implemented")
+        xyz = self._check_points(xyz)
+        st = self._state(_abi.SD_MLP_FP32)
+        n, N, _ = xyz.shape
+        nv = st["rgb"].shape[1]
+        rgb = torch.empty((n, N, nv, 3), dtype=torch.float32, device=xyz.device)
+        inv = torch.empty((n, N, nv), dtype=torch.uint8, device=xyz.device)
+        lib = _abi.lib()
+        for b in range(n):
+            sc = self._scene(st, b)
+            _abi.check(lib.sd_sample_colors(C.byref(sc), _ptr(xyz[b]), N, _ptr(rgb[b]), _ptr(inv[b]), _stream()),
+                       "sd_sample_colors")
+        return rgb.permute(0, 2, 1, 3), inv.view(torch.bool).permute(0, 2, 1).unsqueeze(-1)
+
+    # ---- BTSNet.forward (bts.py:476-595) -----------------------------------------------------------
+    def forward(self, xyz: torch.Tensor, **kwargs):
+        only_density = kwargs.get("only_density", False)
+        predict_segmentation = kwargs.get("predict_segmentation", False)
+        prediction_mode = kwargs.get("prediction_mode", "stego_kmeans")
+        if kwargs.get("render_flow", False):
+            raise NotImplementedError("render_flow is not implemented")
+        if not self.predict_dino:
+            raise NotImplementedError("predict_dino=False heads are not implemented")
+        with torch.profiler.record_function("model_inference"):
+            xyz = self._check_points(xyz)
+            prec = self._precision()
+            st = self._state(prec)
+            mlp = self._mlp(prec)
+            n, N, _ = xyz.shape
+            nv_c = st["rgb"].shape[1]
+            D = mlp.d_out - 1
+            dev = xyz.device
+            sigma = torch.empty((n, N, 1), dtype=torch.float32, device=dev)
+            dino = torch.empty((n, N, D), dtype=torch.float32, device=dev)
+            invf = torch.empty((n, N, 1), dtype=torch.uint8, device=dev)
+            want_colors = not (predict_segmentation or only_density)
+            rgb = torch.empty((n, N, 3 * nv_c), dtype=torch.float32, device=dev) if want_colors else None
+            invalid = torch.empty((n, N, nv_c), dtype=torch.float32, device=dev) if want_colors else None
+            lib = _abi.lib()
+            for b in range(n):
+                sc = self._scene(st, b)
+                _abi.check(lib.sd_query_points(
+                    C.byref(sc), C.byref(mlp), _ptr(xyz[b]), N, _ptr(sigma[b]), _ptr(dino[b]),
+                    _ptr(rgb[b]) if want_colors else None, _ptr(invalid[b]) if want_colors else None,
+                    _ptr(invf[b]), _stream()), "sd_query_points")
+            invalid_features = invf.view(torch.bool)
+
+        if predict_segmentation:  # bts.py:528-533, 584-592
+            dino_full = self.encoder.expand_dim(dino)
+            seg = None
+            if self.downstream_head is not None:
+                seg = self.downstream_head(dino_full, mode=prediction_mode)
+                seg = torch.nn.functional.one_hot(seg, self.gt_classes)
+            return dino_full, None, sigma, seg
+        if only_density:  # bts.py:570-572
+            rgb = torch.zeros((n, N, nv_c * 3), device=dev)
+            invalid = invalid_features.to(sigma.dtype)
+        state_dict = {"invalid_features": invalid_features.flatten(0, 1)[None], "dino_features": dino}
+        return rgb, invalid, sigma, None, state_dict

@@ -1,0 +1,134 @@
+// extern "C" surface of libscenedino_b200.so: error plumbing and the composite entry points that
+// dispatch between the fp32 CUDA-core path (field_simt.cu) and the fused tcgen05 path (field_tc.cu).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace sd {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return SD_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" int sd_abi_version(void) { return SD_ABI_VERSION; }
+extern "C" const char *sd_last_error(void) { return g_err; }
+extern "C" long long sd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int sd_device_sm_count(void) {
+    int dev = 0, n = 0;
+    SD_CUDA_OK(cudaGetDevice(&dev));
+    SD_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    return n;
+}
+
+extern "C" int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, float *out, void *stream) {
+    SD_REQUIRE(mlp, "sd_mlp_forward: mlp is NULL");
+    SD_REQUIRE(N >= 0, "sd_mlp_forward: bad N");
+    // ResnetFC.forward asserts the input width (resnetfc.py:155); widths are carried by sd_mlp here.
+    if (mlp->precision == SD_MLP_BF16_TC) return launch_mlp_tc(mlp, x, N, out, (cudaStream_t)stream);
+    return launch_mlp_simt(mlp, x, N, out, false, (cudaStream_t)stream);
+}
+
+extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                               float *sigma, float *dino, float *rgb, float *invalid,
+                               unsigned char *invalid_feat, void *stream) {
+    FieldParams fp;
+    int rc = make_field_params(scene, &fp);
+    if (rc) return rc;
+    SD_REQUIRE(mlp, "sd_query_points: mlp is NULL");
+    SD_REQUIRE(xyz && N >= 0, "sd_query_points: bad points");
+    PointSrc src = {xyz, nullptr, nullptr, 0, 1};
+    if (mlp->precision == SD_MLP_BF16_TC) {
+        TcOut o = {};
+        o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
+        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream);
+    }
+    SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);
+    SimtOut out = {};
+    out.sigma = sigma; out.dino = dino; out.rgb = rgb; out.invalid = invalid; out.invalid_feat = invalid_feat;
+    return launch_field_simt(MODE_QUERY_, fp, src, N, mlp, out, (cudaStream_t)stream);
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" size_t sd_render_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long R, int K) {
+    if (!scene || !mlp || R <= 0 || K <= 0) return 0;
+    if (mlp->precision == SD_MLP_BF16_TC && tc_supported(scene, mlp, K)) return 0;
+    const size_t N = (size_t)R * K;
+    const int D = mlp->d_out - 1;
+    // sigma [N], dino [N,D], rgb [N,3nv_c]
+    return align256(N * 4) + align256(N * D * 4) + align256(N * 3 * (size_t)(scene->nv_c > 0 ? scene->nv_c : 1) * 4);
+}
+
+extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_cfg *cfg,
+                              const float *rays, long long R, int r_dim, const float *z, int K, float *depth,
+                              float *dino, float *rgb_out, float *weights, float *alphas, float *invalid,
+                              unsigned char *invalid_feat, float *rgb_samps, float *sigma, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+    FieldParams fp;
+    int rc = make_field_params(scene, &fp);
+    if (rc) return rc;
+    SD_REQUIRE(mlp && cfg && rays && z, "sd_render_pass: null pointer");
+    SD_REQUIRE(R >= 0 && K > 0 && r_dim >= 8, "sd_render_pass: bad shape (rays need >= 8 columns)");
+    if (R == 0) return SD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = R * K;
+    const int D = mlp->d_out - 1;
+    const int Crgb = 3 * fp.nv_c;
+    PointSrc src = {nullptr, rays, z, r_dim, K};
+
+    if (mlp->precision == SD_MLP_BF16_TC && tc_supported(scene, mlp, K)) {
+        TcRender rr = {};
+        rr.cfg = *cfg; rr.depth = depth; rr.dino = dino; rr.rgb_out = rgb_out; rr.weights = weights;
+        rr.alphas = alphas; rr.rgb_samps = rgb_samps;
+        TcOut o = {};
+        o.sigma = sigma; o.invalid = invalid; o.invalid_feat = invalid_feat;
+        return launch_field_tc(fp, src, N, mlp, &rr, o, st);
+    }
+
+    const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);
+    if (workspace_bytes < need || !workspace) {
+        set_error("sd_render_pass: workspace of %zu B needed, %zu B given", need, workspace_bytes);
+        return SD_ERR_WORKSPACE;
+    }
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    float *w_sigma = sigma ? sigma : reinterpret_cast<float *>(ws);
+    ws += align256((size_t)N * 4);
+    float *w_dino = reinterpret_cast<float *>(ws);
+    ws += align256((size_t)N * D * 4);
+    float *w_rgb = rgb_samps ? rgb_samps : reinterpret_cast<float *>(ws);
+
+    if (mlp->precision == SD_MLP_BF16_TC) {
+        TcOut o = {};
+        o.sigma = w_sigma; o.dino = w_dino; o.rgb = Crgb ? w_rgb : nullptr; o.invalid = invalid; o.invalid_feat = invalid_feat;
+        rc = launch_field_tc(fp, src, N, mlp, nullptr, o, st);
+    } else {
+        SimtOut out = {};
+        out.sigma = w_sigma; out.dino = w_dino; out.rgb = Crgb ? w_rgb : nullptr; out.invalid = invalid;
+        out.invalid_feat = invalid_feat;
+        rc = launch_field_simt(MODE_QUERY_, fp, src, N, mlp, out, st);
+    }
+    if (rc) return rc;
+    return sd_composite(z, w_sigma, w_dino, Crgb ? w_rgb : nullptr, R, K, D, Crgb, cfg, weights, alphas, depth,
+                        dino, rgb_out, stream);
+}

@@ -1,0 +1,68 @@
+// Internal launch interface shared by abi.cu, field_simt.cu and field_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sd {
+
+// Where the query points come from: an explicit [N,3] array, or implicitly o + z*d along rays
+// (nerf.py:252-253) so that the [R*K,3] point cloud never exists in HBM.
+struct PointSrc {
+    const float *xyz;   // [N,3] or NULL
+    const float *rays;  // [R,r_dim]  (ray mode: point i = ray i / K at depth z[i])
+    const float *z;     // [R,K]
+    int r_dim, K;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void load_point(const PointSrc &s, long long i, float &px, float &py, float &pz) {
+    if (s.xyz) {
+        px = __ldg(s.xyz + 3 * i); py = __ldg(s.xyz + 3 * i + 1); pz = __ldg(s.xyz + 3 * i + 2);
+    } else {
+        const long long r = i / s.K;
+        const float *ry = s.rays + r * s.r_dim;
+        const float zz = __ldg(s.z + i);
+        px = ray_point(__ldg(ry + 0), __ldg(ry + 3), zz);
+        py = ray_point(__ldg(ry + 1), __ldg(ry + 4), zz);
+        pz = ray_point(__ldg(ry + 2), __ldg(ry + 5), zz);
+    }
+}
+#endif
+
+struct SimtOut {
+    float *feat;                 // [N, d_in]           (features mode)
+    unsigned char *invalid_feat; // [N]
+    float *sigma;                // [N]
+    float *dino;                 // [N, d_out-1]
+    float *rgb;                  // [N, 3*nv_c]
+    float *invalid;              // [N, nv_c]
+    float *raw;                  // unused
+};
+
+enum { MODE_FEATURES_ = 0, MODE_QUERY_ = 1 };
+
+int launch_field_simt(int mode, const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp,
+                      const SimtOut &out, cudaStream_t st);
+int launch_mlp_simt(const sd_mlp *mlp, const float *x, long long N, float *out, bool normalize, cudaStream_t st);
+
+// ---- fused tcgen05 path -----------------------------------------------------------------------
+struct TcOut {            // per-point / per-sample outputs (any may be NULL)
+    float *sigma;         // [N]
+    float *dino;          // [N, D]        (point mode only)
+    float *rgb;           // [N, 3*nv_c]   (point mode: BTSNet.forward rgb; render mode: rgb_samps)
+    float *invalid;       // [N, nv_c]
+    unsigned char *invalid_feat;  // [N]
+};
+
+struct TcRender {         // per-ray outputs of the fused composite
+    sd_render_cfg cfg;
+    float *depth, *dino, *rgb_out, *weights, *alphas, *rgb_samps;
+};
+
+// true when the fused kernel handles this (scene, head) in render mode with K samples per ray
+bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K);
+int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp,
+                    const TcRender *render, const TcOut &out, cudaStream_t st);
+// ResnetFC.forward on explicit rows through the same tcgen05 pipeline (unit test of the MMA path)
+int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st);
+
+}  // namespace sd

@@ -1,0 +1,139 @@
+// One-off re-layout kernels: feature map planar -> channels-last, MLP weights -> packed blob.
+#include "common.cuh"
+
+namespace sd {
+
+// ---- feature map: [n, C, H, W] fp32 -> [n, H, W, C] fp32 | bf16 ---------------------------------
+// Tile = 64 channels x 32 pixels through shared memory: reads are 128 B per warp along W, writes
+// are 256 B (fp32) / 128 B (bf16) per warp along C.  HBM-bound: 4*C*H*W read + esize*C*H*W written.
+template <bool BF16>
+__global__ void __launch_bounds__(256) featmap_pack_kernel(const float *__restrict__ src, void *__restrict__ dst,
+                                                           int C, long long HW) {
+    __shared__ float tile[64][33];
+    const int img = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+    const float *s = src + (size_t)img * C * HW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + warp * 8 + i;
+        const long long p = p0 + lane;
+        tile[warp * 8 + i][lane] = (c < C && p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pl = warp * 4 + i;
+        const long long p = p0 + pl;
+        if (p >= HW) continue;
+        const int c = c0 + lane * 2;
+        if (c >= C) continue;
+        const float a = tile[lane * 2][pl], b = tile[lane * 2 + 1][pl];
+        const size_t o = ((size_t)img * HW + p) * C + c;
+        if (BF16) {
+            __nv_bfloat16 *d = reinterpret_cast<__nv_bfloat16 *>(dst);
+            if (c + 1 < C) *reinterpret_cast<__nv_bfloat162 *>(d + o) = __floats2bfloat162_rn(a, b);
+            else d[o] = __float2bfloat16_rn(a);
+        } else {
+            float *d = reinterpret_cast<float *>(dst);
+            if (c + 1 < C) *reinterpret_cast<float2 *>(d + o) = make_float2(a, b);
+            else d[o] = a;
+        }
+    }
+}
+
+// ---- MLP blob ---------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
+    MlpLayout L;
+    L.d_in = d_in; L.d_hidden = d_hidden; L.d_out = d_out;
+    L.d_in_pad = (int)align_up((size_t)d_in, 64);   // whole 64-wide K blocks (SW128 atoms)
+    L.d_out_pad = (int)align_up((size_t)d_out, 16);
+    size_t o = 0;
+    L.off_w_in_t = o;   o = align_up(o + sizeof(float) * (size_t)L.d_in_pad * d_hidden, 1024);
+    L.off_b_in = o;     o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
+    L.off_w_out_t = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden * L.d_out_pad, 1024);
+    L.off_b_out = o;    o = align_up(o + sizeof(float) * (size_t)L.d_out_pad, 1024);
+    L.off_w_in_bf = o;  o = align_up(o + 2 * (size_t)L.d_in_pad * d_hidden, 1024);
+    // feature rows of W_out (rows 1..d_out-1), padded to a multiple of 16 rows
+    const int n2 = (int)align_up((size_t)(d_out > 1 ? d_out - 1 : 1), 16);
+    L.off_w_out_bf = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden, 64), 1024);
+    L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
+    L.total = o;
+    return L;
+}
+
+__global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__restrict__ b_in,
+                                const float *__restrict__ w_out, const float *__restrict__ b_out,
+                                MlpLayout L, unsigned char *__restrict__ blob) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    float *w_in_t = reinterpret_cast<float *>(blob + L.off_w_in_t);
+    float *bi = reinterpret_cast<float *>(blob + L.off_b_in);
+    float *w_out_t = reinterpret_cast<float *>(blob + L.off_w_out_t);
+    float *bo = reinterpret_cast<float *>(blob + L.off_b_out);
+    __nv_bfloat16 *w_in_bf = reinterpret_cast<__nv_bfloat16 *>(blob + L.off_w_in_bf);
+    __nv_bfloat16 *w_out_bf = reinterpret_cast<__nv_bfloat16 *>(blob + L.off_w_out_bf);
+    float *w_sigma = reinterpret_cast<float *>(blob + L.off_w_sigma);
+    const int H = L.d_hidden;
+    for (int i = tid; i < L.d_in_pad * H; i += nth) {
+        const int k = i / H, j = i - k * H;
+        const float v = k < L.d_in ? w_in[(size_t)j * L.d_in + k] : 0.0f;
+        w_in_t[i] = v;
+        w_in_bf[umma_sw128_offset(j, k, H) / 2] = __float2bfloat16_rn(v);
+    }
+    for (int i = tid; i < H; i += nth) {
+        bi[i] = b_in[i];
+        w_sigma[i] = w_out[i];  // row 0 of W_out
+    }
+    for (int i = tid; i < H * L.d_out_pad; i += nth) {
+        const int k = i / L.d_out_pad, o = i - k * L.d_out_pad;
+        w_out_t[i] = o < L.d_out ? w_out[(size_t)o * H + k] : 0.0f;
+    }
+    for (int i = tid; i < L.d_out_pad; i += nth) bo[i] = i < L.d_out ? b_out[i] : 0.0f;
+    const int n2 = ((L.d_out > 1 ? L.d_out - 1 : 1) + 15) / 16 * 16;
+    const int Hp = (H + 63) / 64 * 64;
+    for (int i = tid; i < n2 * Hp; i += nth) {
+        const int r = i / Hp, k = i - r * Hp;  // feature row r <-> W_out row r+1
+        const float v = (r + 1 < L.d_out && k < H) ? w_out[(size_t)(r + 1) * H + k] : 0.0f;
+        w_out_bf[umma_sw128_offset(r, k, n2) / 2] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace sd
+
+extern "C" int sd_featmap_pack(const float *nchw, int n_img, int C, int H, int W, void *nhwc,
+                               int dst_dtype, void *stream) {
+    SD_REQUIRE(nchw && nhwc, "sd_featmap_pack: null pointer");
+    SD_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0, "sd_featmap_pack: bad shape");
+    SD_REQUIRE(C % 2 == 0, "sd_featmap_pack: C must be even (got %d)", C);
+    SD_REQUIRE(dst_dtype == SD_F32 || dst_dtype == SD_BF16, "sd_featmap_pack: bad dst_dtype");
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)n_img);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == SD_BF16)
+        sd::featmap_pack_kernel<true><<<grid, 256, 0, st>>>(nchw, nhwc, C, HW);
+    else
+        sd::featmap_pack_kernel<false><<<grid, 256, 0, st>>>(nchw, nhwc, C, HW);
+    SD_LAUNCH_OK("featmap_pack_kernel");
+    return SD_OK;
+}
+
+extern "C" size_t sd_mlp_pack_bytes(int d_in, int d_hidden, int d_out) {
+    if (d_in <= 0 || d_hidden <= 0 || d_out <= 0) return 0;
+    return sd::mlp_layout(d_in, d_hidden, d_out).total;
+}
+
+extern "C" int sd_mlp_pack(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
+                           int d_in, int d_hidden, int d_out, void *packed, void *stream) {
+    SD_REQUIRE(w_in && b_in && w_out && b_out && packed, "sd_mlp_pack: null pointer");
+    SD_REQUIRE(d_in > 0 && d_hidden > 0 && d_out > 0, "sd_mlp_pack: bad dims");
+    SD_REQUIRE(((uintptr_t)packed & 127) == 0, "sd_mlp_pack: packed must be 128-byte aligned");
+    const sd::MlpLayout L = sd::mlp_layout(d_in, d_hidden, d_out);
+    sd::mlp_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w_in, b_in, w_out, b_out, L,
+                                                              reinterpret_cast<unsigned char *>(packed));
+    SD_LAUNCH_OK("mlp_pack_kernel");
+    return SD_OK;
+}

@@ -1,0 +1,356 @@
+"""``NeRFRenderer`` -- host-side mirror of scenedino/renderer/nerf.py:12-658.
+
+Same constructor / ``from_conf`` keys, ``sample_*`` / ``composite`` / ``forward`` signatures, output
+dictionary keys and shapes, persistent buffers (``iter_idx``, ``last_sched``) and ``bind_parallel``
+wrapper.  Random draws are made with the SAME torch calls, in the same order and shapes as the
+reference (so a shared seed gives the same samples); all arithmetic runs in libscenedino_b200:
+
+  sample_coarse            -> sd_sample_coarse            (nerf.py:121-141)
+  sample_coarse_from_dist  -> sd_sample_coarse_from_dist  (nerf.py:143-179)
+  sample_fine              -> sd_sample_fine              (nerf.py:181-212)
+  sample_fine_depth        -> sd_sample_fine_depth        (nerf.py:214-228)
+  torch.sort of the merge  -> sd_sort_rows                (nerf.py:490,522)
+  composite                -> sd_render_pass (native BTSNet: points, field query and compositing in
+                              one call) or model(...) + sd_composite (any other model)  (nerf.py:230-449)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from .heads import _f32c, _ptr, _stream, require_cuda
+
+
+class DotMap(dict):
+    """Attribute-access dict with ``toDict`` -- the subset of dotmap.DotMap the reference uses
+    (nerf.py:9,499-509,571)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def toDict(self):
+        return {k: (v.toDict() if isinstance(v, DotMap) else v) for k, v in self.items()}
+
+
+class _RenderWrapper(torch.nn.Module):
+    """nerf.py:12-53."""
+
+    def __init__(self, net, renderer, simple_output):
+        super().__init__()
+        self.net = net
+        self.renderer = renderer
+        self.simple_output = simple_output
+
+    def forward(self, rays, want_weights=False, want_alphas=False, want_z_samps=False, want_rgb_samps=False,
+                sample_from_dist=None):
+        if rays.shape[0] == 0:
+            return torch.zeros(0, 3, device=rays.device), torch.zeros(0, device=rays.device)
+        so = self.simple_output
+        outputs = self.renderer(self.net, rays, want_weights=want_weights and not so,
+                                want_alphas=want_alphas and not so, want_z_samps=want_z_samps and not so,
+                                want_rgb_samps=want_rgb_samps and not so, sample_from_dist=sample_from_dist)
+        if so:
+            o = outputs.fine if self.renderer.using_fine else outputs.coarse
+            return o.rgb, o.depth
+        return outputs.toDict()
+
+
+class NeRFRenderer(torch.nn.Module):
+    def __init__(self, n_coarse=128, n_fine=0, n_fine_depth=0, noise_std=0.0, depth_std=0.01,
+                 eval_batch_size=100000, white_bkgd=False, lindisp=False, sched=None, hard_alpha_cap=False,
+                 render_mode="volumetric", surface_sigmoid_scale=.1, render_flow=False, normalize_dino=False):
+        super().__init__()
+        self.n_coarse, self.n_fine = n_coarse, n_fine
+        self.n_fine_depth = n_fine_depth
+        self.noise_std = noise_std
+        self.depth_std = depth_std
+        self.eval_batch_size = eval_batch_size  # kept for config compatibility; the fused path does not chunk
+        self.white_bkgd = white_bkgd
+        self.lindisp = lindisp
+        self.using_fine = n_fine > 0
+        self.sched = sched if (sched is None or len(sched) > 0) else None
+        self.register_buffer("iter_idx", torch.tensor(0, dtype=torch.long), persistent=True)
+        self.register_buffer("last_sched", torch.tensor(0, dtype=torch.long), persistent=True)
+        self.hard_alpha_cap = hard_alpha_cap
+        assert render_mode in ("volumetric", "surface", "neus")
+        self.render_mode = render_mode
+        self.only_surface_color = (self.render_mode == "surface")
+        self.surface_sigmoid_scale = surface_sigmoid_scale
+        self.render_flow = render_flow
+        self.normalize_dino = normalize_dino
+        #: the reference scans six tensors for NaN after every composite and exits the process
+        #: (nerf.py:428-432); here the per-ray results are scanned and FloatingPointError is raised.
+        self.nan_check = True
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    @staticmethod
+    def _rays2d(rays):
+        require_cuda(rays, "rays")
+        if rays.dim() != 2 or rays.shape[1] < 8:
+            raise ValueError(f"rays must be [B, >=8], got {tuple(rays.shape)}")
+        return _f32c(rays)
+
+    def _cfg(self) -> _abi.SdRenderCfg:
+        c = _abi.SdRenderCfg()
+        c.lindisp, c.hard_alpha_cap, c.white_bkgd = int(bool(self.lindisp)), int(bool(self.hard_alpha_cap)), int(bool(self.white_bkgd))
+        return c
+
+    # ---- sampling ------------------------------------------------------------------------------------
+    def sample_coarse(self, rays):
+        """nerf.py:121-141: stratified samples, (B, Kc)."""
+        rays = self._rays2d(rays)
+        B, Kc = rays.shape[0], self.n_coarse
+        step = 1.0 / Kc
+        lin = torch.linspace(0, 1 - step, Kc, device=rays.device)
+        u = torch.rand_like(torch.empty((B, Kc), dtype=torch.float32, device=rays.device))
+        z = torch.empty((B, Kc), dtype=torch.float32, device=rays.device)
+        _abi.check(_abi.lib().sd_sample_coarse(_ptr(rays), B, rays.shape[1], _ptr(u), _ptr(lin), Kc,
+                                               int(bool(self.lindisp)), _ptr(z), _stream()), "sd_sample_coarse")
+        return z
+
+    def sample_coarse_from_dist(self, rays, weights, z_samp):
+        """nerf.py:143-179: resampling of a proposal histogram, (B, Kc), unsorted."""
+        rays = self._rays2d(rays)
+        B, Kc = rays.shape[0], self.n_coarse
+        w, zs = _f32c(weights), _f32c(z_samp)
+        Kp = w.shape[-1]
+        u0 = torch.rand(B, Kc, dtype=torch.float32, device=rays.device)
+        u1 = torch.rand_like(u0, dtype=torch.float32)
+        z = torch.empty((B, Kc), dtype=torch.float32, device=rays.device)
+        _abi.check(_abi.lib().sd_sample_coarse_from_dist(B, _ptr(w), _ptr(zs), Kp, _ptr(u0), _ptr(u1), Kc,
+                                                         int(bool(self.lindisp)), _ptr(z), None, _stream()),
+                   "sd_sample_coarse_from_dist")
+        return z
+
+    def sample_fine(self, rays, weights):
+        """nerf.py:181-212: importance samples, (B, Kf - Kfd)."""
+        rays = self._rays2d(rays)
+        B = rays.shape[0]
+        w = _f32c(weights)
+        Kc, Kf = w.shape[-1], self.n_fine - self.n_fine_depth
+        u0 = torch.rand(B, Kf, dtype=torch.float32, device=rays.device)
+        u1 = torch.rand_like(u0)
+        z = torch.empty((B, Kf), dtype=torch.float32, device=rays.device)
+        # the reference divides by self.n_coarse (nerf.py:202), which equals the histogram width
+        if Kc != self.n_coarse:
+            raise ValueError("sample_fine: weights must have n_coarse columns")
+        _abi.check(_abi.lib().sd_sample_fine(_ptr(rays), B, rays.shape[1], _ptr(w), Kc, _ptr(u0), _ptr(u1), Kf,
+                                             int(bool(self.lindisp)), _ptr(z), None, _stream()), "sd_sample_fine")
+        return z
+
+    def sample_fine_depth(self, rays, depth):
+        """nerf.py:214-228: samples around the expected depth, (B, Kfd)."""
+        rays = self._rays2d(rays)
+        B, Kfd = rays.shape[0], self.n_fine_depth
+        d = _f32c(depth)
+        noise = torch.randn_like(torch.empty((B, Kfd), dtype=torch.float32, device=rays.device))
+        z = torch.empty((B, Kfd), dtype=torch.float32, device=rays.device)
+        _abi.check(_abi.lib().sd_sample_fine_depth(_ptr(rays), B, rays.shape[1], _ptr(d), _ptr(noise), Kfd,
+                                                   float(self.depth_std), _ptr(z), _stream()), "sd_sample_fine_depth")
+        return z
+
+    @staticmethod
+    def _sort_rows(z):
+        z = z.contiguous()
+        _abi.check(_abi.lib().sd_sort_rows(_ptr(z), z.shape[0], z.shape[1], _stream()), "sd_sort_rows")
+        return z
+
+    # ---- composite -----------------------------------------------------------------------------------
+    def composite(self, model, rays, z_samp, coarse=True, sb=0):
+        """nerf.py:230-449.  Returns the reference's 10-tuple
+        (weights, rgb, depth, alphas, invalid, z_samp, rgbs, ray_info, extras, state_dicts)."""
+        return self._composite(model, rays, z_samp, coarse, sb, want_rgb_samps=True)
+
+    def _composite(self, model, rays, z_samp, coarse, sb, want_rgb_samps):
+        with torch.profiler.record_function("renderer_composite"):
+            if self.render_mode != "volumetric":
+                raise NotImplementedError(f"render_mode={self.render_mode!r}: only 'volumetric' is implemented")
+            if self.training and self.noise_std > 0.0:
+                raise NotImplementedError("noise_std > 0 in training mode is not implemented")
+            rays = self._rays2d(rays)
+            z_samp = _f32c(z_samp)
+            B, K = z_samp.shape
+            if hasattr(model, "_sd_render_pass") or hasattr(model, "_scene"):
+                out = self._composite_native(model, rays, z_samp, max(sb, 1), want_rgb_samps)
+            else:
+                out = self._composite_generic(model, rays, z_samp, coarse, sb)
+            weights, rgb_final, depth, alphas, invalid, rgbs, state = out
+            if self.nan_check:
+                bad = torch.isnan(depth).any() | torch.isnan(rgb_final).any() | torch.isnan(z_samp).any()
+                if bool(bad):
+                    raise FloatingPointError("NaN in rendered depth / rgb / z_samp (reference: nerf.py:428-432)")
+            ray_info = rays[:, None, 8:] if rays.shape[-1] > 8 else None
+            return weights, rgb_final, depth, alphas, invalid, z_samp, rgbs, ray_info, None, state
+
+    def _composite_native(self, net, rays, z, sb, want_rgb_samps):
+        if B_ := rays.shape[0] % sb:
+            raise ValueError(f"{rays.shape[0]} rays do not split into {sb} scenes ({B_} left over)")
+        prec = net._precision()
+        st = net._state(prec)
+        mlp = net._mlp(prec)
+        if st["n"] != sb:
+            raise ValueError(f"super-batch {sb} but the field was encoded with batch {st['n']}")
+        B, K = z.shape
+        Bp = B // sb
+        nv_c, D = st["rgb"].shape[1], mlp.d_out - 1
+        dev = rays.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        weights, alphas = torch.empty((B, K), **f32), torch.empty((B, K), **f32)
+        depth, dino, rgb = torch.empty((B,), **f32), torch.empty((B, D), **f32), torch.empty((B, 3 * nv_c), **f32)
+        invalid = torch.empty((B, K, nv_c), **f32)
+        invf = torch.empty((B, K, 1), dtype=torch.uint8, device=dev)
+        rgbs = torch.empty((B, K, 3 * nv_c), **f32) if want_rgb_samps else None
+        cfg = self._cfg()
+        lib = _abi.lib()
+        for b in range(sb):
+            sc = net._scene(st, b)
+            sl = slice(b * Bp, (b + 1) * Bp)
+            need = lib.sd_render_workspace_bytes(C.byref(sc), C.byref(mlp), Bp, K)
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
+            _abi.check(lib.sd_render_pass(
+                C.byref(sc), C.byref(mlp), C.byref(cfg), _ptr(rays[sl]), Bp, rays.shape[1], _ptr(z[sl]), K,
+                _ptr(depth[sl]), _ptr(dino[sl]), _ptr(rgb[sl]), _ptr(weights[sl]), _ptr(alphas[sl]),
+                _ptr(invalid[sl]), _ptr(invf[sl]), _ptr(rgbs[sl]) if want_rgb_samps else None, None,
+                _ptr(ws), need, _stream()), "sd_render_pass")
+        state = {"invalid_features": invf.view(torch.bool), "dino_features": dino}
+        return weights, rgb, depth, alphas, invalid, rgbs, state
+
+    def _composite_generic(self, model, rays, z, coarse, sb):
+        """Any other model: evaluate it in eval_batch_size chunks like nerf.py:268-341, then
+        sd_composite."""
+        B, K = z.shape
+        pts = (rays[:, None, :3] + z.unsqueeze(2) * rays[:, None, 3:6]).reshape(-1, 3)
+        info = rays[:, None, 8:].expand(-1, K, -1) if rays.shape[-1] > 8 else None
+        if sb > 0:
+            pts = pts.reshape(sb, -1, 3)
+            info = info.reshape(sb, -1, info.shape[-1]) if info is not None else None
+            dim, ebs = 1, (self.eval_batch_size - 1) // sb + 1
+        else:
+            dim, ebs = 0, self.eval_batch_size
+        r_all, i_all, s_all, st_all = [], [], [], []
+        infos = torch.split(info, ebs, dim=dim) if info is not None else None
+        for i, p in enumerate(torch.split(pts, ebs, dim=dim)):
+            rgbs, invalid, sigmas, extras, sd = model(p, coarse=coarse, only_density=self.only_surface_color,
+                                                      ray_info=None if infos is None else infos[i],
+                                                      render_flow=self.render_flow)
+            if extras is not None:
+                raise NotImplementedError("models returning extras are not implemented")
+            r_all.append(rgbs); i_all.append(invalid); s_all.append(sigmas); st_all.append(sd)
+        rgbs = _f32c(torch.cat(r_all, dim=dim)).reshape(B, K, -1)
+        invalid = torch.cat(i_all, dim=dim).reshape(B, K, -1)
+        sigmas = _f32c(torch.cat(s_all, dim=dim)).reshape(B, K)
+        state = {k: torch.cat([s[k] for s in st_all], dim=dim) for k in st_all[0].keys()}
+        state = {k: v.reshape(B, K, *v.shape[2:]) for k, v in state.items()}
+        feat = _f32c(state["dino_features"])
+        D, Crgb = feat.shape[-1], rgbs.shape[-1]
+        f32 = dict(dtype=torch.float32, device=rays.device)
+        weights, alphas = torch.empty((B, K), **f32), torch.empty((B, K), **f32)
+        depth, dino, rgb = torch.empty((B,), **f32), torch.empty((B, D), **f32), torch.empty((B, Crgb), **f32)
+        cfg = self._cfg()
+        _abi.check(_abi.lib().sd_composite(_ptr(z), _ptr(sigmas), _ptr(feat), _ptr(rgbs), B, K, D, Crgb, C.byref(cfg),
+                                           _ptr(weights), _ptr(alphas), _ptr(depth), _ptr(dino), _ptr(rgb),
+                                           _stream()), "sd_composite")
+        state["dino_features"] = dino
+        return weights, rgb, depth, alphas, invalid, rgbs, state
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, model, rays, want_weights=False, want_alphas=False, want_z_samps=False,
+                want_rgb_samps=False, sample_from_dist=None):
+        """nerf.py:451-539: rays (SB, B, >=8) -> DotMap(coarse=..., [fine=...], state_dict=...)."""
+        with torch.profiler.record_function("renderer_forward"):
+            if self.sched is not None and self.last_sched.item() > 0:
+                self.n_coarse = self.sched[1][self.last_sched.item() - 1]
+                self.n_fine = self.sched[2][self.last_sched.item() - 1]
+            assert len(rays.shape) == 3
+            sb = rays.shape[0]
+            rays = rays.reshape(-1, rays.shape[-1])
+            if sample_from_dist is None:
+                z_coarse = self.sample_coarse(rays)
+            else:
+                pw, pz = sample_from_dist
+                n = pw.shape[-1]
+                z_coarse = self._sort_rows(self.sample_coarse_from_dist(rays, pw.reshape(-1, n), pz.reshape(-1, n)))
+            fmt = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
+                       want_rgb_samps=want_rgb_samps)
+            coarse = self._composite(model, rays, z_coarse, True, sb, want_rgb_samps)
+            outputs = DotMap(coarse=self._format_outputs(coarse, sb, **fmt))
+            outputs.state_dict = coarse[-1]
+            if self.using_fine:
+                samps = [z_coarse]
+                if self.n_fine - self.n_fine_depth > 0:
+                    samps.append(self.sample_fine(rays, coarse[0].detach()))
+                if self.n_fine_depth > 0:
+                    samps.append(self.sample_fine_depth(rays, coarse[2]))
+                z_all = self._sort_rows(torch.cat(samps, dim=-1))
+                fine = self._composite(model, rays, z_all, False, sb, want_rgb_samps)
+                outputs.fine = self._format_outputs(fine, sb, **fmt)
+            return outputs
+
+    def _format_outputs(self, rendered_outputs, superbatch_size, want_weights=False, want_alphas=False,
+                        want_z_samps=False, want_rgb_samps=False):
+        """nerf.py:541-598 (shapes, keys and the invalid_features reshape quirk included)."""
+        weights, rgb_final, depth, alphas, invalid, z_samps, rgb_samps, ray_info, extras, state_dict = rendered_outputs
+        n_smps = weights.shape[-1]
+        out_d_rgb, out_d_i = rgb_final.shape[-1], invalid.shape[-1]
+        out_d_dino = state_dict["dino_features"].shape[-1]
+        sb = superbatch_size
+        if sb > 0:
+            rgb_final = rgb_final.reshape(sb, -1, out_d_rgb)
+            depth = depth.reshape(sb, -1)
+            invalid = invalid.reshape(sb, -1, n_smps, out_d_i)
+        ret = DotMap(rgb=rgb_final, depth=depth, invalid=invalid)
+        if ray_info is not None:
+            ret.ray_info = ray_info.reshape(sb, -1, ray_info.shape[-1])
+        if extras is not None:
+            ret.extras = extras.reshape(sb, -1, extras.shape[-1])
+        if want_weights:
+            ret.weights = weights.reshape(sb, -1, n_smps)
+        if want_alphas:
+            ret.alphas = alphas.reshape(sb, -1, n_smps)
+        if want_z_samps:
+            ret.z_samps = z_samps.reshape(sb, -1, n_smps)
+        if want_rgb_samps:
+            ret.rgb_samps = rgb_samps.reshape(sb, -1, n_smps, out_d_rgb)
+        if "dino_features" in state_dict:
+            ret.dino_features = state_dict["dino_features"].reshape(sb, -1, out_d_dino)
+        if "invalid_features" in state_dict:
+            ret.invalid_features = state_dict["invalid_features"].reshape(sb, -1, n_smps, out_d_i)
+        return ret
+
+    def sched_step(self, steps=1):
+        """nerf.py:600-620."""
+        if self.sched is None:
+            return
+        self.iter_idx += steps
+        while self.last_sched.item() < len(self.sched[0]) and self.iter_idx.item() >= self.sched[0][self.last_sched.item()]:
+            self.n_coarse = self.sched[1][self.last_sched.item()]
+            self.n_fine = self.sched[2][self.last_sched.item()]
+            print("INFO: NeRF sampling resolution changed on schedule ==> c", self.n_coarse, "f", self.n_fine)
+            self.last_sched += 1
+
+    @classmethod
+    def from_conf(cls, conf, white_bkgd=False, eval_batch_size=100000):
+        """nerf.py:622-639 (note lindisp defaults to True here, False in __init__)."""
+        return cls(
+            conf.get("n_coarse", 128), conf.get("n_fine", 0), n_fine_depth=conf.get("n_fine_depth", 0),
+            noise_std=conf.get("noise_std", 0.0), depth_std=conf.get("depth_std", 0.01),
+            white_bkgd=conf.get("white_bkgd", white_bkgd), lindisp=conf.get("lindisp", True),
+            eval_batch_size=conf.get("eval_batch_size", eval_batch_size), sched=conf.get("sched", None),
+            hard_alpha_cap=conf.get("hard_alpha_cap", False), render_mode=conf.get("render_mode", "volumetric"),
+            surface_sigmoid_scale=conf.get("surface_sigmoid_scale", 1), render_flow=conf.get("render_flow", False),
+            normalize_dino=conf.get("normalize_dino", False))
+
+    def bind_parallel(self, net, gpus=None, simple_output=False):
+        """nerf.py:641-658.  Multi-GPU here is one process per GPU (scenedino_b200.sharding), not
+        nn.DataParallel, so ``gpus`` with more than one entry is rejected."""
+        if gpus is not None and len(gpus) > 1:
+            raise NotImplementedError("use scenedino_b200.sharding (one process per GPU) instead of DataParallel")
+        return _RenderWrapper(net, self, simple_output=simple_output)

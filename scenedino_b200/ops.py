@@ -1,0 +1,284 @@
+"""Functional layer over the C ABI: one Python function per entry point of
+include/scenedino_b200.h, taking CUDA tensors.  ``BTSNet`` / ``NeRFRenderer`` are the reference-shaped
+surface; this module is what the parity tests and bench.py drive directly.
+
+Every function launches on ``torch.cuda.current_stream()`` and returns freshly allocated tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _abi
+from .heads import _f32c, _ptr, _stream, require_cuda
+
+FP32, BF16 = _abi.SD_MLP_FP32, _abi.SD_MLP_BF16_TC
+
+
+def _dev(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def featmap_pack(nchw: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """[n, C, H, W] fp32 -> [n, H, W, C] fp32 | bf16 (sd_featmap_pack)."""
+    require_cuda(nchw, "feature map")
+    src = _f32c(nchw)
+    n, c, h, w = src.shape
+    dst = torch.empty((n, h, w, c), dtype=dtype, device=src.device)
+    dt = _abi.SD_BF16 if dtype == torch.bfloat16 else _abi.SD_F32
+    _abi.check(_abi.lib().sd_featmap_pack(_ptr(src), n, c, h, w, _ptr(dst), dt, _stream()), "sd_featmap_pack")
+    return dst
+
+
+class Mlp:
+    """Packed two-layer head (nn.Linear layout in: w_in [H, d_in], w_out [d_out, H])."""
+
+    def __init__(self, w_in, b_in, w_out, b_out, device="cuda", precision: int = FP32):
+        self.w = [_dev(t, device) for t in (w_in, b_in, w_out, b_out)]
+        self.d_hidden, self.d_in = self.w[0].shape
+        self.d_out = self.w[2].shape[0]
+        self.precision = precision
+        lib = _abi.lib()
+        nbytes = lib.sd_mlp_pack_bytes(self.d_in, self.d_hidden, self.d_out)
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        off = (-raw.data_ptr()) % 1024
+        self.blob = raw[off:off + nbytes]
+        _abi.check(lib.sd_mlp_pack(*[_ptr(t) for t in self.w], self.d_in, self.d_hidden, self.d_out, _ptr(self.blob),
+                                   _stream()), "sd_mlp_pack")
+
+    def c(self, precision: int | None = None) -> _abi.SdMlp:
+        m = _abi.SdMlp()
+        m.packed = self.blob.data_ptr()
+        m.d_in, m.d_hidden, m.d_out = self.d_in, self.d_hidden, self.d_out
+        m.precision = self.precision if precision is None else precision
+        return m
+
+
+@dataclass
+class Scene:
+    """Device-side state of one batch element (what BTSNet.encode stashes, bts.py:246-257)."""
+    feat: torch.Tensor                  # [Hf, Wf, C] channels-last, fp32 or bf16
+    K_f: torch.Tensor                   # [1,3,3]
+    w2c_f: torch.Tensor                 # [1,4,4]
+    rgb: torch.Tensor | None = None     # [nv_c,3,Hc,Wc]
+    K_c: torch.Tensor | None = None
+    w2c_c: torch.Tensor | None = None
+    d_min: float = 3.0
+    d_max: float = 80.0
+    inv_z: bool = True
+    num_freqs: int = 6
+    freq_factor: float = 1.5
+    include_input: bool = True
+    learn_empty: bool = False
+    empty_feature: torch.Tensor | None = None
+
+    @classmethod
+    def from_arrays(cls, feat_nchw, K_f, w2c_f, rgb=None, K_c=None, w2c_c=None, device="cuda",
+                    feat_dtype=torch.float32, **kw):
+        """feat_nchw [1, C, Hf, Wf] (reference layout) is packed channels-last on the device."""
+        f = featmap_pack(_dev(feat_nchw, device), feat_dtype)[0]
+        s = cls(feat=f, K_f=_dev(K_f, device).reshape(1, 3, 3), w2c_f=_dev(w2c_f, device).reshape(1, 4, 4), **kw)
+        if rgb is not None:
+            s.rgb, s.K_c, s.w2c_c = _dev(rgb, device), _dev(K_c, device), _dev(w2c_c, device)
+        if s.empty_feature is not None:
+            s.empty_feature = _dev(s.empty_feature, device)
+        return s
+
+    def with_feat_dtype(self, feat_nchw, dtype):
+        import dataclasses
+        return dataclasses.replace(self, feat=featmap_pack(_dev(feat_nchw, self.feat.device), dtype)[0])
+
+    @property
+    def nv_c(self) -> int:
+        return 0 if self.rgb is None else self.rgb.shape[0]
+
+    @property
+    def code_dim(self) -> int:
+        return (3 if self.include_input else 0) + 6 * self.num_freqs
+
+    def c(self) -> _abi.SdScene:
+        s = _abi.SdScene()
+        s.feat = self.feat.data_ptr()
+        s.feat_dtype = _abi.SD_BF16 if self.feat.dtype == torch.bfloat16 else _abi.SD_F32
+        s.nv_f = 1
+        s.Hf, s.Wf, s.C = self.feat.shape
+        s.K_f, s.w2c_f = self.K_f.data_ptr(), self.w2c_f.data_ptr()
+        if self.rgb is not None:
+            s.rgb = self.rgb.data_ptr()
+            s.nv_c, _, s.Hc, s.Wc = self.rgb.shape
+            s.K_c, s.w2c_c = self.K_c.data_ptr(), self.w2c_c.data_ptr()
+        s.d_min, s.d_max, s.inv_z = self.d_min, self.d_max, int(self.inv_z)
+        s.num_freqs, s.freq_factor, s.include_input = self.num_freqs, self.freq_factor, int(self.include_input)
+        s.learn_empty = int(self.learn_empty)
+        if self.empty_feature is not None:
+            s.empty_feature = self.empty_feature.data_ptr()
+        return s
+
+
+def _e(shape, ref, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=ref.device)
+
+
+def project_points(K, w2c, xyz):
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    N = xyz.shape[0]
+    xy, z, inv = _e((N, 2), xyz), _e((N,), xyz), _e((N,), xyz, torch.uint8)
+    _abi.check(_abi.lib().sd_project_points(_ptr(_f32c(K)), _ptr(_f32c(w2c)), _ptr(xyz), N, _ptr(xy), _ptr(z), _ptr(inv),
+                                            _stream()), "sd_project_points")
+    return xy, z, inv.view(torch.bool)
+
+
+def sample_features(scene: Scene, xyz):
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    N = xyz.shape[0]
+    feat = _e((N, scene.feat.shape[-1] + scene.code_dim), xyz)
+    inv = _e((N,), xyz, torch.uint8)
+    sc = scene.c()
+    _abi.check(_abi.lib().sd_sample_features(C.byref(sc), _ptr(xyz), N, _ptr(feat), _ptr(inv), _stream()),
+               "sd_sample_features")
+    return feat, inv.view(torch.bool)
+
+
+def sample_colors(scene: Scene, xyz):
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    N = xyz.shape[0]
+    rgb, inv = _e((N, 3 * scene.nv_c), xyz), _e((N, scene.nv_c), xyz, torch.uint8)
+    sc = scene.c()
+    _abi.check(_abi.lib().sd_sample_colors(C.byref(sc), _ptr(xyz), N, _ptr(rgb), _ptr(inv), _stream()), "sd_sample_colors")
+    return rgb, inv.view(torch.bool)
+
+
+def mlp_forward(mlp: Mlp, x, precision=None):
+    x = _f32c(x); require_cuda(x, "x")
+    out = _e((x.shape[0], mlp.d_out), x)
+    m = mlp.c(precision)
+    _abi.check(_abi.lib().sd_mlp_forward(C.byref(m), _ptr(x), x.shape[0], _ptr(out), _stream()), "sd_mlp_forward")
+    return out
+
+
+def expand_dim(mlp: Mlp, f):
+    f = _f32c(f); require_cuda(f, "f")
+    out = _e((f.shape[0], mlp.d_out), f)
+    m = mlp.c(FP32)
+    _abi.check(_abi.lib().sd_expand_dim(C.byref(m), _ptr(f), f.shape[0], _ptr(out), _stream()), "sd_expand_dim")
+    return out
+
+
+def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out=None):
+    """BTSNet.forward for one scene -> dict(sigma[N], dino[N,D], rgb[N,3nv_c], invalid[N,nv_c],
+    invalid_features[N] bool).  ``out`` lets bench.py reuse output buffers."""
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    N = xyz.shape[0]
+    D = mlp.d_out - 1
+    if out is None:
+        out = dict(sigma=_e((N,), xyz), dino=_e((N, D), xyz), invalid_features=_e((N,), xyz, torch.uint8))
+        if want_rgb and scene.nv_c:
+            out.update(rgb=_e((N, 3 * scene.nv_c), xyz), invalid=_e((N, scene.nv_c), xyz))
+    sc, m = scene.c(), mlp.c(precision)
+    _abi.check(_abi.lib().sd_query_points(C.byref(sc), C.byref(m), _ptr(xyz), N, _ptr(out["sigma"]), _ptr(out["dino"]),
+                                          _ptr(out.get("rgb")), _ptr(out.get("invalid")),
+                                          _ptr(out["invalid_features"]), _stream()), "sd_query_points")
+    res = dict(out)
+    res["invalid_features"] = out["invalid_features"].view(torch.bool)
+    return res
+
+
+def sample_coarse(rays, u, lin, lindisp=True):
+    rays, u, lin = _f32c(rays), _f32c(u), _f32c(lin)
+    R, Kc = u.shape
+    z = _e((R, Kc), rays)
+    _abi.check(_abi.lib().sd_sample_coarse(_ptr(rays), R, rays.shape[1], _ptr(u), _ptr(lin), Kc, int(lindisp), _ptr(z),
+                                           _stream()), "sd_sample_coarse")
+    return z
+
+
+def sample_fine(rays, weights, u0, u1, lindisp=True):
+    rays, weights, u0, u1 = _f32c(rays), _f32c(weights), _f32c(u0), _f32c(u1)
+    R, Kc = weights.shape
+    Kf = u0.shape[1]
+    z, inds = _e((R, Kf), rays), _e((R, Kf), rays, torch.int32)
+    _abi.check(_abi.lib().sd_sample_fine(_ptr(rays), R, rays.shape[1], _ptr(weights), Kc, _ptr(u0), _ptr(u1), Kf,
+                                         int(lindisp), _ptr(z), _ptr(inds), _stream()), "sd_sample_fine")
+    return z, inds
+
+
+def sample_fine_depth(rays, depth, noise, depth_std):
+    rays, depth, noise = _f32c(rays), _f32c(depth), _f32c(noise)
+    R, Kfd = noise.shape
+    z = _e((R, Kfd), rays)
+    _abi.check(_abi.lib().sd_sample_fine_depth(_ptr(rays), R, rays.shape[1], _ptr(depth), _ptr(noise), Kfd,
+                                               float(depth_std), _ptr(z), _stream()), "sd_sample_fine_depth")
+    return z
+
+
+def sample_coarse_from_dist(weights, z_samp, u0, u1, lindisp=True):
+    weights, z_samp, u0, u1 = _f32c(weights), _f32c(z_samp), _f32c(u0), _f32c(u1)
+    R, Kp = weights.shape
+    Kc = u0.shape[1]
+    z, inds = _e((R, Kc), weights), _e((R, Kc), weights, torch.int32)
+    _abi.check(_abi.lib().sd_sample_coarse_from_dist(R, _ptr(weights), _ptr(z_samp), Kp, _ptr(u0), _ptr(u1), Kc,
+                                                     int(lindisp), _ptr(z), _ptr(inds), _stream()),
+               "sd_sample_coarse_from_dist")
+    return z, inds
+
+
+def sort_rows(z):
+    z = _f32c(z).clone()
+    _abi.check(_abi.lib().sd_sort_rows(_ptr(z), z.shape[0], z.shape[1], _stream()), "sd_sort_rows")
+    return z
+
+
+def _cfg(lindisp=True, hard_alpha_cap=False, white_bkgd=False):
+    c = _abi.SdRenderCfg()
+    c.lindisp, c.hard_alpha_cap, c.white_bkgd = int(lindisp), int(hard_alpha_cap), int(white_bkgd)
+    return c
+
+
+def composite(z, sigma, feat, rgb=None, hard_alpha_cap=False, white_bkgd=False):
+    z, sigma, feat = _f32c(z), _f32c(sigma), _f32c(feat)
+    R, K = z.shape
+    D = feat.shape[-1]
+    Crgb = 0 if rgb is None else rgb.shape[-1]
+    rgb = None if rgb is None else _f32c(rgb)
+    out = dict(weights=_e((R, K), z), alphas=_e((R, K), z), depth=_e((R,), z), dino=_e((R, D), z),
+               rgb=_e((R, Crgb), z) if Crgb else None)
+    cfg = _cfg(True, hard_alpha_cap, white_bkgd)
+    _abi.check(_abi.lib().sd_composite(_ptr(z), _ptr(sigma), _ptr(feat), _ptr(rgb), R, K, D, Crgb, C.byref(cfg),
+                                       _ptr(out["weights"]), _ptr(out["alphas"]), _ptr(out["depth"]), _ptr(out["dino"]),
+                                       _ptr(out["rgb"]), _stream()), "sd_composite")
+    return out
+
+
+def render_pass(scene: Scene, mlp: Mlp, rays, z, hard_alpha_cap=False, white_bkgd=False, want_rgb_samps=False,
+                want_sigma=True, per_sample=True, precision=None, out=None):
+    """One NeRFRenderer.composite call for one scene (sd_render_pass)."""
+    rays, z = _f32c(rays), _f32c(z)
+    R, K = z.shape
+    D, nv_c = mlp.d_out - 1, scene.nv_c
+    if out is None:
+        out = dict(depth=_e((R,), z), dino_features=_e((R, D), z), rgb=_e((R, 3 * nv_c), z))
+        if per_sample:
+            out.update(weights=_e((R, K), z), alphas=_e((R, K), z), invalid=_e((R, K, nv_c), z),
+                       invalid_features=_e((R, K), z, torch.uint8))
+            if want_sigma:
+                out["sigma"] = _e((R, K), z)
+        if want_rgb_samps:
+            out["rgb_samps"] = _e((R, K, 3 * nv_c), z)
+    sc, m, cfg = scene.c(), mlp.c(precision), _cfg(True, hard_alpha_cap, white_bkgd)
+    lib = _abi.lib()
+    need = lib.sd_render_workspace_bytes(C.byref(sc), C.byref(m), R, K)
+    ws = torch.empty((need,), dtype=torch.uint8, device=z.device) if need else None
+    _abi.check(lib.sd_render_pass(C.byref(sc), C.byref(m), C.byref(cfg), _ptr(rays), R, rays.shape[1], _ptr(z), K,
+                                  _ptr(out["depth"]), _ptr(out["dino_features"]), _ptr(out["rgb"]),
+                                  _ptr(out.get("weights")), _ptr(out.get("alphas")), _ptr(out.get("invalid")),
+                                  _ptr(out.get("invalid_features")), _ptr(out.get("rgb_samps")), _ptr(out.get("sigma")),
+                                  _ptr(ws), need, _stream()), "sd_render_pass")
+    res = dict(out)
+    if "invalid_features" in res:
+        res["invalid_features"] = res["invalid_features"].view(torch.bool)
+    res["z_samps"] = z
+    return res

@@ -1,0 +1,203 @@
+"""The reference-shaped Python surface (BTSNet / NeRFRenderer / _RenderWrapper) against the golden
+dictionaries the unmodified reference produced: same keys, same shapes, values within tolerance,
+random draws injected in the reference's call order.  Needs a B200: ``-m gpu``."""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+import scenedino_b200 as sd
+from helpers import TOL_BF16, TOL_FP32, assert_close, golden_scene_arrays
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+class FakeEncoder(torch.nn.Module):
+    """Seeded map standing in for the DINO ViT + DPT encoder (cf. EncoderDummy,
+    training/trainer_overfit.py:21-30 in the reference)."""
+
+    def __init__(self, feat):
+        super().__init__()
+        self.latent_size, self.extra_outs = feat.shape[1], 0
+        self.dim_reduction = sd.MlpDimReduction(768, 64, 128)
+        self.register_buffer("feat", feat)
+
+    def forward(self, x, ground_truth=False):
+        if ground_truth:
+            return [torch.zeros(x.shape[0], 8, 2, 2, device=x.device)]
+        return [self.feat.clone()]
+
+    def expand_dim(self, f):
+        return self.dim_reduction.transform_expand(f)
+
+
+def build(g, n=1, nv=None, learn_empty=False, precision="fp32"):
+    feat, imgs = golden_scene_arrays(g, n=n)
+    conf = {"predict_dino": True, "dino_dims": 64, "inv_z": True, "learn_empty": learn_empty, "code_mode": "z",
+            "sd_precision": precision}
+    code = sd.PositionalEncoding.from_conf({"num_freqs": 6, "freq_factor": 1.5, "include_input": True}, d_in=3)
+    enc = FakeEncoder(torch.from_numpy(feat))
+    head = sd.make_head({"type": "resnet", "name": "normal_head", "args": {"n_blocks": 0, "d_hidden": 128}},
+                        enc.latent_size + code.d_out, 65)
+    net = sd.BTSNet(conf, enc, code, {"normal_head": head}, None)
+    # weights arrive the way a reference checkpoint would: by state-dict key
+    state = {"heads.normal_head.lin_in.weight": g["w_in"], "heads.normal_head.lin_in.bias": g["b_in"],
+             "heads.normal_head.lin_out.weight": g["w_out"], "heads.normal_head.lin_out.bias": g["b_out"]}
+    if "e_w1" in g:
+        state.update({"encoder.dim_reduction.linear_in.weight": g["e_w1"], "encoder.dim_reduction.linear_in.bias": g["e_b1"],
+                      "encoder.dim_reduction.linear_out.weight": g["e_w2"], "encoder.dim_reduction.linear_out.bias": g["e_b2"]})
+    if learn_empty:
+        state["empty_feature"] = g["empty_feature"]
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=False)
+    assert not unexpected
+    net = net.to(DEV).eval()
+    K = g["K"] if n > 1 else g["K"][None]
+    c2w = g["c2w"] if n > 1 else g["c2w"][None]
+    nv = K.shape[1]
+    net.encode(torch.zeros(n, nv, 3, 8, 8, device=DEV), dev(K), dev(c2w), ids_encoder=[0],
+               ids_render=list(range(nv)), images_alt=dev(imgs))
+    net.set_scale(0)
+    return net
+
+
+@contextlib.contextmanager
+def injected_draws(draws):
+    """Replays the reference's recorded torch.rand / rand_like / randn_like results in call order."""
+    q = [dev(d) for d in draws]
+    orig = (torch.rand, torch.rand_like, torch.randn_like)
+
+    def pop(*a, **k):
+        return q.pop(0)
+
+    torch.rand = torch.rand_like = torch.randn_like = pop
+    try:
+        yield
+    finally:
+        torch.rand, torch.rand_like, torch.randn_like = orig
+    assert not q, "the renderer made fewer random draws than the reference"
+
+
+def check_dict(out, g, prefix, tol):
+    keys = [k[len(prefix):] for k in g if k.startswith(prefix)]
+    assert sorted(out.keys()) == sorted(keys)
+    for k in keys:
+        a, b = out[k].detach().cpu().numpy(), g[prefix + k]
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        assert a.dtype == b.dtype, (k, a.dtype, b.dtype)
+        if k in ("invalid", "invalid_features", "ray_info", "rgb_samps"):
+            assert np.array_equal(a, b), k
+        elif k == "z_samps":
+            assert np.array_equal(a, b) or np.mean(np.all(a == b, -1)) > 0.99, k
+        else:
+            assert_close(a, b, tol, prefix + k)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_render_wrapper_coarse(golden, precision, tol):
+    g = golden("render_coarse")
+    net = build(g, precision=precision)
+    ren = sd.NeRFRenderer.from_conf({"n_coarse": 64, "n_fine": 0, "lindisp": True, "eval_batch_size": 4096})
+    ren.hard_alpha_cap = False                      # demo_utils/utils.py:45
+    wrapped = ren.bind_parallel(net, gpus=None).eval()
+    with torch.no_grad(), injected_draws([g["u_coarse"]]):
+        out = wrapped(dev(g["rays"]), want_weights=True, want_alphas=True, want_z_samps=True, want_rgb_samps=True)
+    assert isinstance(out, dict) and set(out.keys()) == {"coarse", "state_dict"}
+    check_dict(out["coarse"], g, "coarse.", tol)
+    assert set(out["state_dict"].keys()) == {"invalid_features", "dino_features"}
+    assert_close(out["state_dict"]["dino_features"].cpu().numpy(), g["state_dict.dino_features"], tol, "state dino")
+    # simple_output
+    with torch.no_grad(), injected_draws([g["u_coarse"]]):
+        rgb, depth = ren.bind_parallel(net, simple_output=True)(dev(g["rays"]))
+    assert_close(depth.cpu().numpy(), g["coarse.depth"], tol, "simple depth")
+    # empty-ray shortcut (nerf.py:28-32)
+    r0, d0 = wrapped(torch.zeros(0, 5, 11, device=DEV))
+    assert r0.shape == (0, 3) and d0.shape == (0,)
+
+
+@pytest.mark.parametrize("name", ["render_fine", "render_fine_lin"])
+def test_render_wrapper_fine(golden, name):
+    g = golden(name)
+    Kc, Kf, Kfd, lindisp, white = [int(v) for v in g["conf"]]
+    net = build(g)
+    ren = sd.NeRFRenderer.from_conf({"n_coarse": Kc, "n_fine": Kf, "n_fine_depth": Kfd, "lindisp": bool(lindisp),
+                                     "depth_std": float(g["depth_std"]), "white_bkgd": bool(white),
+                                     "hard_alpha_cap": True})
+    wrapped = ren.bind_parallel(net).eval()
+    with torch.no_grad(), injected_draws([g["u_coarse"], g["u_fine0"], g["u_fine1"], g["n_depth"]]):
+        out = wrapped(dev(g["rays"]), want_weights=True, want_alphas=True, want_z_samps=True, want_rgb_samps=True)
+    assert set(out.keys()) == {"coarse", "fine", "state_dict"}
+    check_dict(out["coarse"], g, "coarse.", TOL_FP32)
+    # fine pass: rows whose importance indices did not flip at a 1-ulp CDF tie must agree
+    a, b = out["fine"]["z_samps"].cpu().numpy(), g["fine.z_samps"]
+    same = np.all(a == b, -1)[0]
+    assert same.mean() > 0.99
+    for k in ("weights", "alphas", "depth", "rgb", "dino_features"):
+        assert_close(out["fine"][k].cpu().numpy()[0][same], g["fine." + k][0][same], TOL_FP32, "fine." + k)
+
+
+def test_render_wrapper_from_dist(golden):
+    g = golden("render_from_dist")
+    net = build(g)
+    ren = sd.NeRFRenderer.from_conf({"n_coarse": 40, "n_fine": 0, "lindisp": True})
+    with torch.no_grad(), injected_draws([g["u0"], g["u1"]]):
+        out = ren.bind_parallel(net).eval()(dev(g["rays"]), want_weights=True, want_alphas=True, want_z_samps=True,
+                                            want_rgb_samps=True, sample_from_dist=(dev(g["prop_weights"]), dev(g["prop_z"])))
+    check_dict(out["coarse"], g, "coarse.", TOL_FP32)
+
+
+def test_render_wrapper_superbatch(golden):
+    g = golden("render_superbatch")
+    net = build(g, n=2)
+    ren = sd.NeRFRenderer.from_conf({"n_coarse": 32, "n_fine": 0, "lindisp": True, "hard_alpha_cap": True})
+    with torch.no_grad(), injected_draws([g["u_coarse"]]):
+        out = ren.bind_parallel(net).eval()(dev(g["rays"]), want_weights=True, want_alphas=True, want_z_samps=True,
+                                            want_rgb_samps=True)
+    check_dict(out["coarse"], g, "coarse.", TOL_FP32)
+
+
+@pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
+def test_btsnet_forward(golden, tag, learn_empty):
+    g = golden("query")
+    net = build(g, learn_empty=learn_empty)
+    xyz = dev(g["points"])[None]
+    with torch.no_grad():
+        rgb, invalid, sigma, extras, state = net(xyz)
+        sf, sinv = net.sample_features(xyz)
+        col, cinv = net.sample_colors(xyz)
+        dino_full, inv2, sigma2, seg = net(xyz[:, :256], predict_segmentation=True)
+        rgb0, inv0, sigma0, _, _ = net(xyz, only_density=True)
+    N = xyz.shape[1]
+    assert extras is None and seg is None and inv2 is None
+    assert rgb.shape == (1, N, 6) and invalid.shape == (1, N, 2) and sigma.shape == (1, N, 1)
+    assert invalid.dtype == torch.float32 and state["invalid_features"].dtype == torch.bool
+    assert state["invalid_features"].shape == (1, N, 1) and state["dino_features"].shape == (1, N, 64)
+    assert_close(sigma[0, :, 0].cpu().numpy(), g["sigma" + tag], TOL_FP32, "sigma")
+    assert_close(state["dino_features"][0].cpu().numpy(), g["dino" + tag], TOL_FP32, "dino")
+    assert np.array_equal(rgb[0].cpu().numpy(), g["rgb" + tag])
+    assert np.array_equal(invalid[0].cpu().numpy(), g["invalid" + tag])
+    assert np.array_equal(state["invalid_features"][0, :, 0].cpu().numpy(), g["invalid_features" + tag])
+    assert sf.shape == (1, N, 1, 295) and sinv.shape == (1, N, 1) and sinv.dtype == torch.bool
+    n = g["sample_features" + tag].shape[0]
+    assert np.array_equal(sf[0, :n, 0, :256].cpu().numpy(), g["sample_features" + tag][:, :256])
+    assert col.shape == (1, 2, N, 3) and cinv.shape == (1, 2, N, 1)
+    assert np.array_equal(col.permute(0, 2, 1, 3).reshape(N, 6).cpu().numpy(), g["rgb" + tag])
+    assert_close(dino_full[0].cpu().numpy(), g["dino_full" + tag], TOL_FP32, "dino_full")
+    assert_close(sigma2[0, :, 0].cpu().numpy(), g["sigma_seg" + tag], TOL_FP32, "sigma (segmentation call)")
+    assert rgb0.shape == (1, N, 6) and float(rgb0.abs().sum()) == 0.0
+    assert np.array_equal(inv0[0, :, 0].cpu().numpy(), g["invalid_features" + tag].astype(np.float32))
+
+
+def test_no_silent_fallback(golden):
+    g = golden("query")
+    net = build(g)
+    with pytest.raises(sd.SdError):
+        net(torch.zeros(1, 4, 3))                     # CPU tensor
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 4, 3, device=DEV))         # autograd / training is out of scope

@@ -1,0 +1,135 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, compute entry points fail loudly without a GPU (no fallback), and the reference-shaped
+Python surface keeps the reference's names, keys and shapes."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import scenedino_b200 as sd
+from scenedino_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "scenedino_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_symbols()
+    assert len(names) >= 20
+    raw = ctypes.CDLL(_abi.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} is declared in include/scenedino_b200.h but not exported"
+        assert n in _abi.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert sorted(_abi.PROTOTYPES) == names
+    assert _abi.lib().sd_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_gpu_means_error_not_fallback():
+    lib = _abi.lib()
+    assert lib.sd_device_sm_count() == -2          # SD_ERR_CUDA
+    assert "CUDA" in _abi.last_error()
+    z = np.zeros((4, 8), np.float32)
+    rc = lib.sd_sort_rows(z.ctypes.data_as(ctypes.c_void_p), 4, 8, None)
+    assert rc == -2
+    with pytest.raises(sd.SdError):
+        from scenedino_b200 import ops
+        ops.sort_rows(torch.zeros(4, 8))
+
+
+def test_argument_validation_without_gpu():
+    lib = _abi.lib()
+    assert lib.sd_sort_rows(None, 4, 8, None) == -1 and "null" in _abi.last_error()
+    assert lib.sd_mlp_pack_bytes(295, 128, 65) > 4 * (295 * 128 + 128 * 65)
+    assert lib.sd_mlp_pack_bytes(0, 128, 65) == 0
+    assert lib.sd_render_workspace_bytes(None, None, 10, 10) == 0
+
+
+def _net(conf_extra=None):
+    class Enc(torch.nn.Module):
+        latent_size, extra_outs = 256, 0
+
+        def forward(self, x, ground_truth=False):
+            return [torch.zeros(x.shape[0], 256, 4, 4)]
+
+    conf = {"predict_dino": True, "dino_dims": 64, "learn_empty": False, "code_mode": "z"}
+    conf.update(conf_extra or {})
+    code = sd.PositionalEncoding.from_conf({"num_freqs": 6, "freq_factor": 1.5, "include_input": True})
+    head = sd.make_head({"type": "resnet", "name": "normal_head", "args": {"n_blocks": 0, "d_hidden": 128}}, 256 + code.d_out, 65)
+    return sd.BTSNet(conf, Enc(), code, {"normal_head": head}, None)
+
+
+def test_state_dict_keys_match_reference_names():
+    """Checkpoint keys: renderer.net.heads.<name>.lin_in/lin_out.{weight,bias}, renderer.renderer
+    buffers iter_idx / last_sched."""
+    net = _net({"learn_empty": True})
+    ren = sd.NeRFRenderer.from_conf({"n_coarse": 32})
+    wrapped = ren.bind_parallel(net)
+
+    class Wrapper(torch.nn.Module):     # like BTSWrapper: attribute `renderer`
+        def __init__(self):
+            super().__init__()
+            self.renderer = wrapped
+
+    keys = set(Wrapper().state_dict().keys())
+    for k in ("renderer.net.heads.normal_head.lin_in.weight", "renderer.net.heads.normal_head.lin_in.bias",
+              "renderer.net.heads.normal_head.lin_out.weight", "renderer.net.heads.normal_head.lin_out.bias",
+              "renderer.net.empty_feature", "renderer.renderer.iter_idx", "renderer.renderer.last_sched"):
+        assert k in keys, k
+    assert net.heads["normal_head"].lin_in.weight.shape == (128, 295)
+    assert net._d_in == 295 and net._d_out == 65
+    assert float(net.heads["normal_head"].lin_in.bias.detach().abs().sum()) == 0.0     # resnetfc.py:91
+
+
+def test_renderer_conf_and_schedule():
+    ren = sd.NeRFRenderer.from_conf({})
+    assert (ren.n_coarse, ren.n_fine, ren.lindisp, ren.hard_alpha_cap, ren.render_mode) == (128, 0, True, False, "volumetric")
+    assert sd.NeRFRenderer().lindisp is False               # __init__ default differs from from_conf (nerf.py:82,631)
+    ren = sd.NeRFRenderer(n_coarse=8, sched=[[2, 4], [16, 32], [0, 8]])
+    ren.sched_step(); assert ren.n_coarse == 8
+    ren.sched_step(); assert (ren.n_coarse, ren.n_fine, int(ren.last_sched)) == (16, 0, 1)
+    ren.sched_step(2); assert (ren.n_coarse, ren.n_fine, int(ren.last_sched)) == (32, 8, 2)
+    with pytest.raises(NotImplementedError):
+        ren.bind_parallel(None, gpus=[0, 1])
+
+
+def test_format_outputs_shapes_and_quirk():
+    """_format_outputs (nerf.py:541-598): keys, super-batch reshape, and invalid_features reshaped with
+    invalid's last dimension (nv_c) as the reference does."""
+    ren = sd.NeRFRenderer(n_coarse=4)
+    B, K, nv = 8, 4, 2
+    tup = (torch.rand(B, K), torch.rand(B, 3 * nv), torch.rand(B), torch.rand(B, K), torch.zeros(B, K, nv), torch.rand(B, K),
+           torch.rand(B, K, 3 * nv), torch.rand(B, 1, 3), None,
+           {"dino_features": torch.rand(B, 64), "invalid_features": torch.zeros(B, K, 1, dtype=torch.bool)})
+    o = ren._format_outputs(tup, 2, want_weights=True, want_alphas=True, want_z_samps=True, want_rgb_samps=True)
+    assert sorted(o.keys()) == sorted(["rgb", "depth", "invalid", "ray_info", "weights", "alphas", "z_samps", "rgb_samps",
+                                       "dino_features", "invalid_features"])
+    assert o.rgb.shape == (2, 4, 6) and o.depth.shape == (2, 4) and o.invalid.shape == (2, 4, K, nv)
+    assert o.ray_info.shape == (2, 4, 3) and o.rgb_samps.shape == (2, 4, K, 6) and o.dino_features.shape == (2, 4, 64)
+    assert o.invalid_features.shape == (2, 4 // nv, K, nv)      # the reference's reshape with out_d_i = nv_c
+    o = ren._format_outputs(tup, 2)
+    assert sorted(o.keys()) == sorted(["rgb", "depth", "invalid", "ray_info", "dino_features", "invalid_features"])
+    d = sd.DotMap(a=sd.DotMap(b=1), c=2)
+    assert d.a.b == 1 and d.toDict() == {"a": {"b": 1}, "c": 2}
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        _net({"code_mode": "distance"})
+    with pytest.raises(NotImplementedError):
+        _net({"use_viewdirs": True})
+    with pytest.raises(NotImplementedError):
+        sd.ResnetFC(295, d_out=65, n_blocks=5)
+    net = _net()
+    with pytest.raises(RuntimeError, match="encode"):
+        net._state(0)
+    with pytest.raises(sd.SdError):
+        net.eval()(torch.zeros(1, 4, 3))      # CPU points
