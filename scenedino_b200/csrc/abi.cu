@@ -56,7 +56,7 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
     SD_REQUIRE(mlp, "sd_query_points: mlp is NULL");
-    SD_REQUIRE(xyz && N >= 0, "sd_query_points: bad points");
+    SD_REQUIRE(N >= 0 && (xyz || N == 0), "sd_query_points: bad points");
     PointSrc src = {xyz, nullptr, nullptr, 0, 1};
     if (mlp->precision == SD_MLP_BF16_TC) {
         TcOut o = {};
@@ -88,9 +88,10 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
-    SD_REQUIRE(mlp && cfg && rays && z, "sd_render_pass: null pointer");
+    SD_REQUIRE(mlp && cfg, "sd_render_pass: null pointer");
     SD_REQUIRE(R >= 0 && K > 0 && r_dim >= 8, "sd_render_pass: bad shape (rays need >= 8 columns)");
     if (R == 0) return SD_OK;
+    SD_REQUIRE(rays && z, "sd_render_pass: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const long long N = R * K;
     const int D = mlp->d_out - 1;

@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(128) composite_kernel(const float *__restrict_
 extern "C" int sd_composite(const float *z, const float *sigma, const float *feat, const float *rgb,
                             long long R, int K, int D, int Crgb, const sd_render_cfg *cfg, float *weights,
                             float *alphas, float *depth, float *dino, float *rgb_out, void *stream) {
-    SD_REQUIRE(z && sigma && cfg, "sd_composite: null pointer");
+    SD_REQUIRE(cfg, "sd_composite: null pointer");
     SD_REQUIRE(R >= 0 && K > 0, "sd_composite: bad shape");
+    if (R == 0) return SD_OK;
+    SD_REQUIRE(z && sigma, "sd_composite: null pointer");
     SD_REQUIRE(D >= 0 && D <= 1024, "sd_composite: D must be <= 1024 (got %d)", D);
     SD_REQUIRE(Crgb >= 0 && Crgb <= 32, "sd_composite: at most 10 colour views (Crgb=%d)", Crgb);
     SD_REQUIRE(!(dino && D > 0) || feat, "sd_composite: dino requested without feat");

@@ -380,10 +380,11 @@ int launch_field_simt(int mode, const FieldParams &fp, const PointSrc &src, long
 }
 
 int launch_mlp_simt(const sd_mlp *mlp, const float *x, long long N, float *out, bool normalize, cudaStream_t st) {
-    SD_REQUIRE(mlp && mlp->packed && x && out, "mlp_forward: null pointer");
+    SD_REQUIRE(mlp && mlp->packed, "mlp_forward: null pointer");
     SD_REQUIRE(mlp->d_hidden == 128, "mlp: d_hidden must be 128 (got %d)", mlp->d_hidden);
     SD_REQUIRE(mlp->d_in > 0 && mlp->d_in <= 512 && mlp->d_out > 0, "mlp: unsupported dims");
     if (N == 0) return SD_OK;
+    SD_REQUIRE(x && out, "mlp_forward: null pointer");
     const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
     const int XS = (mlp->d_in + 3) / 4 * 4;
     const size_t xfloats = (size_t)TP * XS > (size_t)TP * 65 ? (size_t)TP * XS : (size_t)TP * 65;
@@ -407,9 +408,9 @@ using namespace sd;
 
 extern "C" int sd_project_points(const float *K, const float *w2c, const float *xyz, long long N, float *xy,
                                  float *z, unsigned char *invalid, void *stream) {
-    SD_REQUIRE(K && w2c && xyz, "sd_project_points: null pointer");
     SD_REQUIRE(N >= 0, "sd_project_points: bad N");
     if (N == 0) return SD_OK;
+    SD_REQUIRE(K && w2c && xyz, "sd_project_points: null pointer");
     // camera matrices are tiny: fetch them synchronously w.r.t. the stream, then pass by value
     Camera cam;
     float hK[9], hW[16];
@@ -429,6 +430,8 @@ extern "C" int sd_sample_features(const sd_scene *scene, const float *xyz, long 
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
+    SD_REQUIRE(N >= 0, "sd_sample_features: bad N");
+    if (N == 0) return SD_OK;
     SD_REQUIRE(xyz && feat, "sd_sample_features: null pointer");
     PointSrc src = {xyz, nullptr, nullptr, 0, 1};
     SimtOut out = {};
@@ -441,9 +444,10 @@ extern "C" int sd_sample_colors(const sd_scene *scene, const float *xyz, long lo
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
-    SD_REQUIRE(xyz && N >= 0, "sd_sample_colors: bad points");
+    SD_REQUIRE(N >= 0, "sd_sample_colors: bad N");
     SD_REQUIRE(fp.nv_c > 0, "sd_sample_colors: the scene has no colour views");
     if (N == 0) return SD_OK;
+    SD_REQUIRE(xyz, "sd_sample_colors: null pointer");
     const long long n = N * fp.nv_c;
     sample_colors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fp, xyz, N, rgb, invalid);
     SD_LAUNCH_OK("sample_colors_kernel");

@@ -157,9 +157,9 @@ using namespace sd;
 
 extern "C" int sd_sample_coarse(const float *rays, long long R, int r_dim, const float *u, const float *lin,
                                 int Kc, int lindisp, float *z, void *stream) {
-    SD_REQUIRE(rays && u && lin && z, "sd_sample_coarse: null pointer");
     SD_REQUIRE(R >= 0 && r_dim >= 8 && Kc > 0, "sd_sample_coarse: bad shape");
     if (R == 0) return SD_OK;
+    SD_REQUIRE(rays && u && lin && z, "sd_sample_coarse: null pointer");
     const long long n = R * Kc;
     const float step = (float)(1.0 / (double)Kc);
     sample_coarse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, R, r_dim, u, lin, Kc,
@@ -171,9 +171,9 @@ extern "C" int sd_sample_coarse(const float *rays, long long R, int r_dim, const
 extern "C" int sd_sample_fine(const float *rays, long long R, int r_dim, const float *weights, int Kc,
                               const float *u0, const float *u1, int Kf, int lindisp, float *z, int *inds,
                               void *stream) {
-    SD_REQUIRE(rays && weights && u0 && u1 && z, "sd_sample_fine: null pointer");
     SD_REQUIRE(R >= 0 && r_dim >= 8 && Kc > 0 && Kf > 0 && Kc <= 4096, "sd_sample_fine: bad shape");
     if (R == 0) return SD_OK;
+    SD_REQUIRE(rays && weights && u0 && u1 && z, "sd_sample_fine: null pointer");
     const size_t smem = 4 * (2 * (size_t)Kc + 2) * sizeof(float);
     sample_fine_kernel<<<(unsigned)((R + 3) / 4), 128, smem, (cudaStream_t)stream>>>(rays, R, r_dim, weights, Kc, u0,
                                                                                       u1, Kf, lindisp, z, inds);
@@ -183,9 +183,9 @@ extern "C" int sd_sample_fine(const float *rays, long long R, int r_dim, const f
 
 extern "C" int sd_sample_fine_depth(const float *rays, long long R, int r_dim, const float *depth,
                                     const float *noise, int Kfd, float depth_std, float *z, void *stream) {
-    SD_REQUIRE(rays && depth && noise && z, "sd_sample_fine_depth: null pointer");
     SD_REQUIRE(R >= 0 && r_dim >= 8 && Kfd > 0, "sd_sample_fine_depth: bad shape");
     if (R == 0) return SD_OK;
+    SD_REQUIRE(rays && depth && noise && z, "sd_sample_fine_depth: null pointer");
     const long long n = R * Kfd;
     sample_fine_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, R, r_dim, depth,
                                                                                              noise, Kfd, depth_std, z);
@@ -196,9 +196,9 @@ extern "C" int sd_sample_fine_depth(const float *rays, long long R, int r_dim, c
 extern "C" int sd_sample_coarse_from_dist(long long R, const float *weights, const float *z_samp, int Kp,
                                           const float *u0, const float *u1, int Kc, int lindisp, float *z,
                                           int *inds, void *stream) {
-    SD_REQUIRE(weights && z_samp && u0 && u1 && z, "sd_sample_coarse_from_dist: null pointer");
     SD_REQUIRE(R >= 0 && Kp > 0 && Kc > 0 && Kp <= 2048, "sd_sample_coarse_from_dist: bad shape");
     if (R == 0) return SD_OK;
+    SD_REQUIRE(weights && z_samp && u0 && u1 && z, "sd_sample_coarse_from_dist: null pointer");
     const size_t smem = 4 * (4 * (size_t)Kp + 4) * sizeof(float);
     sample_from_dist_kernel<<<(unsigned)((R + 3) / 4), 128, smem, (cudaStream_t)stream>>>(R, weights, z_samp, Kp, u0,
                                                                                            u1, Kc, lindisp, z, inds);
@@ -207,9 +207,9 @@ extern "C" int sd_sample_coarse_from_dist(long long R, const float *weights, con
 }
 
 extern "C" int sd_sort_rows(float *z, long long R, int K, void *stream) {
-    SD_REQUIRE(z, "sd_sort_rows: null pointer");
     SD_REQUIRE(R >= 0 && K > 0 && K <= 1024, "sd_sort_rows: K must be in [1,1024]");
     if (R == 0 || K == 1) return SD_OK;
+    SD_REQUIRE(z, "sd_sort_rows: null pointer");
     int P = 2;
     while (P < K) P <<= 1;
     sort_rows_kernel<<<(unsigned)((R + 3) / 4), 128, 4 * (size_t)P * sizeof(float), (cudaStream_t)stream>>>(z, R, K, P);

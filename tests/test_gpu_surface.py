@@ -90,8 +90,10 @@ def check_dict(out, g, prefix, tol):
         a, b = out[k].detach().cpu().numpy(), g[prefix + k]
         assert a.shape == b.shape, (k, a.shape, b.shape)
         assert a.dtype == b.dtype, (k, a.dtype, b.dtype)
-        if k in ("invalid", "invalid_features", "ray_info", "rgb_samps"):
+        if k in ("invalid", "invalid_features", "ray_info"):
             assert np.array_equal(a, b), k
+        elif k == "rgb_samps":          # bit-equal for unrotated views; torch's CPU bmm rounds rotated ones differently
+            assert_close(a, b, 1e-5, prefix + k)
         elif k == "z_samps":
             assert np.array_equal(a, b) or np.mean(np.all(a == b, -1)) > 0.99, k
         else:
@@ -135,10 +137,12 @@ def test_render_wrapper_fine(golden, name):
     check_dict(out["coarse"], g, "coarse.", TOL_FP32)
     # fine pass: rows whose importance indices did not flip at a 1-ulp CDF tie must agree
     a, b = out["fine"]["z_samps"].cpu().numpy(), g["fine.z_samps"]
-    same = np.all(a == b, -1)[0]
+    # the fine samples sit on top of the coarse pass's weights / depth (tolerance-level quantities), so
+    # they agree to rounding, except where an importance index flipped at a CDF tie
+    same = np.all(np.abs(a - b) <= 1e-5 * np.abs(b), -1)[0]
     assert same.mean() > 0.99
     for k in ("weights", "alphas", "depth", "rgb", "dino_features"):
-        assert_close(out["fine"][k].cpu().numpy()[0][same], g["fine." + k][0][same], TOL_FP32, "fine." + k)
+        assert_close(out["fine"][k].cpu().numpy()[0][same], g["fine." + k][0][same], 3 * TOL_FP32, "fine." + k)
 
 
 def test_render_wrapper_from_dist(golden):

@@ -48,6 +48,7 @@ def test_no_gpu_means_error_not_fallback():
 def test_argument_validation_without_gpu():
     lib = _abi.lib()
     assert lib.sd_sort_rows(None, 4, 8, None) == -1 and "null" in _abi.last_error()
+    assert lib.sd_sort_rows(None, 0, 8, None) == 0          # empty inputs are fine
     assert lib.sd_mlp_pack_bytes(295, 128, 65) > 4 * (295 * 128 + 128 * 65)
     assert lib.sd_mlp_pack_bytes(0, 128, 65) == 0
     assert lib.sd_render_workspace_bytes(None, None, 10, 10) == 0
