@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the feature-field query-and-render hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|fp32] [--impl reference]
 
 Headline workload (BASELINE.json configs[1]): the SSCBench voxel-grid query -- 256 x 256 x 32 voxels
 @ 0.2 m projected into one 192 x 640 view whose DINO ViT-B/8 feature map is 256 x 384 x 1280, MLP head
@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
@@ -188,8 +188,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
-    prec = ops.BF16 if args.precision == "bf16" else ops.FP32
-    fdt = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    prec = ops.F16 if args.precision == "fp16" else ops.FP32
+    fdt = torch.float16 if args.precision == "fp16" else torch.float32
 
     # ---- scene: seeded random map (encoder stand-in), camera, head -----------------------------------
     g = torch.Generator(device=dev).manual_seed(1)
@@ -283,7 +283,7 @@ def main():
     line = None
     if rank == 0:
         ntex = unique_texels(pts_np, K[0], HF, WF)
-        esize = 2 if args.precision == "bf16" else 4
+        esize = 2 if args.precision == "fp16" else 4
         algo_bytes = N * (12 + 4 + 4 * (D_OUT - 1) + 1) + ntex * C_FEAT * esize
         t_kernel = ms_step * 1e-3
         hbm_ach = algo_bytes / t_kernel / 1e9
@@ -299,7 +299,7 @@ def main():
             primary = roof_hbm   # FFMA head: neither roof binds; report the memory one
         line = {"metric": "ssc_voxel_query_throughput", "value": value, "unit": "voxels/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
                 "data": "synthetic", "config": workload_config(args.precision),
                 "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12,
                         "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,

@@ -11,8 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscenedino_b200.so")
 
-SD_F32, SD_BF16 = 0, 1
-SD_MLP_FP32, SD_MLP_BF16_TC = 0, 1
+SD_F32, SD_F16 = 0, 1
+SD_MLP_FP32, SD_MLP_F16_TC = 0, 1
 ABI_VERSION = 1
 
 

@@ -16,7 +16,7 @@ import torch.nn as nn
 from . import _abi
 from .heads import ResnetFC, _f32c, _ptr, _stream, require_cuda
 
-PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "bf16": _abi.SD_MLP_BF16_TC}
+PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
 
 
 class BTSNet(nn.Module):
@@ -72,8 +72,8 @@ class BTSNet(nn.Module):
         self.gt_classes = downstream_head.gt_classes if downstream_head is not None else None
 
         #: "fp32": CUDA-core FFMA head on the fp32 map (rel 1e-4 parity mode);
-        #: "bf16": tcgen05 head on the bf16 map (rel 2e-2, the throughput mode);
-        #: "auto": bf16 under torch autocast (where the reference runs fp16), fp32 otherwise.
+        #: "fp16": tcgen05 head (half operands, fp32 accumulate) on the fp16 map (rel 2e-2, the throughput mode);
+        #: "auto": fp16 under torch autocast (the dtype the reference runs the head in there), fp32 otherwise.
         self.precision = conf.get("sd_precision", "auto")
         self.encode_loss_features = True
         self._packed = {}
@@ -144,16 +144,16 @@ class BTSNet(nn.Module):
     def _precision(self) -> int:
         p = self.precision
         if p == "auto":
-            p = "bf16" if torch.is_autocast_enabled() else "fp32"
+            p = "fp16" if torch.is_autocast_enabled() else "fp32"
         if p not in PRECISIONS:
-            raise ValueError(f"precision must be one of fp32|bf16|auto, got {self.precision!r}")
+            raise ValueError(f"precision must be one of fp32|fp16|auto, got {self.precision!r}")
         return PRECISIONS[p]
 
     def _state(self, precision: int):
         """Packed, contiguous device state for the current scale: (feat_nhwc, dtype, cams...)."""
         if self.grid_f_features is None:
             raise RuntimeError("BTSNet.encode must be called before querying the field")
-        dt = _abi.SD_BF16 if precision == _abi.SD_MLP_BF16_TC else _abi.SD_F32
+        dt = _abi.SD_F16 if precision == _abi.SD_MLP_F16_TC else _abi.SD_F32
         key = (self._scale, dt)
         st = self._packed.get(key)
         if st is None:
@@ -164,7 +164,7 @@ class BTSNet(nn.Module):
                 raise NotImplementedError("the default head supports exactly one encoder view (ids_encoder=[0])")
             src = _f32c(fmap)
             dst = torch.empty((n, nv, hf, wf, c), device=src.device,
-                              dtype=torch.bfloat16 if dt == _abi.SD_BF16 else torch.float32)
+                              dtype=torch.float16 if dt == _abi.SD_F16 else torch.float32)
             _abi.check(_abi.lib().sd_featmap_pack(_ptr(src), n * nv, c, hf, wf, _ptr(dst), dt, _stream()),
                        "sd_featmap_pack")
             st = dict(

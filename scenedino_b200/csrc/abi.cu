@@ -45,7 +45,7 @@ extern "C" int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, fl
     SD_REQUIRE(mlp, "sd_mlp_forward: mlp is NULL");
     SD_REQUIRE(N >= 0, "sd_mlp_forward: bad N");
     // ResnetFC.forward asserts the input width (resnetfc.py:155); widths are carried by sd_mlp here.
-    if (mlp->precision == SD_MLP_BF16_TC) return launch_mlp_tc(mlp, x, N, out, (cudaStream_t)stream);
+    if (mlp->precision == SD_MLP_F16_TC) return launch_mlp_tc(mlp, x, N, out, (cudaStream_t)stream);
     return launch_mlp_simt(mlp, x, N, out, false, (cudaStream_t)stream);
 }
 
@@ -58,7 +58,7 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
     SD_REQUIRE(mlp, "sd_query_points: mlp is NULL");
     SD_REQUIRE(N >= 0 && (xyz || N == 0), "sd_query_points: bad points");
     PointSrc src = {xyz, nullptr, nullptr, 0, 1};
-    if (mlp->precision == SD_MLP_BF16_TC) {
+    if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
         return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream);
@@ -73,8 +73,10 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" size_t sd_render_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long R, int K) {
     if (!scene || !mlp || R <= 0 || K <= 0) return 0;
-    if (mlp->precision == SD_MLP_BF16_TC && tc_supported(scene, mlp, K)) return 0;
     const size_t N = (size_t)R * K;
+    // fused kernel: only the per-sample colours make a round trip through memory (L2-sized tiles of it)
+    if (mlp->precision == SD_MLP_F16_TC && tc_supported(scene, mlp, K))
+        return scene->nv_c > 0 ? align256(N * 3 * (size_t)scene->nv_c * 4) : 0;
     const int D = mlp->d_out - 1;
     // sigma [N], dino [N,D], rgb [N,3nv_c]
     return align256(N * 4) + align256(N * D * 4) + align256(N * 3 * (size_t)(scene->nv_c > 0 ? scene->nv_c : 1) * 4);
@@ -98,10 +100,18 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
     const int Crgb = 3 * fp.nv_c;
     PointSrc src = {nullptr, rays, z, r_dim, K};
 
-    if (mlp->precision == SD_MLP_BF16_TC && tc_supported(scene, mlp, K)) {
+    if (mlp->precision == SD_MLP_F16_TC && tc_supported(scene, mlp, K)) {
         TcRender rr = {};
         rr.cfg = *cfg; rr.depth = depth; rr.dino = dino; rr.rgb_out = rgb_out; rr.weights = weights;
         rr.alphas = alphas; rr.rgb_samps = rgb_samps;
+        if (!rgb_samps && Crgb > 0 && rgb_out) {
+            const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);
+            if (workspace_bytes < need || !workspace) {
+                set_error("sd_render_pass: workspace of %zu B needed, %zu B given", need, workspace_bytes);
+                return SD_ERR_WORKSPACE;
+            }
+            rr.rgb_samps = reinterpret_cast<float *>(workspace);
+        }
         TcOut o = {};
         o.sigma = sigma; o.invalid = invalid; o.invalid_feat = invalid_feat;
         return launch_field_tc(fp, src, N, mlp, &rr, o, st);
@@ -119,7 +129,7 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
     ws += align256((size_t)N * D * 4);
     float *w_rgb = rgb_samps ? rgb_samps : reinterpret_cast<float *>(ws);
 
-    if (mlp->precision == SD_MLP_BF16_TC) {
+    if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = w_sigma; o.dino = w_dino; o.rgb = Crgb ? w_rgb : nullptr; o.invalid = invalid; o.invalid_feat = invalid_feat;
         rc = launch_field_tc(fp, src, N, mlp, nullptr, o, st);

@@ -5,7 +5,7 @@
 // __fmaf_rn, ...) in the SAME order as oracle/sd_oracle.c, so nvcc can neither fuse nor reorder.
 #pragma once
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -58,7 +58,7 @@ struct EncodeParams {
 // memory once per block into shared memory by the kernels that need them.
 struct FieldParams {
     const void *feat;
-    int feat_bf16;
+    int feat_f16;
     int C, Hf, Wf;
     const float *K_f, *w2c_f;
     const float *rgb;
@@ -81,8 +81,8 @@ struct MlpLayout {
     size_t off_b_in;     // fp32 [d_hidden]
     size_t off_w_out_t;  // fp32 [d_hidden][d_out_pad]     (zero cols beyond d_out)
     size_t off_b_out;    // fp32 [d_out_pad]
-    size_t off_w_in_bf;  // bf16 UMMA K-major SW128 image of W_in:  [d_in_pad/64 blocks][d_hidden rows][64]
-    size_t off_w_out_bf; // bf16 UMMA K-major SW128 image of W_out[1:]: [d_hidden/64 blocks][d_out_pad rows][64]
+    size_t off_w_in_h;   // fp16 UMMA K-major SW128 image of W_in:  [d_in_pad/64 blocks][d_hidden rows][64]
+    size_t off_w_out_h;  // fp16 UMMA K-major SW128 image of W_out[1:]: [d_hidden/64 blocks][d_out_pad rows][64]
     size_t off_w_sigma;  // fp32 [d_hidden]  = W_out[0,:]  (density row, evaluated in fp32)
     size_t total;
 };
@@ -230,6 +230,6 @@ __device__ __forceinline__ void sample_color(const float *__restrict__ img, int 
     }
 }
 
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+__device__ __forceinline__ float2 half2_bits_to_float2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2 *>(&w)); }
 
 }  // namespace sd

@@ -193,20 +193,20 @@ __global__ void __launch_bounds__(NTHREADS) field_simt_kernel(FieldParams fp, Po
         const size_t o_se = o_sw + (t.in_x1 ? fp.C : 0);
         for (int c = lane * 4; c < fp.C; c += 128) {
             float nw[4], ne[4], sw[4], se[4];
-            if (fp.feat_bf16) {
-                const __nv_bfloat16 *f = reinterpret_cast<const __nv_bfloat16 *>(fp.feat);
+            if (fp.feat_f16) {
+                const __half *f = reinterpret_cast<const __half *>(fp.feat);
                 const uint2 a = __ldg(reinterpret_cast<const uint2 *>(f + o_nw + c));
                 const uint2 b = __ldg(reinterpret_cast<const uint2 *>(f + o_ne + c));
                 const uint2 cc = __ldg(reinterpret_cast<const uint2 *>(f + o_sw + c));
                 const uint2 d = __ldg(reinterpret_cast<const uint2 *>(f + o_se + c));
-                nw[0] = bf16_bits_to_float(a.x & 0xffffu); nw[1] = bf16_bits_to_float(a.x >> 16);
-                nw[2] = bf16_bits_to_float(a.y & 0xffffu); nw[3] = bf16_bits_to_float(a.y >> 16);
-                ne[0] = bf16_bits_to_float(b.x & 0xffffu); ne[1] = bf16_bits_to_float(b.x >> 16);
-                ne[2] = bf16_bits_to_float(b.y & 0xffffu); ne[3] = bf16_bits_to_float(b.y >> 16);
-                sw[0] = bf16_bits_to_float(cc.x & 0xffffu); sw[1] = bf16_bits_to_float(cc.x >> 16);
-                sw[2] = bf16_bits_to_float(cc.y & 0xffffu); sw[3] = bf16_bits_to_float(cc.y >> 16);
-                se[0] = bf16_bits_to_float(d.x & 0xffffu); se[1] = bf16_bits_to_float(d.x >> 16);
-                se[2] = bf16_bits_to_float(d.y & 0xffffu); se[3] = bf16_bits_to_float(d.y >> 16);
+                float2 t0 = half2_bits_to_float2(a.x), t1 = half2_bits_to_float2(a.y);
+                nw[0] = t0.x; nw[1] = t0.y; nw[2] = t1.x; nw[3] = t1.y;
+                t0 = half2_bits_to_float2(b.x); t1 = half2_bits_to_float2(b.y);
+                ne[0] = t0.x; ne[1] = t0.y; ne[2] = t1.x; ne[3] = t1.y;
+                t0 = half2_bits_to_float2(cc.x); t1 = half2_bits_to_float2(cc.y);
+                sw[0] = t0.x; sw[1] = t0.y; sw[2] = t1.x; sw[3] = t1.y;
+                t0 = half2_bits_to_float2(d.x); t1 = half2_bits_to_float2(d.y);
+                se[0] = t0.x; se[1] = t0.y; se[2] = t1.x; se[3] = t1.y;
             } else {
                 const float *f = reinterpret_cast<const float *>(fp.feat);
                 const float4 a = __ldg(reinterpret_cast<const float4 *>(f + o_nw + c));
@@ -325,12 +325,12 @@ int make_field_params(const sd_scene *s, FieldParams *o) {
     SD_REQUIRE(s->nv_f == 1, "scene: the default head supports exactly one encoder view (nv_f=%d)", s->nv_f);
     SD_REQUIRE(s->C > 0 && s->C % 8 == 0, "scene: C must be a positive multiple of 8 (got %d)", s->C);
     SD_REQUIRE(s->Hf > 0 && s->Wf > 0, "scene: bad feature map size");
-    SD_REQUIRE(s->feat_dtype == SD_F32 || s->feat_dtype == SD_BF16, "scene: bad feat_dtype");
+    SD_REQUIRE(s->feat_dtype == SD_F32 || s->feat_dtype == SD_F16, "scene: bad feat_dtype");
     SD_REQUIRE(s->nv_c >= 0 && s->nv_c <= MAX_NVC, "scene: at most %d colour views (got %d)", MAX_NVC, s->nv_c);
     SD_REQUIRE(s->nv_c == 0 || (s->rgb && s->K_c && s->w2c_c && s->Hc > 0 && s->Wc > 0), "scene: colour views incomplete");
     SD_REQUIRE(s->num_freqs >= 0 && s->num_freqs <= 16, "scene: bad num_freqs");
     SD_REQUIRE(!s->learn_empty || s->empty_feature, "scene: learn_empty without empty_feature");
-    o->feat = s->feat; o->feat_bf16 = s->feat_dtype == SD_BF16;
+    o->feat = s->feat; o->feat_f16 = s->feat_dtype == SD_F16;
     o->C = s->C; o->Hf = s->Hf; o->Wf = s->Wf;
     o->K_f = s->K_f; o->w2c_f = s->w2c_f;
     o->rgb = s->rgb; o->nv_c = s->nv_c; o->Hc = s->Hc; o->Wc = s->Wc; o->K_c = s->K_c; o->w2c_c = s->w2c_c;

@@ -1,20 +1,770 @@
-// Fused tcgen05 path (placeholder until the kernel lands): reports "unsupported" loudly.
+// Fused tcgen05 implementation of the field query and of one render pass (sd_precision SD_MLP_F16_TC).
+//
+//   BTSNet.forward      models/bts.py:476-595     (projection, mask, gather, code, head, softplus, colours)
+//   NeRFRenderer.composite renderer/nerf.py:230-449 (points along rays, the above, alpha compositing)
+//   ResnetFC.forward    resnetfc.py:135-203        (rows mode: the head alone, unit test of the MMA path)
+//
+// One persistent CTA per SM walks 128-row tiles (rows = points, or samples of 128/K whole rays).
+// Warp roles (16 warps):
+//   warps 0-3   epilogue: TMEM -> registers; bias+ReLU -> fp16 hidden tile (smem, UMMA A operand of
+//               layer 2); density row in fp32; softplus; second epilogue writes the features or
+//               composites them (segmented transmittance scan + butterfly weighted sums)
+//   warp  4     tcgen05.mma issuer (one lane) + TMEM owner
+//   warps 5-8   one thread per row: ray point, projection, frustum mask, bilinear tap, colour
+//               lookup, positional code -> code chunk of the A operand
+//   warps 9-15  gather ((chunk, 16-row group) units dealt round-robin): 8 lanes per row read 4 texels x 64 channels (one 128-byte line each, 128-bit
+//               loads) of the channels-last fp16 map, blend with packed HFMA2, store into the A operand
+// A operand: 5 K-chunks of [128 rows x 64] fp16, K-major SWIZZLE_128B, one mbarrier pair per chunk, so
+// layer-1 MMAs start while later chunks of the same tile are still being gathered and the gather of
+// tile t+1 overlaps the MMAs/epilogues of tile t.  W_in / W_out live in shared memory for the whole
+// kernel (loaded once with cp.async.bulk), accumulators in TMEM (layer 1 double-buffered).
 #include "common.cuh"
 #include "launch.h"
 
 namespace sd {
+namespace tc {
 
-bool tc_supported(const sd_scene *, const sd_mlp *, int) { return false; }
+constexpr int TM = 128;                      // rows per tile = UMMA M
+constexpr int MAX_CHUNKS = 5;                // K chunks of 64 (C = 256 -> 4 feature chunks + 1 code chunk)
+constexpr int CHUNK_BYTES = TM * 128;        // 16 KB: [128 rows][64 fp16]
+constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_GA_WARPS = 7;   // 16 warps -> 128 registers per thread
+constexpr int WARP_MMA = N_EPI_WARPS;
+constexpr int WARP_PT0 = WARP_MMA + 1;
+constexpr int WARP_GA0 = WARP_PT0 + N_PT_WARPS;
+constexpr int NTHREADS = (N_EPI_WARPS + 1 + N_PT_WARPS + N_GA_WARPS) * 32;   // 512
+constexpr int NGEO = 3;
+constexpr int TMEM_COLS = 512;
+constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 at 256
+constexpr int PART_STRIDE = 80;              // per (warp, segment) composite partial: 64 feat + depth + wsum + 12 rgb
+constexpr int MAX_NVC_TC = 4;
 
-int launch_field_tc(const FieldParams &, const PointSrc &, long long, const sd_mlp *, const TcRender *,
-                    const TcOut &, cudaStream_t) {
-    set_error("SD_MLP_BF16_TC: fused tcgen05 kernel not built into this library");
-    return SD_ERR_INVALID;
+enum { MODE_POINTS = 0, MODE_RENDER = 1, MODE_ROWS = 2 };
+
+struct Geo {                                 // per-row hand-off, structure of arrays (3584 B)
+    int off[TM];                             // texel index of the north-west tap
+    float w[4][TM];                          // nw, ne, sw, se
+    int flags[TM];                           // bit0 out of frustum, bit1 x0+1 in range, bit2 y0+1 in range, bit3 row valid
+    float z[TM];                             // sample depth (render mode)
+};
+
+// shared-memory map, offsets from a 1024-byte aligned base
+constexpr int OFF_W1 = 0;
+constexpr int OFF_RING = OFF_W1 + MAX_CHUNKS * CHUNK_BYTES;
+constexpr int OFF_H = OFF_RING + MAX_CHUNKS * CHUNK_BYTES;
+constexpr int OFF_W2 = OFF_H + 2 * CHUNK_BYTES;
+constexpr int OFF_GEO = OFF_W2 + 16384;
+constexpr int OFF_BIN = OFF_GEO + NGEO * (int)sizeof(Geo);
+constexpr int OFF_WSIG = OFF_BIN + 512;
+constexpr int OFF_BOUT = OFF_WSIG + 512;
+constexpr int OFF_EMPTY = OFF_BOUT + 320;    // fp16 empty_feature [256]
+constexpr int OFF_CAM = OFF_EMPTY + 512;     // 21 floats per camera, 1 + 4 cameras
+constexpr int OFF_PART = OFF_CAM + 448;
+constexpr int OFF_TAILS = OFF_PART + 4 * 2 * PART_STRIDE * 4;
+constexpr int OFF_BAR = OFF_TAILS + 32;
+constexpr int NBAR = 2 * MAX_CHUNKS + 2 + 1 + 1 + 2 * NGEO + 1;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
+static_assert(OFF_BAR % 8 == 0 && OFF_PART % 16 == 0 && OFF_GEO % 16 == 0, "alignment");
+
+enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 1,
+       BAR_GEO_FULL = BAR_D2 + 1, BAR_GEO_EMPTY = BAR_GEO_FULL + NGEO, BAR_WLOAD = BAR_GEO_EMPTY + NGEO };
+
+struct Params {
+    int mode;
+    FieldParams fp;
+    PointSrc src;
+    long long n_units;        // points / rays / rows
+    int K;                    // rows per unit (1 unless render)
+    int upt;                  // units per tile
+    long long n_tiles;
+    int nch;                  // K chunks of layer 1
+    int n2;                   // layer-2 N (feature rows padded to 16)
+    int D;                    // feature outputs = d_out - 1
+    const unsigned char *w1_img, *w2_img;
+    const float *b_in, *w_sigma, *b_out;
+    // rows mode
+    const float *x_rows;
+    int d_in;
+    float *out_rows;
+    // per-row outputs (any may be NULL)
+    float *sigma, *dino, *rgb, *invalid;
+    unsigned char *invalid_feat;
+    // per-ray outputs (render)
+    sd_render_cfg cfg;
+    float *depth, *dino_ray, *rgb_ray, *weights, *alphas;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-int launch_mlp_tc(const sd_mlp *, const float *, long long, float *, cudaStream_t) {
-    set_error("SD_MLP_BF16_TC: fused tcgen05 kernel not built into this library");
-    return SD_ERR_INVALID;
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in
+// [0,14), LBO unused for swizzled K-major, SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in
+// [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (c_format 1), A/B fp16 (format 0), both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// ---- the kernel -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_constant__ Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *sm = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm_u = smem_u32(sm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = sm_u + OFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    float *s_bin = reinterpret_cast<float *>(sm + OFF_BIN);
+    float *s_wsig = reinterpret_cast<float *>(sm + OFF_WSIG);
+    float *s_bout = reinterpret_cast<float *>(sm + OFF_BOUT);
+    float *s_cam = reinterpret_cast<float *>(sm + OFF_CAM);
+    Geo *s_geo = reinterpret_cast<Geo *>(sm + OFF_GEO);
+    const bool field = P.mode != MODE_ROWS;
+    const bool render = P.mode == MODE_RENDER;
+
+    // ---- one-time setup ------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int c = 0; c < MAX_CHUNKS; ++c) {
+            mbar_init(BAR(BAR_FULL + c), (field && c == P.nch - 1) ? N_PT_WARPS * 32 : N_GA_WARPS * 32);
+            mbar_init(BAR(BAR_EMPTY + c), 1);
+        }
+        mbar_init(BAR(BAR_D1), 1); mbar_init(BAR(BAR_D1 + 1), 1);
+        mbar_init(BAR(BAR_H), N_EPI_WARPS * 32);
+        mbar_init(BAR(BAR_D2), 1);
+        for (int s = 0; s < NGEO; ++s) {
+            mbar_init(BAR(BAR_GEO_FULL + s), N_PT_WARPS * 32);
+            mbar_init(BAR(BAR_GEO_EMPTY + s), (N_GA_WARPS + N_EPI_WARPS) * 32);
+        }
+        mbar_init(BAR(BAR_WLOAD), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 128; i += NTHREADS) { s_bin[i] = __ldg(P.b_in + i); s_wsig[i] = __ldg(P.w_sigma + i); }
+    for (int i = tid; i < 80; i += NTHREADS) s_bout[i] = i <= P.D ? __ldg(P.b_out + i) : 0.0f;
+    if (field) {
+        for (int i = tid; i < 21 * (1 + P.fp.nv_c); i += NTHREADS) {
+            const int c = i / 21, e = i - 21 * c;
+            const float *K = c == 0 ? P.fp.K_f : P.fp.K_c + 9 * (c - 1);
+            const float *W = c == 0 ? P.fp.w2c_f : P.fp.w2c_c + 16 * (c - 1);
+            s_cam[i] = e < 9 ? __ldg(K + e) : __ldg(W + (e - 9));
+        }
+        __half *s_empty = reinterpret_cast<__half *>(sm + OFF_EMPTY);
+        for (int i = tid; i < 256; i += NTHREADS)
+            s_empty[i] = __float2half_rn((P.fp.learn_empty && i < P.fp.C) ? __ldg(P.fp.empty_feature + i) : 0.0f);
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();   // barrier inits visible before anyone (including the bulk copies) uses them
+    if (tid == 0) {    // weights: global -> shared through the bulk-copy engine (async proxy, as UMMA reads them)
+        const uint32_t w1b = (uint32_t)P.nch * CHUNK_BYTES, w2b = 2u * (uint32_t)P.n2 * 128u;
+        mbar_expect_tx(BAR(BAR_WLOAD), w1b + w2b);
+        for (int c = 0; c < P.nch; ++c)
+            bulk_g2s(sm_u + OFF_W1 + c * CHUNK_BYTES, P.w1_img + (size_t)c * CHUNK_BYTES, CHUNK_BYTES, BAR(BAR_WLOAD));
+        bulk_g2s(sm_u + OFF_W2, P.w2_img, w2b, BAR(BAR_WLOAD));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
+
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_tiles = P.n_tiles > first ? (P.n_tiles - first + stride - 1) / stride : 0;
+
+    if (warp < N_EPI_WARPS) {
+        // =================================== EPILOGUE ================================================
+        const int row = tid;                                     // TMEM lane == tile row
+        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int K = P.K;
+        const int k_i = row % K;
+        const bool row_used = row < P.upt * K;
+        float *s_part = reinterpret_cast<float *>(sm + OFF_PART);
+        float *s_tails = reinterpret_cast<float *>(sm + OFF_TAILS);
+        // state carried from the first to the second epilogue of a tile
+        float sig_keep = 0.0f, w_keep = 0.0f, z_keep = 0.0f;
+        long long grow_keep = -1;
+        for (long long j = 0; j <= my_tiles; ++j) {
+            if (j > 0) {
+                // ---------------- second epilogue of tile j-1 -----------------------------------------
+                mbar_wait(BAR(BAR_D2), (uint32_t)((j - 1) & 1));
+                tc_fence_after();
+                const long long tile = first + (j - 1) * stride;
+                float v[64];
+                tmem_ld32(t_lane + D2_COL, v);
+                tmem_ld32(t_lane + D2_COL + 32, v + 32);
+                const bool ok = grow_keep >= 0;
+                if (!render) {
+                    if (ok) {
+                        if (P.mode == MODE_ROWS) {
+                            float *o = P.out_rows + grow_keep * (P.D + 1);
+                            o[0] = sig_keep;
+                            for (int c = 0; c < P.D; ++c) o[1 + c] = v[c] + s_bout[1 + c];
+                        } else if (P.dino) {
+                            float *o = P.dino + grow_keep * P.D;
+                            if (P.D == 64) {
+#pragma unroll
+                                for (int c = 0; c < 64; c += 4)
+                                    *reinterpret_cast<float4 *>(o + c) = make_float4(v[c] + s_bout[1 + c], v[c + 1] + s_bout[2 + c],
+                                                                                      v[c + 2] + s_bout[3 + c], v[c + 3] + s_bout[4 + c]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 64; ++c)
+                                    if (c < P.D) o[c] = v[c] + s_bout[1 + c];
+                            }
+                        }
+                    }
+                } else {
+                    // ---- composite: weighted sums over the rows of each ray (nerf.py:393-405) ----------
+                    const float wgt = ok ? w_keep : 0.0f;
+                    const int nrgb = 3 * P.fp.nv_c;
+                    float crgb[3 * MAX_NVC_TC];
+#pragma unroll
+                    for (int c = 0; c < 3 * MAX_NVC_TC; ++c)
+                        crgb[c] = (ok && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
+                    const int ua = (warp * 32) / K, ub = (warp * 32 + 31) / K;   // rays this warp's rows belong to
+                    const int my_u = row / K;
+#pragma unroll 1
+                    for (int seg = 0; seg < 2; ++seg) {
+                        const int u = seg == 0 ? ua : ub;
+                        if (seg == 1 && ub == ua) break;
+                        const float ws = (my_u == u) ? wgt : 0.0f;
+                        float *pp = s_part + (warp * 2 + seg) * PART_STRIDE;
+                        // butterfly over 32 columns at a time: after 5 exchange steps lane l holds column l
+                        // summed over the 32 rows of the warp
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float a[32];
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) a[c] = ws * (v[hh * 32 + c] + s_bout[1 + hh * 32 + c]);
+#pragma unroll
+                            for (int step = 0; step < 5; ++step) {
+                                const int m = 16 >> step;
+                                const bool up = lane & m;
+#pragma unroll
+                                for (int c = 0; c < m; ++c) {
+                                    const float send = up ? a[c] : a[c + m];
+                                    const float keep = up ? a[c + m] : a[c];
+                                    a[c] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                                }
+                            }
+                            pp[hh * 32 + lane] = a[0];
+                        }
+                        float sd_ = ws * z_keep, sw_ = ws;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sd_ += __shfl_xor_sync(0xffffffffu, sd_, o);
+                            sw_ += __shfl_xor_sync(0xffffffffu, sw_, o);
+                        }
+                        if (lane == 0) { pp[64] = sd_; pp[65] = sw_; }
+#pragma unroll
+                        for (int c = 0; c < 3 * MAX_NVC_TC; ++c) {
+                            float s = ws * crgb[c];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                            if (lane == 0) pp[66 + c] = s;
+                        }
+                    }
+                    named_bar_sync(1, N_EPI_WARPS * 32);
+                    {   // warp u finishes ray u of the tile: fixed summation order over the warps it spans
+                        const int u = warp;
+                        const long long ray = tile * P.upt + u;
+                        if (u < P.upt && ray < P.n_units) {
+                            const int w_lo = (u * K) / 32, w_hi = (u * K + K - 1) / 32;
+                            float acc[3] = {0.f, 0.f, 0.f};
+                            for (int w = w_lo; w <= w_hi; ++w) {
+                                const int seg = ((w * 32) / K == u) ? 0 : 1;
+                                const float *pp = s_part + (w * 2 + seg) * PART_STRIDE;
+                                acc[0] += pp[lane]; acc[1] += pp[lane + 32];
+                                if (lane + 64 < 78) acc[2] += pp[lane + 64];
+                            }
+                            if (P.dino_ray) {
+                                if (lane < P.D) P.dino_ray[ray * P.D + lane] = acc[0];
+                                if (lane + 32 < P.D) P.dino_ray[ray * P.D + lane + 32] = acc[1];
+                            }
+                            const float wsum = __shfl_sync(0xffffffffu, acc[2], 1);
+                            if (lane == 0 && P.depth) P.depth[ray] = acc[2];
+                            if (lane >= 2 && lane < 2 + nrgb && P.rgb_ray)
+                                P.rgb_ray[ray * nrgb + (lane - 2)] = P.cfg.white_bkgd ? acc[2] + 1.0f - wsum : acc[2];
+                        }
+                    }
+                    named_bar_sync(1, N_EPI_WARPS * 32);   // partials consumed before the next tile overwrites them
+                }
+            }
+            if (j == my_tiles) break;
+            // ---------------- first epilogue of tile j ----------------------------------------------------
+            const long long tile = first + j * stride;
+            const long long unit = tile * P.upt + row / K;
+            const bool ok = row_used && unit < P.n_units;
+            const long long grow = unit * K + k_i;
+            const int slot = (int)(j % NGEO);
+            float z_i = 0.0f, z_n = 0.0f;
+            if (field) {
+                mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
+                if (render) {
+                    z_i = s_geo[slot].z[row];
+                    z_n = row + 1 < TM ? s_geo[slot].z[row + 1] : 0.0f;
+                }
+                mbar_arrive(BAR(BAR_GEO_EMPTY + slot));
+            }
+            const int b = (int)(j & 1);
+            mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            float sig = 0.0f;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float v[32];
+                tmem_ld32(t_lane + b * 128 + cc * 32, v);
+                unsigned char *hrow = sm + OFF_H + (cc >> 1) * CHUNK_BYTES + row * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const int col = cc * 32 + q * 8 + e;
+                        const float h0 = fmaxf(v[q * 8 + e] + s_bin[col], 0.0f);
+                        const float h1 = fmaxf(v[q * 8 + e + 1] + s_bin[col + 1], 0.0f);
+                        sig = fmaf(h0, s_wsig[col], sig);
+                        sig = fmaf(h1, s_wsig[col + 1], sig);
+                        pk[e >> 1] = pack_h2(h0, h1);
+                    }
+                    const int chunk = ((cc & 1) * 4 + q) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(hrow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            sig += s_bout[0];
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(BAR(BAR_H));
+            const float sg = P.mode == MODE_ROWS ? sig : softplus(sig);
+            sig_keep = sg;
+            grow_keep = ok ? grow : -1;
+            if (ok && P.sigma) P.sigma[grow] = sg;
+            if (render) {
+                // alpha, exclusive transmittance (segmented product scan over the tile), weight
+                const bool last = k_i == K - 1;
+                const float delta = last ? 1e10f : z_n - z_i;
+                float alpha = 0.0f;
+                if (ok) {
+                    alpha = 1.0f - expf(-fabsf(delta) * fmaxf(sg, 0.0f));
+                    if (P.cfg.hard_alpha_cap && last) alpha = 1.0f;
+                }
+                float incl = ok ? (1.0f - alpha) + 1e-10f : 1.0f;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o && k_i >= o) incl *= n;
+                }
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0 || k_i == 0) excl = 1.0f;
+                if (lane == 31) s_tails[warp] = incl;
+                named_bar_sync(1, N_EPI_WARPS * 32);
+                float carry = 1.0f;
+                for (int prev = k_i - lane, w = warp - 1; prev > 0 && w >= 0; prev -= 32, --w) carry *= s_tails[w];
+                const float wgt = alpha * (excl * carry);
+                w_keep = wgt;
+                z_keep = z_i;
+                if (ok) {
+                    if (P.weights) P.weights[grow] = wgt;
+                    if (P.alphas) P.alphas[grow] = alpha;
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // =================================== MMA ISSUER ===============================================
+        if (lane == 0) {
+            mbar_wait(BAR(BAR_WLOAD), 0);
+            const uint32_t idesc1 = umma_idesc(TM, 128), idesc2 = umma_idesc(TM, P.n2);
+            auto layer2 = [&](long long jj) {
+                mbar_wait(BAR(BAR_H), (uint32_t)(jj & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem_base + D2_COL, umma_desc(sm_u + OFF_H + kb * CHUNK_BYTES + k * 32),
+                             umma_desc(sm_u + OFF_W2 + kb * P.n2 * 128 + k * 32), idesc2, (kb | k) != 0);
+                umma_commit(BAR(BAR_D2));
+            };
+            for (long long j = 0; j < my_tiles; ++j) {
+                const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
+                for (int c = 0; c < P.nch; ++c) {
+                    mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
+                             umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
+                    umma_commit(BAR(BAR_EMPTY + c));
+                }
+                umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                if (j > 0) layer2(j - 1);
+            }
+            if (my_tiles > 0) layer2(my_tiles - 1);
+        }
+    } else if (warp < WARP_GA0) {
+        // =================================== POINT WARPS ================================================
+        if (field) {
+            const int row = tid - WARP_PT0 * 32;
+            const int K = P.K, k_i = row % K;
+            const bool row_used = row < P.upt * K;
+            const int nv_c = P.fp.nv_c;
+            for (long long j = 0; j < my_tiles; ++j) {
+                const long long tile = first + j * stride;
+                const long long unit = tile * P.upt + row / K;
+                const bool ok = row_used && unit < P.n_units;
+                const long long grow = unit * K + k_i;
+                const int slot = (int)(j % NGEO);
+                mbar_wait(BAR(BAR_GEO_EMPTY + slot), (uint32_t)(((j / NGEO) & 1) ^ 1));
+                float x = 0.f, y = 0.f, zp = 0.f, zs = 0.f;
+                int flags = 0, off = 0;
+                Tap t = {};
+                if (ok) {
+                    float px, py, pz, zc;
+                    bool inv;
+                    if (!P.src.xyz) {
+                        const float *ry = P.src.rays + (grow / P.src.K) * P.src.r_dim;
+                        zs = __ldg(P.src.z + grow);
+                        px = ray_point(__ldg(ry + 0), __ldg(ry + 3), zs);
+                        py = ray_point(__ldg(ry + 1), __ldg(ry + 4), zs);
+                        pz = ray_point(__ldg(ry + 2), __ldg(ry + 5), zs);
+                    } else {
+                        px = __ldg(P.src.xyz + 3 * grow); py = __ldg(P.src.xyz + 3 * grow + 1); pz = __ldg(P.src.xyz + 3 * grow + 2);
+                    }
+                    project_point(s_cam, s_cam + 9, px, py, pz, x, y, zc, inv);
+                    x = clamp_keep_nan(x, -2.0f, 2.0f);
+                    y = clamp_keep_nan(y, -2.0f, 2.0f);
+                    zp = znorm(zc, P.fp.enc);
+                    t = bilinear_tap(x, y, P.fp.Hf, P.fp.Wf);
+                    off = t.y0 * P.fp.Wf + t.x0;
+                    flags = (inv ? 1 : 0) | (t.in_x1 ? 2 : 0) | (t.in_y1 ? 4 : 0) | 8;
+                    if (P.invalid_feat) P.invalid_feat[grow] = inv ? 1 : 0;
+                    if (nv_c > 0 && (P.rgb || P.invalid)) {
+                        for (int v = 0; v < nv_c; ++v) {
+                            float cx, cy, cz;
+                            bool cinv;
+                            const float *c = s_cam + 21 * (1 + v);
+                            project_point(c, c + 9, px, py, pz, cx, cy, cz, cinv);
+                            if (P.rgb) {
+                                float c3[3];
+                                sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
+                                float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
+                                o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
+                            }
+                            if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
+                        }
+                    }
+                }
+                Geo &g = s_geo[slot];
+                g.off[row] = off; g.flags[row] = flags; g.z[row] = zs;
+                g.w[0][row] = t.wnw; g.w[1][row] = t.wne; g.w[2][row] = t.wsw; g.w[3][row] = t.wse;
+                mbar_arrive(BAR(BAR_GEO_FULL + slot));
+                // ---- positional code -> last K chunk (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by
+                //      angle doubling from one accurate sincosf per coordinate) ------------------------------
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pk[i] = 0u;
+                if (ok) {
+                    float code[46];
+                    code[0] = x; code[1] = y; code[2] = zp; code[45] = 0.0f;
+                    // hi/lo split of the raw coordinates into the K padding (see mlp_pack_kernel)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float hi = __half2float(__float2half_rn(code[d]));
+                        code[39 + d] = code[d] - hi;
+                        code[42 + d] = hi;
+                    }
+                    float s[3], c[3];
+                    sincosf(__fmul_rn(x, P.fp.enc.freq_factor), &s[0], &c[0]);
+                    sincosf(__fmul_rn(y, P.fp.enc.freq_factor), &s[1], &c[1]);
+                    sincosf(__fmul_rn(zp, P.fp.enc.freq_factor), &s[2], &c[2]);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            code[3 + 6 * k + d] = s[d];
+                            code[3 + 6 * k + 3 + d] = c[d];
+                            const float s2 = 2.0f * s[d] * c[d], c2 = fmaf(-2.0f * s[d], s[d], 1.0f);
+                            s[d] = s2; c[d] = c2;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 23; ++i) pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
+                }
+                const int cchunk = P.nch - 1;
+                mbar_wait(BAR(BAR_EMPTY + cchunk), (uint32_t)((j & 1) ^ 1));
+                unsigned char *arow = sm + OFF_RING + cchunk * CHUNK_BYTES + row * 128;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4 *>(arow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                fence_proxy_async();
+                mbar_arrive(BAR(BAR_FULL + cchunk));
+            }
+        }
+    } else {
+        // =================================== GATHER WARPS ================================================
+        const int gw = warp - WARP_GA0;                 // units u = 8*chunk + row group, u % N_GA_WARPS == gw
+        const int sub = lane & 7, grp = lane >> 3;
+        const int nfeat = field ? P.nch - 1 : P.nch;
+        const int C = P.fp.C;
+        for (long long j = 0; j < my_tiles; ++j) {
+            const long long tile = first + j * stride;
+            const int slot = (int)(j % NGEO);
+            if (field) mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
+            for (int c = 0; c < nfeat; ++c) {
+                mbar_wait(BAR(BAR_EMPTY + c), (uint32_t)((j & 1) ^ 1));
+                unsigned char *stage = sm + OFF_RING + c * CHUNK_BYTES;
+                for (int rg = (gw + N_GA_WARPS - (8 * c) % N_GA_WARPS) % N_GA_WARPS; rg < 8; rg += N_GA_WARPS)
+                if (field) {
+                    const Geo &g = s_geo[slot];
+                    const __half *fb = reinterpret_cast<const __half *>(P.fp.feat) + c * 64 + sub * 8;
+                    const __half *s_empty = reinterpret_cast<const __half *>(sm + OFF_EMPTY) + c * 64 + sub * 8;
+                    // Branch-free so that all 16 128-bit loads of the unit are in flight before the first use:
+                    // phase 1 reads the hand-off, phase 2 issues every load (rows that are not valid, and taps
+                    // that fall outside the map, read an in-range texel with weight zero), phase 3 blends.
+                    uint4 raw[4][4];
+                    float wq[4][4];
+                    const __half *qp[4];
+                    size_t dxs[4], dys[4];
+                    bool use_empty[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int p = rg * 16 + it * 4 + grp;
+                        const int fl = g.flags[p];
+                        const bool valid = fl & 8;
+                        qp[it] = fb + (size_t)g.off[p] * C;
+                        dxs[it] = (fl & 2) ? (size_t)C : 0;
+                        dys[it] = (fl & 4) ? (size_t)P.fp.Wf * C : 0;
+                        use_empty[it] = P.fp.learn_empty && (fl & 1);          // bts.py:311-319
+                        const bool plain = valid && !use_empty[it];
+                        wq[it][0] = plain ? g.w[0][p] : (valid ? 1.0f : 0.0f);
+                        wq[it][1] = plain ? g.w[1][p] : 0.0f;
+                        wq[it][2] = plain ? g.w[2][p] : 0.0f;
+                        wq[it][3] = plain ? g.w[3][p] : 0.0f;
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        raw[it][0] = ldg128(qp[it]); raw[it][1] = ldg128(qp[it] + dxs[it]);
+                        raw[it][2] = ldg128(qp[it] + dys[it]); raw[it][3] = ldg128(qp[it] + dys[it] + dxs[it]);
+                    }
+                    if (P.fp.learn_empty) {
+                        const uint4 e = *reinterpret_cast<const uint4 *>(s_empty);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it)
+                            if (use_empty[it]) raw[it][0] = e;
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int p = rg * 16 + it * 4 + grp;
+                        const uint32_t *a = reinterpret_cast<const uint32_t *>(&raw[it][0]);
+                        const uint32_t *b = reinterpret_cast<const uint32_t *>(&raw[it][1]);
+                        const uint32_t *cc = reinterpret_cast<const uint32_t *>(&raw[it][2]);
+                        const uint32_t *d = reinterpret_cast<const uint32_t *>(&raw[it][3]);
+                        const __half2 w0 = __float2half2_rn(wq[it][0]), w1 = __float2half2_rn(wq[it][1]);
+                        const __half2 w2 = __float2half2_rn(wq[it][2]), w3 = __float2half2_rn(wq[it][3]);
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {   // two channels per HFMA2, taps in the reference order nw, ne, sw, se
+                            __half2 acc = __hmul2(w0, as_h2(a[e]));
+                            acc = __hfma2(w1, as_h2(b[e]), acc);
+                            acc = __hfma2(w2, as_h2(cc[e]), acc);
+                            acc = __hfma2(w3, as_h2(d[e]), acc);
+                            pk[e] = as_u32(acc);
+                        }
+                        *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else {
+                    // rows mode: x [N, d_in] fp32 -> fp16 chunk c (columns 64c .. 64c+63)
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int p = rg * 16 + it * 4 + grp;
+                        const long long r = tile * TM + p;
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int col = c * 64 + sub * 8 + e;
+                            f[e] = (r < P.n_units && col < P.d_in) ? __ldg(P.x_rows + r * P.d_in + col) : 0.0f;
+                        }
+                        *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) =
+                            make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(BAR(BAR_FULL + c));
+            }
+            if (field) mbar_arrive(BAR(BAR_GEO_EMPTY + slot));
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// ---- host side ------------------------------------------------------------------------------------------
+static bool tc_head_ok(const sd_mlp *mlp) {
+    return mlp && mlp->packed && mlp->d_hidden == 128 && mlp->d_out >= 2 && mlp->d_out - 1 <= 64 && mlp->d_in >= 1 &&
+           mlp->d_in <= 64 * tc::MAX_CHUNKS;
+}
+
+static bool tc_scene_ok(const sd_scene *s, const sd_mlp *mlp) {
+    return s && s->feat_dtype == SD_F16 && s->C == 256 && s->nv_f == 1 && s->include_input && s->num_freqs == 6 &&
+           s->nv_c <= tc::MAX_NVC_TC && tc_head_ok(mlp) && mlp->d_in == s->C + 39;
+}
+
+bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K) {
+    return tc_scene_ok(scene, mlp) && K >= 32 && K <= tc::TM;
+}
+
+static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
+    const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
+    const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
+    SD_REQUIRE(((uintptr_t)blob & 15) == 0, "mlp: packed blob must be 16-byte aligned");
+    P.w1_img = blob + L.off_w_in_h;
+    P.w2_img = blob + L.off_w_out_h;
+    P.b_in = reinterpret_cast<const float *>(blob + L.off_b_in);
+    P.w_sigma = reinterpret_cast<const float *>(blob + L.off_w_sigma);
+    P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
+    P.nch = L.d_in_pad / 64;
+    P.D = mlp->d_out - 1;
+    P.n2 = (P.D + 15) / 16 * 16;
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        SD_CUDA_OK(cudaGetDevice(&dev));
+        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        SD_CUDA_OK(cudaFuncSetAttribute(tc::field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
+    }
+    const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
+    tc::field_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_ALLOC, st>>>(P);
+    SD_LAUNCH_OK("field_tc_kernel");
+    return SD_OK;
+}
+
+int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp, const TcRender *render,
+                    const TcOut &out, cudaStream_t st) {
+    if (N == 0) return SD_OK;
+    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 320, d_hidden = 128, 2 <= d_out <= 65 and packed");
+    SD_REQUIRE(fp.feat_f16, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
+    SD_REQUIRE(fp.C == 256 && fp.code_dim == 39 && fp.enc.include_input && mlp->d_in == fp.C + fp.code_dim,
+               "SD_MLP_F16_TC: supports C = 256 with the 39-d positional code (got C=%d, code=%d, d_in=%d)", fp.C,
+               fp.code_dim, mlp->d_in);
+    SD_REQUIRE(fp.nv_c <= tc::MAX_NVC_TC, "SD_MLP_F16_TC: at most %d colour views (got %d)", tc::MAX_NVC_TC, fp.nv_c);
+    tc::Params P = {};
+    P.fp = fp;
+    P.src = src;
+    if (render) {
+        const int K = src.K;
+        SD_REQUIRE(K >= 32 && K <= tc::TM, "SD_MLP_F16_TC: fused render needs 32 <= K <= 128 samples per ray (got %d)", K);
+        P.mode = tc::MODE_RENDER;
+        P.K = K;
+        P.upt = tc::TM / K;
+        P.n_units = N / K;
+        P.cfg = render->cfg;
+        P.depth = render->depth; P.dino_ray = render->dino; P.rgb_ray = render->rgb_out;
+        P.weights = render->weights; P.alphas = render->alphas;
+        P.rgb = render->rgb_samps;   // per-sample colours: the caller's buffer or workspace
+        SD_REQUIRE(fp.nv_c == 0 || !P.rgb_ray || P.rgb, "SD_MLP_F16_TC: rgb_out needs a per-sample colour buffer");
+    } else {
+        P.mode = tc::MODE_POINTS;
+        P.K = 1;
+        P.upt = tc::TM;
+        P.n_units = N;
+        P.dino = out.dino;
+        P.rgb = out.rgb;
+    }
+    P.n_tiles = (P.n_units + P.upt - 1) / P.upt;
+    P.sigma = out.sigma; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;
+    return tc_launch(P, mlp, st);
+}
+
+int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st) {
+    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 320, d_hidden = 128, 2 <= d_out <= 65 and packed");
+    if (N == 0) return SD_OK;
+    SD_REQUIRE(x && out, "sd_mlp_forward: null pointer");
+    tc::Params P = {};
+    P.mode = tc::MODE_ROWS;
+    P.K = 1; P.upt = tc::TM; P.n_units = N;
+    P.n_tiles = (N + tc::TM - 1) / tc::TM;
+    P.x_rows = x; P.d_in = mlp->d_in; P.out_rows = out;
+    return tc_launch(P, mlp, st);
 }
 
 }  // namespace sd

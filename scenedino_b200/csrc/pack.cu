@@ -3,10 +3,10 @@
 
 namespace sd {
 
-// ---- feature map: [n, C, H, W] fp32 -> [n, H, W, C] fp32 | bf16 ---------------------------------
+// ---- feature map: [n, C, H, W] fp32 -> [n, H, W, C] fp32 | fp16 ---------------------------------
 // Tile = 64 channels x 32 pixels through shared memory: reads are 128 B per warp along W, writes
-// are 256 B (fp32) / 128 B (bf16) per warp along C.  HBM-bound: 4*C*H*W read + esize*C*H*W written.
-template <bool BF16>
+// are 256 B (fp32) / 128 B (fp16) per warp along C.  HBM-bound: 4*C*H*W read + esize*C*H*W written.
+template <bool F16>
 __global__ void __launch_bounds__(256) featmap_pack_kernel(const float *__restrict__ src, void *__restrict__ dst,
                                                            int C, long long HW) {
     __shared__ float tile[64][33];
@@ -31,10 +31,10 @@ __global__ void __launch_bounds__(256) featmap_pack_kernel(const float *__restri
         if (c >= C) continue;
         const float a = tile[lane * 2][pl], b = tile[lane * 2 + 1][pl];
         const size_t o = ((size_t)img * HW + p) * C + c;
-        if (BF16) {
-            __nv_bfloat16 *d = reinterpret_cast<__nv_bfloat16 *>(dst);
-            if (c + 1 < C) *reinterpret_cast<__nv_bfloat162 *>(d + o) = __floats2bfloat162_rn(a, b);
-            else d[o] = __float2bfloat16_rn(a);
+        if (F16) {
+            __half *d = reinterpret_cast<__half *>(dst);
+            if (c + 1 < C) *reinterpret_cast<__half2 *>(d + o) = __floats2half2_rn(a, b);
+            else d[o] = __float2half_rn(a);
         } else {
             float *d = reinterpret_cast<float *>(dst);
             if (c + 1 < C) *reinterpret_cast<float2 *>(d + o) = make_float2(a, b);
@@ -56,10 +56,10 @@ MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     L.off_b_in = o;     o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
     L.off_w_out_t = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden * L.d_out_pad, 1024);
     L.off_b_out = o;    o = align_up(o + sizeof(float) * (size_t)L.d_out_pad, 1024);
-    L.off_w_in_bf = o;  o = align_up(o + 2 * (size_t)L.d_in_pad * d_hidden, 1024);
+    L.off_w_in_h = o;  o = align_up(o + 2 * (size_t)L.d_in_pad * d_hidden, 1024);
     // feature rows of W_out (rows 1..d_out-1), padded to a multiple of 16 rows
     const int n2 = (int)align_up((size_t)(d_out > 1 ? d_out - 1 : 1), 16);
-    L.off_w_out_bf = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden, 64), 1024);
+    L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden, 64), 1024);
     L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
     L.total = o;
     return L;
@@ -74,15 +74,28 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
     float *bi = reinterpret_cast<float *>(blob + L.off_b_in);
     float *w_out_t = reinterpret_cast<float *>(blob + L.off_w_out_t);
     float *bo = reinterpret_cast<float *>(blob + L.off_b_out);
-    __nv_bfloat16 *w_in_bf = reinterpret_cast<__nv_bfloat16 *>(blob + L.off_w_in_bf);
-    __nv_bfloat16 *w_out_bf = reinterpret_cast<__nv_bfloat16 *>(blob + L.off_w_out_bf);
+    __half *w_in_h = reinterpret_cast<__half *>(blob + L.off_w_in_h);
+    __half *w_out_h = reinterpret_cast<__half *>(blob + L.off_w_out_h);
     float *w_sigma = reinterpret_cast<float *>(blob + L.off_w_sigma);
     const int H = L.d_hidden;
+    // fp16 image, K padding put to use: the raw coordinates (x, y, z') sit at columns d_in-39 .. d_in-37 of
+    // the field's input; z' reaches +-6e3 for points next to / behind the camera, where one half-precision
+    // product is coarse.  Columns d_in .. d_in+2 repeat half(w) for the low
+    // halves of the coordinates and d_in+3 .. d_in+5 hold w - half(w) for their high halves, so that
+    // x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.  The kernel fills the matching A columns; callers that pass
+    // plain rows leave them zero.
+    const bool split = L.d_in >= 39 && L.d_in + 6 <= L.d_in_pad;
     for (int i = tid; i < L.d_in_pad * H; i += nth) {
         const int k = i / H, j = i - k * H;
         const float v = k < L.d_in ? w_in[(size_t)j * L.d_in + k] : 0.0f;
         w_in_t[i] = v;
-        w_in_bf[umma_sw128_offset(j, k, H) / 2] = __float2bfloat16_rn(v);
+        float vb = v;
+        if (split && k >= L.d_in && k < L.d_in + 6) {
+            const int e = k - L.d_in;
+            const float w = w_in[(size_t)j * L.d_in + (L.d_in - 39) + (e % 3)];
+            vb = e < 3 ? w : w - __half2float(__float2half_rn(w));
+        }
+        w_in_h[umma_sw128_offset(j, k, H) / 2] = __float2half_rn(vb);
     }
     for (int i = tid; i < H; i += nth) {
         bi[i] = b_in[i];
@@ -98,7 +111,7 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
     for (int i = tid; i < n2 * Hp; i += nth) {
         const int r = i / Hp, k = i - r * Hp;  // feature row r <-> W_out row r+1
         const float v = (r + 1 < L.d_out && k < H) ? w_out[(size_t)(r + 1) * H + k] : 0.0f;
-        w_out_bf[umma_sw128_offset(r, k, n2) / 2] = __float2bfloat16_rn(v);
+        w_out_h[umma_sw128_offset(r, k, n2) / 2] = __float2half_rn(v);
     }
 }
 
@@ -109,11 +122,11 @@ extern "C" int sd_featmap_pack(const float *nchw, int n_img, int C, int H, int W
     SD_REQUIRE(nchw && nhwc, "sd_featmap_pack: null pointer");
     SD_REQUIRE(n_img > 0 && C > 0 && H > 0 && W > 0, "sd_featmap_pack: bad shape");
     SD_REQUIRE(C % 2 == 0, "sd_featmap_pack: C must be even (got %d)", C);
-    SD_REQUIRE(dst_dtype == SD_F32 || dst_dtype == SD_BF16, "sd_featmap_pack: bad dst_dtype");
+    SD_REQUIRE(dst_dtype == SD_F32 || dst_dtype == SD_F16, "sd_featmap_pack: bad dst_dtype");
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 63) / 64), (unsigned)n_img);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dst_dtype == SD_BF16)
+    if (dst_dtype == SD_F16)
         sd::featmap_pack_kernel<true><<<grid, 256, 0, st>>>(nchw, nhwc, C, HW);
     else
         sd::featmap_pack_kernel<false><<<grid, 256, 0, st>>>(nchw, nhwc, C, HW);

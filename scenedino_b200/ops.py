@@ -14,7 +14,7 @@ import torch
 from . import _abi
 from .heads import _f32c, _ptr, _stream, require_cuda
 
-FP32, BF16 = _abi.SD_MLP_FP32, _abi.SD_MLP_BF16_TC
+FP32, F16 = _abi.SD_MLP_FP32, _abi.SD_MLP_F16_TC
 
 
 def _dev(t, device):
@@ -24,12 +24,14 @@ def _dev(t, device):
 
 
 def featmap_pack(nchw: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """[n, C, H, W] fp32 -> [n, H, W, C] fp32 | bf16 (sd_featmap_pack)."""
+    """[n, C, H, W] fp32 -> [n, H, W, C] fp32 | fp16 (sd_featmap_pack)."""
     require_cuda(nchw, "feature map")
     src = _f32c(nchw)
     n, c, h, w = src.shape
     dst = torch.empty((n, h, w, c), dtype=dtype, device=src.device)
-    dt = _abi.SD_BF16 if dtype == torch.bfloat16 else _abi.SD_F32
+    if dtype not in (torch.float32, torch.float16):
+        raise ValueError("feature maps are packed as float32 or float16")
+    dt = _abi.SD_F16 if dtype == torch.float16 else _abi.SD_F32
     _abi.check(_abi.lib().sd_featmap_pack(_ptr(src), n, c, h, w, _ptr(dst), dt, _stream()), "sd_featmap_pack")
     return dst
 
@@ -61,7 +63,7 @@ class Mlp:
 @dataclass
 class Scene:
     """Device-side state of one batch element (what BTSNet.encode stashes, bts.py:246-257)."""
-    feat: torch.Tensor                  # [Hf, Wf, C] channels-last, fp32 or bf16
+    feat: torch.Tensor                  # [Hf, Wf, C] channels-last, fp32 or fp16
     K_f: torch.Tensor                   # [1,3,3]
     w2c_f: torch.Tensor                 # [1,4,4]
     rgb: torch.Tensor | None = None     # [nv_c,3,Hc,Wc]
@@ -103,7 +105,7 @@ class Scene:
     def c(self) -> _abi.SdScene:
         s = _abi.SdScene()
         s.feat = self.feat.data_ptr()
-        s.feat_dtype = _abi.SD_BF16 if self.feat.dtype == torch.bfloat16 else _abi.SD_F32
+        s.feat_dtype = _abi.SD_F16 if self.feat.dtype == torch.float16 else _abi.SD_F32
         s.nv_f = 1
         s.Hf, s.Wf, s.C = self.feat.shape
         s.K_f, s.w2c_f = self.K_f.data_ptr(), self.w2c_f.data_ptr()

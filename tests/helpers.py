@@ -3,11 +3,11 @@ import numpy as np
 
 from scenedino_b200 import synthetic as syn
 
-# north_star tolerances: rel 1e-4 in fp32 mode, 2e-2 in bf16 mode.  "rel" is measured against the
+# north_star tolerances: rel 1e-4 in fp32 mode, 2e-2 in the reduced-precision (fp16 tensor-core) mode.  "rel" is measured against the
 # magnitude of the reference tensor: |a-b| <= tol * max(|b|, rms(b)); near-zero entries of a tensor
 # are therefore compared against the tensor's own scale rather than against themselves.
 TOL_FP32 = 1e-4
-TOL_BF16 = 2e-2
+TOL_F16 = 2e-2
 
 
 def rel_err(a, b):

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import scenedino_b200 as sd
-from helpers import TOL_BF16, TOL_FP32, assert_close, golden_scene_arrays
+from helpers import TOL_F16, TOL_FP32, assert_close, golden_scene_arrays
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -93,14 +93,14 @@ def check_dict(out, g, prefix, tol):
         if k in ("invalid", "invalid_features", "ray_info"):
             assert np.array_equal(a, b), k
         elif k == "rgb_samps":          # bit-equal for unrotated views; torch's CPU bmm rounds rotated ones differently
-            assert_close(a, b, 1e-5, prefix + k)
+            assert_close(a, b, TOL_FP32, prefix + k)
         elif k == "z_samps":
             assert np.array_equal(a, b) or np.mean(np.all(a == b, -1)) > 0.99, k
         else:
             assert_close(a, b, tol, prefix + k)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("fp16", TOL_F16)])
 def test_render_wrapper_coarse(golden, precision, tol):
     g = golden("render_coarse")
     net = build(g, precision=precision)
