@@ -34,16 +34,17 @@ constexpr int WARP_GA0 = WARP_PT0 + N_PT_WARPS;
 constexpr int NTHREADS = (N_EPI_WARPS + 1 + N_PT_WARPS + N_GA_WARPS) * 32;   // 512
 constexpr int NGEO = 3;
 constexpr int TMEM_COLS = 512;
-constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 at 256
+constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 (<= 80 columns) at 256
 constexpr int PART_STRIDE = 80;              // per (warp, segment) composite partial: 64 feat + depth + wsum + 12 rgb
 constexpr int MAX_NVC_TC = 4;
+constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
 
 enum { MODE_POINTS = 0, MODE_RENDER = 1, MODE_ROWS = 2 };
 
-struct Geo {                                 // per-row hand-off, structure of arrays (3584 B)
-    int off[TM];                             // texel index of the north-west tap
-    float w[4][TM];                          // nw, ne, sw, se
-    int flags[TM];                           // bit0 out of frustum, bit1 x0+1 in range, bit2 y0+1 in range, bit3 row valid
+struct Geo {                                 // per-row hand-off from the point warps, structure of arrays (2560 B)
+    uint32_t o[TM];                          // byte offset of the north-west texel row; bit0: x0+1 in range, bit1: y0+1 in range
+    uint32_t w01[TM], w23[TM];               // bilinear weights as halves (nw, ne), (sw, se); zero for unused rows
+    int flags[TM];                           // bit0 out of frustum, bit3 row valid
     float z[TM];                             // sample depth (render mode)
 };
 
@@ -52,11 +53,8 @@ constexpr int OFF_W1 = 0;
 constexpr int OFF_RING = OFF_W1 + MAX_CHUNKS * CHUNK_BYTES;
 constexpr int OFF_H = OFF_RING + MAX_CHUNKS * CHUNK_BYTES;
 constexpr int OFF_W2 = OFF_H + 2 * CHUNK_BYTES;
-constexpr int OFF_GEO = OFF_W2 + 16384;
-constexpr int OFF_BIN = OFF_GEO + NGEO * (int)sizeof(Geo);
-constexpr int OFF_WSIG = OFF_BIN + 512;
-constexpr int OFF_BOUT = OFF_WSIG + 512;
-constexpr int OFF_EMPTY = OFF_BOUT + 320;    // fp16 empty_feature [256]
+constexpr int OFF_GEO = OFF_W2 + W2_BYTES;
+constexpr int OFF_EMPTY = OFF_GEO + NGEO * (int)sizeof(Geo);   // fp16 empty_feature [256]
 constexpr int OFF_CAM = OFF_EMPTY + 512;     // 21 floats per camera, 1 + 4 cameras
 constexpr int OFF_PART = OFF_CAM + 448;
 constexpr int OFF_TAILS = OFF_PART + 4 * 2 * PART_STRIDE * 4;
@@ -66,7 +64,7 @@ constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
-static_assert(OFF_BAR % 8 == 0 && OFF_PART % 16 == 0 && OFF_GEO % 16 == 0, "alignment");
+static_assert(OFF_BAR % 8 == 0 && OFF_PART % 16 == 0 && OFF_GEO % 16 == 0 && OFF_W2 % 1024 == 0, "alignment");
 
 enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 1,
        BAR_GEO_FULL = BAR_D2 + 1, BAR_GEO_EMPTY = BAR_GEO_FULL + NGEO, BAR_WLOAD = BAR_GEO_EMPTY + NGEO };
@@ -80,10 +78,10 @@ struct Params {
     int upt;                  // units per tile
     long long n_tiles;
     int nch;                  // K chunks of layer 1
-    int n2;                   // layer-2 N (feature rows padded to 16)
+    int n2;                   // layer-2 N: D feature rows + the density row, padded to 16
     int D;                    // feature outputs = d_out - 1
     const unsigned char *w1_img, *w2_img;
-    const float *b_in, *w_sigma, *b_out;
+    const float *b_out;
     // rows mode
     const float *x_rows;
     int d_in;
@@ -169,6 +167,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -185,9 +190,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    float *s_bin = reinterpret_cast<float *>(sm + OFF_BIN);
-    float *s_wsig = reinterpret_cast<float *>(sm + OFF_WSIG);
-    float *s_bout = reinterpret_cast<float *>(sm + OFF_BOUT);
     float *s_cam = reinterpret_cast<float *>(sm + OFF_CAM);
     Geo *s_geo = reinterpret_cast<Geo *>(sm + OFF_GEO);
     const bool field = P.mode != MODE_ROWS;
@@ -209,8 +211,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
         mbar_init(BAR(BAR_WLOAD), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 128; i += NTHREADS) { s_bin[i] = __ldg(P.b_in + i); s_wsig[i] = __ldg(P.w_sigma + i); }
-    for (int i = tid; i < 80; i += NTHREADS) s_bout[i] = i <= P.D ? __ldg(P.b_out + i) : 0.0f;
     if (field) {
         for (int i = tid; i < 21 * (1 + P.fp.nv_c); i += NTHREADS) {
             const int c = i / 21, e = i - 21 * c;
@@ -244,15 +244,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 
     if (warp < N_EPI_WARPS) {
         // =================================== EPILOGUE ================================================
+        // Per tile: (1) layer-1 accumulator -> ReLU -> fp16 hidden tile (the bias came out of the MMA);
+        // (2) layer-2 accumulator -> density (+softplus) and features; the features leave the SM through
+        // the warp's own 8 KB of the hidden tile as fully coalesced 512-byte stores, or are composited.
         const int row = tid;                                     // TMEM lane == tile row
         const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int K = P.K;
+        const int K = P.K, D = P.D;
         const int k_i = row % K;
         const bool row_used = row < P.upt * K;
         float *s_part = reinterpret_cast<float *>(sm + OFF_PART);
         float *s_tails = reinterpret_cast<float *>(sm + OFF_TAILS);
-        // state carried from the first to the second epilogue of a tile
-        float sig_keep = 0.0f, w_keep = 0.0f, z_keep = 0.0f;
+        const float bo_sigma = __ldg(P.b_out);
+        float bo4[4];                                            // output bias of the 4 columns this lane stores
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int c = 4 * (lane & 15) + e; bo4[e] = c < D ? __ldg(P.b_out + 1 + c) : 0.0f; }
+        unsigned char *stage0 = sm + OFF_H + warp * 4096, *stage1 = stage0 + CHUNK_BYTES;   // this warp's rows of H
+        float z_keep = 0.0f, zn_keep = 0.0f;
         long long grow_keep = -1;
         for (long long j = 0; j <= my_tiles; ++j) {
             if (j > 0) {
@@ -263,30 +270,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 float v[64];
                 tmem_ld32(t_lane + D2_COL, v);
                 tmem_ld32(t_lane + D2_COL + 32, v + 32);
+                const float sig = tmem_ld1(t_lane + D2_COL + D) + bo_sigma;    // density column sits behind the features
+                const float sg = P.mode == MODE_ROWS ? sig : softplus(sig);
                 const bool ok = grow_keep >= 0;
-                if (!render) {
+                if (ok && P.sigma) P.sigma[grow_keep] = sg;
+                if (P.mode == MODE_ROWS) {
                     if (ok) {
-                        if (P.mode == MODE_ROWS) {
-                            float *o = P.out_rows + grow_keep * (P.D + 1);
-                            o[0] = sig_keep;
-                            for (int c = 0; c < P.D; ++c) o[1 + c] = v[c] + s_bout[1 + c];
-                        } else if (P.dino) {
-                            float *o = P.dino + grow_keep * P.D;
-                            if (P.D == 64) {
+                        float *o = P.out_rows + grow_keep * (D + 1);
+                        o[0] = sg;
 #pragma unroll
-                                for (int c = 0; c < 64; c += 4)
-                                    *reinterpret_cast<float4 *>(o + c) = make_float4(v[c] + s_bout[1 + c], v[c + 1] + s_bout[2 + c],
-                                                                                      v[c + 2] + s_bout[3 + c], v[c + 3] + s_bout[4 + c]);
-                            } else {
+                        for (int c = 0; c < 64; ++c)
+                            if (c < D) o[1 + c] = v[c] + __ldg(P.b_out + 1 + c);
+                    }
+                } else if (!render) {
+                    if (P.dino && D == 64) {
+                        // transpose through shared memory: lane = row writes its 16 chunks (XOR-swizzled, conflict
+                        // free), then 16 lanes read one row back and the warp stores two whole rows per request
 #pragma unroll
-                                for (int c = 0; c < 64; ++c)
-                                    if (c < P.D) o[c] = v[c] + s_bout[1 + c];
-                            }
+                        for (int q = 0; q < 16; ++q)
+                            *reinterpret_cast<float4 *>((q < 8 ? stage0 : stage1) + lane * 128 + (((q & 7) ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        __syncwarp();
+                        const long long row0 = tile * TM + warp * 32;
+                        const int c16 = lane & 15;
+                        const unsigned char *src = (c16 < 8 ? stage0 : stage1);
+#pragma unroll 4
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = 2 * i + (lane >> 4);
+                            float4 x = *reinterpret_cast<const float4 *>(src + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
+                            x.x += bo4[0]; x.y += bo4[1]; x.z += bo4[2]; x.w += bo4[3];
+                            if (row0 + r < P.n_units) *reinterpret_cast<float4 *>(P.dino + (row0 + r) * 64 + c16 * 4) = x;
                         }
+                        __syncwarp();
+                    } else if (P.dino && ok) {
+                        float *o = P.dino + grow_keep * D;
+#pragma unroll
+                        for (int c = 0; c < 64; ++c)
+                            if (c < D) o[c] = v[c] + __ldg(P.b_out + 1 + c);
                     }
                 } else {
-                    // ---- composite: weighted sums over the rows of each ray (nerf.py:393-405) ----------
-                    const float wgt = ok ? w_keep : 0.0f;
+                    // ---- alpha, exclusive transmittance (segmented product scan over the tile), weight
+                    //      (nerf.py:376-389) --------------------------------------------------------------
+                    const bool last = k_i == K - 1;
+                    const float delta = last ? 1e10f : zn_keep - z_keep;
+                    float alpha = 0.0f;
+                    if (ok) {
+                        alpha = 1.0f - expf(-fabsf(delta) * fmaxf(sg, 0.0f));
+                        if (P.cfg.hard_alpha_cap && last) alpha = 1.0f;
+                    }
+                    float incl = ok ? (1.0f - alpha) + 1e-10f : 1.0f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o && k_i >= o) incl *= n;
+                    }
+                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0 || k_i == 0) excl = 1.0f;
+                    if (lane == 31) s_tails[warp] = incl;
+                    named_bar_sync(1, N_EPI_WARPS * 32);
+                    float carry = 1.0f;
+                    for (int prev = k_i - lane, w = warp - 1; prev > 0 && w >= 0; prev -= 32, --w) carry *= s_tails[w];
+                    const float wgt = ok ? alpha * (excl * carry) : 0.0f;
+                    if (ok) {
+                        if (P.weights) P.weights[grow_keep] = wgt;
+                        if (P.alphas) P.alphas[grow_keep] = alpha;
+                    }
+                    // ---- weighted sums over the rows of each ray (nerf.py:393-405) ----------------------
                     const int nrgb = 3 * P.fp.nv_c;
                     float crgb[3 * MAX_NVC_TC];
 #pragma unroll
@@ -306,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         for (int hh = 0; hh < 2; ++hh) {
                             float a[32];
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) a[c] = ws * (v[hh * 32 + c] + s_bout[1 + hh * 32 + c]);
+                            for (int c = 0; c < 32; ++c) a[c] = ws * v[hh * 32 + c];
 #pragma unroll
                             for (int step = 0; step < 5; ++step) {
                                 const int m = 16 >> step;
@@ -329,10 +378,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         if (lane == 0) { pp[64] = sd_; pp[65] = sw_; }
 #pragma unroll
                         for (int c = 0; c < 3 * MAX_NVC_TC; ++c) {
-                            float s = ws * crgb[c];
+                            float sc = ws * crgb[c];
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                            if (lane == 0) pp[66 + c] = s;
+                            for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                            if (lane == 0) pp[66 + c] = sc;
                         }
                     }
                     named_bar_sync(1, N_EPI_WARPS * 32);
@@ -348,17 +397,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                                 acc[0] += pp[lane]; acc[1] += pp[lane + 32];
                                 if (lane + 64 < 78) acc[2] += pp[lane + 64];
                             }
-                            if (P.dino_ray) {
-                                if (lane < P.D) P.dino_ray[ray * P.D + lane] = acc[0];
-                                if (lane + 32 < P.D) P.dino_ray[ray * P.D + lane + 32] = acc[1];
-                            }
                             const float wsum = __shfl_sync(0xffffffffu, acc[2], 1);
+                            if (P.dino_ray) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
+                                if (lane < D) P.dino_ray[ray * D + lane] = fmaf(__ldg(P.b_out + 1 + lane), wsum, acc[0]);
+                                if (lane + 32 < D) P.dino_ray[ray * D + lane + 32] = fmaf(__ldg(P.b_out + 33 + lane), wsum, acc[1]);
+                            }
                             if (lane == 0 && P.depth) P.depth[ray] = acc[2];
                             if (lane >= 2 && lane < 2 + nrgb && P.rgb_ray)
                                 P.rgb_ray[ray * nrgb + (lane - 2)] = P.cfg.white_bkgd ? acc[2] + 1.0f - wsum : acc[2];
                         }
                     }
-                    named_bar_sync(1, N_EPI_WARPS * 32);   // partials consumed before the next tile overwrites them
+                    named_bar_sync(1, N_EPI_WARPS * 32);   // partials / tails consumed before the next tile overwrites them
                 }
             }
             if (j == my_tiles) break;
@@ -366,21 +415,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             const long long tile = first + j * stride;
             const long long unit = tile * P.upt + row / K;
             const bool ok = row_used && unit < P.n_units;
-            const long long grow = unit * K + k_i;
+            grow_keep = ok ? unit * K + k_i : -1;
             const int slot = (int)(j % NGEO);
-            float z_i = 0.0f, z_n = 0.0f;
             if (field) {
                 mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
                 if (render) {
-                    z_i = s_geo[slot].z[row];
-                    z_n = row + 1 < TM ? s_geo[slot].z[row + 1] : 0.0f;
+                    z_keep = s_geo[slot].z[row];
+                    zn_keep = row + 1 < TM ? s_geo[slot].z[row + 1] : 0.0f;
                 }
                 mbar_arrive(BAR(BAR_GEO_EMPTY + slot));
             }
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
             tc_fence_after();
-            float sig = 0.0f;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 float v[32];
@@ -390,55 +437,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 for (int q = 0; q < 4; ++q) {
                     uint32_t pk[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        const int col = cc * 32 + q * 8 + e;
-                        const float h0 = fmaxf(v[q * 8 + e] + s_bin[col], 0.0f);
-                        const float h1 = fmaxf(v[q * 8 + e + 1] + s_bin[col + 1], 0.0f);
-                        sig = fmaf(h0, s_wsig[col], sig);
-                        sig = fmaf(h1, s_wsig[col + 1], sig);
-                        pk[e >> 1] = pack_h2(h0, h1);
-                    }
+                    for (int e = 0; e < 8; e += 2)
+                        pk[e >> 1] = pack_h2(fmaxf(v[q * 8 + e], 0.0f), fmaxf(v[q * 8 + e + 1], 0.0f));
                     const int chunk = ((cc & 1) * 4 + q) ^ (row & 7);
                     *reinterpret_cast<uint4 *>(hrow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
-            sig += s_bout[0];
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(BAR(BAR_H));
-            const float sg = P.mode == MODE_ROWS ? sig : softplus(sig);
-            sig_keep = sg;
-            grow_keep = ok ? grow : -1;
-            if (ok && P.sigma) P.sigma[grow] = sg;
-            if (render) {
-                // alpha, exclusive transmittance (segmented product scan over the tile), weight
-                const bool last = k_i == K - 1;
-                const float delta = last ? 1e10f : z_n - z_i;
-                float alpha = 0.0f;
-                if (ok) {
-                    alpha = 1.0f - expf(-fabsf(delta) * fmaxf(sg, 0.0f));
-                    if (P.cfg.hard_alpha_cap && last) alpha = 1.0f;
-                }
-                float incl = ok ? (1.0f - alpha) + 1e-10f : 1.0f;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float n = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o && k_i >= o) incl *= n;
-                }
-                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0 || k_i == 0) excl = 1.0f;
-                if (lane == 31) s_tails[warp] = incl;
-                named_bar_sync(1, N_EPI_WARPS * 32);
-                float carry = 1.0f;
-                for (int prev = k_i - lane, w = warp - 1; prev > 0 && w >= 0; prev -= 32, --w) carry *= s_tails[w];
-                const float wgt = alpha * (excl * carry);
-                w_keep = wgt;
-                z_keep = z_i;
-                if (ok) {
-                    if (P.weights) P.weights[grow] = wgt;
-                    if (P.alphas) P.alphas[grow] = alpha;
-                }
-            }
         }
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
@@ -526,8 +533,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     }
                 }
                 Geo &g = s_geo[slot];
-                g.off[row] = off; g.flags[row] = flags; g.z[row] = zs;
-                g.w[0][row] = t.wnw; g.w[1][row] = t.wne; g.w[2][row] = t.wsw; g.w[3][row] = t.wse;
+                {
+                    const uint32_t tex = (uint32_t)P.fp.C * 2u;                       // bytes per texel row
+                    const uint32_t o_nw = (uint32_t)off * tex;
+                    const bool plain = ok && !(P.fp.learn_empty && (flags & 1));
+                    g.o[row] = o_nw | (uint32_t)((flags >> 1) & 3);
+                    g.w01[row] = plain ? pack_h2(t.wnw, t.wne) : 0u;
+                    g.w23[row] = plain ? pack_h2(t.wsw, t.wse) : 0u;
+                    g.flags[row] = flags; g.z[row] = zs;
+                    if (plain) {   // pull the two texel-row pairs towards L2 one to two tiles ahead of the gather
+                        const unsigned char *fbp = reinterpret_cast<const unsigned char *>(P.fp.feat);
+                        const uint32_t dx = (flags & 2) ? tex : 0u;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw), "r"(tex + dx) : "memory");
+                        if (flags & 4)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw + (size_t)P.fp.Wf * tex), "r"(tex + dx) : "memory");
+                    }
+                }
                 mbar_arrive(BAR(BAR_GEO_FULL + slot));
                 // ---- positional code -> last K chunk (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by
                 //      angle doubling from one accurate sincosf per coordinate) ------------------------------
@@ -535,8 +556,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 32; ++i) pk[i] = 0u;
                 if (ok) {
-                    float code[46];
-                    code[0] = x; code[1] = y; code[2] = zp; code[45] = 0.0f;
+                    float code[48];
+                    code[0] = x; code[1] = y; code[2] = zp;
+                    code[45] = 1.0f; code[46] = 1.0f; code[47] = 0.0f;   // constant-1 columns: layer-1 bias (hi, lo) comes out of the MMA
                     // hi/lo split of the raw coordinates into the K padding (see mlp_pack_kernel)
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
@@ -559,7 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 23; ++i) pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
+                    for (int i = 0; i < 24; ++i) pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
                 }
                 const int cchunk = P.nch - 1;
                 mbar_wait(BAR(BAR_EMPTY + cchunk), (uint32_t)((j & 1) ^ 1));
@@ -587,41 +609,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 for (int rg = (gw + N_GA_WARPS - (8 * c) % N_GA_WARPS) % N_GA_WARPS; rg < 8; rg += N_GA_WARPS)
                 if (field) {
                     const Geo &g = s_geo[slot];
-                    const __half *fb = reinterpret_cast<const __half *>(P.fp.feat) + c * 64 + sub * 8;
                     const __half *s_empty = reinterpret_cast<const __half *>(sm + OFF_EMPTY) + c * 64 + sub * 8;
-                    // Branch-free so that all 16 128-bit loads of the unit are in flight before the first use:
-                    // phase 1 reads the hand-off, phase 2 issues every load (rows that are not valid, and taps
-                    // that fall outside the map, read an in-range texel with weight zero), phase 3 blends.
-                    uint4 raw[4][4];
-                    float wq[4][4];
-                    const __half *qp[4];
-                    size_t dxs[4], dys[4];
-                    bool use_empty[4];
+                    // Branch-free: per row three scalar hand-off words (offset+flags, two weight pairs), then all 16
+                    // LDG.128 of the unit are in flight before the first use; 64 HFMA2 and 4 STS.128 finish it.
+                    const unsigned char *fbase = reinterpret_cast<const unsigned char *>(P.fp.feat) + c * 128 + sub * 16;
+                    const uint32_t tex = (uint32_t)C * 2u, trow = (uint32_t)P.fp.Wf * tex;
+                    uint4 raw[4][4], wv[4];
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int p = rg * 16 + it * 4 + grp;
-                        const int fl = g.flags[p];
-                        const bool valid = fl & 8;
-                        qp[it] = fb + (size_t)g.off[p] * C;
-                        dxs[it] = (fl & 2) ? (size_t)C : 0;
-                        dys[it] = (fl & 4) ? (size_t)P.fp.Wf * C : 0;
-                        use_empty[it] = P.fp.learn_empty && (fl & 1);          // bts.py:311-319
-                        const bool plain = valid && !use_empty[it];
-                        wq[it][0] = plain ? g.w[0][p] : (valid ? 1.0f : 0.0f);
-                        wq[it][1] = plain ? g.w[1][p] : 0.0f;
-                        wq[it][2] = plain ? g.w[2][p] : 0.0f;
-                        wq[it][3] = plain ? g.w[3][p] : 0.0f;
+                        const uint32_t ow = g.o[p], w01 = g.w01[p], w23 = g.w23[p];
+                        const uint32_t o = ow & ~3u, dx = (ow & 1u) ? tex : 0u, dy = (ow & 2u) ? trow : 0u;
+                        wv[it] = make_uint4(__byte_perm(w01, 0, 0x1010), __byte_perm(w01, 0, 0x3232),
+                                            __byte_perm(w23, 0, 0x1010), __byte_perm(w23, 0, 0x3232));
+                        raw[it][0] = ldg128(fbase + o); raw[it][1] = ldg128(fbase + o + dx);
+                        raw[it][2] = ldg128(fbase + o + dy); raw[it][3] = ldg128(fbase + o + dy + dx);
                     }
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        raw[it][0] = ldg128(qp[it]); raw[it][1] = ldg128(qp[it] + dxs[it]);
-                        raw[it][2] = ldg128(qp[it] + dys[it]); raw[it][3] = ldg128(qp[it] + dys[it] + dxs[it]);
-                    }
-                    if (P.fp.learn_empty) {
+                    if (P.fp.learn_empty) {                                     // bts.py:311-319
                         const uint4 e = *reinterpret_cast<const uint4 *>(s_empty);
+                        const uint32_t one = as_u32(__float2half2_rn(1.0f));
 #pragma unroll
-                        for (int it = 0; it < 4; ++it)
-                            if (use_empty[it]) raw[it][0] = e;
+                        for (int it = 0; it < 4; ++it) {
+                            const int fl = g.flags[rg * 16 + it * 4 + grp];
+                            if ((fl & 9) == 9) { raw[it][0] = e; wv[it].x = one; }
+                        }
                     }
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
@@ -630,8 +641,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         const uint32_t *b = reinterpret_cast<const uint32_t *>(&raw[it][1]);
                         const uint32_t *cc = reinterpret_cast<const uint32_t *>(&raw[it][2]);
                         const uint32_t *d = reinterpret_cast<const uint32_t *>(&raw[it][3]);
-                        const __half2 w0 = __float2half2_rn(wq[it][0]), w1 = __float2half2_rn(wq[it][1]);
-                        const __half2 w2 = __float2half2_rn(wq[it][2]), w3 = __float2half2_rn(wq[it][3]);
+                        const __half2 w0 = as_h2(wv[it].x), w1 = as_h2(wv[it].y), w2 = as_h2(wv[it].z), w3 = as_h2(wv[it].w);
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {   // two channels per HFMA2, taps in the reference order nw, ne, sw, se
@@ -653,7 +663,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int col = c * 64 + sub * 8 + e;
-                            f[e] = (r < P.n_units && col < P.d_in) ? __ldg(P.x_rows + r * P.d_in + col) : 0.0f;
+                            f[e] = (r < P.n_units && col < P.d_in) ? __ldg(P.x_rows + r * P.d_in + col)
+                                   : ((col == P.d_in + 6 || col == P.d_in + 7) ? 1.0f : 0.0f);   // bias columns
                         }
                         *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) =
                             make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
@@ -681,7 +692,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 // ---- host side ------------------------------------------------------------------------------------------
 static bool tc_head_ok(const sd_mlp *mlp) {
     return mlp && mlp->packed && mlp->d_hidden == 128 && mlp->d_out >= 2 && mlp->d_out - 1 <= 64 && mlp->d_in >= 1 &&
-           mlp->d_in <= 64 * tc::MAX_CHUNKS;
+           mlp->d_in + 8 <= 64 * tc::MAX_CHUNKS;
 }
 
 static bool tc_scene_ok(const sd_scene *s, const sd_mlp *mlp) {
@@ -699,12 +710,10 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
     SD_REQUIRE(((uintptr_t)blob & 15) == 0, "mlp: packed blob must be 16-byte aligned");
     P.w1_img = blob + L.off_w_in_h;
     P.w2_img = blob + L.off_w_out_h;
-    P.b_in = reinterpret_cast<const float *>(blob + L.off_b_in);
-    P.w_sigma = reinterpret_cast<const float *>(blob + L.off_w_sigma);
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
     P.nch = L.d_in_pad / 64;
     P.D = mlp->d_out - 1;
-    P.n2 = (P.D + 15) / 16 * 16;
+    P.n2 = (mlp->d_out + 15) / 16 * 16;
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -721,7 +730,7 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp, const TcRender *render,
                     const TcOut &out, cudaStream_t st) {
     if (N == 0) return SD_OK;
-    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 320, d_hidden = 128, 2 <= d_out <= 65 and packed");
+    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 and packed");
     SD_REQUIRE(fp.feat_f16, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
     SD_REQUIRE(fp.C == 256 && fp.code_dim == 39 && fp.enc.include_input && mlp->d_in == fp.C + fp.code_dim,
                "SD_MLP_F16_TC: supports C = 256 with the 39-d positional code (got C=%d, code=%d, d_in=%d)", fp.C,
@@ -756,7 +765,7 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
 }
 
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st) {
-    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 320, d_hidden = 128, 2 <= d_out <= 65 and packed");
+    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 and packed");
     if (N == 0) return SD_OK;
     SD_REQUIRE(x && out, "sd_mlp_forward: null pointer");
     tc::Params P = {};

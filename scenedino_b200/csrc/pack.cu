@@ -49,7 +49,9 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     MlpLayout L;
     L.d_in = d_in; L.d_hidden = d_hidden; L.d_out = d_out;
-    L.d_in_pad = (int)align_up((size_t)d_in, 64);   // whole 64-wide K blocks (SW128 atoms)
+    // whole 64-wide K blocks (SW128 atoms) with at least 8 spare columns behind d_in: the tensor-core
+    // image keeps the coordinate hi/lo split there (6) and the layer-1 bias as two constant-1 columns (2)
+    L.d_in_pad = (int)align_up((size_t)d_in + 8, 64);
     L.d_out_pad = (int)align_up((size_t)d_out, 16);
     size_t o = 0;
     L.off_w_in_t = o;   o = align_up(o + sizeof(float) * (size_t)L.d_in_pad * d_hidden, 1024);
@@ -57,8 +59,8 @@ MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     L.off_w_out_t = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden * L.d_out_pad, 1024);
     L.off_b_out = o;    o = align_up(o + sizeof(float) * (size_t)L.d_out_pad, 1024);
     L.off_w_in_h = o;  o = align_up(o + 2 * (size_t)L.d_in_pad * d_hidden, 1024);
-    // feature rows of W_out (rows 1..d_out-1), padded to a multiple of 16 rows
-    const int n2 = (int)align_up((size_t)(d_out > 1 ? d_out - 1 : 1), 16);
+    // tensor-core image of W_out: feature rows 1..d_out-1 first, then the density row 0, padded to 16 rows
+    const int n2 = (int)align_up((size_t)d_out, 16);
     L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden, 64), 1024);
     L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
     L.total = o;
@@ -78,22 +80,28 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
     __half *w_out_h = reinterpret_cast<__half *>(blob + L.off_w_out_h);
     float *w_sigma = reinterpret_cast<float *>(blob + L.off_w_sigma);
     const int H = L.d_hidden;
-    // fp16 image, K padding put to use: the raw coordinates (x, y, z') sit at columns d_in-39 .. d_in-37 of
-    // the field's input; z' reaches +-6e3 for points next to / behind the camera, where one half-precision
-    // product is coarse.  Columns d_in .. d_in+2 repeat half(w) for the low
-    // halves of the coordinates and d_in+3 .. d_in+5 hold w - half(w) for their high halves, so that
-    // x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.  The kernel fills the matching A columns; callers that pass
-    // plain rows leave them zero.
-    const bool split = L.d_in >= 39 && L.d_in + 6 <= L.d_in_pad;
+    // fp16 image, K padding put to use.
+    //  * The raw coordinates (x, y, z') sit at columns d_in-39 .. d_in-37 of the field's input; z' reaches
+    //    +-6e3 for points next to / behind the camera, where one half-precision product is coarse.  Columns
+    //    d_in .. d_in+2 repeat half(w) for the low halves of the coordinates and d_in+3 .. d_in+5 hold
+    //    w - half(w) for their high halves, so that x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo.
+    //  * Columns d_in+6, d_in+7 carry the layer-1 bias as half(b) and b - half(b); the kernel feeds them
+    //    the constant 1, so the bias comes out of the MMA and the epilogue needs no per-column constants.
+    // The kernel fills the matching A columns; all other padding stays zero on both sides.
+    const bool split = L.d_in >= 39;
     for (int i = tid; i < L.d_in_pad * H; i += nth) {
         const int k = i / H, j = i - k * H;
         const float v = k < L.d_in ? w_in[(size_t)j * L.d_in + k] : 0.0f;
         w_in_t[i] = v;
         float vb = v;
-        if (split && k >= L.d_in && k < L.d_in + 6) {
-            const int e = k - L.d_in;
+        const int e = k - L.d_in;
+        if (split && e >= 0 && e < 6) {
             const float w = w_in[(size_t)j * L.d_in + (L.d_in - 39) + (e % 3)];
             vb = e < 3 ? w : w - __half2float(__float2half_rn(w));
+        } else if (e == 6) {
+            vb = b_in[j];
+        } else if (e == 7) {
+            vb = b_in[j] - __half2float(__float2half_rn(b_in[j]));
         }
         w_in_h[umma_sw128_offset(j, k, H) / 2] = __float2half_rn(vb);
     }
@@ -106,11 +114,12 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
         w_out_t[i] = o < L.d_out ? w_out[(size_t)o * H + k] : 0.0f;
     }
     for (int i = tid; i < L.d_out_pad; i += nth) bo[i] = i < L.d_out ? b_out[i] : 0.0f;
-    const int n2 = ((L.d_out > 1 ? L.d_out - 1 : 1) + 15) / 16 * 16;
+    const int n2 = (L.d_out + 15) / 16 * 16;
     const int Hp = (H + 63) / 64 * 64;
     for (int i = tid; i < n2 * Hp; i += nth) {
-        const int r = i / Hp, k = i - r * Hp;  // feature row r <-> W_out row r+1
-        const float v = (r + 1 < L.d_out && k < H) ? w_out[(size_t)(r + 1) * H + k] : 0.0f;
+        const int r = i / Hp, k = i - r * Hp;  // image row r <-> W_out row r+1 (features), row d_out-1 <-> W_out row 0 (density)
+        const int src = r < L.d_out - 1 ? r + 1 : (r == L.d_out - 1 ? 0 : -1);
+        const float v = (src >= 0 && k < H) ? w_out[(size_t)src * H + k] : 0.0f;
         w_out_h[umma_sw128_offset(r, k, n2) / 2] = __float2half_rn(v);
     }
 }
