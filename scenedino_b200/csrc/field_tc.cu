@@ -42,7 +42,7 @@ constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
 enum { MODE_POINTS = 0, MODE_RENDER = 1, MODE_ROWS = 2 };
 
 struct Geo {                                 // per-row hand-off from the point warps, structure of arrays (2560 B)
-    uint32_t o[TM];                          // byte offset of the north-west texel row; bit0: x0+1 in range, bit1: y0+1 in range
+    uint32_t o[TM];                          // byte offset of the north-west texel of the (clamped) 2x2 footprint
     uint32_t w01[TM], w23[TM];               // bilinear weights as halves (nw, ne), (sw, se); zero for unused rows
     int flags[TM];                           // bit0 out of frustum, bit3 row valid
     float z[TM];                             // sample depth (render mode)
@@ -184,8 +184,10 @@ __device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpre
 
 // ---- the kernel -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_constant__ Params P) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *sm = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the shared array itself: going through
+    // an integer would make every shared access of the kernel a generic LD/ST
+    unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = sm_u + OFF_BAR;
@@ -513,8 +515,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     y = clamp_keep_nan(y, -2.0f, 2.0f);
                     zp = znorm(zc, P.fp.enc);
                     t = bilinear_tap(x, y, P.fp.Hf, P.fp.Wf);
+                    // keep the 2x2 footprint inside the map so the gather can use fixed +1 texel / +1 row offsets:
+                    // at the last column / row the out-of-range taps have weight zero, so shifting the base by one
+                    // and moving the weights over is exact
+                    if (!t.in_x1) { t.x0 -= 1; t.wne = t.wnw; t.wse = t.wsw; t.wnw = 0.0f; t.wsw = 0.0f; }
+                    if (!t.in_y1) { t.y0 -= 1; t.wsw = t.wnw; t.wse = t.wne; t.wnw = 0.0f; t.wne = 0.0f; }
                     off = t.y0 * P.fp.Wf + t.x0;
-                    flags = (inv ? 1 : 0) | (t.in_x1 ? 2 : 0) | (t.in_y1 ? 4 : 0) | 8;
+                    flags = (inv ? 1 : 0) | 8;
                     if (P.invalid_feat) P.invalid_feat[grow] = inv ? 1 : 0;
                     if (nv_c > 0 && (P.rgb || P.invalid)) {
                         for (int v = 0; v < nv_c; ++v) {
@@ -537,16 +544,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     const uint32_t tex = (uint32_t)P.fp.C * 2u;                       // bytes per texel row
                     const uint32_t o_nw = (uint32_t)off * tex;
                     const bool plain = ok && !(P.fp.learn_empty && (flags & 1));
-                    g.o[row] = o_nw | (uint32_t)((flags >> 1) & 3);
+                    g.o[row] = o_nw;
                     g.w01[row] = plain ? pack_h2(t.wnw, t.wne) : 0u;
                     g.w23[row] = plain ? pack_h2(t.wsw, t.wse) : 0u;
                     g.flags[row] = flags; g.z[row] = zs;
                     if (plain) {   // pull the two texel-row pairs towards L2 one to two tiles ahead of the gather
                         const unsigned char *fbp = reinterpret_cast<const unsigned char *>(P.fp.feat);
-                        const uint32_t dx = (flags & 2) ? tex : 0u;
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw), "r"(tex + dx) : "memory");
-                        if (flags & 4)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw + (size_t)P.fp.Wf * tex), "r"(tex + dx) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw), "r"(2u * tex) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw + (size_t)P.fp.Wf * tex), "r"(2u * tex) : "memory");
                     }
                 }
                 mbar_arrive(BAR(BAR_GEO_FULL + slot));
@@ -618,12 +623,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int p = rg * 16 + it * 4 + grp;
-                        const uint32_t ow = g.o[p], w01 = g.w01[p], w23 = g.w23[p];
-                        const uint32_t o = ow & ~3u, dx = (ow & 1u) ? tex : 0u, dy = (ow & 2u) ? trow : 0u;
+                        const uint32_t w01 = g.w01[p], w23 = g.w23[p];
+                        const unsigned char *q = fbase + g.o[p];
                         wv[it] = make_uint4(__byte_perm(w01, 0, 0x1010), __byte_perm(w01, 0, 0x3232),
                                             __byte_perm(w23, 0, 0x1010), __byte_perm(w23, 0, 0x3232));
-                        raw[it][0] = ldg128(fbase + o); raw[it][1] = ldg128(fbase + o + dx);
-                        raw[it][2] = ldg128(fbase + o + dy); raw[it][3] = ldg128(fbase + o + dy + dx);
+                        raw[it][0] = ldg128(q); raw[it][1] = ldg128(q + tex);
+                        raw[it][2] = ldg128(q + trow); raw[it][3] = ldg128(q + trow + tex);
                     }
                     if (P.fp.learn_empty) {                                     // bts.py:311-319
                         const uint4 e = *reinterpret_cast<const uint4 *>(s_empty);
@@ -696,7 +701,7 @@ static bool tc_head_ok(const sd_mlp *mlp) {
 }
 
 static bool tc_scene_ok(const sd_scene *s, const sd_mlp *mlp) {
-    return s && s->feat_dtype == SD_F16 && s->C == 256 && s->nv_f == 1 && s->include_input && s->num_freqs == 6 &&
+    return s && s->feat_dtype == SD_F16 && s->C == 256 && s->Hf >= 2 && s->Wf >= 2 && s->nv_f == 1 && s->include_input && s->num_freqs == 6 &&
            s->nv_c <= tc::MAX_NVC_TC && tc_head_ok(mlp) && mlp->d_in == s->C + 39;
 }
 
@@ -736,6 +741,7 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
                "SD_MLP_F16_TC: supports C = 256 with the 39-d positional code (got C=%d, code=%d, d_in=%d)", fp.C,
                fp.code_dim, mlp->d_in);
     SD_REQUIRE(fp.nv_c <= tc::MAX_NVC_TC, "SD_MLP_F16_TC: at most %d colour views (got %d)", tc::MAX_NVC_TC, fp.nv_c);
+    SD_REQUIRE(fp.Hf >= 2 && fp.Wf >= 2, "SD_MLP_F16_TC: the feature map must be at least 2 x 2");
     tc::Params P = {};
     P.fp = fp;
     P.src = src;

@@ -1,0 +1,92 @@
+"""Multi-GPU execution of the hot path: one process per GPU, rays / voxels sharded, outputs all-gathered.
+
+The reference exposes ray parallelism as ``nn.DataParallel(dim=1)`` inside ``NeRFRenderer.bind_parallel``
+(renderer/nerf.py:654-658, never enabled by any caller) and walks the SSC grid in independent chunks
+(sscbench/evaluate_model_sscbench.py:711-717).  Rays and voxel queries never interact, so here every
+rank holds a replica of the scene (feature map, cameras, head weights), works on a contiguous shard --
+image-row tiles of rays, x-slabs of the voxel grid -- and the only communication is ONE all-gather of
+each (small) output over NCCL / NVLink.  There is no collective inside the data path.
+
+The functions take any ``torch.distributed`` process group (NCCL on GPUs; gloo in the CPU tests of the
+plumbing) and a callable that does the local work, so they are independent of the kernels.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced [start, end) ranges: the first ``n % world`` ranks get one extra unit."""
+    if world <= 0:
+        raise ValueError("world size must be positive")
+    base, rem = divmod(n, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def shard_slice(n: int, rank: int, world: int) -> slice:
+    s, e = shard_bounds(n, world)[rank]
+    return slice(s, e)
+
+
+def all_gather_ragged(local: torch.Tensor, n_total: int, dim: int = 0, group=None) -> torch.Tensor:
+    """All-gathers shards produced by :func:`shard_bounds` along ``dim`` (shard sizes differ by at most one,
+    so shards are padded to the largest and trimmed after one ``all_gather_into_tensor``)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    bounds = shard_bounds(n_total, world)
+    mx = max(e - s for s, e in bounds)
+    x = local.movedim(dim, 0).contiguous()
+    if x.shape[0] != bounds[dist.get_rank(group)][1] - bounds[dist.get_rank(group)][0]:
+        raise ValueError("local shard does not have the size shard_bounds() assigns to this rank")
+    if x.shape[0] < mx:
+        pad = torch.zeros((mx - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], 0)
+    out = torch.empty((world * mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x, group=group)
+    parts = [out[r * mx: r * mx + (e - s)] for r, (s, e) in enumerate(bounds)]
+    return torch.cat(parts, 0).movedim(0, dim)
+
+
+def render_rays_sharded(render_fn: Callable[[torch.Tensor], dict], rays: torch.Tensor, group=None,
+                        keys: Sequence[str] = ("rgb", "depth", "dino_features")) -> dict:
+    """rays [n, R, r_dim] -> each rank renders rays[:, shard] with ``render_fn`` (the wrapped renderer of
+    NeRFRenderer.bind_parallel) and the per-ray outputs named in ``keys`` are all-gathered along the ray
+    dimension.  Returns {"coarse": {...}[, "fine": {...}]} with full-size tensors on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    R = rays.shape[1]
+    sl = shard_slice(R, rank, world)
+    local = render_fn(rays[:, sl].contiguous())
+    out = {}
+    for level in ("coarse", "fine"):
+        if level in local:
+            out[level] = {k: all_gather_ragged(local[level][k], R, dim=1, group=group) for k in keys if k in local[level]}
+    return out
+
+
+def query_voxels_sharded(query_fn: Callable[[torch.Tensor], dict], xyz: torch.Tensor, grid_dims: Sequence[int],
+                         group=None, keys: Sequence[str] = ("sigma",)) -> dict:
+    """xyz [X*Y*Z, 3] in 'ij' order -> each rank queries a slab of x indices with ``query_fn`` and the
+    outputs named in ``keys`` (by default only the density grid: 4 B/voxel; the 64-d features stay
+    sharded for the per-voxel head) are all-gathered.  ``local`` holds this rank's full result."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    X, Y, Z = grid_dims
+    if xyz.shape[0] != X * Y * Z:
+        raise ValueError("xyz does not match grid_dims")
+    sx = shard_slice(X, rank, world)
+    local = query_fn(xyz[sx.start * Y * Z: sx.stop * Y * Z])
+    gathered = {}
+    for k in keys:
+        t = local[k]
+        t = t.reshape((sx.stop - sx.start, Y * Z) + tuple(t.shape[1:]))
+        g = all_gather_ragged(t, X, dim=0, group=group)
+        gathered[k] = g.reshape((X * Y * Z,) + tuple(t.shape[2:]))
+    return {"local": local, "x_range": (sx.start, sx.stop), **gathered}
