@@ -158,7 +158,7 @@ def workload_config(precision):
     return {"workload": "SSC voxel-grid query 256x256x32 @0.2m (51.2 m), DINO ViT-B/8 map 256x384x1280, "
                         "MLP 295->128->65, outputs sigma+64-d features+mask",
             "voxels_per_step": GRID[0] * GRID[1] * GRID[2], "feature_map": [C_FEAT, HF, WF],
-            "mlp": [D_IN, D_HID, D_OUT], "precision": precision,
+            "mlp": [D_IN, D_HID, D_OUT],
             "l2": "working set per step (map + 25 MB points + 545 MB outputs) exceeds the 126 MB L2; no explicit flush"}
 
 

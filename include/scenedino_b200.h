@@ -120,10 +120,14 @@ int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, float *out, v
 
 /* ---- BTSNet.forward (bts.py:476-595) --------------------------------------------------------- */
 /* sigma [N], dino [N,d_out-1], rgb [N,3*nv_c], invalid [N,nv_c] (fp32 0/1, = invalid_colors |
- * all(invalid_features), bts.py:566-569), invalid_feat [N] (0/1).  Any output may be NULL. */
+ * all(invalid_features), bts.py:566-569), invalid_feat [N] (0/1).  Any output may be NULL.
+ * `workspace` is optional scratch (sd_query_workspace_bytes; may be NULL / 0): with it the tensor-core path
+ * first sorts the point indices by the 8x8-texel block of the feature map they project to, so that the
+ * rows of a tile share texels (results per point do not depend on the order). */
+size_t sd_query_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long N);
 int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                     float *sigma, float *dino, float *rgb, float *invalid,
-                    unsigned char *invalid_feat, void *stream);
+                    unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- NeRFRenderer sampling (renderer/nerf.py:121-228) --------------------------------------- */
 /* sample_coarse (nerf.py:121-141).  u [R,Kc] = torch.rand_like draw, lin [Kc] = torch.linspace. */

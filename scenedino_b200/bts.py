@@ -277,10 +277,12 @@ class BTSNet(nn.Module):
             lib = _abi.lib()
             for b in range(n):
                 sc = self._scene(st, b)
+                need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(mlp), N)
+                ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
                 _abi.check(lib.sd_query_points(
                     C.byref(sc), C.byref(mlp), _ptr(xyz[b]), N, _ptr(sigma[b]), _ptr(dino[b]),
                     _ptr(rgb[b]) if want_colors else None, _ptr(invalid[b]) if want_colors else None,
-                    _ptr(invf[b]), _stream()), "sd_query_points")
+                    _ptr(invf[b]), _ptr(ws), need, _stream()), "sd_query_points")
             invalid_features = invf.view(torch.bool)
 
         if predict_segmentation:  # bts.py:528-533, 584-592

@@ -49,9 +49,16 @@ extern "C" int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, fl
     return launch_mlp_simt(mlp, x, N, out, false, (cudaStream_t)stream);
 }
 
+extern "C" size_t sd_query_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long N) {
+    if (!scene || !mlp || N <= 0) return 0;
+    // only the tensor-core path reorders the points; below a few tiles per SM it is not worth three launches
+    if (mlp->precision != SD_MLP_F16_TC || N < 65536) return 0;
+    return bin_workspace_bytes(scene->Hf, scene->Wf, N);
+}
+
 extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                                float *sigma, float *dino, float *rgb, float *invalid,
-                               unsigned char *invalid_feat, void *stream) {
+                               unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream) {
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
@@ -61,7 +68,13 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
     if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
-        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream);
+        const unsigned int *perm = nullptr;
+        const size_t need = sd_query_workspace_bytes(scene, mlp, N);
+        if (need && workspace && workspace_bytes >= need) {   // walk the points bin by bin of the feature map
+            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &perm, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, perm);
     }
     SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);
     SimtOut out = {};

@@ -18,6 +18,8 @@
 // layer-1 MMAs start while later chunks of the same tile are still being gathered and the gather of
 // tile t+1 overlaps the MMAs/epilogues of tile t.  W_in / W_out live in shared memory for the whole
 // kernel (loaded once with cp.async.bulk), accumulators in TMEM (layer 1 double-buffered).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -41,11 +43,12 @@ constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
 
 enum { MODE_POINTS = 0, MODE_RENDER = 1, MODE_ROWS = 2 };
 
-struct Geo {                                 // per-row hand-off from the point warps, structure of arrays (2560 B)
+struct Geo {                                 // per-row hand-off from the point warps, structure of arrays (3072 B)
     uint32_t o[TM];                          // byte offset of the north-west texel of the (clamped) 2x2 footprint
     uint32_t w01[TM], w23[TM];               // bilinear weights as halves (nw, ne), (sw, se); zero for unused rows
     int flags[TM];                           // bit0 out of frustum, bit3 row valid
     float z[TM];                             // sample depth (render mode)
+    int grow[TM];                            // global row (point / sample index) this tile row stands for, -1 if unused
 };
 
 // shared-memory map, offsets from a 1024-byte aligned base
@@ -71,8 +74,10 @@ enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BA
 
 struct Params {
     int mode;
+    int dbg;                   // SD_TC_DEBUG ablation mask (timing experiments only; results are wrong when non-zero)
     FieldParams fp;
     PointSrc src;
+    const unsigned int *perm;  // point mode: tile row r of tile t stands for point perm[128 t + r] (texel-binned order) or NULL
     long long n_units;        // points / rays / rows
     int K;                    // rows per unit (1 unless render)
     int upt;                  // units per tile
@@ -94,6 +99,9 @@ struct Params {
     float *depth, *dino_ray, *rgb_ray, *weights, *alphas;
 };
 
+__device__ long long g_trace[4 * 64 * 8];   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
+__constant__ int c_dbg;   // copy of Params::dbg for the PTX wrappers (timing experiments)
+
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,6 +110,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// One arrival per warp: every lane has finished (and fenced) its part, __syncwarp orders the lanes, lane 0 arrives.
+// (All-thread arrives cost ~1600 serialized shared-memory atomics per tile: 30 % of the kernel.)
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -150,8 +164,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t *r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -162,18 +175,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-    uint32_t r;
+__device__ __forceinline__ void tmem_ld1_issue(uint32_t taddr, uint32_t &r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return __uint_as_float(r);
 }
-
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -181,6 +187,12 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 __device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+#define SD_TRACE(role, j, ev)                                                                    \
+    do {                                                                                         \
+        if ((c_dbg & 8192) && blockIdx.x == 0 && (j) < 64 && (threadIdx.x & 31) == 0)             \
+            g_trace[((role) * 64 + (int)(j)) * 8 + (ev)] = clock64();                            \
+    } while (0)
 
 // ---- the kernel -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_constant__ Params P) {
@@ -200,15 +212,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
     // ---- one-time setup ------------------------------------------------------------------------------
     if (tid == 0) {
         for (int c = 0; c < MAX_CHUNKS; ++c) {
-            mbar_init(BAR(BAR_FULL + c), (field && c == P.nch - 1) ? N_PT_WARPS * 32 : N_GA_WARPS * 32);
+            mbar_init(BAR(BAR_FULL + c), (field && c == P.nch - 1) ? N_PT_WARPS : N_GA_WARPS);   // [0]: all gathered chunks of a tile
             mbar_init(BAR(BAR_EMPTY + c), 1);
         }
         mbar_init(BAR(BAR_D1), 1); mbar_init(BAR(BAR_D1 + 1), 1);
-        mbar_init(BAR(BAR_H), N_EPI_WARPS * 32);
+        mbar_init(BAR(BAR_H), N_EPI_WARPS);
         mbar_init(BAR(BAR_D2), 1);
         for (int s = 0; s < NGEO; ++s) {
-            mbar_init(BAR(BAR_GEO_FULL + s), N_PT_WARPS * 32);
-            mbar_init(BAR(BAR_GEO_EMPTY + s), (N_GA_WARPS + N_EPI_WARPS) * 32);
+            mbar_init(BAR(BAR_GEO_FULL + s), N_PT_WARPS);
+            mbar_init(BAR(BAR_GEO_EMPTY + s), N_GA_WARPS + N_EPI_WARPS);
         }
         mbar_init(BAR(BAR_WLOAD), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,11 +280,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 // ---------------- second epilogue of tile j-1 -----------------------------------------
                 mbar_wait(BAR(BAR_D2), (uint32_t)((j - 1) & 1));
                 tc_fence_after();
+                if (warp == 0) SD_TRACE(0, j, 0);
                 const long long tile = first + (j - 1) * stride;
+                uint32_t vr[64], sr;
+                tmem_ld32_issue(t_lane + D2_COL, vr);
+                tmem_ld32_issue(t_lane + D2_COL + 32, vr + 32);
+                tmem_ld1_issue(t_lane + D2_COL + D, sr);                          // density column sits behind the features
+                tmem_ld_wait();
                 float v[64];
-                tmem_ld32(t_lane + D2_COL, v);
-                tmem_ld32(t_lane + D2_COL + 32, v + 32);
-                const float sig = tmem_ld1(t_lane + D2_COL + D) + bo_sigma;    // density column sits behind the features
+#pragma unroll
+                for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(vr[c]);
+                const float sig = __uint_as_float(sr) + bo_sigma;
                 const float sg = P.mode == MODE_ROWS ? sig : softplus(sig);
                 const bool ok = grow_keep >= 0;
                 if (ok && P.sigma) P.sigma[grow_keep] = sg;
@@ -293,15 +311,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                             *reinterpret_cast<float4 *>((q < 8 ? stage0 : stage1) + lane * 128 + (((q & 7) ^ (lane & 7)) << 4)) =
                                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                         __syncwarp();
-                        const long long row0 = tile * TM + warp * 32;
+                        (void)tile;
                         const int c16 = lane & 15;
                         const unsigned char *src = (c16 < 8 ? stage0 : stage1);
-#pragma unroll 4
+                        const int g32 = (int)grow_keep;
+#pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int r = 2 * i + (lane >> 4);
                             float4 x = *reinterpret_cast<const float4 *>(src + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
                             x.x += bo4[0]; x.y += bo4[1]; x.z += bo4[2]; x.w += bo4[3];
-                            if (row0 + r < P.n_units) *reinterpret_cast<float4 *>(P.dino + (row0 + r) * 64 + c16 * 4) = x;
+                            const int dst = __shfl_sync(0xffffffffu, g32, r);
+                            if (dst >= 0) *reinterpret_cast<float4 *>(P.dino + (long long)dst * 64 + c16 * 4) = x;
                         }
                         __syncwarp();
                     } else if (P.dino && ok) {
@@ -412,6 +432,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     named_bar_sync(1, N_EPI_WARPS * 32);   // partials / tails consumed before the next tile overwrites them
                 }
             }
+            if (warp == 0) SD_TRACE(0, j, 1);
             if (j == my_tiles) break;
             // ---------------- first epilogue of tile j ----------------------------------------------------
             const long long tile = first + j * stride;
@@ -421,33 +442,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             const int slot = (int)(j % NGEO);
             if (field) {
                 mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
+                grow_keep = s_geo[slot].grow[row];
                 if (render) {
                     z_keep = s_geo[slot].z[row];
                     zn_keep = row + 1 < TM ? s_geo[slot].z[row + 1] : 0.0f;
                 }
-                mbar_arrive(BAR(BAR_GEO_EMPTY + slot));
+                mbar_arrive_warp(BAR(BAR_GEO_EMPTY + slot));
             }
+            if (warp == 0) SD_TRACE(0, j, 2);
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
             tc_fence_after();
+            if (warp == 0) SD_TRACE(0, j, 3);
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                float v[32];
-                tmem_ld32(t_lane + b * 128 + cc * 32, v);
-                unsigned char *hrow = sm + OFF_H + (cc >> 1) * CHUNK_BYTES + row * 128;
+            for (int kb = 0; kb < 2; ++kb) {                     // 64 hidden units = one K block of the layer-2 A operand
+                uint32_t vr[64];
+                tmem_ld32_issue(t_lane + b * 128 + kb * 64, vr);
+                tmem_ld32_issue(t_lane + b * 128 + kb * 64 + 32, vr + 32);
+                tmem_ld_wait();
+                unsigned char *hrow = sm + OFF_H + kb * CHUNK_BYTES + row * 128;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     uint32_t pk[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2)
-                        pk[e >> 1] = pack_h2(fmaxf(v[q * 8 + e], 0.0f), fmaxf(v[q * 8 + e + 1], 0.0f));
-                    const int chunk = ((cc & 1) * 4 + q) ^ (row & 7);
-                    *reinterpret_cast<uint4 *>(hrow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        pk[e >> 1] = pack_h2(fmaxf(__uint_as_float(vr[q * 8 + e]), 0.0f), fmaxf(__uint_as_float(vr[q * 8 + e + 1]), 0.0f));
+                    *reinterpret_cast<uint4 *>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(BAR(BAR_H));
+            mbar_arrive_warp(BAR(BAR_H));
+            if (warp == 0) SD_TRACE(0, j, 4);
         }
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
@@ -457,6 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             auto layer2 = [&](long long jj) {
                 mbar_wait(BAR(BAR_H), (uint32_t)(jj & 1));
                 tc_fence_after();
+                SD_TRACE(1, jj + 1, 6);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -467,9 +494,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             };
             for (long long j = 0; j < my_tiles; ++j) {
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
+                // the gather warps fence and arrive once per tile (FULL[0]) for all the chunks they fill -- every
+                // fence.proxy.async / mbarrier round trip queues behind their loads in the LSU --, the point warps
+                // arrive on FULL[nch-1] for the code chunk; the stages are still released one by one (EMPTY[c])
+                const int ngath = field ? P.nch - 1 : P.nch;
                 for (int c = 0; c < P.nch; ++c) {
-                    mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
-                    tc_fence_after();
+                    if (c == 0 || c == ngath) {
+                        mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
+                        tc_fence_after();
+                        SD_TRACE(1, j, c == 0 ? 0 : 4);
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
@@ -477,7 +511,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     umma_commit(BAR(BAR_EMPTY + c));
                 }
                 umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                SD_TRACE(1, j, 5);
                 if (j > 0) layer2(j - 1);
+                SD_TRACE(1, j, 7);
             }
             if (my_tiles > 0) layer2(my_tiles - 1);
         }
@@ -488,28 +524,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             const int K = P.K, k_i = row % K;
             const bool row_used = row < P.upt * K;
             const int nv_c = P.fp.nv_c;
+            // inputs of a tile row (global row index, 3-D point, sample depth), fetched one tile ahead so that the
+            // dependent perm -> xyz (or ray + z) loads are off the critical path
+            struct RowIn { long long grow; float px, py, pz, zs; };
+            auto fetch = [&](long long jj) {
+                RowIn r;
+                r.grow = -1; r.px = r.py = r.pz = r.zs = 0.0f;
+                if (jj >= my_tiles) return r;
+                const long long unit = (first + jj * stride) * P.upt + row / K;
+                if (!(row_used && unit < P.n_units)) return r;
+                r.grow = P.perm ? (long long)__ldg(P.perm + unit) : unit * K + k_i;
+                if (!P.src.xyz) {
+                    const float *ry = P.src.rays + (r.grow / P.src.K) * P.src.r_dim;
+                    r.zs = __ldg(P.src.z + r.grow);
+                    r.px = ray_point(__ldg(ry + 0), __ldg(ry + 3), r.zs);
+                    r.py = ray_point(__ldg(ry + 1), __ldg(ry + 4), r.zs);
+                    r.pz = ray_point(__ldg(ry + 2), __ldg(ry + 5), r.zs);
+                } else {
+                    r.px = __ldg(P.src.xyz + 3 * r.grow); r.py = __ldg(P.src.xyz + 3 * r.grow + 1); r.pz = __ldg(P.src.xyz + 3 * r.grow + 2);
+                }
+                return r;
+            };
+            RowIn nxt = fetch(0);
             for (long long j = 0; j < my_tiles; ++j) {
-                const long long tile = first + j * stride;
-                const long long unit = tile * P.upt + row / K;
-                const bool ok = row_used && unit < P.n_units;
-                const long long grow = unit * K + k_i;
+                const RowIn cur = nxt;
+                nxt = fetch(j + 1);
+                const bool ok = cur.grow >= 0;
+                const long long grow = cur.grow;
                 const int slot = (int)(j % NGEO);
                 mbar_wait(BAR(BAR_GEO_EMPTY + slot), (uint32_t)(((j / NGEO) & 1) ^ 1));
-                float x = 0.f, y = 0.f, zp = 0.f, zs = 0.f;
+                if (warp == WARP_PT0) SD_TRACE(2, j, 0);
+                float x = 0.f, y = 0.f, zp = 0.f;
+                const float zs = cur.zs;
                 int flags = 0, off = 0;
                 Tap t = {};
                 if (ok) {
-                    float px, py, pz, zc;
+                    const float px = cur.px, py = cur.py, pz = cur.pz;
+                    float zc;
                     bool inv;
-                    if (!P.src.xyz) {
-                        const float *ry = P.src.rays + (grow / P.src.K) * P.src.r_dim;
-                        zs = __ldg(P.src.z + grow);
-                        px = ray_point(__ldg(ry + 0), __ldg(ry + 3), zs);
-                        py = ray_point(__ldg(ry + 1), __ldg(ry + 4), zs);
-                        pz = ray_point(__ldg(ry + 2), __ldg(ry + 5), zs);
-                    } else {
-                        px = __ldg(P.src.xyz + 3 * grow); py = __ldg(P.src.xyz + 3 * grow + 1); pz = __ldg(P.src.xyz + 3 * grow + 2);
-                    }
                     project_point(s_cam, s_cam + 9, px, py, pz, x, y, zc, inv);
                     x = clamp_keep_nan(x, -2.0f, 2.0f);
                     y = clamp_keep_nan(y, -2.0f, 2.0f);
@@ -547,14 +599,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     g.o[row] = o_nw;
                     g.w01[row] = plain ? pack_h2(t.wnw, t.wne) : 0u;
                     g.w23[row] = plain ? pack_h2(t.wsw, t.wse) : 0u;
-                    g.flags[row] = flags; g.z[row] = zs;
-                    if (plain) {   // pull the two texel-row pairs towards L2 one to two tiles ahead of the gather
-                        const unsigned char *fbp = reinterpret_cast<const unsigned char *>(P.fp.feat);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw), "r"(2u * tex) : "memory");
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(fbp + o_nw + (size_t)P.fp.Wf * tex), "r"(2u * tex) : "memory");
-                    }
+                    g.flags[row] = flags; g.z[row] = zs; g.grow[row] = (int)grow;
                 }
-                mbar_arrive(BAR(BAR_GEO_FULL + slot));
+                mbar_arrive_warp(BAR(BAR_GEO_FULL + slot));
+                if (warp == WARP_PT0) SD_TRACE(2, j, 1);
                 // ---- positional code -> last K chunk (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by
                 //      angle doubling from one accurate sincosf per coordinate) ------------------------------
                 uint32_t pk[32];
@@ -589,13 +637,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     for (int i = 0; i < 24; ++i) pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
                 }
                 const int cchunk = P.nch - 1;
+                if (warp == WARP_PT0) SD_TRACE(2, j, 2);
                 mbar_wait(BAR(BAR_EMPTY + cchunk), (uint32_t)((j & 1) ^ 1));
+                if (warp == WARP_PT0) SD_TRACE(2, j, 3);
                 unsigned char *arow = sm + OFF_RING + cchunk * CHUNK_BYTES + row * 128;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     *reinterpret_cast<uint4 *>(arow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 fence_proxy_async();
-                mbar_arrive(BAR(BAR_FULL + cchunk));
+                mbar_arrive_warp(BAR(BAR_FULL + cchunk));
+                if (warp == WARP_PT0) SD_TRACE(2, j, 4);
             }
         }
     } else {
@@ -604,49 +655,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
         const int sub = lane & 7, grp = lane >> 3;
         const int nfeat = field ? P.nch - 1 : P.nch;
         const int C = P.fp.C;
+        const int n_units = nfeat * 8;                 // (chunk, 16-row group) units of a tile; mine: gw, gw+7, ...
+        const uint32_t tex = (uint32_t)C * 2u, trow = (uint32_t)P.fp.Wf * tex;
         for (long long j = 0; j < my_tiles; ++j) {
             const long long tile = first + j * stride;
             const int slot = (int)(j % NGEO);
-            if (field) mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
-            for (int c = 0; c < nfeat; ++c) {
-                mbar_wait(BAR(BAR_EMPTY + c), (uint32_t)((j & 1) ^ 1));
-                unsigned char *stage = sm + OFF_RING + c * CHUNK_BYTES;
-                for (int rg = (gw + N_GA_WARPS - (8 * c) % N_GA_WARPS) % N_GA_WARPS; rg < 8; rg += N_GA_WARPS)
-                if (field) {
-                    const Geo &g = s_geo[slot];
-                    const __half *s_empty = reinterpret_cast<const __half *>(sm + OFF_EMPTY) + c * 64 + sub * 8;
-                    // Branch-free: per row three scalar hand-off words (offset+flags, two weight pairs), then all 16
-                    // LDG.128 of the unit are in flight before the first use; 64 HFMA2 and 4 STS.128 finish it.
-                    const unsigned char *fbase = reinterpret_cast<const unsigned char *>(P.fp.feat) + c * 128 + sub * 16;
-                    const uint32_t tex = (uint32_t)C * 2u, trow = (uint32_t)P.fp.Wf * tex;
-                    uint4 raw[4][4], wv[4];
+            if (field) {
+                mbar_wait(BAR(BAR_GEO_FULL + slot), (uint32_t)((j / NGEO) & 1));
+                if (gw == 0) SD_TRACE(3, j, 0);
+                const Geo &g = s_geo[slot];
+                const unsigned char *fmap = reinterpret_cast<const unsigned char *>(P.fp.feat) + sub * 16;
+                const __half *s_empty = reinterpret_cast<const __half *>(sm + OFF_EMPTY) + sub * 8;
+                // A unit is two halves of 8 rows (2 x 4 rows per request).  Software pipeline: the 8 LDG.128 of the
+                // next half are issued before the current half is blended, so a load batch is always in flight
+                // behind the HFMA2 work; loads do not need the ring stage, only the stores wait for it.
+                uint4 rawA[2][4], rawB[2][4];
+                uint2 wA[2], wB[2];
+                auto issue = [&](int u, int half, uint4 (&raw)[2][4], uint2 (&w)[2]) {
+                    const int c = u >> 3, rg = u & 7;
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int p = rg * 16 + it * 4 + grp;
-                        const uint32_t w01 = g.w01[p], w23 = g.w23[p];
-                        const unsigned char *q = fbase + g.o[p];
-                        wv[it] = make_uint4(__byte_perm(w01, 0, 0x1010), __byte_perm(w01, 0, 0x3232),
-                                            __byte_perm(w23, 0, 0x1010), __byte_perm(w23, 0, 0x3232));
+                    for (int it = 0; it < 2; ++it) {
+                        const int p = rg * 16 + (half * 2 + it) * 4 + grp;
+                        const unsigned char *q = fmap + c * 128 + g.o[p];
+                        w[it] = make_uint2(g.w01[p], g.w23[p]);
                         raw[it][0] = ldg128(q); raw[it][1] = ldg128(q + tex);
                         raw[it][2] = ldg128(q + trow); raw[it][3] = ldg128(q + trow + tex);
                     }
-                    if (P.fp.learn_empty) {                                     // bts.py:311-319
-                        const uint4 e = *reinterpret_cast<const uint4 *>(s_empty);
-                        const uint32_t one = as_u32(__float2half2_rn(1.0f));
+                };
+                auto blend = [&](int u, int half, uint4 (&raw)[2][4], uint2 (&w)[2]) {
+                    const int c = u >> 3, rg = u & 7;
+                    unsigned char *stage = sm + OFF_RING + c * CHUNK_BYTES;
 #pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int fl = g.flags[rg * 16 + it * 4 + grp];
-                            if ((fl & 9) == 9) { raw[it][0] = e; wv[it].x = one; }
+                    for (int it = 0; it < 2; ++it) {
+                        const int p = rg * 16 + (half * 2 + it) * 4 + grp;
+                        uint32_t w0u = __byte_perm(w[it].x, 0, 0x1010), w1u = __byte_perm(w[it].x, 0, 0x3232);
+                        const uint32_t w2u = __byte_perm(w[it].y, 0, 0x1010), w3u = __byte_perm(w[it].y, 0, 0x3232);
+                        if (P.fp.learn_empty && (g.flags[p] & 9) == 9) {      // bts.py:311-319
+                            raw[it][0] = *reinterpret_cast<const uint4 *>(s_empty + c * 64);
+                            w0u = as_u32(__float2half2_rn(1.0f));
                         }
-                    }
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int p = rg * 16 + it * 4 + grp;
+                        const __half2 w0 = as_h2(w0u), w1 = as_h2(w1u), w2 = as_h2(w2u), w3 = as_h2(w3u);
                         const uint32_t *a = reinterpret_cast<const uint32_t *>(&raw[it][0]);
                         const uint32_t *b = reinterpret_cast<const uint32_t *>(&raw[it][1]);
                         const uint32_t *cc = reinterpret_cast<const uint32_t *>(&raw[it][2]);
                         const uint32_t *d = reinterpret_cast<const uint32_t *>(&raw[it][3]);
-                        const __half2 w0 = as_h2(wv[it].x), w1 = as_h2(wv[it].y), w2 = as_h2(wv[it].z), w3 = as_h2(wv[it].w);
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {   // two channels per HFMA2, taps in the reference order nw, ne, sw, se
@@ -658,27 +710,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         }
                         *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                } else {
-                    // rows mode: x [N, d_in] fp32 -> fp16 chunk c (columns 64c .. 64c+63)
+                };
+                int cur_c = -1;
+                if (gw < n_units) issue(gw, 0, rawA, wA);
+                for (int u = gw; u < n_units; u += N_GA_WARPS) {
+                    const int c = u >> 3;
+                    issue(u, 1, rawB, wB);
+                    if (c != cur_c) {                       // first unit of mine in this chunk: the stage must be free
+                        mbar_wait(BAR(BAR_EMPTY + c), (uint32_t)((j & 1) ^ 1));
+                        cur_c = c;
+                        if (gw == 0) SD_TRACE(3, j, 1 + c);
+                    }
+                    blend(u, 0, rawA, wA);
+                    if (u + N_GA_WARPS < n_units) issue(u + N_GA_WARPS, 0, rawA, wA);
+                    blend(u, 1, rawB, wB);
+                }
+                fence_proxy_async();
+                mbar_arrive_warp(BAR(BAR_FULL + 0));
+                mbar_arrive_warp(BAR(BAR_GEO_EMPTY + slot));
+                if (gw == 0) SD_TRACE(3, j, 5);
+            } else {
+                // rows mode: x [N, d_in] fp32 -> fp16 chunk c (columns 64c .. 64c+63)
+                for (int c = 0; c < nfeat; ++c) {
+                    mbar_wait(BAR(BAR_EMPTY + c), (uint32_t)((j & 1) ^ 1));
+                    unsigned char *stage = sm + OFF_RING + c * CHUNK_BYTES;
+                    for (int rg = (gw + N_GA_WARPS - (8 * c) % N_GA_WARPS) % N_GA_WARPS; rg < 8; rg += N_GA_WARPS) {
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int p = rg * 16 + it * 4 + grp;
-                        const long long r = tile * TM + p;
-                        float f[8];
+                        for (int it = 0; it < 4; ++it) {
+                            const int p = rg * 16 + it * 4 + grp;
+                            const long long r = tile * TM + p;
+                            float f[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int col = c * 64 + sub * 8 + e;
-                            f[e] = (r < P.n_units && col < P.d_in) ? __ldg(P.x_rows + r * P.d_in + col)
-                                   : ((col == P.d_in + 6 || col == P.d_in + 7) ? 1.0f : 0.0f);   // bias columns
+                            for (int e = 0; e < 8; ++e) {
+                                const int col = c * 64 + sub * 8 + e;
+                                f[e] = (r < P.n_units && col < P.d_in) ? __ldg(P.x_rows + r * P.d_in + col)
+                                       : ((col == P.d_in + 6 || col == P.d_in + 7) ? 1.0f : 0.0f);   // bias columns
+                            }
+                            *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) =
+                                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
                         }
-                        *reinterpret_cast<uint4 *>(stage + p * 128 + ((sub ^ (p & 7)) << 4)) =
-                            make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive(BAR(BAR_FULL + c));
+                mbar_arrive_warp(BAR(BAR_FULL + 0));
             }
-            if (field) mbar_arrive(BAR(BAR_GEO_EMPTY + slot));
         }
     }
 
@@ -693,6 +768,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 }
 
 }  // namespace tc
+
+// debug: copies the clock64 trace of the last launch made with SD_TC_DEBUG & 8192 (not part of the public header)
+extern "C" int sd_debug_read_trace(long long *host_out) {
+    SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tc::g_trace, sizeof(long long) * 4 * 64 * 8));
+    return SD_OK;
+}
 
 // ---- host side ------------------------------------------------------------------------------------------
 static bool tc_head_ok(const sd_mlp *mlp) {
@@ -716,6 +797,15 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
     P.w1_img = blob + L.off_w_in_h;
     P.w2_img = blob + L.off_w_out_h;
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
+    {
+        const char *e = getenv("SD_TC_DEBUG");
+        P.dbg = e ? atoi(e) : 0;
+    }
+    static int last_dbg = 0;
+    if (P.dbg != last_dbg) {
+        SD_CUDA_OK(cudaMemcpyToSymbol(tc::c_dbg, &P.dbg, sizeof(int)));
+        last_dbg = P.dbg;
+    }
     P.nch = L.d_in_pad / 64;
     P.D = mlp->d_out - 1;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
@@ -733,8 +823,9 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
 }
 
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp, const TcRender *render,
-                    const TcOut &out, cudaStream_t st) {
+                    const TcOut &out, cudaStream_t st, const unsigned int *perm) {
     if (N == 0) return SD_OK;
+    SD_REQUIRE(N < (1ll << 31), "SD_MLP_F16_TC: at most 2^31 - 1 rows per call (got %lld)", N);
     SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 and packed");
     SD_REQUIRE(fp.feat_f16, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
     SD_REQUIRE(fp.C == 256 && fp.code_dim == 39 && fp.enc.include_input && mlp->d_in == fp.C + fp.code_dim,
@@ -764,6 +855,7 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
         P.n_units = N;
         P.dino = out.dino;
         P.rgb = out.rgb;
+        P.perm = src.xyz ? perm : nullptr;
     }
     P.n_tiles = (P.n_units + P.upt - 1) / P.upt;
     P.sigma = out.sigma; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;

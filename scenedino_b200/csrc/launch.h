@@ -61,7 +61,12 @@ struct TcRender {         // per-ray outputs of the fused composite
 // true when the fused kernel handles this (scene, head) in render mode with K samples per ray
 bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K);
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp,
-                    const TcRender *render, const TcOut &out, cudaStream_t st);
+                    const TcRender *render, const TcOut &out, cudaStream_t st, const unsigned int *perm = nullptr);
+
+// ---- texel binning of query points (binning.cu) ------------------------------------------------------
+size_t bin_workspace_bytes(int Hf, int Wf, long long N);
+int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
+                      const unsigned int **perm_out, cudaStream_t st);
 // ResnetFC.forward on explicit rows through the same tcgen05 pipeline (unit test of the MMA path)
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st);
 

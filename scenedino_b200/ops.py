@@ -170,7 +170,7 @@ def expand_dim(mlp: Mlp, f):
     return out
 
 
-def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out=None):
+def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out=None, binned=True):
     """BTSNet.forward for one scene -> dict(sigma[N], dino[N,D], rgb[N,3nv_c], invalid[N,nv_c],
     invalid_features[N] bool).  ``out`` lets bench.py reuse output buffers."""
     xyz = _f32c(xyz); require_cuda(xyz, "xyz")
@@ -181,10 +181,15 @@ def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out
         if want_rgb and scene.nv_c:
             out.update(rgb=_e((N, 3 * scene.nv_c), xyz), invalid=_e((N, scene.nv_c), xyz))
     sc, m = scene.c(), mlp.c(precision)
-    _abi.check(_abi.lib().sd_query_points(C.byref(sc), C.byref(m), _ptr(xyz), N, _ptr(out["sigma"]), _ptr(out["dino"]),
-                                          _ptr(out.get("rgb")), _ptr(out.get("invalid")),
-                                          _ptr(out["invalid_features"]), _stream()), "sd_query_points")
-    res = dict(out)
+    lib = _abi.lib()
+    need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(m), N) if binned else 0
+    ws = out.get("_workspace")
+    if need and (ws is None or ws.numel() < need):
+        ws = out["_workspace"] = torch.empty((need,), dtype=torch.uint8, device=xyz.device)
+    _abi.check(lib.sd_query_points(C.byref(sc), C.byref(m), _ptr(xyz), N, _ptr(out["sigma"]), _ptr(out["dino"]),
+                                   _ptr(out.get("rgb")), _ptr(out.get("invalid")), _ptr(out["invalid_features"]),
+                                   _ptr(ws) if need else None, need, _stream()), "sd_query_points")
+    res = {k: v for k, v in out.items() if not k.startswith("_")}
     res["invalid_features"] = out["invalid_features"].view(torch.bool)
     return res
 

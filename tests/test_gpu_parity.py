@@ -286,6 +286,10 @@ def test_ssc_grid_full_size(precision, tol, feat_dtype):
     q2 = ops.query_points(dsc, dmlp, dp[perm].contiguous(), precision=precision)
     assert torch.equal(q2["sigma"], q["sigma"][perm]) and torch.equal(q2["dino"], q["dino"][perm])
     assert torch.isfinite(q["sigma"]).all() and torch.isfinite(q["dino"]).all()
+    # the tensor-core path walks the points in texel-binned order when given scratch space: same bits
+    q3 = ops.query_points(dsc, dmlp, dp, precision=precision, binned=False)
+    assert torch.equal(q3["sigma"], q["sigma"]) and torch.equal(q3["dino"], q["dino"])
+    assert torch.equal(q3["invalid_features"], q["invalid_features"])
 
 
 # ---- edge cases and error behaviour ----------------------------------------------------------------
