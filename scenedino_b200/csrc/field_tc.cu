@@ -6,9 +6,9 @@
 //
 // One persistent CTA per SM walks 128-row tiles (rows = points, or samples of 128/K whole rays).
 // Warp roles (16 warps):
-//   warps 0-3   epilogue: TMEM -> registers; bias+ReLU -> fp16 hidden tile (smem, UMMA A operand of
-//               layer 2); density row in fp32; softplus; second epilogue writes the features or
-//               composites them (segmented transmittance scan + butterfly weighted sums)
+//   warps 0-3   epilogue: layer-1 accumulator -> ReLU -> fp16 hidden tile written back to TMEM (the A operand of
+//               layer 2, tcgen05.st); second epilogue: density + softplus, features out through shared memory
+//               as coalesced stores, or composited (segmented transmittance scan + butterfly weighted sums)
 //   warp  4     tcgen05.mma issuer (one lane) + TMEM owner
 //   warps 5-8   one thread per row: ray point, projection, frustum mask, bilinear tap, colour
 //               lookup, positional code -> code chunk of the A operand
@@ -37,6 +37,7 @@ constexpr int NTHREADS = (N_EPI_WARPS + 1 + N_PT_WARPS + N_GA_WARPS) * 32;   // 
 constexpr int NGEO = 3;
 constexpr int TMEM_COLS = 512;
 constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 (<= 80 columns) at 256
+constexpr int H_COL = 384;                   // fp16 hidden tile (A operand of layer 2): 64 columns, two halves per column
 constexpr int PART_STRIDE = 80;              // per (warp, segment) composite partial: 64 feat + depth + wsum + 12 rgb
 constexpr int MAX_NVC_TC = 4;
 constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
@@ -161,6 +162,25 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -455,23 +475,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             tc_fence_after();
             if (warp == 0) SD_TRACE(0, j, 3);
 #pragma unroll 1
-            for (int kb = 0; kb < 2; ++kb) {                     // 64 hidden units = one K block of the layer-2 A operand
-                uint32_t vr[64];
+            for (int kb = 0; kb < 2; ++kb) {                     // 64 hidden units -> 32 packed columns of the layer-2 A operand
+                uint32_t vr[64], pk[32];
                 tmem_ld32_issue(t_lane + b * 128 + kb * 64, vr);
                 tmem_ld32_issue(t_lane + b * 128 + kb * 64 + 32, vr + 32);
                 tmem_ld_wait();
-                unsigned char *hrow = sm + OFF_H + kb * CHUNK_BYTES + row * 128;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        pk[e >> 1] = pack_h2(fmaxf(__uint_as_float(vr[q * 8 + e]), 0.0f), fmaxf(__uint_as_float(vr[q * 8 + e + 1]), 0.0f));
-                    *reinterpret_cast<uint4 *>(hrow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
+                for (int e = 0; e < 32; ++e)
+                    pk[e] = pack_h2(fmaxf(__uint_as_float(vr[2 * e]), 0.0f), fmaxf(__uint_as_float(vr[2 * e + 1]), 0.0f));
+                tmem_st32(t_lane + H_COL + kb * 32, pk);
             }
+            tmem_st_wait();
             tc_fence_before();
-            fence_proxy_async();
             mbar_arrive_warp(BAR(BAR_H));
             if (warp == 0) SD_TRACE(0, j, 4);
         }
@@ -485,11 +500,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 tc_fence_after();
                 SD_TRACE(1, jj + 1, 6);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma(tmem_base + D2_COL, umma_desc(sm_u + OFF_H + kb * CHUNK_BYTES + k * 32),
-                             umma_desc(sm_u + OFF_W2 + kb * P.n2 * 128 + k * 32), idesc2, (kb | k) != 0);
+                for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                    umma_ts(tmem_base + D2_COL, tmem_base + H_COL + k * 8,
+                            umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
                 umma_commit(BAR(BAR_D2));
             };
             for (long long j = 0; j < my_tiles; ++j) {
