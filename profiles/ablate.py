@@ -27,9 +27,9 @@ def t(binned, flag):
 import ctypes
 from scenedino_b200 import _abi
 raw=ctypes.CDLL(_abi.LIB_PATH)
-def trace(flag, label):
+def trace(flag, label, binned=False):
     os.environ['SD_TC_DEBUG']=str(flag+8192)
-    for _ in range(2): ops.query_points(scene,mlp,pts,want_rgb=False,out=out,binned=False)
+    for _ in range(2): ops.query_points(scene,mlp,pts,want_rgb=False,out=out,binned=binned)
     torch.cuda.synchronize()
     buf=(ctypes.c_longlong*(4*64*8))()
     raw.sd_debug_read_trace(buf)
@@ -38,8 +38,9 @@ def trace(flag, label):
     a=np.where(a>0,a-t0,-1)
     print('=== trace', label)
     names=['epi','mma','pt ','ga ']
-    for j in range(8,16):
+    for j in range(20,28):
         for r in range(4):
             print(f"tile {j:2d} {names[r]}", ' '.join(f"{v:7d}" for v in a[r,j]))
-trace(0,'full')
+trace(0,'full unbinned')
+trace(0,'full binned', True)
 print('full unbinned', t(False,0)*1000, 'us;  binned', t(True,0)*1000,'us')
