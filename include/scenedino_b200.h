@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2
 
 typedef enum sd_status {
     SD_OK = 0,
@@ -66,6 +66,8 @@ typedef struct sd_scene {
     int          include_input;
     int          learn_empty;   /* bts.py:311-319                                          */
     const float *empty_feature; /* [C] or NULL                                             */
+    const void  *feat_proj;     /* optional: blob written by sd_field_project for the head these queries
+                                   will use (NULL = absent); enables the projected-map tile kernel */
 } sd_scene;
 
 /* ResnetFC head with n_blocks = 0 (models/prediction_heads/resnetfc.py:90-96,162-199).
@@ -101,6 +103,15 @@ int    sd_featmap_pack(const float *nchw, int n_img, int C, int H, int W, void *
 size_t sd_mlp_pack_bytes(int d_in, int d_hidden, int d_out);
 int    sd_mlp_pack(const float *w_in, const float *b_in, const float *w_out, const float *b_out,
                    int d_in, int d_hidden, int d_out, void *packed, void *stream);
+
+/* Pushes the channels-last fp16 map through the feature columns of the head's first layer, once per
+ * encode: P[texel] = W_in[:, :C] . F[texel] (bilinear sampling, bts.py:299-309, and lin_in,
+ * resnetfc.py:162-163, are both linear, so sampling P equals lin_in of the sampled features).  With
+ * scene->feat_proj set to the result, sd_query_points (SD_MLP_F16_TC, with workspace) interpolates the
+ * 128 hidden pre-activations on the tensor cores straight from TMA-fetched tiles of P.  The blob is
+ * tied to `mlp` (and to empty_feature when learn_empty); `proj` must be 1024-byte aligned. */
+size_t sd_field_project_bytes(const sd_scene *scene);
+int    sd_field_project(const sd_scene *scene, const sd_mlp *mlp, void *proj, size_t proj_bytes, void *stream);
 
 /* ---- point ops, one per reference function (unfused; for 1:1 parity tests) -------------------- */
 /* pts_into_camera + project_to_image + outside_frustum (common/cameras/pinhole.py:40-112) for one

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libscenedino_b200.so")
 
 SD_F32, SD_F16 = 0, 1
 SD_MLP_FP32, SD_MLP_F16_TC = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SdError(RuntimeError):
@@ -30,6 +30,7 @@ class SdScene(C.Structure):
         ("d_min", C.c_float), ("d_max", C.c_float), ("inv_z", C.c_int),
         ("num_freqs", C.c_int), ("freq_factor", C.c_float), ("include_input", C.c_int),
         ("learn_empty", C.c_int), ("empty_feature", C.c_void_p),
+        ("feat_proj", C.c_void_p),
     ]
 
 
@@ -54,6 +55,8 @@ PROTOTYPES = {
     "sd_featmap_pack": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "sd_mlp_pack_bytes": (_SZ, [_I, _I, _I]),
     "sd_mlp_pack": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "sd_field_project_bytes": (_SZ, [_SC]),
+    "sd_field_project": (_I, [_SC, _ML, _P, _SZ, _P]),
     "sd_project_points": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P]),
     "sd_sample_features": (_I, [_SC, _P, _LL, _P, _P, _P]),
     "sd_sample_colors": (_I, [_SC, _P, _LL, _P, _P, _P]),

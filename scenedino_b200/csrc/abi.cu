@@ -68,13 +68,17 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
     if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
-        const unsigned int *perm = nullptr;
+        BinOrder order = {};
         const size_t need = sd_query_workspace_bytes(scene, mlp, N);
         if (need && workspace && workspace_bytes >= need) {   // walk the points bin by bin of the feature map
-            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &perm, (cudaStream_t)stream);
+            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream);
             if (rc) return rc;
+            // projected scene: interpolation on the tensor cores from TMA tiles of P (field_bin.cu).  Worth it when
+            // the bins are well filled (a chunk of 64 texels is fetched per bin a tile touches)
+            if (scene->feat_proj && order.bw == SD_BIN && bin_kernel_supported(scene, mlp) && N >= 16ll * order.nbins)
+                return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
         }
-        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, perm);
+        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm);
     }
     SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);
     SimtOut out = {};

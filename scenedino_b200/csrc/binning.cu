@@ -1,5 +1,6 @@
-// Texel binning of query points: a counting sort of the point indices by the 8x8-texel block of the
-// feature map their bilinear footprint starts in.
+// Texel binning of query points: a counting sort of the point indices by the 7x7-texel block of the
+// feature map their (clamped) bilinear footprint starts in -- so the footprints of a bin cover an 8x8-texel box,
+// exactly one 64-row operand chunk of the tile kernel (field_bin.cu).
 //
 // The field query (BTSNet.forward, models/bts.py:476-595) treats every point independently, so the order in
 // which the fused kernel walks the points is free.  In the caller's order (e.g. the SSC voxel grid,
@@ -11,8 +12,9 @@
 // atomics on the few corner texels that collect all behind-camera points made the sort itself 3x slower.)
 //
 // Three launches: (1) bin id per point + histogram (shared-memory pre-aggregation), (2) exclusive scan of the
-// histogram (one block), (3) scatter of the point indices (per-block ranges reserved with one global atomic
-// per non-empty bin, ranks from shared-memory atomics).  The order inside a bin depends on atomics and is not
+// histogram (one block) together with a compact numbering of the non-empty bins, (3) scatter of the point
+// indices and of their compact bin number (per-block ranges reserved with one global atomic per non-empty bin,
+// ranks from shared-memory atomics).  The order inside a bin depends on atomics and is not
 // reproducible; the results per point are (the fused kernel computes each row independently).
 #include "common.cuh"
 #include "launch.h"
@@ -23,17 +25,16 @@ constexpr int BIN_THREADS = 256;
 constexpr int MAX_BINS = 12288;   // 48 KB of shared-memory counters
 
 struct BinGeom {
-    int Hf, Wf, shift, nbx, nbins;
+    int Hf, Wf, bw, nbx, nbins;   // bins of bw x bw texels (bw = SD_BIN unless the map is huge)
 };
 
 __device__ __forceinline__ int point_bin(const float *cam, const BinGeom &bg, const float *__restrict__ xyz, long long i) {
     float x, y, z;
     bool inv;
     project_point(cam, cam + 9, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, z, inv);
-    const Tap t = bilinear_tap(clamp_keep_nan(x, -2.0f, 2.0f), clamp_keep_nan(y, -2.0f, 2.0f), bg.Hf, bg.Wf);
-    // NaN coordinates give an arbitrary tap; keep the bin inside the table whatever happens
-    const int bx = min(max(t.x0, 0), bg.Wf - 1) >> bg.shift, by = min(max(t.y0, 0), bg.Hf - 1) >> bg.shift;
-    return by * bg.nbx + bx;
+    Tap t = bilinear_tap(clamp_keep_nan(x, -2.0f, 2.0f), clamp_keep_nan(y, -2.0f, 2.0f), bg.Hf, bg.Wf);
+    clamp_footprint(t, bg.Hf, bg.Wf);   // the same base texel as the kernels that consume the order
+    return (t.y0 / bg.bw) * bg.nbx + t.x0 / bg.bw;
 }
 
 __global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(const float *__restrict__ K, const float *__restrict__ w2c,
@@ -57,36 +58,44 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(const float *__r
         if (sh[b]) atomicAdd(&hist[b], sh[b]);
 }
 
-// exclusive scan of hist[0..nbins) in place, one block of 1024 threads
-__global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict__ hist, int nbins) {
-    __shared__ unsigned int warp_tot[32];
+// exclusive scan of hist[0..nbins) in place, one block of 1024 threads; cidx[b] = number of non-empty bins before
+// b (the compact number of b when it is non-empty), cbin[c] = bin with compact number c, meta[0] = their count
+__global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict__ hist, int nbins,
+                                                        unsigned int *__restrict__ cidx, unsigned int *__restrict__ cbin,
+                                                        unsigned int *__restrict__ meta) {
+    __shared__ unsigned int warp_tot[32], warp_ne[32];
     const int per = (nbins + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = min(nbins, lo + per);
-    unsigned int s = 0;
-    for (int b = lo; b < hi; ++b) s += hist[b];
+    unsigned int s = 0, ne = 0;
+    for (int b = lo; b < hi; ++b) { const unsigned int c = hist[b]; s += c; ne += c != 0; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int incl = s;
+    unsigned int incl = s, incl_ne = ne;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
+        const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o), m = __shfl_up_sync(0xffffffffu, incl_ne, o);
+        if (lane >= o) { incl += n; incl_ne += m; }
     }
-    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 31) { warp_tot[warp] = incl; warp_ne[warp] = incl_ne; }
     __syncthreads();
     if (warp == 0) {
-        unsigned int w = warp_tot[lane], wi = w;
+        const unsigned int w = warp_tot[lane], v = warp_ne[lane];
+        unsigned int wi = w, vi = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += n;
+            const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o), m = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o) { wi += n; vi += m; }
         }
         warp_tot[lane] = wi - w;
+        warp_ne[lane] = vi - v;
+        if (lane == 31) meta[0] = vi;
     }
     __syncthreads();
-    unsigned int run = warp_tot[warp] + incl - s;
+    unsigned int run = warp_tot[warp] + incl - s, run_ne = warp_ne[warp] + incl_ne - ne;
     for (int b = lo; b < hi; ++b) {
         const unsigned int c = hist[b];
         hist[b] = run;
+        cidx[b] = run_ne;
+        if (c) cbin[run_ne++] = (unsigned int)b;
         run += c;
     }
 }
@@ -94,7 +103,9 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict
 __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
                                                                   const unsigned short *__restrict__ bins,
                                                                   unsigned int *__restrict__ cursor,
-                                                                  unsigned int *__restrict__ perm) {
+                                                                  const unsigned int *__restrict__ cidx,
+                                                                  unsigned int *__restrict__ perm,
+                                                                  unsigned short *__restrict__ pcb) {
     extern __shared__ unsigned int sh[];          // [nbins] counts, then [nbins] bases
     unsigned int *cnt = sh, *base = sh + bg.nbins;
     for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS) cnt[b] = 0;
@@ -111,18 +122,20 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, lo
     __syncthreads();
     for (long long i = lo + threadIdx.x; i < hi; i += BIN_THREADS) {
         const int b = bins[i];
-        perm[base[b] + atomicAdd(&cnt[b], 1u)] = (unsigned int)i;
+        const unsigned int pos = base[b] + atomicAdd(&cnt[b], 1u);
+        perm[pos] = (unsigned int)i;
+        pcb[pos] = (unsigned short)__ldg(cidx + b);
     }
 }
 
 static BinGeom bin_geom(int Hf, int Wf) {
     BinGeom g;
-    g.Hf = Hf; g.Wf = Wf; g.shift = 3;
+    g.Hf = Hf; g.Wf = Wf; g.bw = SD_BIN;
     for (;;) {
-        g.nbx = ((Wf - 1) >> g.shift) + 1;
-        g.nbins = g.nbx * (((Hf - 1) >> g.shift) + 1);
+        g.nbx = (Wf - 1) / g.bw + 1;
+        g.nbins = g.nbx * ((Hf - 1) / g.bw + 1);
         if (g.nbins <= MAX_BINS) return g;
-        ++g.shift;
+        g.bw += SD_BIN;
     }
 }
 
@@ -131,22 +144,27 @@ static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 size_t bin_workspace_bytes(int Hf, int Wf, long long N) {
     if (N <= 0 || N >= (1ll << 31)) return 0;
     const BinGeom g = bin_geom(Hf, Wf);
-    return a256((size_t)N * 4) + a256((size_t)N * 2) + a256((size_t)g.nbins * 4);
+    return a256((size_t)N * 4) + 2 * a256((size_t)N * 2) + 3 * a256((size_t)g.nbins * 4) + 256;
 }
 
-// perm = workspace (first N uint32).  Returns SD_OK and *perm_out, or an error.
+// Sorts the point indices by bin.  Fills `out` with device pointers into the workspace.
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      const unsigned int **perm_out, cudaStream_t st) {
+                      BinOrder *out, cudaStream_t st) {
     const size_t need = bin_workspace_bytes(fp.Hf, fp.Wf, N);
     if (need == 0 || workspace_bytes < need || !workspace) {
         set_error("binning: workspace of %zu B needed, %zu B given", need, workspace_bytes);
         return SD_ERR_WORKSPACE;
     }
+    SD_REQUIRE(fp.Hf >= 2 && fp.Wf >= 2, "binning: the feature map must be at least 2 x 2");
     const BinGeom g = bin_geom(fp.Hf, fp.Wf);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
-    unsigned int *perm = reinterpret_cast<unsigned int *>(ws);
-    unsigned short *bins = reinterpret_cast<unsigned short *>(ws + a256((size_t)N * 4));
-    unsigned int *hist = reinterpret_cast<unsigned int *>(ws + a256((size_t)N * 4) + a256((size_t)N * 2));
+    unsigned int *perm = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)N * 4);
+    unsigned short *bins = reinterpret_cast<unsigned short *>(ws);           ws += a256((size_t)N * 2);
+    unsigned short *pcb = reinterpret_cast<unsigned short *>(ws);            ws += a256((size_t)N * 2);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
+    unsigned int *cidx = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
+    unsigned int *cbin = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
+    unsigned int *meta = reinterpret_cast<unsigned int *>(ws);
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -160,11 +178,11 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     SD_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)g.nbins * 4, st));
     bin_count_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist);
     SD_LAUNCH_OK("bin_count_kernel");
-    bin_scan_kernel<<<1, 1024, 0, st>>>(hist, g.nbins);
+    bin_scan_kernel<<<1, 1024, 0, st>>>(hist, g.nbins, cidx, cbin, meta);
     SD_LAUNCH_OK("bin_scan_kernel");
-    bin_scatter_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, perm);
+    bin_scatter_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb);
     SD_LAUNCH_OK("bin_scatter_kernel");
-    *perm_out = perm;
+    out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
     return SD_OK;
 }
 

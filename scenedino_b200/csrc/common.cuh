@@ -12,6 +12,7 @@
 #include "../../include/scenedino_b200.h"
 
 #define SD_EPS 1e-3f  // common/cameras/pinhole.py:3
+#define SD_BIN 7      // texel bins of 7 x 7: the 2 x 2 footprints that start in a bin cover an 8 x 8 box
 
 namespace sd {
 
@@ -187,6 +188,17 @@ __device__ __forceinline__ Tap bilinear_tap(float x, float y, int H, int W) {
     t.in_x1 = t.x0 + 1 <= W - 1;
     t.in_y1 = t.y0 + 1 <= H - 1;
     return t;
+}
+
+// Keeps the 2x2 footprint of a tap inside the map, so that a gather can use fixed +1 texel / +1 row offsets: at
+// the last column / row the out-of-range taps have weight zero, so shifting the base by one and moving the
+// weights over is exact.  (NaN coordinates give an arbitrary tap: the base is clamped into the map whatever
+// happens.)  Used by the tensor-core kernels AND by the texel binning, which must agree on the base texel.
+__device__ __forceinline__ void clamp_footprint(Tap &t, int H, int W) {
+    if (!t.in_x1) { t.x0 -= 1; t.wne = t.wnw; t.wse = t.wsw; t.wnw = 0.0f; t.wsw = 0.0f; }
+    if (!t.in_y1) { t.y0 -= 1; t.wsw = t.wnw; t.wse = t.wne; t.wnw = 0.0f; t.wne = 0.0f; }
+    t.x0 = min(max(t.x0, 0), W - 2);
+    t.y0 = min(max(t.y0, 0), H - 2);
 }
 
 // blend in the oracle's order: nw, ne, sw, se (out-of-range corners are skipped)

@@ -64,9 +64,22 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
                     const TcRender *render, const TcOut &out, cudaStream_t st, const unsigned int *perm = nullptr);
 
 // ---- texel binning of query points (binning.cu) ------------------------------------------------------
+struct BinOrder {
+    const unsigned int *perm;     // [N] sorted position -> point index
+    const unsigned short *pcb;    // [N] compact number of the bin of the point at each sorted position (non-decreasing)
+    const unsigned int *cbin;     // [#non-empty bins] compact number -> bin id (row-major over the bin grid)
+    int bw, nbx, nbins;           // bin width in texels, bins per row, total bins
+};
 size_t bin_workspace_bytes(int Hf, int Wf, long long N);
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      const unsigned int **perm_out, cudaStream_t st);
+                      BinOrder *out, cudaStream_t st);
+// ---- projected-map tile kernel (field_proj.cu, field_bin.cu) ---------------------------------------------
+// encodes a tiled fp16 tensor map (SWIZZLE_128B) into the 128 bytes at tmap_out (64-byte aligned)
+int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,
+                  const unsigned long long *strides_bytes, const unsigned int *box);
+bool bin_kernel_supported(const sd_scene *scene, const sd_mlp *mlp);
+int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *xyz, long long N, const sd_mlp *mlp,
+                     const BinOrder &order, const TcOut &out, cudaStream_t st);
 // ResnetFC.forward on explicit rows through the same tcgen05 pipeline (unit test of the MMA path)
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st);
 

@@ -77,6 +77,7 @@ class Scene:
     include_input: bool = True
     learn_empty: bool = False
     empty_feature: torch.Tensor | None = None
+    proj: torch.Tensor | None = None    # blob of sd_field_project (tied to one head), see project()
 
     @classmethod
     def from_arrays(cls, feat_nchw, K_f, w2c_f, rgb=None, K_c=None, w2c_c=None, device="cuda",
@@ -93,6 +94,21 @@ class Scene:
     def with_feat_dtype(self, feat_nchw, dtype):
         import dataclasses
         return dataclasses.replace(self, feat=featmap_pack(_dev(feat_nchw, self.feat.device), dtype)[0])
+
+    def project(self, mlp: "Mlp") -> "Scene":
+        """Pushes the fp16 map through the feature columns of ``mlp``'s first layer (sd_field_project), once per
+        encode; queries with that head then run the projected-map tile kernel.  Returns a copy of the scene."""
+        import dataclasses
+        if self.feat.dtype != torch.float16:
+            raise ValueError("project() needs the fp16 channels-last map")
+        sc, m = dataclasses.replace(self, proj=None).c(), mlp.c(F16)
+        lib = _abi.lib()
+        nbytes = lib.sd_field_project_bytes(C.byref(sc))
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.feat.device)
+        off = (-raw.data_ptr()) % 1024
+        blob = raw[off:off + nbytes]
+        _abi.check(lib.sd_field_project(C.byref(sc), C.byref(m), _ptr(blob), nbytes, _stream()), "sd_field_project")
+        return dataclasses.replace(self, proj=blob)
 
     @property
     def nv_c(self) -> int:
@@ -118,6 +134,8 @@ class Scene:
         s.learn_empty = int(self.learn_empty)
         if self.empty_feature is not None:
             s.empty_feature = self.empty_feature.data_ptr()
+        if self.proj is not None:
+            s.feat_proj = self.proj.data_ptr()
         return s
 
 
