@@ -60,8 +60,10 @@ MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     L.off_b_out = o;    o = align_up(o + sizeof(float) * (size_t)L.d_out_pad, 1024);
     L.off_w_in_h = o;  o = align_up(o + 2 * (size_t)L.d_in_pad * d_hidden, 1024);
     // tensor-core image of W_out: feature rows 1..d_out-1 first, then the density row 0, padded to 16 rows
+    // ... plus one more 64-wide K block whose first two columns carry the output bias as half(b), b - half(b)
+    // (field_bin.cu feeds them the constant 1 from TMEM, so the bias comes out of the layer-2 MMA)
     const int n2 = (int)align_up((size_t)d_out, 16);
-    L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden, 64), 1024);
+    L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden + 2, 64), 1024);
     L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
     L.total = o;
     return L;
@@ -115,11 +117,13 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
     }
     for (int i = tid; i < L.d_out_pad; i += nth) bo[i] = i < L.d_out ? b_out[i] : 0.0f;
     const int n2 = (L.d_out + 15) / 16 * 16;
-    const int Hp = (H + 63) / 64 * 64;
+    const int Hp = (H + 2 + 63) / 64 * 64;
     for (int i = tid; i < n2 * Hp; i += nth) {
         const int r = i / Hp, k = i - r * Hp;  // image row r <-> W_out row r+1 (features), row d_out-1 <-> W_out row 0 (density)
         const int src = r < L.d_out - 1 ? r + 1 : (r == L.d_out - 1 ? 0 : -1);
-        const float v = (src >= 0 && k < H) ? w_out[(size_t)src * H + k] : 0.0f;
+        float v = (src >= 0 && k < H) ? w_out[(size_t)src * H + k] : 0.0f;
+        if (src >= 0 && k == H) v = b_out[src];
+        if (src >= 0 && k == H + 1) v = b_out[src] - __half2float(__float2half_rn(b_out[src]));
         w_out_h[umma_sw128_offset(r, k, n2) / 2] = __float2half_rn(v);
     }
 }

@@ -9,6 +9,9 @@ namespace tcx {
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifdef SD_DEBUG_WAIT
+__device__ unsigned int g_wait_timeout[260];
+#endif
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -24,8 +27,11 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  try_wait is given a
+// suspend-time hint so that a waiting warp sleeps in hardware instead of spinning through the issue slots of the
+// warps that share its scheduler (without the hint ~90 five-instruction spins per tile and waiting role were measured).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef SD_DEBUG_WAIT
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
@@ -35,8 +41,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 24)) __trap();
+        if (spin > (1u << 18)) {   // debug build: record who timed out on what and carry on (results are garbage)
+            const unsigned int k = atomicAdd(&g_wait_timeout[0], 1u);
+            if (k < 40) { g_wait_timeout[4 + 4 * k] = bar; g_wait_timeout[5 + 4 * k] = parity; g_wait_timeout[6 + 4 * k] = threadIdx.x; g_wait_timeout[7 + 4 * k] = blockIdx.x; }
+            return;
+        }
     }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "SD_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 100000;\n\t"
+        "@p bra SD_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 4000000;\n\t"
+        "@p bra SD_WAIT_LOOP;\n\t"
+        "trap;\n\t"
+        "SD_WAIT_DONE:\n\t"
+        "}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -83,6 +111,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -106,6 +146,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
+}
+// two fp32 -> packed fp16 with ReLU in the conversion (lo in the low half)
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
@@ -150,6 +196,36 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared load / global store as volatile asm: the compiler keeps them in program order (used to keep a batch of
+// loads ahead of the stores that consume them instead of a load-store-load-store chain on one register set)
+__device__ __forceinline__ float4 lds128_ordered(uint32_t saddr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg128_ordered(void *p, const float4 &v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// F.softplus(beta=1, threshold=20) with hardware exp2 / log2 (reduced-precision path: abs error ~1e-6)
+__device__ __forceinline__ float softplus_fast(float x) {
+    if (x > 15.0f) return x;
+    const float ex = __expf(x);
+    return x < -10.0f ? ex : __logf(1.0f + ex);
+}
+// positional_encoding.py:13-21 with an approximate reciprocal (the tensor-core path rounds z' to fp16 hi + lo anyway)
+__device__ __forceinline__ float znorm_fast(float z, const EncodeParams &e, float inv_denom) {
+    float zn;
+    if (e.inv_z) {
+        float zc = z > SD_EPS ? z : SD_EPS;
+        if (z != z) zc = z;
+        zn = (__frcp_rn(zc) - e.inv_dmax) * inv_denom;
+    } else {
+        zn = (z - e.d_min) * inv_denom;
+    }
+    return 2.0f * zn - 1.0f;
+}
 
 }  // namespace tcx
 }  // namespace sd
