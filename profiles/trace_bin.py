@@ -28,6 +28,14 @@ for j in list(range(0, 2)) + list(range(34, 40)):
     for r in range(7):
         v = a[r, j]
         print(f"tile {j:2d} {names[r]}", ' '.join(f"{(x - t0) if x > 100000 else x:8d}" for x in v))
+cb = (ctypes.c_ulonglong * 512)()
+raw.sd_debug_read_cta_ns(cb)
+c = np.array(cb[:]).reshape(256, 2)[:148].astype(np.int64)
+t0c = c[:, 0].min()
+dur = (c[:, 1] - t0c) / 1000.0
+print('CTA end times (us after first start): min %.1f median %.1f max %.1f; starts spread %.1f us' % (dur.min(), np.median(dur), dur.max(), (c[:,0].max()-t0c)/1000.0))
+np.save('gpurun_out/cta_dur.npy', dur)
+print('slowest CTAs:', np.argsort(-dur)[:8], np.sort(-dur)[:8] * -1)
 os.environ['SD_TC_DEBUG'] = '0'
 def tm(flag, n=20):
     os.environ['SD_TC_DEBUG'] = str(flag)

@@ -71,12 +71,14 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
         BinOrder order = {};
         const size_t need = sd_query_workspace_bytes(scene, mlp, N);
         if (need && workspace && workspace_bytes >= need) {   // walk the points bin by bin of the feature map
-            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream);
-            if (rc) return rc;
             // projected scene: interpolation on the tensor cores from TMA tiles of P (field_bin.cu).  Worth it when
-            // the bins are well filled (a chunk of 64 texels is fetched per bin a tile touches)
-            if (scene->feat_proj && order.bw == SD_BIN && bin_kernel_supported(scene, mlp) && N >= 16ll * order.nbins)
-                return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
+            // the bins are well filled (a chunk of 64 texels is fetched per bin a tile touches): the sort then also
+            // leaves the per-point geometry (coordinates, bilinear weights, frustum mask) at the sorted positions
+            const bool tile = scene->feat_proj && bin_kernel_supported(scene, mlp) &&
+                              N >= 16ll * ((scene->Wf - 1) / SD_BIN + 1) * ((scene->Hf - 1) / SD_BIN + 1);
+            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream, tile, tile ? invalid_feat : nullptr);
+            if (rc) return rc;
+            if (tile && order.has_geo) return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
         }
         return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm);
     }

@@ -18,6 +18,7 @@
 // reproducible; the results per point are (the fused kernel computes each row independently).
 #include "common.cuh"
 #include "launch.h"
+#include "tc_common.cuh"
 
 namespace sd {
 
@@ -114,15 +115,31 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict
     }
 }
 
+// Per-point record of the projected-map tile kernel (field_bin.cu), written at the SORTED position of the point as
+// ONE 32-byte store (a whole sector: seven separate scattered 4-byte stores were measured at +80 us per 2 M points),
+// so that the tile kernel reads it with coalesced loads and never projects anything itself.
+struct GeoOut {
+    GeoRec *rec;                  // [N]
+    unsigned char *invalid_feat;  // caller order [N] or NULL
+    EncodeParams enc;
+    int learn_empty;
+};
+
+template <bool GEO>
 __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
                                                                   const unsigned short *__restrict__ bins,
                                                                   unsigned int *__restrict__ cursor,
                                                                   const unsigned int *__restrict__ cidx,
                                                                   unsigned int *__restrict__ perm,
-                                                                  unsigned short *__restrict__ pcb) {
+                                                                  unsigned short *__restrict__ pcb,
+                                                                  const float *__restrict__ K, const float *__restrict__ w2c,
+                                                                  const float *__restrict__ xyz, GeoOut go) {
     extern __shared__ unsigned int sh[];          // [nbins] counts, then [nbins] bases
+    __shared__ float cam[21];
     unsigned int *cnt = sh, *base = sh + bg.nbins;
     for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS) cnt[b] = 0;
+    if (GEO)
+        for (int i = threadIdx.x; i < 21; i += BIN_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
     __syncthreads();
     const long long per = (N + gridDim.x - 1) / gridDim.x;
     const long long lo = per * blockIdx.x, hi = min(N, lo + per);
@@ -137,8 +154,25 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, lo
     for (long long i = lo + threadIdx.x; i < hi; i += BIN_THREADS) {
         const int b = bins[i];
         const unsigned int pos = base[b] + atomicAdd(&cnt[b], 1u);
-        perm[pos] = (unsigned int)i;
-        pcb[pos] = (unsigned short)__ldg(cidx + b);
+        const unsigned int ci = __ldg(cidx + b);
+        if (!GEO) {
+            perm[pos] = (unsigned int)i;
+            pcb[pos] = (unsigned short)ci;
+        } else {
+            float x, y, zc;
+            bool inv;
+            project_point(cam, cam + 9, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, zc, inv);
+            x = clamp_keep_nan(x, -2.0f, 2.0f);
+            y = clamp_keep_nan(y, -2.0f, 2.0f);
+            Tap t = bilinear_tap(x, y, bg.Hf, bg.Wf);
+            clamp_footprint(t, bg.Hf, bg.Wf);
+            const int lx = t.x0 - (t.x0 / SD_BIN) * SD_BIN, ly = t.y0 - (t.y0 / SD_BIN) * SD_BIN;
+            const unsigned int slot = (go.learn_empty && inv) ? 0xFFu : (unsigned int)(ly * 8 + lx);
+            uint4 *dst = reinterpret_cast<uint4 *>(go.rec + pos);
+            dst[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(znorm(zc, go.enc)), tcx::pack_h2(t.wnw, t.wne));
+            dst[1] = make_uint4(tcx::pack_h2(t.wsw, t.wse), (unsigned int)i, ci | (slot << 16), (unsigned int)b);
+            if (go.invalid_feat) go.invalid_feat[i] = inv ? 1 : 0;
+        }
     }
 }
 
@@ -158,12 +192,13 @@ static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 size_t bin_workspace_bytes(int Hf, int Wf, long long N) {
     if (N <= 0 || N >= (1ll << 31)) return 0;
     const BinGeom g = bin_geom(Hf, Wf);
-    return a256((size_t)N * 4) + 2 * a256((size_t)N * 2) + 3 * a256((size_t)g.nbins * 4) + 256;
+    return a256((size_t)N * 4) + 2 * a256((size_t)N * 2) + 3 * a256((size_t)g.nbins * 4) + 256 +
+           a256((size_t)N * sizeof(GeoRec));                // per-point records of the tile kernel
 }
 
 // Sorts the point indices by bin.  Fills `out` with device pointers into the workspace.
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      BinOrder *out, cudaStream_t st) {
+                      BinOrder *out, cudaStream_t st, bool want_geo, unsigned char *invalid_feat) {
     const size_t need = bin_workspace_bytes(fp.Hf, fp.Wf, N);
     if (need == 0 || workspace_bytes < need || !workspace) {
         set_error("binning: workspace of %zu B needed, %zu B given", need, workspace_bytes);
@@ -178,27 +213,40 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     unsigned int *hist = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
     unsigned int *cidx = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
     unsigned int *cbin = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
-    unsigned int *meta = reinterpret_cast<unsigned int *>(ws);
+    unsigned int *meta = reinterpret_cast<unsigned int *>(ws);                                        ws += 256;
+    GeoOut go = {};
+    go.rec = reinterpret_cast<GeoRec *>(ws);
+    go.invalid_feat = invalid_feat;
+    go.enc = fp.enc;
+    go.learn_empty = fp.learn_empty;
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
         SD_CUDA_OK(cudaGetDevice(&dev));
         SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
     }
     const long long blocks_wanted = (N + 4 * BIN_THREADS - 1) / (4 * BIN_THREADS);
     const unsigned grid = (unsigned)(blocks_wanted < 4 * sm_count ? blocks_wanted : 4 * sm_count);
     const unsigned grid2 = (unsigned)(blocks_wanted < 2 * sm_count ? blocks_wanted : 2 * sm_count);
     SD_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)g.nbins * 4, st));
+    SD_CUDA_OK(cudaMemsetAsync(meta, 0, 256, st));            // meta[1]: tile counter of the tile kernel
     bin_count_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist);
     SD_LAUNCH_OK("bin_count_kernel");
     bin_scan_kernel<<<1, 1024, (size_t)g.nbins * 8, st>>>(hist, g.nbins, cidx, cbin, meta);
     SD_LAUNCH_OK("bin_scan_kernel");
-    bin_scatter_kernel<<<grid2, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb);
+    if (want_geo && g.bw == SD_BIN)
+        bin_scatter_kernel<true><<<grid2, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+    else
+        bin_scatter_kernel<false><<<grid2, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     SD_LAUNCH_OK("bin_scatter_kernel");
     out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
+    out->has_geo = want_geo && g.bw == SD_BIN;
+    out->rec = go.rec;
+    out->tile_ctr = meta + 1;
     return SD_OK;
 }
 

@@ -58,33 +58,42 @@ constexpr int OFF_B = OFF_A + NRING * CHUNK;
 constexpr int OFF_CODE = OFF_B + NRING * CHUNK;
 constexpr int OFF_W2 = OFF_CODE + NCODE * CHUNK;
 constexpr int OFF_STAGE = OFF_W2 + W2_BYTES;
-constexpr int STAGE_ROW = 272;               // output row (256 B) + 16 B: thread = row stores are bank-conflict free
-constexpr int OFF_BO = OFF_STAGE + TM * STAGE_ROW;   // output bias of the 64 feature columns
-constexpr int OFF_DIRTY = OFF_BO + 256;
+constexpr int NREC = 3;                      // ring of per-tile record blocks (128 x 32 B), filled by bulk copies
+constexpr int REC_BYTES = TM * 32;
+constexpr int NPERM = 8;                     // ring of per-tile point indices handed from the point warps to epilogue 2
+constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * 8192;
+constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
+constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: {rows of the tile (0 = no more tiles), chunks}
+constexpr int OFF_NTILES = OFF_HDR + NREC * 8;            // tiles this CTA processed, published by the MMA issuer at the end
+constexpr int OFF_DIRTY = OFF_NTILES + 8;
 constexpr int OFF_CAM = OFF_DIRTY + NRING * TM;
 constexpr int OFF_BAR = OFF_CAM + 448;
 enum { BAR_FULL_A = 0, BAR_FULL_B = NRING, BAR_EMPTY = 2 * NRING, BAR_FULL_C = 3 * NRING, BAR_EMPTY_C = BAR_FULL_C + NCODE,
        BAR_D1 = BAR_EMPTY_C + NCODE, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 2, BAR_D2_EMPTY = BAR_D2 + 2,
-       BAR_WLOAD = BAR_D2_EMPTY + 2, NBAR = BAR_WLOAD + 1 };
+       BAR_WLOAD = BAR_D2_EMPTY + 2, BAR_REC_FULL = BAR_WLOAD + 1, BAR_REC_EMPTY = BAR_REC_FULL + NREC,
+       NBAR = BAR_REC_EMPTY + NREC };
+// consumers of a record-ring entry: the point warps and the MMA issuer (chunk count)
+constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS + 1;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_ALLOC = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
-__device__ long long g_trace[8 * 64 * 8];   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
+__device__ long long g_trace[8 * 64 * 8];
+__device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globaltimer (SD_TC_DEBUG & 8192)   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
 #define TB_TRACE(role, j, ev)                                                                    \
     do {                                                                                         \
-        if ((P.dbg & 8192) && blockIdx.x == 0 && (j) < 64 && (role) < 8 && (threadIdx.x & 31) == 0)        \
-            g_trace[((role) * 64 + (int)(j)) * 8 + (ev)] = clock64();                            \
+        if ((P.dbg & 8192) && blockIdx.x == 0 && (j) >= 40 && (j) < 104 && (role) < 8 && (threadIdx.x & 31) == 0) \
+            g_trace[((role) * 64 + (int)(j) - 40) * 8 + (ev)] = clock64();   /* tiles 40..103 of CTA 0 */                            \
     } while (0)
 
 struct Params {
     CUtensorMap tmap;          // P as [Hf][Wf][128] fp16, box 8 x 8 x 64 channels, SWIZZLE_128B
     FieldParams fp;
     const float *xyz;
-    const unsigned int *perm;
-    const unsigned short *pcb;
-    const unsigned int *cbin;
+    unsigned int *tile_ctr;    // next unclaimed tile (zeroed by the sort): CTAs claim tiles dynamically
+    const GeoRec *rec;         // per-point records at the sorted positions (binning.cu)
+    const unsigned int *cbin;  // compact bin number -> bin id
     int nbx;
     int dbg;                   // SD_TC_DEBUG & 8192: clock64 trace of CTA 0
     long long N, n_tiles;
@@ -106,6 +115,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     unsigned char *s_dirty = sm + OFF_DIRTY;
 
     // ---- one-time setup ------------------------------------------------------------------------------
+    if ((P.dbg & 8192) && blockIdx.x < 256 && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_cta_ns[2 * blockIdx.x] = t; g_cta_ns[2 * blockIdx.x + 1] = 0;
+    }
     if (tid == 0) {
         for (int e = 0; e < NRING; ++e) {
             mbar_init(BAR(BAR_FULL_A + e), N_PT_WARPS);
@@ -118,6 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             mbar_init(BAR(BAR_D2 + b), 1); mbar_init(BAR(BAR_D2_EMPTY + b), N_EPI_WARPS);
         }
         mbar_init(BAR(BAR_WLOAD), 1);
+        for (int r = 0; r < NREC; ++r) { mbar_init(BAR(BAR_REC_FULL + r), 1); mbar_init(BAR(BAR_REC_EMPTY + r), REC_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 21 * (1 + P.fp.nv_c); i += NTHREADS) {
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     // the weight operands start out all zero and are kept so by the undo log of the point warps
     for (int i = tid; i < NRING * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NRING * TM; i += NTHREADS) s_dirty[i] = 0xFF;
-    for (int i = tid; i < 64; i += NTHREADS) reinterpret_cast<float *>(sm + OFF_BO)[i] = i < P.D ? __ldg(P.b_out + 1 + i) : 0.0f;
+    if (tid == 0) *reinterpret_cast<volatile int *>(sm + OFF_NTILES) = 0x7FFFFFFF;
     fence_proxy_async();
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
@@ -147,19 +162,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
 
-    const long long first = blockIdx.x, stride = gridDim.x;
-    const long long my_tiles = P.n_tiles > first ? (P.n_tiles - first + stride - 1) / stride : 0;
-    // compact bins touched by my tile number jj: the first and the last one (the sorted order makes them consecutive).
-    // Raw loads only: callers do the arithmetic (count = last - first + 1) an iteration later, so that nobody
-    // waits for a load in the iteration that issues it.
-    auto span = [&](long long jj, int &c0, int &c1) {
-        c0 = 0; c1 = 0;
-        if (jj < 0 || jj >= my_tiles) return;
-        const long long a = (first + jj * stride) * TM;
-        const long long b = (a + TM < P.N ? a + TM : P.N) - 1;
-        c0 = (int)__ldg(P.pcb + a);
-        c1 = (int)__ldg(P.pcb + b);
-    };
+    // Tiles are claimed dynamically by the TMA producer (atomic counter): the time a tile takes varies with the chunks it
+    // touches and, more, from SM to SM (measured: static striding left CTAs finishing between 218 and 335 us).  The j-th
+    // tile of this CTA travels through record-ring entry j % NREC: header {rows, chunks}, then 128 records.
+    struct Hdr { int rows, m; };
+    volatile Hdr *s_hdr = reinterpret_cast<volatile Hdr *>(sm + OFF_HDR);
+    volatile int *s_ntiles = reinterpret_cast<volatile int *>(sm + OFF_NTILES);
+    auto rec_wait = [&](long long jj) { mbar_wait(BAR(BAR_REC_FULL + (int)(jj % NREC)), (uint32_t)((jj / NREC) & 1)); };
+    auto rec_ptr = [&](long long jj) { return reinterpret_cast<const GeoRec *>(sm + OFF_REC + (int)(jj % NREC) * REC_BYTES); };
 
     if (warp < N_EPI_WARPS) {
         // =================================== EPILOGUE 1 ==============================================
@@ -169,9 +179,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             tmem_st8(t_lane + ONE_COL, one);
         }
-        for (long long j = 0; j < my_tiles; ++j) {
+        for (long long j = 0;; ++j) {
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
+            if (j >= *s_ntiles) break;                    // the MMA issuer's closing arrival, not a tile
             tc_fence_after();
             if (warp == 0) TB_TRACE(0, j, 2);
 #pragma unroll 1
@@ -198,19 +209,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
         const int D = P.D;
         unsigned char *stage0 = sm + OFF_STAGE + wq * 8192, *stage1 = stage0 + 4096;
-        auto load_grow = [&](long long jj) {
-            if (jj >= my_tiles) return -1;
-            const long long gpos = (first + jj * stride) * TM + row;
-            return gpos < P.N ? (int)__ldg(P.perm + gpos) : -1;
-        };
-        int grow_next = load_grow(0);
-        for (long long j = 0; j < my_tiles; ++j) {
-            const int grow_keep = grow_next;                     // point this thread's row of tile j stands for
-            grow_next = load_grow(j + 1);
+        // The point index of this thread's row was left in the perm ring by the point warps when they processed the tile.
+        // No barrier of its own: the write is ordered before this read by the chain FULL_C -> MMA -> D1 -> H -> D2, and
+        // an entry is rewritten 8 tiles later, while the point warps can be at most 5 tiles ahead of this role (two
+        // code operands, layer 2 behind layer 1, two D2 buffers).
+        const int *s_perm = reinterpret_cast<const int *>(sm + OFF_PERM);
+        for (long long j = 0;; ++j) {
             const int b1 = (int)(j & 1);
             mbar_wait(BAR(BAR_D2 + b1), (uint32_t)((j >> 1) & 1));
+            if (j >= *s_ntiles) break;                    // the MMA issuer's closing arrival, not a tile
             tc_fence_after();
             if (wq == 0) TB_TRACE(0, j, 0);
+            const int grow_keep = s_perm[(int)(j % NPERM) * TM + row];       // point this thread's row of tile j stands for
             const uint32_t t_d2 = t_lane + D2_COL + b1 * D2_STRIDE;
             const bool ok = grow_keep >= 0;
             if (P.dino && D == 64) {
@@ -294,12 +304,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             };
             int e = 0;
             uint32_t ph = 0;
-            int c0n, c1n;
-            span(0, c0n, c1n);
-            for (long long j = 0; j < my_tiles; ++j) {
-                const int m = c1n - c0n + 1;
-                span(j + 1, c0n, c1n);
-                if (j > 0) layer2(j - 1);
+            long long j = 0;
+            for (;; ++j) {
+                rec_wait(j);
+                const int rows = s_hdr[j % NREC].rows, m = s_hdr[j % NREC].m;
+                mbar_arrive(BAR(BAR_REC_EMPTY + (int)(j % NREC)));
+                if (rows == 0) { if (j > 0) layer2(j - 1); break; }
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
@@ -328,25 +338,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     umma(d1, umma_desc(sm_u + OFF_CODE + cs * CHUNK + k * 32), umma_desc(sm_u + OFF_WC + k * 32), idesc_k, 1);
                 umma_commit(BAR(BAR_EMPTY_C + cs));
                 umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                // layer 2 of the previous tile behind layer 1 of this one: its hidden tile is being produced by the first
+                // epilogue while the MMAs above are issued and run
+                if (j > 0) layer2(j - 1);
                 TB_TRACE(1, j, 6);
             }
-            if (my_tiles > 0) layer2(my_tiles - 1);
+            // closing: tell the epilogues how many tiles there were and complete the barrier phases they wait on
+            *s_ntiles = (int)j;
+            mbar_arrive(BAR(BAR_D1 + (int)(j & 1)));
+            mbar_arrive(BAR(BAR_D2 + (int)(j & 1)));
         }
     } else if (warp == WARP_TMA) {
         // =================================== TMA PRODUCER =============================================
         if (lane == 0) tma_prefetch_desc(&P.tmap);
         int e = 0;
         uint32_t ph = 0;
-        int c0, c1, c0n, c1n;
-        span(0, c0, c1);
-        span(1, c0n, c1n);
-        unsigned int mybin = lane <= c1 - c0 ? __ldg(P.cbin + c0 + lane) : 0u;
-        for (long long j = 0; j < my_tiles; ++j) {
-            // next tile's bins and the span of the tile after it are in flight while this tile's boxes are issued
-            const int m = c1 - c0 + 1;
-            const unsigned int mybin_n = lane <= c1n - c0n ? __ldg(P.cbin + c0n + lane) : 0u;
-            int c0nn, c1nn;
-            span(j + 2, c0nn, c1nn);
+        // Five-stage software pipeline over this CTA's tiles (slot s = its s-th tile): claim a tile for slot s+4, load the
+        // chunk span of slot s+3, publish header + records of slot s+2, load the bin ids of slot s+1, issue the boxes of
+        // slot s -- no global load is consumed in the iteration that issues it (they queue behind the epilogue's stores).
+        auto claim = [&]() -> long long {             // lane 0's value is the one used
+            // from the last tile down: the tiles that touch many bins (near field) sit at the end of the sorted order and
+            // must not be the last ones handed out.  Past the end the result is negative.
+            return lane == 0 ? P.n_tiles - 1 - (long long)atomicAdd(P.tile_ctr, 1u) : 0;
+        };
+        auto rows_of = [&](long long t) { return t >= 0 ? (int)(P.N - t * TM < TM ? P.N - t * TM : TM) : 0; };
+        auto gspan = [&](long long t, int &c0, int &c1) {          // raw loads; all lanes load the same words
+            c0 = 0; c1 = 0;
+            const int rows = rows_of(t);
+            if (rows == 0) return;
+            c0 = (int)(__ldg(&P.rec[t * TM].cs) & 0xFFFFu);
+            c1 = (int)(__ldg(&P.rec[t * TM + rows - 1].cs) & 0xFFFFu);
+        };
+        bool sentinel_sent = false;
+        auto publish = [&](long long slot, long long t, int c0, int c1) {     // header + records of a slot -> ring
+            if (lane != 0 || sentinel_sent) return;
+            const int r = (int)(slot % NREC);
+            const int rows = rows_of(t);
+            mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
+            s_hdr[r].rows = rows; s_hdr[r].m = c1 - c0 + 1;
+            if (rows == 0) {                                                   // no more tiles: a header alone
+                mbar_arrive(BAR(BAR_REC_FULL + r));
+                sentinel_sent = true;
+                return;
+            }
+            mbar_expect_tx(BAR(BAR_REC_FULL + r), (uint32_t)rows * 32u);
+            bulk_g2s(sm_u + OFF_REC + r * REC_BYTES, P.rec + t * TM, (uint32_t)rows * 32u, BAR(BAR_REC_FULL + r));
+        };
+        auto bcast = [&](long long v) { return __shfl_sync(0xffffffffu, v, 0); };
+        // prologue: slots 0..3 claimed, spans of 0..2 loaded, slots 0..1 published, bins of slot 0 loaded
+        long long t0 = bcast(claim()), t1 = bcast(claim()), t2 = bcast(claim()), t3 = bcast(claim());
+        int a0, b0, a1, b1, a2, b2;
+        gspan(t0, a0, b0); gspan(t1, a1, b1); gspan(t2, a2, b2);
+        publish(0, t0, a0, b0);
+        publish(1, t1, a1, b1);
+        unsigned int mybin = (rows_of(t0) && lane <= b0 - a0) ? __ldg(P.cbin + a0 + lane) : 0u;
+        for (long long j = 0;; ++j) {
+            if (rows_of(t0) == 0) break;
+            const long long t4 = claim();                                      // slot j+4 (used next iteration)
+            int a3, b3;
+            gspan(t3, a3, b3);                                                 // slot j+3
+            publish(j + 2, t2, a2, b2);                                        // slot j+2
+            const unsigned int mybin_n = (rows_of(t1) && lane <= b1 - a1) ? __ldg(P.cbin + a1 + lane) : 0u;   // slot j+1
+            const int c0 = a0, m = b0 - a0 + 1;                                // slot j: boxes
             for (int base = 0; base < m; base += 32) {
                 if (base > 0) mybin = base + lane < m ? __ldg(P.cbin + c0 + base + lane) : 0u;
                 const int cnt = m - base < 32 ? m - base : 32;
@@ -367,9 +420,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 __syncwarp();
             }
             TB_TRACE(6, j, 2);
-            if (lane == 0 && (P.dbg & 8192) && blockIdx.x == 0 && j < 64) g_trace[(6 * 64 + (int)j) * 8 + 7] = m;
-            c0 = c0n; c1 = c1n; mybin = mybin_n;
-            c0n = c0nn; c1n = c1nn;
+            if (lane == 0 && (P.dbg & 8192) && blockIdx.x == 0 && j >= 40 && j < 104) g_trace[(6 * 64 + (int)j - 40) * 8 + 7] = m;
+            t0 = t1; t1 = t2; t2 = t3; t3 = bcast(t4);
+            a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
+            mybin = mybin_n;
         }
     } else {
         // =================================== POINT WARPS ================================================
@@ -378,74 +432,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         const int grp = (warp - WARP_PT0) / N_PT_WARPS;
         const int row = tid - (WARP_PT0 + grp * N_PT_WARPS) * 32;
         const int nv_c = P.fp.nv_c;
-        const float inv_denom = 1.0f / P.fp.enc.denom;
         const int pt_role = 2 + (warp - WARP_PT0) % N_PT_WARPS + (grp ? 8 : 0);   // trace: group 0 only (slots 2..5)
-        // inputs of a tile row, fetched in two stages so that no load is consumed in the iteration that issues it:
-        // sorted position -> (point index, compact bin) two of my tiles ahead, point index -> coordinates one ahead
-        struct RowIdx { int grow, cr, c0, c1, p0, p1; };
-        struct RowIn { int grow; float px, py, pz; int c0, c1, cr, p0, p1; };
-        auto fetch_idx = [&](long long jj) {
-            RowIdx r;
-            r.grow = -1; r.cr = 0;
-            span(jj, r.c0, r.c1);
-            span(jj - 1, r.p0, r.p1);          // the other group's tile in between (jj = 0: nothing, see below)
-            if (jj >= my_tiles) return r;
-            const long long gpos = (first + jj * stride) * TM + row;
-            if (gpos >= P.N) return r;
-            r.grow = (int)__ldg(P.perm + gpos);
-            r.cr = (int)__ldg(P.pcb + gpos);
-            return r;
-        };
-        auto fetch_pt = [&](const RowIdx &ix) {
-            RowIn r;
-            r.grow = ix.grow; r.cr = ix.cr; r.c0 = ix.c0; r.c1 = ix.c1; r.p0 = ix.p0; r.p1 = ix.p1;
-            r.px = r.py = r.pz = 0.0f;
-            if (ix.grow >= 0) {
-                r.px = __ldg(P.xyz + 3ll * ix.grow); r.py = __ldg(P.xyz + 3ll * ix.grow + 1); r.pz = __ldg(P.xyz + 3ll * ix.grow + 2);
-            }
-            return r;
-        };
+        // inputs of a tile row: its record in the ring (shared memory: nothing here queues behind the epilogue's store
+        // bursts in the global load/store path) and the tile's chunk span
+        struct RowIn { bool ok; int cr, c0, c1, slot, grow; float x, y, zp; uint32_t w01, w23; };
         int e = 0;
         uint32_t ph = 0;
-        RowIdx ix1 = fetch_idx(grp);
-        RowIn nxt = fetch_pt(ix1);
-        ix1 = fetch_idx(grp + N_PT_GROUPS);
-        for (long long j = grp; j < my_tiles; j += N_PT_GROUPS) {
-            const RowIn cur = nxt;
+        for (long long j = 0;; ++j) {
+            RowIn cur;
+            rec_wait(j);
+            const int rows = s_hdr[j % NREC].rows;
+            if (rows == 0) break;                          // no more tiles for this CTA
+            const GeoRec *rr = rec_ptr(j);
+            cur.c0 = (int)(rr[0].cs & 0xFFFFu);            // compact bins the tile touches: first, last
+            cur.c1 = (int)(rr[rows - 1].cs & 0xFFFFu);
+            const bool mine = (int)(j % N_PT_GROUPS) == grp;
+            cur.ok = mine && row < rows;
+            cur.cr = 0; cur.slot = 0xFF; cur.grow = -1; cur.x = cur.y = cur.zp = 0.0f; cur.w01 = cur.w23 = 0u;
+            if (cur.ok) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(rr + row);
+                const uint4 ra = rp[0], rb = rp[1];
+                cur.x = __uint_as_float(ra.x); cur.y = __uint_as_float(ra.y); cur.zp = __uint_as_float(ra.z);
+                cur.w01 = ra.w; cur.w23 = rb.x; cur.grow = (int)rb.y;
+                cur.cr = (int)(rb.z & 0xFFFFu); cur.slot = (int)((rb.z >> 16) & 0xFFu);
+            }
+            mbar_arrive_warp(BAR(BAR_REC_EMPTY + (int)(j % NREC)));
             TB_TRACE(pt_role, j, 0);
-            nxt = fetch_pt(ix1);
-            ix1 = fetch_idx(j + 2 * N_PT_GROUPS);
-            if (N_PT_GROUPS == 2 && j > 0) {
-                // Walk over the ring positions of the other group's tile j-1, WAITING on each: an mbarrier wait tells
-                // apart only adjacent phases, so nobody may get two phases ahead on an entry (a tile can span more
-                // chunks than the ring has entries).
-                for (int i = cur.p1 - cur.p0 + 1; i > 0; --i) {
+            if (!mine) {
+                // Walk over the ring positions of the other group's tile, WAITING on each: an mbarrier wait tells apart
+                // only adjacent phases, so nobody may get two phases ahead on an entry (a tile can span more chunks
+                // than the ring has entries).
+                for (int i = cur.c1 - cur.c0 + 1; i > 0; --i) {
                     mbar_wait(BAR(BAR_EMPTY + e), ph ^ 1);
                     if (++e == NRING) { e = 0; ph ^= 1; }
                 }
+                continue;
             }
-            const bool ok = cur.grow >= 0;
-            const long long grow = cur.grow;
-            float x = 0.f, y = 0.f, zp = 0.f;
-            bool inv = false;
-            Tap t = {};
-            if (ok) {
-                float zc;
-                project_point(s_cam, s_cam + 9, cur.px, cur.py, cur.pz, x, y, zc, inv);
-                x = clamp_keep_nan(x, -2.0f, 2.0f);
-                y = clamp_keep_nan(y, -2.0f, 2.0f);
-                zp = znorm_fast(zc, P.fp.enc, inv_denom);
-                t = bilinear_tap(x, y, P.fp.Hf, P.fp.Wf);
-                clamp_footprint(t, P.fp.Hf, P.fp.Wf);
-            }
+            const bool ok = cur.ok;
+            const float x = cur.x, y = cur.y, zp = cur.zp;
             // ---- bilinear weights -> this row's 4 slots of its bin's chunk; every other slot of the row stays zero.
             //      Slots (nw, ne) = (s, s+1) share one 16-byte piece of the row (lx <= 6), (sw, se) the next one:
             //      the dirty byte keeps (ly << 3 | lx) and the undo clears the same two pairs.
-            const bool plain = ok && !(P.fp.learn_empty && inv);
-            const int bx7 = (int)(((unsigned)t.x0 * 9363u) >> 16), by7 = (int)(((unsigned)t.y0 * 9363u) >> 16);   // / 7 for < 2^15
-            const int lx = t.x0 - bx7 * SD_BIN, ly = t.y0 - by7 * SD_BIN;
+            const bool plain = ok && cur.slot != 0xFF;
+            const int lx = cur.slot & 7, ly = (cur.slot >> 3) & 7;
             const int q = cur.cr - cur.c0;
-            const uint32_t w_top = pack_h2(t.wnw, t.wne), w_bot = pack_h2(t.wsw, t.wse);
+            const uint32_t w_top = cur.w01, w_bot = cur.w23;
             auto pair_off = [&](int lyy, int lxx) {      // byte offset of slot (lyy, lxx) inside the row
                 return (uint32_t)(((lyy ^ (row & 7)) << 4) + lxx * 2);
             };
@@ -466,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off(ly + 1, lx));
                     p0[0] = (unsigned short)w_top; p0[1] = (unsigned short)(w_top >> 16);
                     p1[0] = (unsigned short)w_bot; p1[1] = (unsigned short)(w_bot >> 16);
-                    s_dirty[e * TM + row] = (unsigned char)(ly * 8 + lx);
+                    s_dirty[e * TM + row] = (unsigned char)cur.slot;
                 } else if (d != 0xFF) {
                     s_dirty[e * TM + row] = 0xFF;
                 }
@@ -475,23 +506,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 if (++e == NRING) { e = 0; ph ^= 1; }
             }
             TB_TRACE(pt_role, j, 3);
-            // ---- per-point outputs that do not need the head ---------------------------------------------------
-            if (ok) {
-                if (P.invalid_feat && !(P.dbg & 2)) P.invalid_feat[grow] = inv ? 1 : 0;
-                if (nv_c > 0 && (P.rgb || P.invalid)) {
-                    for (int v = 0; v < nv_c; ++v) {
-                        float cx, cy, cz;
-                        bool cinv;
-                        const float *c = s_cam + 21 * (1 + v);
-                        project_point(c, c + 9, cur.px, cur.py, cur.pz, cx, cy, cz, cinv);
-                        if (P.rgb) {
-                            float c3[3];
-                            sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
-                            float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
-                            o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
-                        }
-                        if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
+            // ---- colours of the render views (bts.py:330-441, 557-569): only when asked for; the point and its
+            //      frustum flag are fetched / recomputed here (the SSC query does not take this path)
+            if (ok && nv_c > 0 && (P.rgb || P.invalid)) {
+                const long long grow = cur.grow;
+                const float px = __ldg(P.xyz + 3 * grow), py = __ldg(P.xyz + 3 * grow + 1), pz = __ldg(P.xyz + 3 * grow + 2);
+                float ex, ey, ez;
+                bool inv;
+                project_point(s_cam, s_cam + 9, px, py, pz, ex, ey, ez, inv);
+                for (int v = 0; v < nv_c; ++v) {
+                    float cx, cy, cz;
+                    bool cinv;
+                    const float *c = s_cam + 21 * (1 + v);
+                    project_point(c, c + 9, px, py, pz, cx, cy, cz, cinv);
+                    if (P.rgb) {
+                        float c3[3];
+                        sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
+                        float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
+                        o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
                     }
+                    if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
                 }
             }
             // ---- positional code -> code operand (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by angle
@@ -534,6 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             TB_TRACE(pt_role, j, 4);
             mbar_wait(BAR(BAR_EMPTY_C + cs), (uint32_t)(((j / NCODE) & 1) ^ 1));
             TB_TRACE(pt_role, j, 5);
+            reinterpret_cast<int *>(sm + OFF_PERM)[(int)(j % NPERM) * TM + row] = ok ? cur.grow : -1;
             unsigned char *crow = sm + OFF_CODE + cs * CHUNK + row * 128;
 #pragma unroll
             for (int qq = 0; qq < 6; ++qq)
@@ -545,6 +580,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------
+    if ((P.dbg & 8192) && blockIdx.x < 256 && (tid & 31) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(&g_cta_ns[2 * blockIdx.x + 1], t);
+    }
     bulk_wait<0>();            // output rows still in flight (epilogue threads)
     tc_fence_before();
     __syncthreads();
@@ -558,6 +598,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
 }  // namespace tb
 
 // debug: clock64 trace of the last launch made with SD_TC_DEBUG & 8192 (not part of the public header)
+extern "C" int sd_debug_read_cta_ns(unsigned long long *host_out) {
+    SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_cta_ns, sizeof(unsigned long long) * 512));
+    return SD_OK;
+}
 extern "C" int sd_debug_read_trace_bin(long long *host_out) {
     SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_trace, sizeof(long long) * 8 * 64 * 8));
     return SD_OK;
@@ -590,7 +634,10 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     tb::Params P = {};
     P.fp = fp;
     P.xyz = xyz;
-    P.perm = order.perm; P.pcb = order.pcb; P.cbin = order.cbin; P.nbx = order.nbx;
+    P.cbin = order.cbin; P.nbx = order.nbx;
+    SD_REQUIRE(order.has_geo, "field_bin: the point order carries no geometry records");
+    P.rec = order.rec;
+    P.tile_ctr = order.tile_ctr;
     P.N = N;
     {
         const char *e = getenv("SD_TC_DEBUG");

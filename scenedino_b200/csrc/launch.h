@@ -64,15 +64,30 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
                     const TcRender *render, const TcOut &out, cudaStream_t st, const unsigned int *perm = nullptr);
 
 // ---- texel binning of query points (binning.cu) ------------------------------------------------------
+// What the tile kernel needs of a point, at its sorted position: encoder-view coordinates (x, y clamped to +-2, z' of
+// positional_encoding.py:13-21), the four bilinear weights as packed halves (nw, ne) / (sw, se), the point's index in
+// the caller's order, the compact number of its bin (low 16 bits of cs) and the position of its footprint inside the
+// bin's 8x8 box (bits 16-23 of cs: ly * 8 + lx, or 0xFF when the row takes the learned empty feature instead of taps),
+// and the id of its bin (row-major over the bin grid).
+struct GeoRec {
+    float x, y, zp;
+    unsigned int w01, w23, perm, cs, bin;
+};
+static_assert(sizeof(GeoRec) == 32, "one sector per record");
+
 struct BinOrder {
     const unsigned int *perm;     // [N] sorted position -> point index
     const unsigned short *pcb;    // [N] compact number of the bin of the point at each sorted position (non-decreasing)
     const unsigned int *cbin;     // [#non-empty bins] compact number -> bin id (row-major over the bin grid)
     int bw, nbx, nbins;           // bin width in texels, bins per row, total bins
+    // want_geo: one 32-byte record per sorted position instead of perm / pcb (which then stay unwritten)
+    bool has_geo;
+    const GeoRec *rec;
+    unsigned int *tile_ctr;       // zeroed counter from which the tile kernel's CTAs claim tiles
 };
 size_t bin_workspace_bytes(int Hf, int Wf, long long N);
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      BinOrder *out, cudaStream_t st);
+                      BinOrder *out, cudaStream_t st, bool want_geo = false, unsigned char *invalid_feat = nullptr);
 // ---- projected-map tile kernel (field_proj.cu, field_bin.cu) ---------------------------------------------
 // encodes a tiled fp16 tensor map (SWIZZLE_128B) into the 128 bytes at tmap_out (64-byte aligned)
 int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,
