@@ -176,6 +176,24 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, lo
     }
 }
 
+// Table of the tile kernel's tiles (128 consecutive sorted points each), in the order they are handed out (last tile
+// first): what its producer needs, so that it never waits for a load of its own.
+__global__ void __launch_bounds__(256) bin_tiles_kernel(const GeoRec *__restrict__ rec, const unsigned int *__restrict__ cbin,
+                                                        long long N, long long n_tiles, TileInfo *__restrict__ tiles) {
+    const long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (v >= n_tiles + 8) return;
+    TileInfo ti = {0u, 0u, 0u, 0u};
+    if (v < n_tiles) {
+        const long long t = n_tiles - 1 - v, a = t * 128;
+        const unsigned int rows = (unsigned int)(N - a < 128 ? N - a : 128);
+        const unsigned int c0 = rec[a].cs & 0xFFFFu, c1 = rec[a + rows - 1].cs & 0xFFFFu, m = c1 - c0 + 1;
+        unsigned int b[4];
+        for (int i = 0; i < 4; ++i) b[i] = (unsigned int)i < m ? cbin[c0 + i] : 0u;
+        ti.c0m = c0 | (m << 16); ti.b01 = b[0] | (b[1] << 16); ti.b23 = b[2] | (b[3] << 16); ti.rows = rows;
+    }
+    tiles[v] = ti;
+}
+
 static BinGeom bin_geom(int Hf, int Wf) {
     BinGeom g;
     g.Hf = Hf; g.Wf = Wf; g.bw = SD_BIN;
@@ -193,7 +211,8 @@ size_t bin_workspace_bytes(int Hf, int Wf, long long N) {
     if (N <= 0 || N >= (1ll << 31)) return 0;
     const BinGeom g = bin_geom(Hf, Wf);
     return a256((size_t)N * 4) + 2 * a256((size_t)N * 2) + 3 * a256((size_t)g.nbins * 4) + 256 +
-           a256((size_t)N * sizeof(GeoRec));                // per-point records of the tile kernel
+           a256((size_t)N * sizeof(GeoRec)) +               // per-point records of the tile kernel
+           a256((size_t)((N + 127) / 128 + 8) * sizeof(TileInfo));
 }
 
 // Sorts the point indices by bin.  Fills `out` with device pointers into the workspace.
@@ -215,7 +234,8 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     unsigned int *cbin = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
     unsigned int *meta = reinterpret_cast<unsigned int *>(ws);                                        ws += 256;
     GeoOut go = {};
-    go.rec = reinterpret_cast<GeoRec *>(ws);
+    go.rec = reinterpret_cast<GeoRec *>(ws);                                                           ws += a256((size_t)N * sizeof(GeoRec));
+    TileInfo *tiles = reinterpret_cast<TileInfo *>(ws);
     go.invalid_feat = invalid_feat;
     go.enc = fp.enc;
     go.learn_empty = fp.learn_empty;
@@ -247,6 +267,12 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     out->has_geo = want_geo && g.bw == SD_BIN;
     out->rec = go.rec;
     out->tile_ctr = meta + 1;
+    out->tiles = tiles;
+    if (out->has_geo) {
+        const long long n_tiles = (N + 127) / 128;
+        bin_tiles_kernel<<<(unsigned)((n_tiles + 8 + 255) / 256), 256, 0, st>>>(go.rec, cbin, N, n_tiles, tiles);
+        SD_LAUNCH_OK("bin_tiles_kernel");
+    }
     return SD_OK;
 }
 

@@ -20,7 +20,7 @@
 //   warp  5    TMA producer: one 8x8x128-channel box of P per chunk
 //   warps 6-9  one thread per row: point -> projection, mask, tap, colours, weights into the chunk's A operand
 //              (an undo log keeps the rest of the operand zero), positional code -> code operand
-// Rings: NRING (A chunk, B chunk) pairs released by tcgen05.commit, 2 code operands, layer-1 and layer-2
+// Rings: 2 weight (A) chunks and 4 box (B) chunks released by tcgen05.commit, 2 code operands, layer-1 and layer-2
 // accumulators double buffered in TMEM.
 #include <cuda.h>
 
@@ -40,7 +40,7 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #ifndef SD_TB_PT_GROUPS
 #define SD_TB_PT_GROUPS 1
 #endif
-constexpr int NRING = 3, NCODE = 2;
+constexpr int NRA = 2, NRB = 4, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
 constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_PT_GROUPS = SD_TB_PT_GROUPS;
 constexpr int WARP_EPI2 = N_EPI_WARPS, WARP_MMA = 2 * N_EPI_WARPS, WARP_TMA = WARP_MMA + 1, WARP_PT0 = WARP_TMA + 1;
 constexpr int NTHREADS = (WARP_PT0 + N_PT_GROUPS * N_PT_WARPS) * 32;
@@ -54,8 +54,8 @@ constexpr int KCODE = 3;                     // K steps of the code block (48 co
 
 constexpr int OFF_WC = 0;
 constexpr int OFF_A = OFF_WC + CHUNK;
-constexpr int OFF_B = OFF_A + NRING * CHUNK;
-constexpr int OFF_CODE = OFF_B + NRING * CHUNK;
+constexpr int OFF_B = OFF_A + NRA * CHUNK;
+constexpr int OFF_CODE = OFF_B + NRB * CHUNK;
 constexpr int OFF_W2 = OFF_CODE + NCODE * CHUNK;
 constexpr int OFF_STAGE = OFF_W2 + W2_BYTES;
 constexpr int NREC = 3;                      // ring of per-tile record blocks (128 x 32 B), filled by bulk copies
@@ -63,15 +63,18 @@ constexpr int REC_BYTES = TM * 32;
 constexpr int NPERM = 8;                     // ring of per-tile point indices handed from the point warps to epilogue 2
 constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * 8192;
 constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
-constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: {rows of the tile (0 = no more tiles), chunks}
-constexpr int OFF_NTILES = OFF_HDR + NREC * 8;            // tiles this CTA processed, published by the MMA issuer at the end
+constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: the tile's table entry (TileInfo, 16 B)
+constexpr int BATCH = 4;                                  // tiles claimed per atomic
+constexpr int OFF_TAB = OFF_HDR + NREC * 16;              // two batches of table entries, fetched by bulk copies
+constexpr int OFF_NTILES = OFF_TAB + 2 * BATCH * 16;      // tiles this CTA processed, published by the MMA issuer at the end
 constexpr int OFF_DIRTY = OFF_NTILES + 8;
-constexpr int OFF_CAM = OFF_DIRTY + NRING * TM;
+constexpr int OFF_CAM = OFF_DIRTY + NRA * TM;
 constexpr int OFF_BAR = OFF_CAM + 448;
-enum { BAR_FULL_A = 0, BAR_FULL_B = NRING, BAR_EMPTY = 2 * NRING, BAR_FULL_C = 3 * NRING, BAR_EMPTY_C = BAR_FULL_C + NCODE,
+enum { BAR_FULL_A = 0, BAR_EMPTY_A = NRA, BAR_FULL_B = 2 * NRA, BAR_EMPTY_B = 2 * NRA + NRB, BAR_FULL_C = 2 * NRA + 2 * NRB,
+       BAR_EMPTY_C = BAR_FULL_C + NCODE,
        BAR_D1 = BAR_EMPTY_C + NCODE, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 2, BAR_D2_EMPTY = BAR_D2 + 2,
        BAR_WLOAD = BAR_D2_EMPTY + 2, BAR_REC_FULL = BAR_WLOAD + 1, BAR_REC_EMPTY = BAR_REC_FULL + NREC,
-       NBAR = BAR_REC_EMPTY + NREC };
+       BAR_TAB = BAR_REC_EMPTY + NREC, NBAR = BAR_TAB + 2 };
 // consumers of a record-ring entry: the point warps and the MMA issuer (chunk count)
 constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS + 1;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
@@ -92,6 +95,7 @@ struct Params {
     FieldParams fp;
     const float *xyz;
     unsigned int *tile_ctr;    // next unclaimed tile (zeroed by the sort): CTAs claim tiles dynamically
+    const TileInfo *tiles;     // per-tile table in claim order (binning.cu), padded with empty entries
     const GeoRec *rec;         // per-point records at the sorted positions (binning.cu)
     const unsigned int *cbin;  // compact bin number -> bin id
     int nbx;
@@ -121,11 +125,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         g_cta_ns[2 * blockIdx.x] = t; g_cta_ns[2 * blockIdx.x + 1] = 0;
     }
     if (tid == 0) {
-        for (int e = 0; e < NRING; ++e) {
-            mbar_init(BAR(BAR_FULL_A + e), N_PT_WARPS);
-            mbar_init(BAR(BAR_FULL_B + e), 1);
-            mbar_init(BAR(BAR_EMPTY + e), 1);
-        }
+        for (int e = 0; e < NRA; ++e) { mbar_init(BAR(BAR_FULL_A + e), N_PT_WARPS); mbar_init(BAR(BAR_EMPTY_A + e), 1); }
+        for (int e = 0; e < NRB; ++e) { mbar_init(BAR(BAR_FULL_B + e), 1); mbar_init(BAR(BAR_EMPTY_B + e), 1); }
         for (int s = 0; s < NCODE; ++s) { mbar_init(BAR(BAR_FULL_C + s), N_PT_WARPS); mbar_init(BAR(BAR_EMPTY_C + s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(BAR(BAR_D1 + b), 1); mbar_init(BAR(BAR_H + b), N_EPI_WARPS);
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         }
         mbar_init(BAR(BAR_WLOAD), 1);
         for (int r = 0; r < NREC; ++r) { mbar_init(BAR(BAR_REC_FULL + r), 1); mbar_init(BAR(BAR_REC_EMPTY + r), REC_CONSUMERS); }
+        mbar_init(BAR(BAR_TAB), 1); mbar_init(BAR(BAR_TAB + 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 21 * (1 + P.fp.nv_c); i += NTHREADS) {
@@ -142,8 +144,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         s_cam[i] = e < 9 ? __ldg(K + e) : __ldg(W + (e - 9));
     }
     // the weight operands start out all zero and are kept so by the undo log of the point warps
-    for (int i = tid; i < NRING * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NRING * TM; i += NTHREADS) s_dirty[i] = 0xFF;
+    for (int i = tid; i < NRA * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NRA * TM; i += NTHREADS) s_dirty[i] = 0xFF;
     if (tid == 0) *reinterpret_cast<volatile int *>(sm + OFF_NTILES) = 0x7FFFFFFF;
     fence_proxy_async();
     if (warp == WARP_MMA) {
@@ -165,8 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     // Tiles are claimed dynamically by the TMA producer (atomic counter): the time a tile takes varies with the chunks it
     // touches and, more, from SM to SM (measured: static striding left CTAs finishing between 218 and 335 us).  The j-th
     // tile of this CTA travels through record-ring entry j % NREC: header {rows, chunks}, then 128 records.
-    struct Hdr { int rows, m; };
-    volatile Hdr *s_hdr = reinterpret_cast<volatile Hdr *>(sm + OFF_HDR);
+    volatile TileInfo *s_hdr = reinterpret_cast<volatile TileInfo *>(sm + OFF_HDR);
     volatile int *s_ntiles = reinterpret_cast<volatile int *>(sm + OFF_NTILES);
     auto rec_wait = [&](long long jj) { mbar_wait(BAR(BAR_REC_FULL + (int)(jj % NREC)), (uint32_t)((jj / NREC) & 1)); };
     auto rec_ptr = [&](long long jj) { return reinterpret_cast<const GeoRec *>(sm + OFF_REC + (int)(jj % NREC) * REC_BYTES); };
@@ -302,19 +303,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
                 umma_commit(BAR(BAR_D2 + b));
             };
-            int e = 0;
-            uint32_t ph = 0;
+            int e = 0, eb = 0;                       // ring positions: weight chunks, box chunks
+            uint32_t ph = 0, phb = 0;
             long long j = 0;
             for (;; ++j) {
                 rec_wait(j);
-                const int rows = s_hdr[j % NREC].rows, m = s_hdr[j % NREC].m;
+                const int rows = (int)s_hdr[j % NREC].rows, m = (int)(s_hdr[j % NREC].c0m >> 16);
                 mbar_arrive(BAR(BAR_REC_EMPTY + (int)(j % NREC)));
                 if (rows == 0) { if (j > 0) layer2(j - 1); break; }
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
                 for (int i = 0; i < m; ++i) {
-                    mbar_wait(BAR(BAR_FULL_B + e), ph);
+                    mbar_wait(BAR(BAR_FULL_B + eb), phb);
                     if (i == 0) TB_TRACE(1, j, 1);
                     mbar_wait(BAR(BAR_FULL_A + e), ph);
                     tc_fence_after();
@@ -322,11 +323,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {    // 16 texel slots per instruction
                         umma(d1, umma_desc(sm_u + OFF_A + e * CHUNK + k * 32),
-                             umma_desc_mn(sm_u + OFF_B + e * CHUNK + k * 2048, CHUNK / 2, 1024), idesc_mn, acc);
+                             umma_desc_mn(sm_u + OFF_B + eb * CHUNK + k * 2048, CHUNK / 2, 1024), idesc_mn, acc);
                         acc = 1;
                     }
-                    umma_commit(BAR(BAR_EMPTY + e));
-                    if (++e == NRING) { e = 0; ph ^= 1; }
+                    umma_commit(BAR(BAR_EMPTY_A + e));
+                    umma_commit(BAR(BAR_EMPTY_B + eb));
+                    if (++e == NRA) { e = 0; ph ^= 1; }
+                    if (++eb == NRB) { eb = 0; phb ^= 1; }
                 }
                 const int cs = (int)(j % NCODE);
                 TB_TRACE(1, j, 3);
@@ -353,77 +356,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         if (lane == 0) tma_prefetch_desc(&P.tmap);
         int e = 0;
         uint32_t ph = 0;
-        // Five-stage software pipeline over this CTA's tiles (slot s = its s-th tile): claim a tile for slot s+4, load the
-        // chunk span of slot s+3, publish header + records of slot s+2, load the bin ids of slot s+1, issue the boxes of
-        // slot s -- no global load is consumed in the iteration that issues it (they queue behind the epilogue's stores).
-        auto claim = [&]() -> long long {             // lane 0's value is the one used
-            // from the last tile down: the tiles that touch many bins (near field) sit at the end of the sorted order and
-            // must not be the last ones handed out.  Past the end the result is negative.
-            return lane == 0 ? P.n_tiles - 1 - (long long)atomicAdd(P.tile_ctr, 1u) : 0;
-        };
-        auto rows_of = [&](long long t) { return t >= 0 ? (int)(P.N - t * TM < TM ? P.N - t * TM : TM) : 0; };
-        auto gspan = [&](long long t, int &c0, int &c1) {          // raw loads; all lanes load the same words
-            c0 = 0; c1 = 0;
-            const int rows = rows_of(t);
-            if (rows == 0) return;
-            c0 = (int)(__ldg(&P.rec[t * TM].cs) & 0xFFFFu);
-            c1 = (int)(__ldg(&P.rec[t * TM + rows - 1].cs) & 0xFFFFu);
-        };
-        bool sentinel_sent = false;
-        auto publish = [&](long long slot, long long t, int c0, int c1) {     // header + records of a slot -> ring
-            if (lane != 0 || sentinel_sent) return;
-            const int r = (int)(slot % NREC);
-            const int rows = rows_of(t);
-            mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
-            s_hdr[r].rows = rows; s_hdr[r].m = c1 - c0 + 1;
-            if (rows == 0) {                                                   // no more tiles: a header alone
-                mbar_arrive(BAR(BAR_REC_FULL + r));
-                sentinel_sent = true;
-                return;
-            }
-            mbar_expect_tx(BAR(BAR_REC_FULL + r), (uint32_t)rows * 32u);
-            bulk_g2s(sm_u + OFF_REC + r * REC_BYTES, P.rec + t * TM, (uint32_t)rows * 32u, BAR(BAR_REC_FULL + r));
-        };
+        // Tiles are claimed BATCH at a time with one atomic; the table entries of a batch (rows, chunk span, first bins: all
+        // the producer needs to know about a tile) arrive by a bulk copy.  In steady state this warp issues no load through
+        // the load/store unit, whose queue is full of the epilogue's stores: a claim and a table fetch have a whole batch
+        // of tiles to complete.  Per tile: publish header + records of slot j+2 (the point warps run ahead of the MMAs),
+        // then issue the boxes of slot j from the header written two iterations ago.
+        const TileInfo *s_tab = reinterpret_cast<const TileInfo *>(sm + OFF_TAB);
+        auto claim = [&]() -> long long { return lane == 0 ? (long long)atomicAdd(P.tile_ctr, (unsigned)BATCH) : 0; };
         auto bcast = [&](long long v) { return __shfl_sync(0xffffffffu, v, 0); };
-        // prologue: slots 0..3 claimed, spans of 0..2 loaded, slots 0..1 published, bins of slot 0 loaded
-        long long t0 = bcast(claim()), t1 = bcast(claim()), t2 = bcast(claim()), t3 = bcast(claim());
-        int a0, b0, a1, b1, a2, b2;
-        gspan(t0, a0, b0); gspan(t1, a1, b1); gspan(t2, a2, b2);
-        publish(0, t0, a0, b0);
-        publish(1, t1, a1, b1);
-        unsigned int mybin = (rows_of(t0) && lane <= b0 - a0) ? __ldg(P.cbin + a0 + lane) : 0u;
-        for (long long j = 0;; ++j) {
-            if (rows_of(t0) == 0) break;
-            const long long t4 = claim();                                      // slot j+4 (used next iteration)
-            int a3, b3;
-            gspan(t3, a3, b3);                                                 // slot j+3
-            publish(j + 2, t2, a2, b2);                                        // slot j+2
-            const unsigned int mybin_n = (rows_of(t1) && lane <= b1 - a1) ? __ldg(P.cbin + a1 + lane) : 0u;   // slot j+1
-            const int c0 = a0, m = b0 - a0 + 1;                                // slot j: boxes
-            for (int base = 0; base < m; base += 32) {
-                if (base > 0) mybin = base + lane < m ? __ldg(P.cbin + c0 + base + lane) : 0u;
-                const int cnt = m - base < 32 ? m - base : 32;
-                for (int i = 0; i < cnt; ++i) {
-                    const unsigned int b = __shfl_sync(0xffffffffu, mybin, i);
-                    if (lane == 0) {
-                        const int by = (int)(b / (unsigned)P.nbx), bx = (int)(b - (unsigned)by * (unsigned)P.nbx);
-                        if (i == 0 && base == 0) TB_TRACE(6, j, 0);
-                        mbar_wait(BAR(BAR_EMPTY + e), ph ^ 1);
-                        if (i == 0 && base == 0) TB_TRACE(6, j, 1);
-                        mbar_expect_tx(BAR(BAR_FULL_B + e), CHUNK);
-                        const uint32_t dst = sm_u + OFF_B + e * CHUNK;
-                        tma_load_3d(dst, &P.tmap, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
-                        tma_load_3d(dst + CHUNK / 2, &P.tmap, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
-                    }
-                    if (++e == NRING) { e = 0; ph ^= 1; }
-                }
-                __syncwarp();
+        auto fetch_tab = [&](long long k, long long base) {        // batch k -> table slot k & 1
+            if (lane != 0 || base >= P.n_tiles) return;
+            mbar_expect_tx(BAR(BAR_TAB + (int)(k & 1)), BATCH * 16);
+            bulk_g2s(sm_u + OFF_TAB + (int)(k & 1) * BATCH * 16, P.tiles + base, BATCH * 16, BAR(BAR_TAB + (int)(k & 1)));
+        };
+        // stream of this CTA's tiles: batch k, entry i
+        long long k = 0, base = bcast(claim()), base_n;
+        int bi = 0;
+        fetch_tab(0, base);
+        base_n = claim();                                           // (lane 0; broadcast when batch 1 starts)
+        bool ended = false, tab_ready = false;
+        auto publish_next = [&](long long slot) {                   // next tile of the stream -> ring entry slot % NREC
+            if (ended) return;
+            const int r = (int)(slot % NREC);
+            TileInfo ti;
+            ti.c0m = 0; ti.b01 = 0; ti.b23 = 0; ti.rows = 0;
+            long long v = -1;                                       // position in claim order
+            if (base < P.n_tiles) {
+                if (!tab_ready) { mbar_wait(BAR(BAR_TAB + (int)(k & 1)), (uint32_t)((k >> 1) & 1)); tab_ready = true; }
+                ti = s_tab[(int)(k & 1) * BATCH + bi];
+                v = base + bi;
             }
-            TB_TRACE(6, j, 2);
-            if (lane == 0 && (P.dbg & 8192) && blockIdx.x == 0 && j >= 40 && j < 104) g_trace[(6 * 64 + (int)j - 40) * 8 + 7] = m;
-            t0 = t1; t1 = t2; t2 = t3; t3 = bcast(t4);
-            a0 = a1; b0 = b1; a1 = a2; b1 = b2; a2 = a3; b2 = b3;
-            mybin = mybin_n;
+            if (lane == 0) {
+                mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
+                s_hdr[r].c0m = ti.c0m; s_hdr[r].b01 = ti.b01; s_hdr[r].b23 = ti.b23; s_hdr[r].rows = ti.rows;
+                if (ti.rows == 0) {
+                    mbar_arrive(BAR(BAR_REC_FULL + r));             // no more tiles: a header alone
+                } else {
+                    const long long t = P.n_tiles - 1 - v;          // claim order runs from the last tile down
+                    mbar_expect_tx(BAR(BAR_REC_FULL + r), ti.rows * 32u);
+                    bulk_g2s(sm_u + OFF_REC + r * REC_BYTES, P.rec + t * TM, ti.rows * 32u, BAR(BAR_REC_FULL + r));
+                }
+            }
+            if (ti.rows == 0) { ended = true; return; }
+            if (++bi == BATCH) {                                    // next batch: its claim was made a batch ago
+                bi = 0; ++k; tab_ready = false;
+                base = bcast(base_n);
+                fetch_tab(k, base);
+                base_n = claim();
+            }
+        };
+        publish_next(0);
+        publish_next(1);
+        for (long long j = 0;; ++j) {
+            publish_next(j + 2);
+            __syncwarp();
+            const int r = (int)(j % NREC);
+            const unsigned int rows = s_hdr[r].rows, c0m = s_hdr[r].c0m, b01 = s_hdr[r].b01, b23 = s_hdr[r].b23;
+            if (rows == 0) break;
+            const int c0 = (int)(c0m & 0xFFFFu), m = (int)(c0m >> 16);
+            if (lane == 0) {
+                for (int i = 0; i < m; ++i) {
+                    unsigned int b = i == 0 ? (b01 & 0xFFFFu) : i == 1 ? (b01 >> 16) : i == 2 ? (b23 & 0xFFFFu) : (b23 >> 16);
+                    if (i >= 4) b = __ldg(P.cbin + c0 + i);          // a tile that touches more than four bins (rare)
+                    const int by = (int)(b / (unsigned)P.nbx), bx = (int)(b - (unsigned)by * (unsigned)P.nbx);
+                    if (i == 0) TB_TRACE(6, j, 0);
+                    mbar_wait(BAR(BAR_EMPTY_B + e), ph ^ 1);
+                    if (i == 0) TB_TRACE(6, j, 1);
+                    mbar_expect_tx(BAR(BAR_FULL_B + e), CHUNK);
+                    const uint32_t dst = sm_u + OFF_B + e * CHUNK;
+                    tma_load_3d(dst, &P.tmap, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                    tma_load_3d(dst + CHUNK / 2, &P.tmap, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                    if (++e == NRB) { e = 0; ph ^= 1; }
+                }
+                TB_TRACE(6, j, 2);
+                if ((P.dbg & 8192) && blockIdx.x == 0 && j >= 40 && j < 104) g_trace[(6 * 64 + (int)j - 40) * 8 + 7] = m;
+            }
+            __syncwarp();
         }
     } else {
         // =================================== POINT WARPS ================================================
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         for (long long j = 0;; ++j) {
             RowIn cur;
             rec_wait(j);
-            const int rows = s_hdr[j % NREC].rows;
+            const int rows = (int)s_hdr[j % NREC].rows;
             if (rows == 0) break;                          // no more tiles for this CTA
             const GeoRec *rr = rec_ptr(j);
             cur.c0 = (int)(rr[0].cs & 0xFFFFu);            // compact bins the tile touches: first, last
@@ -463,8 +471,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 // only adjacent phases, so nobody may get two phases ahead on an entry (a tile can span more chunks
                 // than the ring has entries).
                 for (int i = cur.c1 - cur.c0 + 1; i > 0; --i) {
-                    mbar_wait(BAR(BAR_EMPTY + e), ph ^ 1);
-                    if (++e == NRING) { e = 0; ph ^= 1; }
+                    mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
+                    if (++e == NRA) { e = 0; ph ^= 1; }
                 }
                 continue;
             }
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             TB_TRACE(pt_role, j, 1);
             const int m = cur.c1 - cur.c0 + 1;
             for (int i = 0; i < m; ++i) {
-                mbar_wait(BAR(BAR_EMPTY + e), ph ^ 1);
+                mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
                 if (i == 0) TB_TRACE(pt_role, j, 2);
                 unsigned char *arow = sm + OFF_A + e * CHUNK + row * 128;
                 const int d = s_dirty[e * TM + row];
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 }
                 fence_proxy_async();
                 mbar_arrive_warp(BAR(BAR_FULL_A + e));
-                if (++e == NRING) { e = 0; ph ^= 1; }
+                if (++e == NRA) { e = 0; ph ^= 1; }
             }
             TB_TRACE(pt_role, j, 3);
             // ---- colours of the render views (bts.py:330-441, 557-569): only when asked for; the point and its
@@ -637,6 +645,7 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     P.cbin = order.cbin; P.nbx = order.nbx;
     SD_REQUIRE(order.has_geo, "field_bin: the point order carries no geometry records");
     P.rec = order.rec;
+    P.tiles = order.tiles;
     P.tile_ctr = order.tile_ctr;
     P.N = N;
     {

@@ -75,6 +75,14 @@ struct GeoRec {
 };
 static_assert(sizeof(GeoRec) == 32, "one sector per record");
 
+// What the tile kernel's producer needs to know about a 128-point tile, in the order the tiles are handed out (entry v
+// describes tile n_tiles - 1 - v): rows (0 = past the end), first compact bin and number of bins it touches (c0 | m << 16)
+// and the ids of the first four of them.
+struct TileInfo {
+    unsigned int c0m, b01, b23, rows;
+};
+static_assert(sizeof(TileInfo) == 16, "bulk-copied in batches");
+
 struct BinOrder {
     const unsigned int *perm;     // [N] sorted position -> point index
     const unsigned short *pcb;    // [N] compact number of the bin of the point at each sorted position (non-decreasing)
@@ -84,6 +92,7 @@ struct BinOrder {
     bool has_geo;
     const GeoRec *rec;
     unsigned int *tile_ctr;       // zeroed counter from which the tile kernel's CTAs claim tiles
+    const TileInfo *tiles;        // [n_tiles + 8] table in claim order, empty entries behind the end
 };
 size_t bin_workspace_bytes(int Hf, int Wf, long long N);
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
