@@ -94,6 +94,11 @@ int         sd_device_sm_count(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 long long   sd_launch_count(void);
 
+/* Measurement hook: the next launch of the path's dominant kernel (the fused field kernel of sd_query_points /
+ * sd_render_pass) made by the calling host thread records the two caller-owned cudaEvent_t handles around
+ * itself, on the stream it is launched on.  bench.py's roofline uses it; NULL handles switch it off. */
+int         sd_profile_next_kernel(void *ev_start, void *ev_stop);
+
 /* ---- one-off packing ------------------------------------------------------------------------ */
 /* BTSNet.encode stash (bts.py:214-257): [n_img, C, H, W] fp32 planar -> [n_img, H, W, C]
  * channels-last in dst_dtype.  Replaces the no-op F.interpolate copy at bts.py:217-222. */

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "sd_last_error": (C.c_char_p, []),
     "sd_device_sm_count": (_I, []),
     "sd_launch_count": (_LL, []),
+    "sd_profile_next_kernel": (_I, [_P, _P]),
     "sd_featmap_pack": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "sd_mlp_pack_bytes": (_SZ, [_I, _I, _I]),
     "sd_mlp_pack": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),

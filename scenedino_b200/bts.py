@@ -179,8 +179,27 @@ class BTSNet(nn.Module):
             self._packed[key] = st
         return st
 
-    def _scene(self, st, b: int) -> _abi.SdScene:
+    def _projection(self, st, b: int, mlp: _abi.SdMlp):
+        """Blob of sd_field_project for batch element ``b`` and this head, made once per encode: the fp16 map pushed
+        through the feature columns of the head's first layer, for the projected-map tile kernel."""
+        cache = st.setdefault("proj", {})
+        key = (b, int(mlp.packed))
+        blob = cache.get(key)
+        if blob is None:
+            sc = self._scene(st, b)
+            lib = _abi.lib()
+            nbytes = lib.sd_field_project_bytes(C.byref(sc))
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=st["feat"].device)
+            off = (-raw.data_ptr()) % 1024
+            blob = raw[off:off + nbytes]
+            _abi.check(lib.sd_field_project(C.byref(sc), C.byref(mlp), _ptr(blob), nbytes, _stream()), "sd_field_project")
+            cache[key] = blob
+        return blob
+
+    def _scene(self, st, b: int, proj=None) -> _abi.SdScene:
         s = _abi.SdScene()
+        if proj is not None:
+            s.feat_proj = proj.data_ptr()
         s.feat = st["feat"][b].data_ptr()
         s.feat_dtype = st["dt"]
         s.nv_f, s.C, s.Hf, s.Wf = 1, st["C"], st["Hf"], st["Wf"]
@@ -275,8 +294,12 @@ class BTSNet(nn.Module):
             rgb = torch.empty((n, N, 3 * nv_c), dtype=torch.float32, device=dev) if want_colors else None
             invalid = torch.empty((n, N, nv_c), dtype=torch.float32, device=dev) if want_colors else None
             lib = _abi.lib()
+            # big reduced-precision queries (SSC voxel chunks) run on the projected map: made once per encode and head
+            hf, wf = st["Hf"], st["Wf"]
+            use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
+                        and N >= 16 * ((hf + 5) // 7 + 1) * ((wf + 5) // 7 + 1))
             for b in range(n):
-                sc = self._scene(st, b)
+                sc = self._scene(st, b, self._projection(st, b, mlp) if use_proj else None)
                 need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(mlp), N)
                 ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
                 _abi.check(lib.sd_query_points(

@@ -26,6 +26,17 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// sd_profile_next_kernel: a pair of caller-owned events recorded around the next launch of a field kernel
+static thread_local cudaEvent_t g_prof0 = nullptr, g_prof1 = nullptr;
+void profile_before(cudaStream_t st) {
+    if (g_prof0) cudaEventRecord(g_prof0, st);
+    g_prof0 = nullptr;
+}
+void profile_after(cudaStream_t st) {
+    if (g_prof1) cudaEventRecord(g_prof1, st);
+    g_prof1 = nullptr;
+}
+
 }  // namespace sd
 
 using namespace sd;
@@ -33,6 +44,12 @@ using namespace sd;
 extern "C" int sd_abi_version(void) { return SD_ABI_VERSION; }
 extern "C" const char *sd_last_error(void) { return g_err; }
 extern "C" long long sd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int sd_profile_next_kernel(void *ev_start, void *ev_stop) {
+    g_prof0 = reinterpret_cast<cudaEvent_t>(ev_start);
+    g_prof1 = reinterpret_cast<cudaEvent_t>(ev_stop);
+    return SD_OK;
+}
 
 extern "C" int sd_device_sm_count(void) {
     int dev = 0, n = 0;

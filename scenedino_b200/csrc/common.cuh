@@ -20,6 +20,8 @@ namespace sd {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch(int n = 1);
+void profile_before(cudaStream_t st);   // sd_profile_next_kernel: events around the dominant (field) kernel
+void profile_after(cudaStream_t st);
 
 #define SD_CUDA_OK(expr)                                                    \
     do {                                                                    \

@@ -672,7 +672,9 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
         SD_CUDA_OK(cudaFuncSetAttribute(tb::field_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
+    profile_before(st);
     tb::field_bin_kernel<<<grid, tb::NTHREADS, tb::SMEM_ALLOC, st>>>(P);
+    profile_after(st);
     SD_LAUNCH_OK("field_bin_kernel");
     return SD_OK;
 }

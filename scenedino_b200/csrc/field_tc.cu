@@ -727,7 +727,9 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
         SD_CUDA_OK(cudaFuncSetAttribute(tc::field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
+    profile_before(st);
     tc::field_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_ALLOC, st>>>(P);
+    profile_after(st);
     SD_LAUNCH_OK("field_tc_kernel");
     return SD_OK;
 }

@@ -114,6 +114,58 @@ def test_query_points(golden, precision, tol, feat_dtype, tag, learn_empty):
         assert np.array_equal(g2n(q["invalid_features"]), ref["invalid_features"])
 
 
+# ---- projected-map tile kernel (sd_field_project + texel sort + field_bin_kernel) ---------------------------------
+def test_field_project_matches_matmul(golden):
+    """P = W_in[:, :C] . F per texel, fp16 operands, fp32 accumulation (field_proj.cu) against a torch matmul of the same
+    operands; the code-block image carries W_feat . empty_feature in column 47."""
+    g = golden("query")
+    _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=torch.float16, learn_empty=True, empty_feature=g["empty_feature"])
+    p = dsc.project(dmlp)
+    Hf, Wf, C_ = dsc.feat.shape
+    P = p.proj[16384:].view(torch.float16).view(Hf * Wf, 128).float()
+    W = dev(g["w_in"][:, :C_]).half().float()
+    ref = dsc.feat.view(Hf * Wf, C_).float() @ W.T
+    assert (P - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    img = g2n(p.proj[:16384].view(torch.float16)).astype(np.float32)
+    pe = (W @ dev(g["empty_feature"]).half().float()).cpu().numpy()
+    for n in (0, 5, 127):   # UMMA K-major SWIZZLE_128B: element (row n, k = 47) sits in chunk (47 >> 3) ^ (n & 7)
+        got = img[(n * 128 + ((5 ^ (n & 7)) << 4) + 7 * 2) // 2]
+        assert abs(got - pe[n]) <= 2e-3 * max(1.0, abs(pe[n]))
+
+
+@pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
+def test_query_points_projected(golden, tag, learn_empty):
+    """The tile kernel against the reference's own outputs (golden points, repeated so that the bins fill up) and against
+    the oracle on random points: masks and colours bit-exact, densities / features within the reduced-precision bar."""
+    from scenedino_b200 import _abi
+    g = golden("query")
+    kw = dict(learn_empty=learn_empty, empty_feature=g["empty_feature"] if learn_empty else None)
+    osc, dsc, omlp, dmlp = scenes_from_golden(g, feat_dtype=torch.float16, **kw)
+    dscp = dsc.project(dmlp)
+    n_g = len(g["points"])
+    pts = np.concatenate([g["points"], g["points"], syn.random_points(7, 70000 - 2 * n_g + 77)]).astype(np.float32)
+    n0 = _abi.launch_count()
+    q = ops.query_points(dscp, dmlp, dev(pts), precision=ops.F16)
+    assert _abi.launch_count() - n0 == 5, "expected sort (4 launches) + field_bin_kernel"
+    o = O.query_points(osc, omlp, pts)
+    for lo in (0, n_g):   # both copies of the golden points against the reference
+        sl = slice(lo, lo + n_g)
+        assert_close(g2n(q["sigma"])[sl], g["sigma" + tag], TOL_F16, "sigma vs reference")
+        assert_close(g2n(q["dino"])[sl], g["dino" + tag], TOL_F16, "dino vs reference")
+        assert np.array_equal(g2n(q["rgb"])[sl], g["rgb" + tag])
+        assert np.array_equal(g2n(q["invalid"])[sl], g["invalid" + tag])
+        assert np.array_equal(g2n(q["invalid_features"])[sl], g["invalid_features" + tag])
+    assert_close(g2n(q["sigma"]), o["sigma"], TOL_F16, "sigma vs oracle")
+    assert_close(g2n(q["dino"]), o["dino"], TOL_F16, "dino vs oracle")
+    assert np.array_equal(g2n(q["rgb"]), o["rgb"])
+    assert np.array_equal(g2n(q["invalid"]), o["invalid"])
+    assert np.array_equal(g2n(q["invalid_features"]), o["invalid_features"])
+    # same bits as the gather kernel's masks, and close to its values (two roundings of the same contraction)
+    q2 = ops.query_points(dsc, dmlp, dev(pts), precision=ops.F16)
+    assert torch.equal(q2["invalid_features"], q["invalid_features"]) and torch.equal(q2["rgb"], q["rgb"])
+    assert_close(g2n(q["dino"]), g2n(q2["dino"]), TOL_F16, "tile kernel vs gather kernel")
+
+
 @pytest.mark.parametrize("precision,tol", [(ops.FP32, TOL_FP32), (ops.F16, TOL_F16)])
 @pytest.mark.parametrize("d_in,d_out,n", [(295, 65, 1000), (295, 769, 300), (64, 768, 257), (40, 3, 65), (312, 33, 129)])
 def test_mlp_forward(precision, tol, d_in, d_out, n):
@@ -257,11 +309,12 @@ def test_render_superbatch_vs_reference(golden):
 
 
 # ---- BASELINE-size properties --------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol,feat_dtype", [
-    (ops.FP32, TOL_FP32, torch.float32),
-    (ops.F16, TOL_F16, torch.float16),
+@pytest.mark.parametrize("precision,tol,feat_dtype,projected", [
+    (ops.FP32, TOL_FP32, torch.float32, False),
+    (ops.F16, TOL_F16, torch.float16, False),
+    (ops.F16, TOL_F16, torch.float16, True),
 ])
-def test_ssc_grid_full_size(precision, tol, feat_dtype):
+def test_ssc_grid_full_size(precision, tol, feat_dtype, projected):
     """configs[1]: the 256x256x32 voxel grid against a DINOv2-sized map: masks bit-exact on all
     2 097 152 voxels, values against the oracle on a strided subset, and batch-position independence
     (a permuted query returns the permuted result bit for bit)."""
@@ -273,6 +326,8 @@ def test_ssc_grid_full_size(precision, tol, feat_dtype):
     assert pts.shape == (2097152, 3)
     dsc = ops.Scene.from_arrays(feat, K, w2c, device=DEV, feat_dtype=feat_dtype)
     dmlp = ops.Mlp(*mlp_w, device=DEV)
+    if projected:   # the path bench.py times: texel sort + projected-map tile kernel
+        dsc = dsc.project(dmlp)
     dp = dev(pts)
     q = ops.query_points(dsc, dmlp, dp, precision=precision)
     _, _, oinv = O.project(K[0], w2c[0], pts)
@@ -286,10 +341,14 @@ def test_ssc_grid_full_size(precision, tol, feat_dtype):
     q2 = ops.query_points(dsc, dmlp, dp[perm].contiguous(), precision=precision)
     assert torch.equal(q2["sigma"], q["sigma"][perm]) and torch.equal(q2["dino"], q["dino"][perm])
     assert torch.isfinite(q["sigma"]).all() and torch.isfinite(q["dino"]).all()
-    # the tensor-core path walks the points in texel-binned order when given scratch space: same bits
+    # the tensor-core path walks the points in texel-binned order when given scratch space: same bits (without scratch
+    # space a projected scene falls back to the gather kernel: same masks, values within the bar)
     q3 = ops.query_points(dsc, dmlp, dp, precision=precision, binned=False)
-    assert torch.equal(q3["sigma"], q["sigma"]) and torch.equal(q3["dino"], q["dino"])
     assert torch.equal(q3["invalid_features"], q["invalid_features"])
+    if projected:
+        assert_close(g2n(q3["sigma"])[sub], g2n(q["sigma"])[sub], tol, "gather vs tile kernel")
+    else:
+        assert torch.equal(q3["sigma"], q["sigma"]) and torch.equal(q3["dino"], q["dino"])
 
 
 # ---- edge cases and error behaviour ----------------------------------------------------------------

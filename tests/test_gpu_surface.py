@@ -197,6 +197,34 @@ def test_btsnet_forward(golden, tag, learn_empty):
     assert np.array_equal(inv0[0, :, 0].cpu().numpy(), g["invalid_features" + tag].astype(np.float32))
 
 
+def test_btsnet_forward_large_fp16_uses_projected_map(golden):
+    """A big reduced-precision point query (the SSC voxel chunks of sscbench/evaluate_model_sscbench.py:711-717) runs
+    on the projected map made once per encode: texel sort + tile kernel, same masks as fp32, values within 2e-2."""
+    from scenedino_b200 import _abi
+    from scenedino_b200 import synthetic as syn
+    g = golden("query")
+    net = build(g, learn_empty=True)
+    pts = np.concatenate([g["points"], syn.random_points(3, 70000)]).astype(np.float32)
+    xyz = dev(pts)[None]
+    with torch.no_grad():
+        net.precision = "fp32"
+        _, _, sigma32, _, st32 = net(xyz, only_density=True)
+        net.precision = "fp16"
+        _, _, sigma16, _, st16 = net(xyz, only_density=True)
+        n0 = _abi.launch_count()
+        dino_full, _, sigma_seg, _ = net(xyz, predict_segmentation=True)
+        second = _abi.launch_count() - n0
+    projs = [st["proj"] for st in net._packed.values() if "proj" in st]
+    assert len(projs) == 1 and len(projs[0]) == 1, "one projection per encode, batch element and head"
+    assert 5 <= second <= 8, "sort (4 launches) + tile kernel (+ expand_dim), no second projection"
+    assert torch.equal(st16["invalid_features"], st32["invalid_features"])
+    assert_close(sigma16[0, :, 0].cpu().numpy(), sigma32[0, :, 0].cpu().numpy(), TOL_F16, "sigma fp16 vs fp32")
+    assert_close(st16["dino_features"][0].cpu().numpy(), st32["dino_features"][0].cpu().numpy(), TOL_F16, "dino fp16 vs fp32")
+    n = len(g["points"])
+    assert_close(sigma16[0, :n, 0].cpu().numpy(), g["sigma_le"], TOL_F16, "sigma vs reference")
+    assert dino_full.shape == (1, xyz.shape[1], 768) and sigma_seg.shape == (1, xyz.shape[1], 1)
+
+
 def test_no_silent_fallback(golden):
     g = golden("query")
     net = build(g)
