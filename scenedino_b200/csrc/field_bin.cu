@@ -66,7 +66,8 @@ constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
 constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: the tile's table entry (TileInfo, 16 B)
 constexpr int BATCH = 4;                                  // tiles claimed per atomic
 constexpr int OFF_TAB = OFF_HDR + NREC * 16;              // two batches of table entries, fetched by bulk copies
-constexpr int OFF_NTILES = OFF_TAB + 2 * BATCH * 16;      // tiles this CTA processed, published by the MMA issuer at the end
+constexpr int OFF_MINFO = OFF_TAB + 2 * BATCH * 16;       // per weight-ring entry: chunks of the tile whose first chunk sits there
+constexpr int OFF_NTILES = OFF_MINFO + 16;      // tiles this CTA processed, published by the MMA issuer at the end
 constexpr int OFF_DIRTY = OFF_NTILES + 8;
 constexpr int OFF_CAM = OFF_DIRTY + NRA * TM;
 constexpr int OFF_BAR = OFF_CAM + 448;
@@ -75,8 +76,8 @@ enum { BAR_FULL_A = 0, BAR_EMPTY_A = NRA, BAR_FULL_B = 2 * NRA, BAR_EMPTY_B = 2 
        BAR_D1 = BAR_EMPTY_C + NCODE, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 2, BAR_D2_EMPTY = BAR_D2 + 2,
        BAR_WLOAD = BAR_D2_EMPTY + 2, BAR_REC_FULL = BAR_WLOAD + 1, BAR_REC_EMPTY = BAR_REC_FULL + NREC,
        BAR_TAB = BAR_REC_EMPTY + NREC, NBAR = BAR_TAB + 2 };
-// consumers of a record-ring entry: the point warps and the MMA issuer (chunk count)
-constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS + 1;
+// consumers of a record-ring entry: the point warps
+constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_ALLOC = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
@@ -306,18 +307,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             int e = 0, eb = 0;                       // ring positions: weight chunks, box chunks
             uint32_t ph = 0, phb = 0;
             long long j = 0;
+            volatile int *s_minfo = reinterpret_cast<volatile int *>(sm + OFF_MINFO);
             for (;; ++j) {
-                rec_wait(j);
-                const int rows = (int)s_hdr[j % NREC].rows, m = (int)(s_hdr[j % NREC].c0m >> 16);
-                mbar_arrive(BAR(BAR_REC_EMPTY + (int)(j % NREC)));
-                if (rows == 0) { if (j > 0) layer2(j - 1); break; }
+                // The tile's first weight chunk carries its chunk count (0: no more tiles) and stands for the code operand
+                // too: one barrier test where there were three (each costs a round trip through the busy load/store unit).
+                mbar_wait(BAR(BAR_FULL_A + e), ph);
+                const int m = s_minfo[e];
+                if (m == 0) { if (j > 0) layer2(j - 1); break; }
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
                 for (int i = 0; i < m; ++i) {
-                    mbar_wait(BAR(BAR_FULL_B + eb), phb);
+                    if (i > 0) mbar_wait(BAR(BAR_FULL_A + e), ph);
                     if (i == 0) TB_TRACE(1, j, 1);
-                    mbar_wait(BAR(BAR_FULL_A + e), ph);
+                    mbar_wait(BAR(BAR_FULL_B + eb), phb);
                     tc_fence_after();
                     if (i == 0) TB_TRACE(1, j, 2);
 #pragma unroll
@@ -332,9 +335,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     if (++eb == NRB) { eb = 0; phb ^= 1; }
                 }
                 const int cs = (int)(j % NCODE);
-                TB_TRACE(1, j, 3);
-                mbar_wait(BAR(BAR_FULL_C + cs), (uint32_t)((j / NCODE) & 1));
-                tc_fence_after();
                 TB_TRACE(1, j, 4);
 #pragma unroll
                 for (int k = 0; k < KCODE; ++k)
@@ -444,13 +444,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         // inputs of a tile row: its record in the ring (shared memory: nothing here queues behind the epilogue's store
         // bursts in the global load/store path) and the tile's chunk span
         struct RowIn { bool ok; int cr, c0, c1, slot, grow; float x, y, zp; uint32_t w01, w23; };
+        volatile int *s_minfo = reinterpret_cast<volatile int *>(sm + OFF_MINFO);
         int e = 0;
         uint32_t ph = 0;
         for (long long j = 0;; ++j) {
             RowIn cur;
             rec_wait(j);
             const int rows = (int)s_hdr[j % NREC].rows;
-            if (rows == 0) break;                          // no more tiles for this CTA
+            if (rows == 0) {                               // no more tiles for this CTA: tell the MMA issuer (chunk count 0)
+                if ((int)(j % N_PT_GROUPS) == grp) {
+                    mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
+                    if (row == 0) s_minfo[e] = 0;
+                    mbar_arrive_warp(BAR(BAR_FULL_A + e));
+                }
+                break;
+            }
             const GeoRec *rr = rec_ptr(j);
             cur.c0 = (int)(rr[0].cs & 0xFFFFu);            // compact bins the tile touches: first, last
             cur.c1 = (int)(rr[rows - 1].cs & 0xFFFFu);
@@ -478,64 +486,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             }
             const bool ok = cur.ok;
             const float x = cur.x, y = cur.y, zp = cur.zp;
-            // ---- bilinear weights -> this row's 4 slots of its bin's chunk; every other slot of the row stays zero.
-            //      Slots (nw, ne) = (s, s+1) share one 16-byte piece of the row (lx <= 6), (sw, se) the next one:
-            //      the dirty byte keeps (ly << 3 | lx) and the undo clears the same two pairs.
-            const bool plain = ok && cur.slot != 0xFF;
-            const int lx = cur.slot & 7, ly = (cur.slot >> 3) & 7;
-            const int q = cur.cr - cur.c0;
-            const uint32_t w_top = cur.w01, w_bot = cur.w23;
-            auto pair_off = [&](int lyy, int lxx) {      // byte offset of slot (lyy, lxx) inside the row
-                return (uint32_t)(((lyy ^ (row & 7)) << 4) + lxx * 2);
-            };
-            TB_TRACE(pt_role, j, 1);
-            const int m = cur.c1 - cur.c0 + 1;
-            for (int i = 0; i < m; ++i) {
-                mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
-                if (i == 0) TB_TRACE(pt_role, j, 2);
-                unsigned char *arow = sm + OFF_A + e * CHUNK + row * 128;
-                const int d = s_dirty[e * TM + row];
-                if (d != 0xFF) {
-                    unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(d >> 3, d & 7));
-                    unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off((d >> 3) + 1, d & 7));
-                    p0[0] = 0; p0[1] = 0; p1[0] = 0; p1[1] = 0;
-                }
-                if (plain && i == q) {
-                    unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(ly, lx));
-                    unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off(ly + 1, lx));
-                    p0[0] = (unsigned short)w_top; p0[1] = (unsigned short)(w_top >> 16);
-                    p1[0] = (unsigned short)w_bot; p1[1] = (unsigned short)(w_bot >> 16);
-                    s_dirty[e * TM + row] = (unsigned char)cur.slot;
-                } else if (d != 0xFF) {
-                    s_dirty[e * TM + row] = 0xFF;
-                }
-                fence_proxy_async();
-                mbar_arrive_warp(BAR(BAR_FULL_A + e));
-                if (++e == NRA) { e = 0; ph ^= 1; }
-            }
-            TB_TRACE(pt_role, j, 3);
-            // ---- colours of the render views (bts.py:330-441, 557-569): only when asked for; the point and its
-            //      frustum flag are fetched / recomputed here (the SSC query does not take this path)
-            if (ok && nv_c > 0 && (P.rgb || P.invalid)) {
-                const long long grow = cur.grow;
-                const float px = __ldg(P.xyz + 3 * grow), py = __ldg(P.xyz + 3 * grow + 1), pz = __ldg(P.xyz + 3 * grow + 2);
-                float ex, ey, ez;
-                bool inv;
-                project_point(s_cam, s_cam + 9, px, py, pz, ex, ey, ez, inv);
-                for (int v = 0; v < nv_c; ++v) {
-                    float cx, cy, cz;
-                    bool cinv;
-                    const float *c = s_cam + 21 * (1 + v);
-                    project_point(c, c + 9, px, py, pz, cx, cy, cz, cinv);
-                    if (P.rgb) {
-                        float c3[3];
-                        sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
-                        float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
-                        o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
-                    }
-                    if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
-                }
-            }
+            const bool plain = ok && cur.slot != 0xFF;     // bilinear taps (else: the learned empty feature, bts.py:311-319)
             // ---- positional code -> code operand (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by angle
             //      doubling from one accurate sincosf per coordinate) -------------------------------------------
             uint32_t pk[24];
@@ -581,8 +532,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
 #pragma unroll
             for (int qq = 0; qq < 6; ++qq)
                 *reinterpret_cast<uint4 *>(crow + ((qq ^ (row & 7)) << 4)) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-            fence_proxy_async();
-            mbar_arrive_warp(BAR(BAR_FULL_C + cs));
+            // (made visible to the tensor cores by the fence + arrival of the tile's first weight chunk below)
+            // ---- bilinear weights -> this row's 4 slots of its bin's chunk; every other slot of the row stays zero.
+            //      Slots (nw, ne) = (s, s+1) share one 16-byte piece of the row (lx <= 6), (sw, se) the next one:
+            //      the dirty byte keeps (ly << 3 | lx) and the undo clears the same two pairs.
+            const int lx = cur.slot & 7, ly = (cur.slot >> 3) & 7;
+            const int q = cur.cr - cur.c0;
+            const uint32_t w_top = cur.w01, w_bot = cur.w23;
+            auto pair_off = [&](int lyy, int lxx) {      // byte offset of slot (lyy, lxx) inside the row
+                return (uint32_t)(((lyy ^ (row & 7)) << 4) + lxx * 2);
+            };
+            TB_TRACE(pt_role, j, 1);
+            const int m = cur.c1 - cur.c0 + 1;
+            for (int i = 0; i < m; ++i) {
+                mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
+                if (i == 0) TB_TRACE(pt_role, j, 2);
+                unsigned char *arow = sm + OFF_A + e * CHUNK + row * 128;
+                const int d = s_dirty[e * TM + row];
+                if (d != 0xFF) {
+                    unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(d >> 3, d & 7));
+                    unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off((d >> 3) + 1, d & 7));
+                    p0[0] = 0; p0[1] = 0; p1[0] = 0; p1[1] = 0;
+                }
+                if (plain && i == q) {
+                    unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(ly, lx));
+                    unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off(ly + 1, lx));
+                    p0[0] = (unsigned short)w_top; p0[1] = (unsigned short)(w_top >> 16);
+                    p1[0] = (unsigned short)w_bot; p1[1] = (unsigned short)(w_bot >> 16);
+                    s_dirty[e * TM + row] = (unsigned char)cur.slot;
+                } else if (d != 0xFF) {
+                    s_dirty[e * TM + row] = 0xFF;
+                }
+                if (i == 0 && row == 0) s_minfo[e] = m;           // chunks of this tile, read by the MMA issuer behind FULL_A
+                fence_proxy_async();
+                mbar_arrive_warp(BAR(BAR_FULL_A + e));
+                if (++e == NRA) { e = 0; ph ^= 1; }
+            }
+            TB_TRACE(pt_role, j, 3);
+            // ---- colours of the render views (bts.py:330-441, 557-569): only when asked for; the point and its
+            //      frustum flag are fetched / recomputed here (the SSC query does not take this path)
+            if (ok && nv_c > 0 && (P.rgb || P.invalid)) {
+                const long long grow = cur.grow;
+                const float px = __ldg(P.xyz + 3 * grow), py = __ldg(P.xyz + 3 * grow + 1), pz = __ldg(P.xyz + 3 * grow + 2);
+                float ex, ey, ez;
+                bool inv;
+                project_point(s_cam, s_cam + 9, px, py, pz, ex, ey, ez, inv);
+                for (int v = 0; v < nv_c; ++v) {
+                    float cx, cy, cz;
+                    bool cinv;
+                    const float *c = s_cam + 21 * (1 + v);
+                    project_point(c, c + 9, px, py, pz, cx, cy, cz, cinv);
+                    if (P.rgb) {
+                        float c3[3];
+                        sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
+                        float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
+                        o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
+                    }
+                    if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
+                }
+            }
             TB_TRACE(pt_role, j, 6);
         }
     }
