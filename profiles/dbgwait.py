@@ -1,3 +1,4 @@
+"""Debug build helper (-DSD_DEBUG_WAIT): which barrier waits time out in field_bin_kernel."""
 import sys, ctypes
 import numpy as np, torch
 sys.path.insert(0, '.')
@@ -15,10 +16,9 @@ torch.cuda.synchronize()
 raw = ctypes.CDLL(_abi.LIB_PATH)
 buf = (ctypes.c_uint * 260)()
 raw.sd_debug_read_timeout(buf)
-n=buf[0]
+n = buf[0]
 print('timeouts', n)
-for k in range(min(n,10)):
-    bar,par,tid=buf[4+4*k],buf[5+4*k],buf[6+4*k]
-    print('bar idx',(bar-1024-203840)//8,'parity',par,'warp',tid//32,'lane',tid%32)
-
-print('progress at first timeout [mma, tma, grp0, grp1, epi1, epi2]:', list(buf[200:206]))
+base = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+for k in range(min(n, 40)):
+    bar, par, tid, blk = buf[4 + 4 * k], buf[5 + 4 * k], buf[6 + 4 * k], buf[7 + 4 * k]
+    print('bar addr', bar, 'idx', (bar - 1024 - base) // 8 if base else '?', 'parity', par, 'warp', tid // 32, 'lane', tid % 32, 'block', blk)

@@ -42,7 +42,8 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #endif
 constexpr int NRA = 2, NRB = 4, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
 constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_PT_GROUPS = SD_TB_PT_GROUPS;
-constexpr int WARP_EPI2 = N_EPI_WARPS, WARP_MMA = 2 * N_EPI_WARPS, WARP_TMA = WARP_MMA + 1, WARP_PT0 = WARP_TMA + 1;
+constexpr int WARP_EPI2 = N_EPI_WARPS, WARP_MMA = 2 * N_EPI_WARPS, WARP_MMA2 = WARP_MMA + 1, WARP_TMA = WARP_MMA2 + 1,
+              WARP_PT0 = WARP_TMA + 1;
 constexpr int NTHREADS = (WARP_PT0 + N_PT_GROUPS * N_PT_WARPS) * 32;
 static_assert(NCODE % N_PT_GROUPS == 0, "a code operand is always filled by the same point group");
 constexpr int TMEM_COLS = 512;
@@ -75,7 +76,7 @@ enum { BAR_FULL_A = 0, BAR_EMPTY_A = NRA, BAR_FULL_B = 2 * NRA, BAR_EMPTY_B = 2 
        BAR_EMPTY_C = BAR_FULL_C + NCODE,
        BAR_D1 = BAR_EMPTY_C + NCODE, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 2, BAR_D2_EMPTY = BAR_D2 + 2,
        BAR_WLOAD = BAR_D2_EMPTY + 2, BAR_REC_FULL = BAR_WLOAD + 1, BAR_REC_EMPTY = BAR_REC_FULL + NREC,
-       BAR_TAB = BAR_REC_EMPTY + NREC, NBAR = BAR_TAB + 2 };
+       BAR_TAB = BAR_REC_EMPTY + NREC, BAR_D1_FREE = BAR_TAB + 2, NBAR = BAR_D1_FREE + 2 };
 // consumers of a record-ring entry: the point warps
 constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         mbar_init(BAR(BAR_WLOAD), 1);
         for (int r = 0; r < NREC; ++r) { mbar_init(BAR(BAR_REC_FULL + r), 1); mbar_init(BAR(BAR_REC_EMPTY + r), REC_CONSUMERS); }
         mbar_init(BAR(BAR_TAB), 1); mbar_init(BAR(BAR_TAB + 1), 1);
+        mbar_init(BAR(BAR_D1_FREE), 1); mbar_init(BAR(BAR_D1_FREE + 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 21 * (1 + P.fp.nv_c); i += NTHREADS) {
@@ -184,7 +186,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         for (long long j = 0;; ++j) {
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
-            if (j >= *s_ntiles) break;                    // the MMA issuer's closing arrival, not a tile
+            if (j >= *s_ntiles) {                         // the layer-1 issuer's closing arrival, not a tile: pass it on
+                mbar_arrive_warp(BAR(BAR_H + b));
+                break;
+            }
             tc_fence_after();
             if (warp == 0) TB_TRACE(0, j, 2);
 #pragma unroll 1
@@ -288,32 +293,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         }
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
+        // Layer 1.  (Layer 2 is issued by a second thread, warp WARP_MMA2: every barrier test is a round trip through the
+        // load/store unit, ~250 cycles behind the epilogue's stores, and one thread doing all of them was the critical path.)
         if (lane == 0) {
             mbar_wait(BAR(BAR_WLOAD), 0);
-            const uint32_t idesc_k = umma_idesc(TM, 128), idesc_mn = idesc_k | UMMA_B_MN_MAJOR, idesc2 = umma_idesc(TM, P.n2);
-            auto layer2 = [&](long long jj) {
-                const int b = (int)(jj & 1);
-                mbar_wait(BAR(BAR_H + b), (uint32_t)((jj >> 1) & 1));
-                mbar_wait(BAR(BAR_D2_EMPTY + b), (uint32_t)(((jj >> 1) & 1) ^ 1));
-                tc_fence_after();
-                TB_TRACE(1, jj + 1, 5);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
-                            umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
-                umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
-                umma_commit(BAR(BAR_D2 + b));
-            };
+            const uint32_t idesc_k = umma_idesc(TM, 128), idesc_mn = idesc_k | UMMA_B_MN_MAJOR;
             int e = 0, eb = 0;                       // ring positions: weight chunks, box chunks
             uint32_t ph = 0, phb = 0;
             long long j = 0;
             volatile int *s_minfo = reinterpret_cast<volatile int *>(sm + OFF_MINFO);
             for (;; ++j) {
                 // The tile's first weight chunk carries its chunk count (0: no more tiles) and stands for the code operand
-                // too: one barrier test where there were three (each costs a round trip through the busy load/store unit).
+                // too: one barrier test where there were three.
                 mbar_wait(BAR(BAR_FULL_A + e), ph);
                 const int m = s_minfo[e];
-                if (m == 0) { if (j > 0) layer2(j - 1); break; }
+                // the accumulator (its first 64 columns held the hidden tile of tile j-2) is free once layer 2 of j-2 has run.
+                // (Also before the closing arrival below: nobody may complete two phases of a barrier ahead of its waiter.)
+                mbar_wait(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
+                if (m == 0) break;
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
@@ -341,15 +338,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     umma(d1, umma_desc(sm_u + OFF_CODE + cs * CHUNK + k * 32), umma_desc(sm_u + OFF_WC + k * 32), idesc_k, 1);
                 umma_commit(BAR(BAR_EMPTY_C + cs));
                 umma_commit(BAR(BAR_D1 + (int)(j & 1)));
-                // layer 2 of the previous tile behind layer 1 of this one: its hidden tile is being produced by the first
-                // epilogue while the MMAs above are issued and run
-                if (j > 0) layer2(j - 1);
                 TB_TRACE(1, j, 6);
             }
-            // closing: tell the epilogues how many tiles there were and complete the barrier phases they wait on
+            // closing: tell everybody downstream how many tiles there were and complete the phase the first epilogue waits
+            // on; it passes the arrival on to the layer-2 issuer, which passes it on to the second epilogue
             *s_ntiles = (int)j;
             mbar_arrive(BAR(BAR_D1 + (int)(j & 1)));
-            mbar_arrive(BAR(BAR_D2 + (int)(j & 1)));
+        }
+    } else if (warp == WARP_MMA2) {
+        // =================================== MMA ISSUER, LAYER 2 ======================================
+        if (lane == 0) {
+            mbar_wait(BAR(BAR_WLOAD), 0);
+            const uint32_t idesc2 = umma_idesc(TM, P.n2);
+            for (long long j = 0;; ++j) {
+                const int b = (int)(j & 1);
+                mbar_wait(BAR(BAR_H + b), (uint32_t)((j >> 1) & 1));
+                // (the accumulator drained -- also before the closing arrival: nobody may complete two phases of a barrier
+                // ahead of its waiter)
+                mbar_wait(BAR(BAR_D2_EMPTY + b), (uint32_t)(((j >> 1) & 1) ^ 1));
+                if (j >= *s_ntiles) { mbar_arrive(BAR(BAR_D2 + b)); break; }
+                tc_fence_after();
+                TB_TRACE(1, j + 1, 5);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                    umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
+                            umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
+                umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
+                umma_commit(BAR(BAR_D2 + b));
+                umma_commit(BAR(BAR_D1_FREE + b));
+            }
         }
     } else if (warp == WARP_TMA) {
         // =================================== TMA PRODUCER =============================================

@@ -57,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra SD_WAIT_DONE;\n\t"
         "add.u32 n, n, 1;\n\t"
-        "setp.lt.u32 p, n, 40000000;\n\t"
+        "setp.lt.u32 p, n, 2000000;\n\t"
         "@p bra SD_WAIT_LOOP;\n\t"
         "trap;\n\t"
         "SD_WAIT_DONE:\n\t"
