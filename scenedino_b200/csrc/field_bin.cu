@@ -84,12 +84,15 @@ constexpr int SMEM_ALLOC = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 
+#ifndef TB_T0
+#define TB_T0 40   // first traced tile of CTA 0 (SD_TC_DEBUG & 8192): tiles TB_T0 .. TB_T0 + 63
+#endif
 __device__ long long g_trace[8 * 64 * 8];
 __device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globaltimer (SD_TC_DEBUG & 8192)   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
 #define TB_TRACE(role, j, ev)                                                                    \
     do {                                                                                         \
-        if ((P.dbg & 8192) && blockIdx.x == 0 && (j) >= 40 && (j) < 104 && (role) < 8 && (threadIdx.x & 31) == 0) \
-            g_trace[((role) * 64 + (int)(j) - 40) * 8 + (ev)] = clock64();   /* tiles 40..103 of CTA 0 */                            \
+        if ((P.dbg & 8192) && blockIdx.x == 0 && (j) >= TB_T0 && (j) < TB_T0 + 64 && (role) < 8 && (threadIdx.x & 31) == 0) \
+            g_trace[((role) * 64 + (int)(j) - TB_T0) * 8 + (ev)] = clock64();                            \
     } while (0)
 
 struct Params {
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     if (++e == NRB) { e = 0; ph ^= 1; }
                 }
                 TB_TRACE(6, j, 2);
-                if ((P.dbg & 8192) && blockIdx.x == 0 && j >= 40 && j < 104) g_trace[(6 * 64 + (int)j - 40) * 8 + 7] = m;
+                if ((P.dbg & 8192) && blockIdx.x == 0 && j >= TB_T0 && j < TB_T0 + 64) g_trace[(6 * 64 + (int)j - TB_T0) * 8 + 7] = m;
             }
             __syncwarp();
         }
