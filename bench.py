@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("SD_BENCH_WATCHDOG"):      # debugging aid: Python stacks of a run that takes too long
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["SD_BENCH_WATCHDOG"]), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -292,9 +295,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def note(msg):
+        if os.environ.get("SD_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    note("setup done")
     for _ in range(args.warmup):
         step()
     fence()
+    note("warm-up done")
     n0 = _abi.launch_count()
     with Clocks(local) as clk:
         fence()
@@ -313,6 +322,7 @@ def main():
             step()
         torch.cuda.synchronize()
     launches = _abi.launch_count() - n0
+    note("timed region done")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,6 +373,7 @@ def main():
     e1.record()
     e2e_fence()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    note("end-to-end done")
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
