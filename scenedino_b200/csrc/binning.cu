@@ -23,6 +23,7 @@
 namespace sd {
 
 constexpr int BIN_THREADS = 256;
+constexpr int SCAT_THREADS = 512;   // scatter: two blocks per SM by shared memory (2 x 80 KB), so bigger blocks for occupancy
 constexpr int MAX_BINS = 12288;   // the scan stages counts and compact numbers in 96 KB of shared memory
 
 struct BinGeom {
@@ -126,7 +127,7 @@ struct GeoOut {
 };
 
 template <bool GEO>
-__global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
+__global__ void __launch_bounds__(SCAT_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
                                                                   const unsigned short *__restrict__ bins,
                                                                   unsigned int *__restrict__ cursor,
                                                                   const unsigned int *__restrict__ cidx,
@@ -137,21 +138,21 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_scatter_kernel(BinGeom bg, lo
     extern __shared__ unsigned int sh[];          // [nbins] counts, then [nbins] bases
     __shared__ float cam[21];
     unsigned int *cnt = sh, *base = sh + bg.nbins;
-    for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS) cnt[b] = 0;
+    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) cnt[b] = 0;
     if (GEO)
-        for (int i = threadIdx.x; i < 21; i += BIN_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
+        for (int i = threadIdx.x; i < 21; i += SCAT_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
     __syncthreads();
     const long long per = (N + gridDim.x - 1) / gridDim.x;
     const long long lo = per * blockIdx.x, hi = min(N, lo + per);
-    for (long long i = lo + threadIdx.x; i < hi; i += BIN_THREADS) atomicAdd(&cnt[bins[i]], 1u);
+    for (long long i = lo + threadIdx.x; i < hi; i += SCAT_THREADS) atomicAdd(&cnt[bins[i]], 1u);
     __syncthreads();
-    for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS) {
+    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) {
         const unsigned int c = cnt[b];
         if (c) base[b] = atomicAdd(&cursor[b], c);
         cnt[b] = 0;
     }
     __syncthreads();
-    for (long long i = lo + threadIdx.x; i < hi; i += BIN_THREADS) {
+    for (long long i = lo + threadIdx.x; i < hi; i += SCAT_THREADS) {
         const int b = bins[i];
         const unsigned int pos = base[b] + atomicAdd(&cnt[b], 1u);
         const unsigned int ci = __ldg(cidx + b);
@@ -259,9 +260,9 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     bin_scan_kernel<<<1, 1024, (size_t)g.nbins * 8, st>>>(hist, g.nbins, cidx, cbin, meta);
     SD_LAUNCH_OK("bin_scan_kernel");
     if (want_geo && g.bw == SD_BIN)
-        bin_scatter_kernel<true><<<grid2, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+        bin_scatter_kernel<true><<<grid2, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     else
-        bin_scatter_kernel<false><<<grid2, BIN_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+        bin_scatter_kernel<false><<<grid2, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     SD_LAUNCH_OK("bin_scatter_kernel");
     out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
     out->has_geo = want_geo && g.bw == SD_BIN;
