@@ -22,7 +22,7 @@ scp = sc.project(mlp)
 torch.cuda.synchronize()
 print('project ok', time.time() - t0, flush=True)
 # --- P against a torch matmul of the same fp16 operands
-Pm = scp.proj[16384:].view(torch.float16).view(Hf * Wf, 128).float()
+Pm = scp.proj[50176:].view(torch.float16).view(Hf * Wf, 128).float()
 Wf16 = torch.from_numpy(mlp_w[0][:, :256]).to(dev).half().float()
 ref = sc.feat.view(Hf * Wf, 256).float() @ Wf16.T
 err = (Pm - ref).abs().max().item()

@@ -97,7 +97,7 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
             if (rc) return rc;
             if (tile && order.has_geo) return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
         }
-        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm);
+        return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm, scene->feat_proj);
     }
     SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);
     SimtOut out = {};
@@ -150,7 +150,7 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
         }
         TcOut o = {};
         o.sigma = sigma; o.invalid = invalid; o.invalid_feat = invalid_feat;
-        return launch_field_tc(fp, src, N, mlp, &rr, o, st);
+        return launch_field_tc(fp, src, N, mlp, &rr, o, st, nullptr, scene->feat_proj);
     }
 
     const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);
@@ -168,7 +168,7 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
     if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = w_sigma; o.dino = w_dino; o.rgb = Crgb ? w_rgb : nullptr; o.invalid = invalid; o.invalid_feat = invalid_feat;
-        rc = launch_field_tc(fp, src, N, mlp, nullptr, o, st);
+        rc = launch_field_tc(fp, src, N, mlp, nullptr, o, st, nullptr, scene->feat_proj);
     } else {
         SimtOut out = {};
         out.sigma = w_sigma; out.dino = w_dino; out.rgb = Crgb ? w_rgb : nullptr; out.invalid = invalid;

@@ -683,14 +683,14 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     P.n_tiles = (N + tb::TM - 1) / tb::TM;
     P.D = mlp->d_out - 1;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
-    P.wc_img = proj;
+    P.wc_img = proj + PROJ_OFF_CODE;
     P.w2_img = blob + L.off_w_out_h;
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
     P.sigma = out.sigma; P.dino = out.dino; P.rgb = out.rgb; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;
     const unsigned long long dims[3] = {128ull, (unsigned long long)fp.Wf, (unsigned long long)fp.Hf};
     const unsigned long long strides[2] = {256ull, 256ull * (unsigned long long)fp.Wf};
     const unsigned int box[3] = {64u, 8u, 8u};
-    int rc = make_tmap_f16(&P.tmap, proj + tb::CHUNK, 3, dims, strides, box);
+    int rc = make_tmap_f16(&P.tmap, proj + PROJ_OFF_MAP, 3, dims, strides, box);
     if (rc) return rc;
     static int sm_count = 0;
     if (sm_count == 0) {

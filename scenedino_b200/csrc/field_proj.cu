@@ -9,11 +9,14 @@
 // texel and 4/5 of the layer-1 contraction gone from the per-sample path.  The learn_empty replacement
 // (bts.py:311-319) is linear too: W_feat . empty_feature rides in a spare column of the code block.
 //
-// Blob written by sd_field_project ("projected scene"):
-//   [0, 16384)      fp16 UMMA K-major SWIZZLE_128B image [128 hidden][64] of the code block of W_in: columns 0..38
-//                   positional code, 39..44 coordinate hi/lo split, 45..46 bias (as in sd_mlp_pack), 47 = W_feat .
-//                   empty_feature (zero unless learn_empty)
-//   [16384, ...)    P: [Hf*Wf][128] fp16
+// Blob written by sd_field_project ("projected scene", offsets in launch.h: PROJ_*):
+//   [0, 32768)      fp16 UMMA K-major SWIZZLE_128B image of the 128 x 128 identity (two K chunks): layer-1 "weights" of the
+//                   projected features for the gather kernel (field_tc.cu), which blends 128 projected channels
+//   [32768, 49152)  the same kind of image [128 hidden][64] of the code block of W_in: columns 0..38 positional code,
+//                   39..44 coordinate hi/lo split, 45..46 bias (as in sd_mlp_pack), 47 = W_feat . empty_feature (zero
+//                   unless learn_empty)
+//   [49152, 50176)  W_feat . empty_feature as 128 halves (the gather kernel's replacement row)
+//   [50176, ...)    P: [Hf*Wf][128] fp16
 //
 // The GEMM: persistent CTAs, 128 texels per tile; A = 128 texel rows x 256 channels of the channels-last fp16 map,
 // brought in by TMA (four 64-channel boxes, SWIZZLE_128B = the UMMA K-major layout); B = the four feature chunks of
@@ -196,13 +199,16 @@ __global__ void __launch_bounds__(128) proj_code_image_kernel(const unsigned cha
     if (learn_empty)
         for (int c = 0; c < C; ++c)   // the operands the tensor cores would see: half(W) * half(empty), fp32 accumulation
             pe = fmaf(__half2float(w[umma_sw128_offset(n, c, 128) / 2]), __half2float(__float2half_rn(__ldg(empty_feature + c))), pe);
-    __half *o = reinterpret_cast<__half *>(wc_img);
+    __half *o = reinterpret_cast<__half *>(wc_img + PROJ_OFF_CODE);
     for (int k = 0; k < 64; ++k) {
         __half v = __float2half_rn(0.0f);
         if (k < 47) v = w[umma_sw128_offset(n, C + k, 128) / 2];
         else if (k == 47) v = __float2half_rn(pe);
         o[umma_sw128_offset(n, k, 128) / 2] = v;
     }
+    __half *id = reinterpret_cast<__half *>(wc_img + PROJ_OFF_IDENT);
+    for (int k = 0; k < 128; ++k) id[umma_sw128_offset(n, k, 128) / 2] = __float2half_rn(k == n ? 1.0f : 0.0f);
+    reinterpret_cast<__half *>(wc_img + PROJ_OFF_EMPTY)[n] = __float2half_rn(pe);
 }
 
 }  // namespace pj
@@ -212,7 +218,7 @@ using namespace sd;
 
 extern "C" size_t sd_field_project_bytes(const sd_scene *scene) {
     if (!scene || scene->Hf <= 0 || scene->Wf <= 0) return 0;
-    return (size_t)pj::CHUNK + (size_t)scene->Hf * scene->Wf * 128 * sizeof(__half);
+    return (size_t)PROJ_OFF_MAP + (size_t)scene->Hf * scene->Wf * 128 * sizeof(__half);
 }
 
 extern "C" int sd_field_project(const sd_scene *scene, const sd_mlp *mlp, void *proj, size_t proj_bytes, void *stream) {
@@ -239,7 +245,7 @@ extern "C" int sd_field_project(const sd_scene *scene, const sd_mlp *mlp, void *
     P.n_texels = (long long)scene->Hf * scene->Wf;
     P.n_tiles = (P.n_texels + pj::TM - 1) / pj::TM;
     P.w1_img = blob + L.off_w_in_h;
-    P.P = reinterpret_cast<__half *>(out + pj::CHUNK);
+    P.P = reinterpret_cast<__half *>(out + PROJ_OFF_MAP);
     const unsigned long long dims[2] = {256ull, (unsigned long long)P.n_texels}, strides[1] = {512ull};
     const unsigned int box[2] = {64u, (unsigned)pj::TM};
     int rc = make_tmap_f16(&P.tmap, scene->feat, 2, dims, strides, box);

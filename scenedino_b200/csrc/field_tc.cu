@@ -88,6 +88,7 @@ struct Params {
     int n2;                   // layer-2 N: D feature rows + the density row, padded to 16
     int D;                    // feature outputs = d_out - 1
     const unsigned char *w1_img, *w2_img;
+    const __half *empty_h;     // projected scene: W_feat . empty_feature as halves (else NULL: fp.empty_feature is used)
     const float *b_out;
     // rows mode
     const float *x_rows;
@@ -151,8 +152,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             s_cam[i] = e < 9 ? __ldg(K + e) : __ldg(W + (e - 9));
         }
         __half *s_empty = reinterpret_cast<__half *>(sm + OFF_EMPTY);
-        for (int i = tid; i < 256; i += NTHREADS)
-            s_empty[i] = __float2half_rn((P.fp.learn_empty && i < P.fp.C) ? __ldg(P.fp.empty_feature + i) : 0.0f);
+        for (int i = tid; i < 256; i += NTHREADS) {
+            __half v = __float2half_rn(0.0f);
+            if (P.fp.learn_empty && i < P.fp.C) v = P.empty_h ? P.empty_h[i] : __float2half_rn(__ldg(P.fp.empty_feature + i));
+            s_empty[i] = v;
+        }
     }
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
@@ -700,11 +704,22 @@ bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K) {
     return tc_scene_ok(scene, mlp) && K >= 32 && K <= tc::TM;
 }
 
-static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
+static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st, const void *proj = nullptr) {
     const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
     SD_REQUIRE(((uintptr_t)blob & 15) == 0, "mlp: packed blob must be 16-byte aligned");
     P.w1_img = blob + L.off_w_in_h;
+    P.nch = L.d_in_pad / 64;
+    if (proj) {   // projected scene: [identity (2 chunks) | code block] instead of W_in, 128 projected channels per texel
+        const unsigned char *pb = reinterpret_cast<const unsigned char *>(proj);
+        SD_REQUIRE(((uintptr_t)pb & 15) == 0, "projected scene: blob must be 16-byte aligned");
+        P.w1_img = pb + PROJ_OFF_IDENT;        // identity chunks and the code chunk are contiguous
+        P.empty_h = reinterpret_cast<const __half *>(pb + PROJ_OFF_EMPTY);
+        P.fp.feat = pb + PROJ_OFF_MAP;
+        P.fp.feat_f16 = 1;
+        P.fp.C = 128;
+        P.nch = 3;
+    }
     P.w2_img = blob + L.off_w_out_h;
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
     {
@@ -716,7 +731,6 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
         SD_CUDA_OK(cudaMemcpyToSymbol(tc::c_dbg, &P.dbg, sizeof(int)));
         last_dbg = P.dbg;
     }
-    P.nch = L.d_in_pad / 64;
     P.D = mlp->d_out - 1;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
     static int sm_count = 0;
@@ -735,11 +749,11 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st) {
 }
 
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp, const TcRender *render,
-                    const TcOut &out, cudaStream_t st, const unsigned int *perm) {
+                    const TcOut &out, cudaStream_t st, const unsigned int *perm, const void *proj) {
     if (N == 0) return SD_OK;
     SD_REQUIRE(N < (1ll << 31), "SD_MLP_F16_TC: at most 2^31 - 1 rows per call (got %lld)", N);
     SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 and packed");
-    SD_REQUIRE(fp.feat_f16, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
+    SD_REQUIRE(fp.feat_f16 || proj, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
     SD_REQUIRE(fp.C == 256 && fp.code_dim == 39 && fp.enc.include_input && mlp->d_in == fp.C + fp.code_dim,
                "SD_MLP_F16_TC: supports C = 256 with the 39-d positional code (got C=%d, code=%d, d_in=%d)", fp.C,
                fp.code_dim, mlp->d_in);
@@ -771,7 +785,7 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
     }
     P.n_tiles = (P.n_units + P.upt - 1) / P.upt;
     P.sigma = out.sigma; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;
-    return tc_launch(P, mlp, st);
+    return tc_launch(P, mlp, st, proj);
 }
 
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st) {

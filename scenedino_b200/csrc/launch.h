@@ -60,8 +60,11 @@ struct TcRender {         // per-ray outputs of the fused composite
 
 // true when the fused kernel handles this (scene, head) in render mode with K samples per ray
 bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K);
+// `proj`: blob of sd_field_project or NULL.  With it the kernel gathers the 128 projected channels (half the bytes per
+// tap) and layer 1 is identity + code block (K 320 -> 192); without it the 256 feature channels and the full W_in.
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp,
-                    const TcRender *render, const TcOut &out, cudaStream_t st, const unsigned int *perm = nullptr);
+                    const TcRender *render, const TcOut &out, cudaStream_t st, const unsigned int *perm = nullptr,
+                    const void *proj = nullptr);
 
 // ---- texel binning of query points (binning.cu) ------------------------------------------------------
 // What the tile kernel needs of a point, at its sorted position: encoder-view coordinates (x, y clamped to +-2, z' of
@@ -97,6 +100,12 @@ struct BinOrder {
 size_t bin_workspace_bytes(int Hf, int Wf, long long N);
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
                       BinOrder *out, cudaStream_t st, bool want_geo = false, unsigned char *invalid_feat = nullptr);
+// ---- projected scene (field_proj.cu): blob layout -----------------------------------------------------------
+constexpr int PROJ_OFF_IDENT = 0;          // 2 x 16 KB: UMMA image of the 128 x 128 identity
+constexpr int PROJ_OFF_CODE = 32768;       // 16 KB: UMMA image of the code block of W_in (+ projected empty feature in column 47)
+constexpr int PROJ_OFF_EMPTY = 49152;      // 128 halves: W_feat . empty_feature
+constexpr int PROJ_OFF_MAP = 50176;        // P [Hf*Wf][128] fp16
+
 // ---- projected-map tile kernel (field_proj.cu, field_bin.cu) ---------------------------------------------
 // encodes a tiled fp16 tensor map (SWIZZLE_128B) into the 128 bytes at tmap_out (64-byte aligned)
 int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,

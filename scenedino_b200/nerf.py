@@ -210,8 +210,12 @@ class NeRFRenderer(torch.nn.Module):
         rgbs = torch.empty((B, K, 3 * nv_c), **f32) if want_rgb_samps else None
         cfg = self._cfg()
         lib = _abi.lib()
+        # reduced precision: render on the projected map (made once per encode and head): the gather reads 128 projected
+        # channels per tap instead of 256 features and layer 1 shrinks to identity + code block
+        use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
+                    and Bp * K >= 65536)
         for b in range(sb):
-            sc = net._scene(st, b)
+            sc = net._scene(st, b, net._projection(st, b, mlp) if use_proj else None)
             sl = slice(b * Bp, (b + 1) * Bp)
             need = lib.sd_render_workspace_bytes(C.byref(sc), C.byref(mlp), Bp, K)
             ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None

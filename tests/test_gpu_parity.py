@@ -122,11 +122,11 @@ def test_field_project_matches_matmul(golden):
     _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=torch.float16, learn_empty=True, empty_feature=g["empty_feature"])
     p = dsc.project(dmlp)
     Hf, Wf, C_ = dsc.feat.shape
-    P = p.proj[16384:].view(torch.float16).view(Hf * Wf, 128).float()
+    P = p.proj[50176:].view(torch.float16).view(Hf * Wf, 128).float()
     W = dev(g["w_in"][:, :C_]).half().float()
     ref = dsc.feat.view(Hf * Wf, C_).float() @ W.T
     assert (P - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
-    img = g2n(p.proj[:16384].view(torch.float16)).astype(np.float32)
+    img = g2n(p.proj[32768:49152].view(torch.float16)).astype(np.float32)
     pe = (W @ dev(g["empty_feature"]).half().float()).cpu().numpy()
     for n in (0, 5, 127):   # UMMA K-major SWIZZLE_128B: element (row n, k = 47) sits in chunk (47 >> 3) ^ (n & 7)
         got = img[(n * 128 + ((5 ^ (n & 7)) << 4) + 7 * 2) // 2]
@@ -160,6 +160,11 @@ def test_query_points_projected(golden, tag, learn_empty):
     assert np.array_equal(g2n(q["rgb"]), o["rgb"])
     assert np.array_equal(g2n(q["invalid"]), o["invalid"])
     assert np.array_equal(g2n(q["invalid_features"]), o["invalid_features"])
+    # a small query on the projected scene takes the gather kernel with the projected map (no sort below 65 536 points)
+    qs = ops.query_points(dscp, dmlp, dev(g["points"]), precision=ops.F16)
+    assert_close(g2n(qs["sigma"]), g["sigma" + tag], TOL_F16, "sigma, gather kernel on the projected map")
+    assert_close(g2n(qs["dino"]), g["dino" + tag], TOL_F16, "dino, gather kernel on the projected map")
+    assert np.array_equal(g2n(qs["invalid_features"]), g["invalid_features" + tag])
     # same bits as the gather kernel's masks, and close to its values (two roundings of the same contraction)
     q2 = ops.query_points(dsc, dmlp, dev(pts), precision=ops.F16)
     assert torch.equal(q2["invalid_features"], q["invalid_features"]) and torch.equal(q2["rgb"], q["rgb"])
@@ -270,13 +275,16 @@ def _check_pass(o, g, prefix, tol, b=None):
     assert np.array_equal(g2n(o["invalid_features"]).ravel(), sl(g[prefix + "invalid_features"]).ravel())
 
 
-@pytest.mark.parametrize("precision,tol,feat_dtype", [
-    (ops.FP32, TOL_FP32, torch.float32),
-    (ops.F16, TOL_F16, torch.float16),
+@pytest.mark.parametrize("precision,tol,feat_dtype,projected", [
+    (ops.FP32, TOL_FP32, torch.float32, False),
+    (ops.F16, TOL_F16, torch.float16, False),
+    (ops.F16, TOL_F16, torch.float16, True),     # gather kernel on the projected map (128 channels, identity layer 1)
 ])
-def test_render_pass_vs_reference(golden, precision, tol, feat_dtype):
+def test_render_pass_vs_reference(golden, precision, tol, feat_dtype, projected):
     g = golden("render_coarse")
     osc, dsc, omlp, dmlp = scenes_from_golden(g, feat_dtype=feat_dtype)
+    if projected:
+        dsc = dsc.project(dmlp)
     rays = g["rays"][0]
     z = ops.sample_coarse(dev(rays), dev(g["u_coarse"]), dev(g["lin"]), True)
     assert np.array_equal(g2n(z), g["coarse.z_samps"][0])
@@ -293,6 +301,8 @@ def test_render_pass_vs_reference(golden, precision, tol, feat_dtype):
     for name in ("render_fine", "render_fine_lin"):
         g = golden(name)
         _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=feat_dtype)
+        if projected:
+            dsc = dsc.project(dmlp)
         white = bool(g["conf"][4])
         for p in ("coarse.", "fine."):
             o = ops.render_pass(dsc, dmlp, dev(g["rays"][0]), dev(g[p + "z_samps"][0]), hard_alpha_cap=True,
