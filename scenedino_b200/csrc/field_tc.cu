@@ -39,6 +39,7 @@ constexpr int NGEO = 3;
 constexpr int TMEM_COLS = 512;
 constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 (<= 80 columns) at 256
 constexpr int H_COL = 384;                   // fp16 hidden tile (A operand of layer 2): 64 columns, two halves per column
+constexpr int D3X_COL = 336, D3F_COL = 448;  // composite on the tensor cores: per-ray sums of (depth, sum w, colours) / of the 64 features
 constexpr int PART_STRIDE = 80;              // per (warp, segment) composite partial: 64 feat + depth + wsum + 12 rgb
 constexpr int MAX_NVC_TC = 4;
 constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
@@ -64,7 +65,7 @@ constexpr int OFF_CAM = OFF_EMPTY + 512;     // 21 floats per camera, 1 + 4 came
 constexpr int OFF_PART = OFF_CAM + 448;
 constexpr int OFF_TAILS = OFF_PART + 4 * 2 * PART_STRIDE * 4;
 constexpr int OFF_BAR = OFF_TAILS + 32;
-constexpr int NBAR = 2 * MAX_CHUNKS + 2 + 1 + 1 + 2 * NGEO + 1;
+constexpr int NBAR = 2 * MAX_CHUNKS + 2 + 1 + 1 + 2 * NGEO + 1 + 2;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
@@ -72,7 +73,14 @@ static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
 static_assert(OFF_BAR % 8 == 0 && OFF_PART % 16 == 0 && OFF_GEO % 16 == 0 && OFF_W2 % 1024 == 0, "alignment");
 
 enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 1,
-       BAR_GEO_FULL = BAR_D2 + 1, BAR_GEO_EMPTY = BAR_GEO_FULL + NGEO, BAR_WLOAD = BAR_GEO_EMPTY + NGEO };
+       BAR_GEO_FULL = BAR_D2 + 1, BAR_GEO_EMPTY = BAR_GEO_FULL + NGEO, BAR_WLOAD = BAR_GEO_EMPTY + NGEO,
+       BAR_B3 = BAR_WLOAD + 1, BAR_D3 = BAR_B3 + 1 };
+// Composite on the tensor cores (render mode on a projected scene, where layer 1 needs 3 of the 5 operand chunks):
+//   out[ray][col] = sum_row Wt[ray][row] * V[row][col],  V = (64 features | depth, 1, colours) of the tile's rows as fp16
+// Wt (A operand, K-major) lives in the two spare chunks of the W_in image, V (B operand, MN-major like the boxes of
+// field_bin.cu) in the output staging area, which render mode does not use.
+constexpr int OFF_A3 = OFF_W1 + 3 * CHUNK_BYTES;
+constexpr int OFF_B3 = OFF_H;
 
 struct Params {
     int mode;
@@ -85,6 +93,7 @@ struct Params {
     int upt;                  // units per tile
     long long n_tiles;
     int nch;                  // K chunks of layer 1
+    int cmma;                 // render mode: composite on the tensor cores (projected scene)
     int n2;                   // layer-2 N: D feature rows + the density row, padded to 16
     int D;                    // feature outputs = d_out - 1
     const unsigned char *w1_img, *w2_img;
@@ -142,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             mbar_init(BAR(BAR_GEO_EMPTY + s), N_GA_WARPS + N_EPI_WARPS);
         }
         mbar_init(BAR(BAR_WLOAD), 1);
+        mbar_init(BAR(BAR_B3), N_EPI_WARPS); mbar_init(BAR(BAR_D3), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (field) {
@@ -157,6 +167,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             if (P.fp.learn_empty && i < P.fp.C) v = P.empty_h ? P.empty_h[i] : __float2half_rn(__ldg(P.fp.empty_feature + i));
             s_empty[i] = v;
         }
+    }
+    if (P.cmma) {   // rows of the weight operand beyond the rays of a tile are never written: keep them zero
+        for (int i = tid; i < 2 * CHUNK_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A3)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
     }
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
@@ -195,8 +209,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const int c = 4 * (lane & 15) + e; bo4[e] = c < D ? __ldg(P.b_out + 1 + c) : 0.0f; }
         unsigned char *stage0 = sm + OFF_H + warp * 4096, *stage1 = stage0 + CHUNK_BYTES;   // this warp's rows of H
+        if (P.cmma) {   // the partial-sum area is free in this mode: keep the output bias of the features there
+            if (tid < 64) s_part[tid] = tid < D ? __ldg(P.b_out + 1 + tid) : 0.0f;
+            named_bar_sync(1, N_EPI_WARPS * 32);
+        }
         float z_keep = 0.0f, zn_keep = 0.0f;
         long long grow_keep = -1;
+        // composite on the tensor cores: the per-ray sums of tile t are read back and written out one tile later
+        long long cm_tile = -1;      // tile whose sums are in flight (or -1)
+        long long cm_n = 0;          // composites handed to the MMA issuer so far
+        auto cm_finish = [&]() {     // all epilogue warps: wait for the sums of cm_tile; warp 0 writes them out
+            if (cm_tile < 0) return;
+            mbar_wait(BAR(BAR_D3), (uint32_t)((cm_n - 1) & 1));
+            tc_fence_after();
+            if (warp == 0) {
+                uint32_t xr[16];
+                tmem_ld16_issue(tmem_base + D3X_COL, xr);
+                tmem_ld_wait();
+                const long long ray = cm_tile * P.upt + lane;            // TMEM lane = ray of the tile
+                const bool live = lane < P.upt && ray < P.n_units;
+                const float wsum = __uint_as_float(xr[1]);
+                if (live) {
+                    const int nrgb = 3 * P.fp.nv_c;
+                    if (P.depth) P.depth[ray] = __uint_as_float(xr[0]);
+                    if (P.rgb_ray)
+                        for (int c = 0; c < nrgb; ++c)
+                            P.rgb_ray[ray * nrgb + c] = P.cfg.white_bkgd ? __uint_as_float(xr[2 + c]) + 1.0f - wsum : __uint_as_float(xr[2 + c]);
+                }
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
+                    uint32_t fr[32];
+                    tmem_ld32_issue(tmem_base + D3F_COL + hh * 32, fr);
+                    tmem_ld_wait();
+                    if (live && P.dino_ray) {
+                        if (D == 64) {           // one 256-byte row per ray: 128-bit stores, bias from shared memory
+                            const float4 *bo = reinterpret_cast<const float4 *>(s_part) + hh * 8;
+                            float4 *o = reinterpret_cast<float4 *>(P.dino_ray + ray * 64 + hh * 32);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b = bo[q];
+                                o[q] = make_float4(fmaf(b.x, wsum, __uint_as_float(fr[4 * q])), fmaf(b.y, wsum, __uint_as_float(fr[4 * q + 1])),
+                                                   fmaf(b.z, wsum, __uint_as_float(fr[4 * q + 2])), fmaf(b.w, wsum, __uint_as_float(fr[4 * q + 3])));
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (hh * 32 + c < D) P.dino_ray[ray * D + hh * 32 + c] = fmaf(s_part[hh * 32 + c], wsum, __uint_as_float(fr[c]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            cm_tile = -1;
+        };
         for (long long j = 0; j <= my_tiles; ++j) {
             if (j > 0) {
                 // ---------------- second epilogue of tile j-1 -----------------------------------------
@@ -287,6 +352,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         crgb[c] = (ok && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
                     const int ua = (warp * 32) / K, ub = (warp * 32 + 31) / K;   // rays this warp's rows belong to
                     const int my_u = row / K;
+                    if (P.cmma) {
+                        // ---- composite on the tensor cores: this row's values and weight go into the operands of
+                        //      out[ray][:] = sum_row Wt[ray][row] * V[row][:]; the MMA issuer does the rest ---------
+                        if (warp == 0) SD_TRACE(0, j, 5);
+                        cm_finish();                                   // the previous tile's operands have been consumed
+                        if (warp == 0) SD_TRACE(0, j, 6);
+                        unsigned char *brow = sm + OFF_B3 + row * 128;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {                  // 64 features (bias added at the output)
+                            uint4 o;
+                            o.x = ok ? pack_h2(v[8 * q + 0], v[8 * q + 1]) : 0u; o.y = ok ? pack_h2(v[8 * q + 2], v[8 * q + 3]) : 0u;
+                            o.z = ok ? pack_h2(v[8 * q + 4], v[8 * q + 5]) : 0u; o.w = ok ? pack_h2(v[8 * q + 6], v[8 * q + 7]) : 0u;
+                            *reinterpret_cast<uint4 *>(brow + ((q ^ (row & 7)) << 4)) = o;
+                        }
+                        {                                              // depth, 1 (sum of weights), colours
+                            float x[16];
+                            x[0] = ok ? z_keep : 0.0f; x[1] = ok ? 1.0f : 0.0f;
+#pragma unroll
+                            for (int c = 0; c < 14; ++c) x[2 + c] = c < 3 * MAX_NVC_TC ? crgb[c] : 0.0f;
+                            unsigned char *xrow = brow + CHUNK_BYTES;
+                            *reinterpret_cast<uint4 *>(xrow + ((0 ^ (row & 7)) << 4)) =
+                                make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
+                            *reinterpret_cast<uint4 *>(xrow + ((1 ^ (row & 7)) << 4)) =
+                                make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
+                        }
+                        const unsigned short wh = __half_as_ushort(__float2half_rn(wgt));
+                        for (int u = 0; u < P.upt; ++u)                // weight matrix: column = this row, row = ray of the tile
+                            *reinterpret_cast<unsigned short *>(sm + OFF_A3 + ((row >> 6) * TM + u) * 128 +
+                                                                ((((row & 63) >> 3) ^ (u & 7)) << 4) + (row & 7) * 2) =
+                                (u == my_u) ? wh : (unsigned short)0;
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive_warp(BAR(BAR_B3));
+                        if (warp == 0) SD_TRACE(0, j, 7);
+                        cm_tile = tile; ++cm_n;
+                        named_bar_sync(1, N_EPI_WARPS * 32);           // s_tails consumed before the next tile overwrites them
+                    } else {
 #pragma unroll 1
                     for (int seg = 0; seg < 2; ++seg) {
                         const int u = seg == 0 ? ua : ub;
@@ -352,6 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         }
                     }
                     named_bar_sync(1, N_EPI_WARPS * 32);   // partials / tails consumed before the next tile overwrites them
+                    }
                 }
             }
             if (warp == 0) SD_TRACE(0, j, 1);
@@ -392,6 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             mbar_arrive_warp(BAR(BAR_H));
             if (warp == 0) SD_TRACE(0, j, 4);
         }
+        cm_finish();                                                   // sums of the last tile
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
         if (lane == 0) {
@@ -406,6 +510,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     umma_ts(tmem_base + D2_COL, tmem_base + H_COL + k * 8,
                             umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
                 umma_commit(BAR(BAR_D2));
+            };
+            const uint32_t idesc3f = umma_idesc(TM, 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
+            auto composite = [&](long long jj) {   // per-ray sums of tile jj: Wt [128 x 128 rows] . V [128 rows x (64 | 16)]
+                mbar_wait(BAR(BAR_B3), (uint32_t)(jj & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t a = umma_desc(sm_u + OFF_A3 + (k >> 2) * CHUNK_BYTES + (k & 3) * 32);
+                    umma(tmem_base + D3F_COL, a, umma_desc_mn(sm_u + OFF_B3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
+                    umma(tmem_base + D3X_COL, a, umma_desc_mn(sm_u + OFF_B3 + CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
+                }
+                umma_commit(BAR(BAR_D3));
             };
             for (long long j = 0; j < my_tiles; ++j) {
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
@@ -428,9 +544,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 umma_commit(BAR(BAR_D1 + (int)(j & 1)));
                 SD_TRACE(1, j, 5);
                 if (j > 0) layer2(j - 1);
+                if (P.cmma && j > 1) composite(j - 2);
                 SD_TRACE(1, j, 7);
             }
             if (my_tiles > 0) layer2(my_tiles - 1);
+            if (P.cmma) {
+                if (my_tiles > 1) composite(my_tiles - 2);
+                if (my_tiles > 0) composite(my_tiles - 1);
+            }
         }
     } else if (warp < WARP_GA0) {
         // =================================== POINT WARPS ================================================
@@ -732,6 +853,7 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st, const vo
         last_dbg = P.dbg;
     }
     P.D = mlp->d_out - 1;
+    P.cmma = proj && P.mode == tc::MODE_RENDER && P.D <= 64;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
     static int sm_count = 0;
     if (sm_count == 0) {
