@@ -65,7 +65,7 @@ constexpr int OFF_CAM = OFF_EMPTY + 512;     // 21 floats per camera, 1 + 4 came
 constexpr int OFF_PART = OFF_CAM + 448;
 constexpr int OFF_TAILS = OFF_PART + 4 * 2 * PART_STRIDE * 4;
 constexpr int OFF_BAR = OFF_TAILS + 32;
-constexpr int NBAR = 2 * MAX_CHUNKS + 2 + 1 + 1 + 2 * NGEO + 1 + 2;
+constexpr int NBAR = 2 * MAX_CHUNKS + 2 + 1 + 1 + 2 * NGEO + 1 + 3;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
@@ -74,7 +74,7 @@ static_assert(OFF_BAR % 8 == 0 && OFF_PART % 16 == 0 && OFF_GEO % 16 == 0 && OFF
 
 enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 1,
        BAR_GEO_FULL = BAR_D2 + 1, BAR_GEO_EMPTY = BAR_GEO_FULL + NGEO, BAR_WLOAD = BAR_GEO_EMPTY + NGEO,
-       BAR_B3 = BAR_WLOAD + 1, BAR_D3 = BAR_B3 + 1 };
+       BAR_B3 = BAR_WLOAD + 1, BAR_D3 = BAR_B3 + 1, BAR_D3_READ = BAR_D3 + 1 };
 // Composite on the tensor cores (render mode on a projected scene, where layer 1 needs 3 of the 5 operand chunks):
 //   out[ray][col] = sum_row Wt[ray][row] * V[row][col],  V = (64 features | depth, 1, colours) of the tile's rows as fp16
 // Wt (A operand, K-major) lives in the two spare chunks of the W_in image, V (B operand, MN-major like the boxes of
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             mbar_init(BAR(BAR_GEO_EMPTY + s), N_GA_WARPS + N_EPI_WARPS);
         }
         mbar_init(BAR(BAR_WLOAD), 1);
-        mbar_init(BAR(BAR_B3), N_EPI_WARPS); mbar_init(BAR(BAR_D3), 1);
+        mbar_init(BAR(BAR_B3), N_EPI_WARPS); mbar_init(BAR(BAR_D3), 1); mbar_init(BAR(BAR_D3_READ), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (field) {
@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
     if (P.cmma) {   // rows of the weight operand beyond the rays of a tile are never written: keep them zero
         for (int i = tid; i < 2 * CHUNK_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A3)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
+        // the partial-sum area is free in this mode: keep the output bias of the features there
+        if (tid < 64) reinterpret_cast<float *>(sm + OFF_PART)[tid] = tid < P.D ? __ldg(P.b_out + 1 + tid) : 0.0f;
     }
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
@@ -209,62 +211,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const int c = 4 * (lane & 15) + e; bo4[e] = c < D ? __ldg(P.b_out + 1 + c) : 0.0f; }
         unsigned char *stage0 = sm + OFF_H + warp * 4096, *stage1 = stage0 + CHUNK_BYTES;   // this warp's rows of H
-        if (P.cmma) {   // the partial-sum area is free in this mode: keep the output bias of the features there
-            if (tid < 64) s_part[tid] = tid < D ? __ldg(P.b_out + 1 + tid) : 0.0f;
-            named_bar_sync(1, N_EPI_WARPS * 32);
-        }
+
         float z_keep = 0.0f, zn_keep = 0.0f;
         long long grow_keep = -1;
-        // composite on the tensor cores: the per-ray sums of tile t are read back and written out one tile later
-        long long cm_tile = -1;      // tile whose sums are in flight (or -1)
+        // composite on the tensor cores: the per-ray sums are read back and written out by point warp 3 (cm_output)
         long long cm_n = 0;          // composites handed to the MMA issuer so far
-        auto cm_finish = [&]() {     // all epilogue warps: wait for the sums of cm_tile; warp 0 writes them out
-            if (cm_tile < 0) return;
-            mbar_wait(BAR(BAR_D3), (uint32_t)((cm_n - 1) & 1));
-            tc_fence_after();
-            if (warp == 0) {
-                uint32_t xr[16];
-                tmem_ld16_issue(tmem_base + D3X_COL, xr);
-                tmem_ld_wait();
-                const long long ray = cm_tile * P.upt + lane;            // TMEM lane = ray of the tile
-                const bool live = lane < P.upt && ray < P.n_units;
-                const float wsum = __uint_as_float(xr[1]);
-                if (live) {
-                    const int nrgb = 3 * P.fp.nv_c;
-                    if (P.depth) P.depth[ray] = __uint_as_float(xr[0]);
-                    if (P.rgb_ray)
-                        for (int c = 0; c < nrgb; ++c)
-                            P.rgb_ray[ray * nrgb + c] = P.cfg.white_bkgd ? __uint_as_float(xr[2 + c]) + 1.0f - wsum : __uint_as_float(xr[2 + c]);
-                }
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
-                    uint32_t fr[32];
-                    tmem_ld32_issue(tmem_base + D3F_COL + hh * 32, fr);
-                    tmem_ld_wait();
-                    if (live && P.dino_ray) {
-                        if (D == 64) {           // one 256-byte row per ray: 128-bit stores, bias from shared memory
-                            const float4 *bo = reinterpret_cast<const float4 *>(s_part) + hh * 8;
-                            float4 *o = reinterpret_cast<float4 *>(P.dino_ray + ray * 64 + hh * 32);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 b = bo[q];
-                                o[q] = make_float4(fmaf(b.x, wsum, __uint_as_float(fr[4 * q])), fmaf(b.y, wsum, __uint_as_float(fr[4 * q + 1])),
-                                                   fmaf(b.z, wsum, __uint_as_float(fr[4 * q + 2])), fmaf(b.w, wsum, __uint_as_float(fr[4 * q + 3])));
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c)
-                                if (hh * 32 + c < D) P.dino_ray[ray * D + hh * 32 + c] = fmaf(s_part[hh * 32 + c], wsum, __uint_as_float(fr[c]));
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            cm_tile = -1;
-        };
         for (long long j = 0; j <= my_tiles; ++j) {
             if (j > 0) {
                 // ---------------- second epilogue of tile j-1 -----------------------------------------
+                // per-sample colours of this row (written by the point warps a tile ago): in flight during the wait
+                const int nrgb = 3 * P.fp.nv_c;
+                float crgb[3 * MAX_NVC_TC];
+#pragma unroll
+                for (int c = 0; c < 3 * MAX_NVC_TC; ++c)
+                    crgb[c] = (render && grow_keep >= 0 && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
                 mbar_wait(BAR(BAR_D2), (uint32_t)((j - 1) & 1));
                 tc_fence_after();
                 if (warp == 0) SD_TRACE(0, j, 0);
@@ -335,28 +295,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     }
                     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
                     if (lane == 0 || k_i == 0) excl = 1.0f;
-                    if (lane == 31) s_tails[warp] = incl;
+                    if (lane == 31) s_tails[(int)(j & 1) * 4 + warp] = incl;
                     named_bar_sync(1, N_EPI_WARPS * 32);
                     float carry = 1.0f;
-                    for (int prev = k_i - lane, w = warp - 1; prev > 0 && w >= 0; prev -= 32, --w) carry *= s_tails[w];
+                    for (int prev = k_i - lane, w = warp - 1; prev > 0 && w >= 0; prev -= 32, --w) carry *= s_tails[(int)(j & 1) * 4 + w];
                     const float wgt = ok ? alpha * (excl * carry) : 0.0f;
                     if (ok) {
                         if (P.weights) P.weights[grow_keep] = wgt;
                         if (P.alphas) P.alphas[grow_keep] = alpha;
                     }
                     // ---- weighted sums over the rows of each ray (nerf.py:393-405) ----------------------
-                    const int nrgb = 3 * P.fp.nv_c;
-                    float crgb[3 * MAX_NVC_TC];
-#pragma unroll
-                    for (int c = 0; c < 3 * MAX_NVC_TC; ++c)
-                        crgb[c] = (ok && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
                     const int ua = (warp * 32) / K, ub = (warp * 32 + 31) / K;   // rays this warp's rows belong to
                     const int my_u = row / K;
                     if (P.cmma) {
                         // ---- composite on the tensor cores: this row's values and weight go into the operands of
                         //      out[ray][:] = sum_row Wt[ray][row] * V[row][:]; the MMA issuer does the rest ---------
                         if (warp == 0) SD_TRACE(0, j, 5);
-                        cm_finish();                                   // the previous tile's operands have been consumed
+                        // the previous composite has consumed the operands and its sums have been read from TMEM
+                        if (cm_n > 0) mbar_wait(BAR(BAR_D3_READ), (uint32_t)((cm_n - 1) & 1));
                         if (warp == 0) SD_TRACE(0, j, 6);
                         unsigned char *brow = sm + OFF_B3 + row * 128;
 #pragma unroll
@@ -386,8 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         tc_fence_before();
                         mbar_arrive_warp(BAR(BAR_B3));
                         if (warp == 0) SD_TRACE(0, j, 7);
-                        cm_tile = tile; ++cm_n;
-                        named_bar_sync(1, N_EPI_WARPS * 32);           // s_tails consumed before the next tile overwrites them
+                        ++cm_n;                                        // (s_tails is double buffered: no barrier needed here)
                     } else {
 #pragma unroll 1
                     for (int seg = 0; seg < 2; ++seg) {
@@ -495,11 +450,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             mbar_arrive_warp(BAR(BAR_H));
             if (warp == 0) SD_TRACE(0, j, 4);
         }
-        cm_finish();                                                   // sums of the last tile
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
-        if (lane == 0) {
-            mbar_wait(BAR(BAR_WLOAD), 0);
+        // Lane 0 issues the MMAs.  In render mode on a projected scene the whole warp (its TMEM lanes are 0..31 = the rays
+        // of a tile) also reads the per-ray sums the composite MMAs leave in TMEM and writes them out.
+        {
+            if (lane == 0) mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc1 = umma_idesc(TM, 128), idesc2 = umma_idesc(TM, P.n2);
             auto layer2 = [&](long long jj) {
                 mbar_wait(BAR(BAR_H), (uint32_t)(jj & 1));
@@ -523,34 +479,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 }
                 umma_commit(BAR(BAR_D3));
             };
-            for (long long j = 0; j < my_tiles; ++j) {
-                const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
-                // the gather warps fence and arrive once per tile (FULL[0]) for all the chunks they fill -- every
-                // fence.proxy.async / mbarrier round trip queues behind their loads in the LSU --, the point warps
-                // arrive on FULL[nch-1] for the code chunk; the stages are still released one by one (EMPTY[c])
-                const int ngath = field ? P.nch - 1 : P.nch;
-                for (int c = 0; c < P.nch; ++c) {
-                    if (c == 0 || c == ngath) {
-                        mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
-                        tc_fence_after();
-                        SD_TRACE(1, j, c == 0 ? 0 : 4);
-                    }
+            auto cm_output = [&](long long jj) {
+                const float *s_bo = reinterpret_cast<const float *>(sm + OFF_PART);
+                const int D = P.D;
+                mbar_wait(BAR(BAR_D3), (uint32_t)(jj & 1));
+                tc_fence_after();
+                uint32_t xr[16], fr[64];
+                tmem_ld16_issue(tmem_base + D3X_COL, xr);
+                tmem_ld32_issue(tmem_base + D3F_COL, fr);
+                tmem_ld32_issue(tmem_base + D3F_COL + 32, fr + 32);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive_warp(BAR(BAR_D3_READ));                       // the accumulators may be overwritten
+                const int lane_ = lane;
+                const long long ray = (first + jj * stride) * P.upt + lane_;   // TMEM lane = ray of the tile
+                if (lane_ < P.upt && ray < P.n_units) {
+                    const float wsum = __uint_as_float(xr[1]);
+                    const int nrgb = 3 * P.fp.nv_c;
+                    if (P.depth) P.depth[ray] = __uint_as_float(xr[0]);
+                    if (P.rgb_ray)
+                        for (int c = 0; c < nrgb; ++c)
+                            P.rgb_ray[ray * nrgb + c] = P.cfg.white_bkgd ? __uint_as_float(xr[2 + c]) + 1.0f - wsum : __uint_as_float(xr[2 + c]);
+                    if (P.dino_ray) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
+                        if (D == 64) {
+                            float4 *o = reinterpret_cast<float4 *>(P.dino_ray + ray * 64);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
-                             umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
-                    umma_commit(BAR(BAR_EMPTY + c));
+                            for (int q = 0; q < 16; ++q) {
+                                const float4 b = reinterpret_cast<const float4 *>(s_bo)[q];
+                                o[q] = make_float4(fmaf(b.x, wsum, __uint_as_float(fr[4 * q])), fmaf(b.y, wsum, __uint_as_float(fr[4 * q + 1])),
+                                                   fmaf(b.z, wsum, __uint_as_float(fr[4 * q + 2])), fmaf(b.w, wsum, __uint_as_float(fr[4 * q + 3])));
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 64; ++c)
+                                if (c < D) P.dino_ray[ray * D + c] = fmaf(s_bo[c], wsum, __uint_as_float(fr[c]));
+                        }
+                    }
                 }
-                umma_commit(BAR(BAR_D1 + (int)(j & 1)));
-                SD_TRACE(1, j, 5);
-                if (j > 0) layer2(j - 1);
-                if (P.cmma && j > 1) composite(j - 2);
-                SD_TRACE(1, j, 7);
+            };
+            for (long long j = 0; j < my_tiles; ++j) {
+                if (lane == 0) {
+                    const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
+                    // the gather warps fence and arrive once per tile (FULL[0]) for all the chunks they fill -- every
+                    // fence.proxy.async / mbarrier round trip queues behind their loads in the LSU --, the point warps
+                    // arrive on FULL[nch-1] for the code chunk; the stages are still released one by one (EMPTY[c])
+                    const int ngath = field ? P.nch - 1 : P.nch;
+                    for (int c = 0; c < P.nch; ++c) {
+                        if (c == 0 || c == ngath) {
+                            mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
+                            tc_fence_after();
+                            SD_TRACE(1, j, c == 0 ? 0 : 4);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
+                                 umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
+                        umma_commit(BAR(BAR_EMPTY + c));
+                    }
+                    umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                    SD_TRACE(1, j, 5);
+                    if (P.cmma && j > 1) composite(j - 2);     // its operands were written a tile ago
+                    if (j > 0) layer2(j - 1);
+                    SD_TRACE(1, j, 7);
+                }
+                __syncwarp();
+                if (P.cmma && j > 1) cm_output(j - 2);
             }
-            if (my_tiles > 0) layer2(my_tiles - 1);
-            if (P.cmma) {
-                if (my_tiles > 1) composite(my_tiles - 2);
-                if (my_tiles > 0) composite(my_tiles - 1);
+            if (lane == 0) {
+                if (P.cmma && my_tiles > 1) composite(my_tiles - 2);
+                if (my_tiles > 0) layer2(my_tiles - 1);
+            }
+            __syncwarp();
+            if (P.cmma && my_tiles > 1) cm_output(my_tiles - 2);
+            if (P.cmma && my_tiles > 0) {
+                if (lane == 0) composite(my_tiles - 1);
+                __syncwarp();
+                cm_output(my_tiles - 1);
             }
         }
     } else if (warp < WARP_GA0) {
