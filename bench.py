@@ -188,9 +188,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
-    if os.environ.get("SD_BENCH_WATCHDOG"):      # debugging aid: Python stacks of a run that takes too long
+    # a run that takes absurdly long dumps its Python stacks and exits instead of hanging its caller (seconds;
+    # SD_BENCH_WATCHDOG=0 switches it off)
+    wd = float(os.environ.get("SD_BENCH_WATCHDOG", "900"))
+    if wd > 0:
         import faulthandler
-        faulthandler.dump_traceback_later(float(os.environ["SD_BENCH_WATCHDOG"]), exit=True)
+        faulthandler.dump_traceback_later(wd, exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

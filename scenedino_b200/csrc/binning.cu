@@ -231,9 +231,9 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     unsigned short *bins = reinterpret_cast<unsigned short *>(ws);           ws += a256((size_t)N * 2);
     unsigned short *pcb = reinterpret_cast<unsigned short *>(ws);            ws += a256((size_t)N * 2);
     unsigned int *hist = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
+    unsigned int *meta = reinterpret_cast<unsigned int *>(ws);               ws += 256;   // right behind hist: one memset
     unsigned int *cidx = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
     unsigned int *cbin = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
-    unsigned int *meta = reinterpret_cast<unsigned int *>(ws);                                        ws += 256;
     GeoOut go = {};
     go.rec = reinterpret_cast<GeoRec *>(ws);                                                           ws += a256((size_t)N * sizeof(GeoRec));
     TileInfo *tiles = reinterpret_cast<TileInfo *>(ws);
@@ -253,8 +253,8 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     const long long blocks_wanted = (N + 4 * BIN_THREADS - 1) / (4 * BIN_THREADS);
     const unsigned grid = (unsigned)(blocks_wanted < 4 * sm_count ? blocks_wanted : 4 * sm_count);
     const unsigned grid2 = (unsigned)(blocks_wanted < 2 * sm_count ? blocks_wanted : 2 * sm_count);
-    SD_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)g.nbins * 4, st));
-    SD_CUDA_OK(cudaMemsetAsync(meta, 0, 256, st));            // meta[1]: tile counter of the tile kernel
+    // histogram and meta (meta[1]: tile counter of the tile kernel) in one go
+    SD_CUDA_OK(cudaMemsetAsync(hist, 0, a256((size_t)g.nbins * 4) + 256, st));
     bin_count_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist);
     SD_LAUNCH_OK("bin_count_kernel");
     bin_scan_kernel<<<1, 1024, (size_t)g.nbins * 8, st>>>(hist, g.nbins, cidx, cbin, meta);

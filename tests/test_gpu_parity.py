@@ -171,6 +171,42 @@ def test_query_points_projected(golden, tag, learn_empty):
     assert_close(g2n(q["dino"]), g2n(q2["dino"]), TOL_F16, "tile kernel vs gather kernel")
 
 
+@pytest.mark.parametrize("Hf,Wf,d_out,nv_c", [(9, 13, 65, 0), (16, 8, 33, 2), (50, 300, 65, 4), (7, 7, 2, 1)])
+def test_tile_kernel_shapes(Hf, Wf, d_out, nv_c):
+    """Tile kernel on awkward shapes: maps smaller than / not a multiple of the 7-texel bins (TMA boxes hang over the
+    border), narrow heads (D < 64: the per-thread output path; D = 1), 0 to 4 colour views, a ragged last tile."""
+    from scenedino_b200 import _abi
+    C_ = 256
+    feat = syn.make_feature_map(21, C_, Hf, Wf)
+    nvc = max(nv_c, 1)
+    imgs = syn.make_images(22, nvc, 24, 40)
+    K = np.broadcast_to(syn.kitti360_K(), (nvc, 3, 3)).copy()
+    c2w = np.stack([syn.view_pose_c2w(v) for v in range(nvc)])
+    w2c = np.linalg.inv(c2w.astype(np.float64)).astype(np.float32)
+    mlp_w = syn.make_mlp(4, 295, 128, d_out, bias_scale=0.1)
+    pts = syn.random_points(9, 65536 + 321)
+    if nv_c:
+        osc = O.Scene(feat=feat, K_f=K[:1], w2c_f=w2c[:1], rgb=imgs, K_c=K, w2c_c=w2c)
+        dsc = ops.Scene.from_arrays(feat, K[:1], w2c[:1], imgs, K, w2c, device=DEV, feat_dtype=torch.float16)
+    else:
+        osc = O.Scene(feat=feat, K_f=K[:1], w2c_f=w2c[:1])
+        dsc = ops.Scene.from_arrays(feat, K[:1], w2c[:1], device=DEV, feat_dtype=torch.float16)
+    dmlp = ops.Mlp(*mlp_w, device=DEV)
+    dscp = dsc.project(dmlp)
+    n0 = _abi.launch_count()
+    q = ops.query_points(dscp, dmlp, dev(pts), precision=ops.F16, want_rgb=nv_c > 0)
+    assert _abi.launch_count() - n0 == 5, "expected the texel sort + the tile kernel"
+    o = O.query_points(osc, O.Mlp(*mlp_w), pts, want_rgb=nv_c > 0)
+    assert q["dino"].shape == (len(pts), d_out - 1)
+    assert np.array_equal(g2n(q["invalid_features"]), o["invalid_features"])
+    assert_close(g2n(q["sigma"]), o["sigma"], TOL_F16, "sigma")
+    if d_out > 1 + 0:
+        assert_close(g2n(q["dino"]), o["dino"], TOL_F16, "dino")
+    if nv_c:
+        assert np.array_equal(g2n(q["rgb"]), o["rgb"]) and np.array_equal(g2n(q["invalid"]), o["invalid"])
+    assert torch.isfinite(q["sigma"]).all() and torch.isfinite(q["dino"]).all()
+
+
 @pytest.mark.parametrize("precision,tol", [(ops.FP32, TOL_FP32), (ops.F16, TOL_F16)])
 @pytest.mark.parametrize("d_in,d_out,n", [(295, 65, 1000), (295, 769, 300), (64, 768, 257), (40, 3, 65), (312, 33, 129)])
 def test_mlp_forward(precision, tol, d_in, d_out, n):
