@@ -322,17 +322,19 @@ def main():
         fence()
         ms = e0.elapsed_time(e1)
         kernel_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in k_events]))
-        # keep the sampler alive long enough to see the load on very short runs
-        t_end = time.time() + max(0.0, 0.6 - ms / 1e3)
-        while time.time() < t_end:
+        launches = _abi.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        # keep the sampler alive long enough to see the load on very short runs.  The number of extra steps comes from
+        # the agreed (max-over-ranks) time, so that every rank issues the same number of all-gathers: a time-based loop
+        # here made ranks disagree and hang now and then.
+        n_extra = int(max(0.0, 0.6 - ms / 1e3) / max(ms / args.steps / 1e3, 1e-6))
+        for _ in range(n_extra):
             step()
-        torch.cuda.synchronize()
-    launches = _abi.launch_count() - n0
+        fence()
     note("timed region done")
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_step = ms / args.steps
     value = world * N / (ms_step * 1e-3)
 
