@@ -162,7 +162,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ssc_voxel_query_throughput", "value": v, "unit": "voxels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": GRID[0] * GRID[1] * GRID[2] / v * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config("fp32"), "cpu_baseline": last,
+            "config": workload_config("fp16"), "cpu_baseline": last,
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -175,7 +175,8 @@ def workload_config(precision):
                      else "fp32 CUDA-core parity path"),
             "voxels_per_step": GRID[0] * GRID[1] * GRID[2], "feature_map": [C_FEAT, HF, WF],
             "mlp": [D_IN, D_HID, D_OUT],
-            "l2": "working set per step (map + 25 MB points + 545 MB outputs) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "working set per step (map + 25 MB points + 545 MB outputs) exceeds the 126 MB L2; no explicit flush",
+            "launch": "one CUDA-graph replay per step (memset + 4 sort kernels + field kernel)" if precision == "fp16" else "direct calls"}
 
 
 def main():
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time direct library calls instead of CUDA-graph replays")
     args = ap.parse_args()
     # a run that takes absurdly long dumps its Python stacks and exits instead of hanging its caller (seconds;
     # SD_BENCH_WATCHDOG=0 switches it off)
@@ -290,8 +292,11 @@ def main():
     done_c = [torch.cuda.Event() for _ in range(NB)]      # all-gather reading buffer b finished
     state = {"i": 0}
 
-    # CUDA events recorded by the library around the dominant kernel of each timed step (sd_profile_next_kernel)
+    # CUDA events recorded by the library around the dominant kernel (sd_profile_next_kernel): a few direct calls before
+    # the timed region give the kernel's own duration for the roofline
     k_events = []
+    # the timed steps replay a CUDA graph of the query (one launch instead of seven per step), one graph per output buffer
+    graphs = [ops.QueryGraph(scene, mlp, pts, outs[i]) for i in range(NB)] if args.precision == "fp16" and not args.no_graph else None
 
     def step(timed=False):
         b = state["i"] % NB
@@ -303,7 +308,10 @@ def main():
             ka.record(); kb.record()                                # materialise the handles
             _abi.check(_abi.lib().sd_profile_next_kernel(ka.cuda_event, kb.cuda_event), "sd_profile_next_kernel")
             k_events.append((ka, kb))
-        ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[b])
+        if graphs is not None and not timed:
+            graphs[b].replay()
+        else:
+            ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[b])
         if world > 1:
             done_k[b].record()
             with torch.cuda.stream(comm):
@@ -331,20 +339,26 @@ def main():
     for _ in range(args.warmup):
         step()
     fence()
+    for _ in range(5):                 # direct calls with the kernel-timing hook (not part of the timed region)
+        step(timed=True)
+    fence()
+    kernel_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in k_events]))
     note("warm-up done")
     n0 = _abi.launch_count()
+    replays0 = state["i"]
     with Clocks(local) as clk:
         fence()
         e0.record()
         for _ in range(args.steps):
-            step(timed=True)
+            step()
         if world > 1:
             torch.cuda.current_stream().wait_stream(comm)
         e1.record()
         fence()
         ms = e0.elapsed_time(e1)
-        kernel_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in k_events]))
         launches = _abi.launch_count() - n0
+        if graphs is not None:         # kernels inside the replayed graphs (the library counts launches at capture time only)
+            launches += (state["i"] - replays0) * graphs[0].launches
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

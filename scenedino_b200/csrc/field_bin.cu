@@ -13,15 +13,24 @@
 // coordinate hi/lo split, the bias and the learn_empty replacement go through a 48-wide K block as before;
 // layer 2 reads the ReLU'd hidden tile from TMEM, written in place over the layer-1 accumulator.
 //
-// Warp roles (10 warps, one persistent CTA per SM):
-//   warps 0-3  epilogue: layer-1 accumulator -> ReLU -> fp16 -> same TMEM columns (A operand of layer 2);
-//              layer-2 accumulator -> softplus density + features, staged through shared memory, coalesced stores
-//   warp  4    tcgen05.mma issuer + TMEM owner
-//   warp  5    TMA producer: one 8x8x128-channel box of P per chunk
-//   warps 6-9  one thread per row: point -> projection, mask, tap, colours, weights into the chunk's A operand
-//              (an undo log keeps the rest of the operand zero), positional code -> code operand
-// Rings: 2 weight (A) chunks and 4 box (B) chunks released by tcgen05.commit, 2 code operands, layer-1 and layer-2
-// accumulators double buffered in TMEM.
+// Per query the sort (binning.cu) leaves, at each point's SORTED position, a 32-byte record (coordinates, weights, point
+// index, bin) and, per 128-point tile, a table entry (rows, bins it touches).  This kernel never projects a point and in
+// steady state issues no global load through the load/store unit.
+//
+// Warp roles (15 warps, one persistent CTA per SM):
+//   warps 0-3    epilogue 1: layer-1 accumulator -> ReLU (in the fp32->fp16 conversion) -> same TMEM columns (A of layer 2)
+//   warps 4-7    epilogue 2: layer-2 accumulator -> softplus density + features, transposed through shared memory, coalesced
+//                128-bit stores to the rows the perm ring names
+//   warp  8      layer-1 MMA issuer + TMEM owner (per chunk 4 MMAs with an MN-major B descriptor, then 3 for the code block)
+//   warp  9      layer-2 MMA issuer (8 TS-form MMAs + 1 for the bias block)
+//   warp  10     producer: claims tiles (atomic, 4 per claim, last tile first), bulk-copies table entries and each tile's 4 KB
+//                record block into rings, issues the TMA boxes
+//   warps 11-14  one thread per row: weights into the chunk's A operand (an undo log keeps the rest of it zero), positional
+//                code -> code operand, point index -> perm ring
+// Rings: 2 weight chunks, 4 box chunks, 2 code operands, 3 record blocks, 8 perm blocks; layer-1 and layer-2 accumulators
+// double buffered in TMEM.  Protocol rules (each was a deadlock first): an mbarrier parity wait tells apart only adjacent
+// phases, so a role that skips ring positions still waits on each of them, and the closing arrivals at the end of the tile
+// stream wait for the same conditions a real tile would.  DESIGN.md section 3.3 has the measurements behind the layout.
 #include <cuda.h>
 
 #include <cstdio>
