@@ -171,6 +171,32 @@ def test_query_points_projected(golden, tag, learn_empty):
     assert_close(g2n(q["dino"]), g2n(q2["dino"]), TOL_F16, "tile kernel vs gather kernel")
 
 
+def test_query_graph_replay_matches_direct_calls(golden):
+    """ops.QueryGraph: the captured query gives the direct call's bits, and follows the CONTENTS of its input buffer."""
+    g = golden("query")
+    _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=torch.float16)
+    dscp = dsc.project(dmlp)
+    pts = dev(syn.random_points(11, 70001))
+    ref = ops.query_points(dscp, dmlp, pts, want_rgb=False, precision=ops.F16)
+    out = dict(sigma=torch.empty_like(ref["sigma"]), dino=torch.empty_like(ref["dino"]),
+               invalid_features=torch.empty(len(pts), dtype=torch.uint8, device=DEV))
+    qg = ops.QueryGraph(dscp, dmlp, pts, out, precision=ops.F16)
+    assert qg.launches == 5
+    for k in out:
+        if not k.startswith("_"):
+            out[k].zero_()
+    qg.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["sigma"], ref["sigma"]) and torch.equal(out["dino"], ref["dino"])
+    assert torch.equal(out["invalid_features"].view(torch.bool), ref["invalid_features"])
+    pts2 = dev(syn.random_points(12, 70001))
+    ref2 = ops.query_points(dscp, dmlp, pts2, want_rgb=False, precision=ops.F16)
+    pts.copy_(pts2)
+    qg.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["sigma"], ref2["sigma"]) and torch.equal(out["dino"], ref2["dino"])
+
+
 @pytest.mark.parametrize("Hf,Wf,d_out,nv_c", [(9, 13, 65, 0), (16, 8, 33, 2), (50, 300, 65, 4), (7, 7, 2, 1)])
 def test_tile_kernel_shapes(Hf, Wf, d_out, nv_c):
     """Tile kernel on awkward shapes: maps smaller than / not a multiple of the 7-texel bins (TMA boxes hang over the
