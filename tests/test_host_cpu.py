@@ -52,6 +52,25 @@ def test_argument_validation_without_gpu():
     assert lib.sd_mlp_pack_bytes(295, 128, 65) > 4 * (295 * 128 + 128 * 65)
     assert lib.sd_mlp_pack_bytes(0, 128, 65) == 0
     assert lib.sd_render_workspace_bytes(None, None, 10, 10) == 0
+    # projected scene: sizes are host arithmetic (header of operand images + 256 B per texel), errors are loud
+    sc = _abi.SdScene()
+    sc.Hf, sc.Wf, sc.C, sc.nv_f = 384, 1280, 256, 1
+    assert lib.sd_field_project_bytes(ctypes.byref(sc)) == 50176 + 384 * 1280 * 256
+    assert lib.sd_field_project_bytes(None) == 0
+    ml = _abi.SdMlp()
+    assert lib.sd_field_project(ctypes.byref(sc), ctypes.byref(ml), None, 0, None) == -1 and "null" in _abi.last_error()
+    buf = ctypes.create_string_buffer(2048)
+    assert lib.sd_field_project(ctypes.byref(sc), ctypes.byref(ml), buf, 2048, None) == -1   # no fp16 map in the scene
+    assert lib.sd_profile_next_kernel(None, None) == 0
+    # the sort's scratch grows with the points: 4 + 2 + 2 B of indices, a 32-byte record, a 16-byte entry per 128-point tile
+    sc.feat_dtype = _abi.SD_F16
+    ml.d_in, ml.d_hidden, ml.d_out, ml.precision = 295, 128, 65, _abi.SD_MLP_F16_TC
+    n = 1 << 21
+    need = lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), n)
+    assert n * (4 + 2 + 2 + 32) + (n // 128) * 16 <= need <= n * 41 + (1 << 20)
+    assert lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), 1000) == 0        # small queries are not sorted
+    ml.precision = _abi.SD_MLP_FP32
+    assert lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), n) == 0           # nor is the fp32 path
 
 
 def _net(conf_extra=None):
