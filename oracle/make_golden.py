@@ -141,6 +141,37 @@ def golden_query(ref):
     print("query.npz:", {k: v.shape for k, v in out.items()})
 
 
+def golden_query_big(ref):
+    """A query big enough for the texel sort + projected-map tile kernel (>= 65 536 points): the reference's outputs for a
+    strided subset of 70 001 points (regenerated from their seed by the test), the frustum mask for all of them."""
+    nv_c = 2
+    feat, imgs, K, c2w = scene_inputs(nv_c)
+    mlp = syn.make_mlp(MLP_SEED, bias_scale=0.1)
+    expand = syn.make_expand(EXP_SEED)
+    n_pts, pts_seed, stride = 70001, 41, 35
+    pts = syn.random_points(pts_seed, n_pts)
+    sub = np.arange(0, n_pts, stride)
+    out = {}
+    for tag, learn_empty in (("", False), ("_le", True)):
+        empty = np.random.RandomState(31).standard_normal(C).astype(np.float32) if learn_empty else None
+        net = build_net(ref, feat, mlp, expand, learn_empty, empty)
+        encode(net, imgs, K, c2w, [0, 1])
+        with torch.no_grad():
+            rgb, invalid, sigma, extras, sd = net(t(pts)[None])
+        if learn_empty:
+            out["empty_feature"] = empty
+        out.update({
+            "sigma" + tag: sigma[0, sub, 0].numpy(),
+            "dino" + tag: sd["dino_features"][0, sub].numpy(),
+            "invalid_features" + tag: np.packbits(sd["invalid_features"][0, :, 0].numpy()),
+        })
+    out.update(n_pts=np.array(n_pts), pts_seed=np.array(pts_seed), stride=np.array(stride), pts_checksum=checksum(pts),
+               K=K[0], c2w=c2w[0], w_in=mlp[0], b_in=mlp[1], w_out=mlp[2], b_out=mlp[3],
+               feat_checksum=checksum(feat), img_checksum=checksum(imgs), shape=np.array([C, HF, WF, HC, WC, nv_c]))
+    np.savez_compressed(os.path.join(OUT, "query_big.npz"), **out)
+    print("query_big.npz:", {k: v.shape for k, v in out.items()})
+
+
 def pick_rays(c2w_list, K, n_each, seed):
     rs = np.random.RandomState(seed)
     rays = []
@@ -253,9 +284,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = ref_shim.import_reference()
-    golden_query(ref)
-    golden_render(ref)
-    golden_superbatch(ref)
+    only = sys.argv[1:]          # e.g. `python oracle/make_golden.py query_big` regenerates one fixture
+    jobs = {"query": golden_query, "query_big": golden_query_big, "render": golden_render, "superbatch": golden_superbatch}
+    for name, fn in jobs.items():
+        if not only or name in only:
+            fn(ref)
 
 
 if __name__ == "__main__":

@@ -43,3 +43,11 @@ def golden_scene_arrays(g, n=1):
 
 def w2c_of(c2w):
     return np.linalg.inv(c2w.astype(np.float64)).astype(np.float32)
+
+
+def big_query_points(g):
+    """Regenerates the points of the query_big fixture from their seed and checks their checksum."""
+    pts = syn.random_points(int(g["pts_seed"]), int(g["n_pts"]))
+    np.testing.assert_allclose(checksum(pts), g["pts_checksum"], rtol=1e-12)
+    sub = np.arange(0, len(pts), int(g["stride"]))
+    return pts, sub

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import TOL_F16, TOL_FP32, assert_close, golden_scene_arrays
+from helpers import TOL_F16, TOL_FP32, assert_close, big_query_points, golden_scene_arrays
 from oracle import oracle as O
 from scenedino_b200 import ops
 from scenedino_b200 import synthetic as syn
@@ -169,6 +169,25 @@ def test_query_points_projected(golden, tag, learn_empty):
     q2 = ops.query_points(dsc, dmlp, dev(pts), precision=ops.F16)
     assert torch.equal(q2["invalid_features"], q["invalid_features"]) and torch.equal(q2["rgb"], q["rgb"])
     assert_close(g2n(q["dino"]), g2n(q2["dino"]), TOL_F16, "tile kernel vs gather kernel")
+
+
+@pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
+def test_tile_kernel_vs_reference_big(golden, tag, learn_empty):
+    """The texel sort + tile kernel against the REFERENCE's own outputs on a 70 001-point query (fixture query_big,
+    oracle/make_golden.py): frustum mask of every point bit-exact, densities / features of the stored subset within 2e-2."""
+    from scenedino_b200 import _abi
+    g = golden("query_big")
+    kw = dict(learn_empty=learn_empty, empty_feature=g["empty_feature"] if learn_empty else None)
+    _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=torch.float16, **kw)
+    dscp = dsc.project(dmlp)
+    pts, sub = big_query_points(g)
+    n0 = _abi.launch_count()
+    q = ops.query_points(dscp, dmlp, dev(pts), want_rgb=False, precision=ops.F16)
+    assert _abi.launch_count() - n0 == 5
+    inv = np.unpackbits(g["invalid_features" + tag])[:len(pts)].astype(bool)
+    assert np.array_equal(g2n(q["invalid_features"]), inv)
+    assert_close(g2n(q["sigma"])[sub], g["sigma" + tag], TOL_F16, "sigma vs reference")
+    assert_close(g2n(q["dino"])[sub], g["dino" + tag], TOL_F16, "dino vs reference")
 
 
 def test_query_graph_replay_matches_direct_calls(golden):

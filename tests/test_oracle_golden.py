@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import TOL_FP32, assert_close, golden_scene_arrays, rel_err
+from helpers import TOL_FP32, assert_close, big_query_points, golden_scene_arrays, rel_err
 from oracle import oracle as O
 
 
@@ -65,6 +65,21 @@ def _check_pass(o, g, prefix, tol=TOL_FP32):
     assert_close(o["rgb"], g[prefix + "rgb"].reshape(R, -1), tol, prefix + "rgb")
     assert_close(o["dino_features"], g[prefix + "dino_features"].reshape(R, -1), tol, prefix + "dino")
     assert np.array_equal(o["invalid"], g[prefix + "invalid"].reshape(R, K, -1))
+
+
+@pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
+def test_query_points_big(golden, tag, learn_empty):
+    """70 001 points (the size class that takes the texel sort + tile kernel on the GPU): mask of every point bit-exact,
+    densities / features of the stored subset within the fp32 bar."""
+    g = golden("query_big")
+    feat, imgs = golden_scene_arrays(g)
+    pts, sub = big_query_points(g)
+    kw = dict(learn_empty=learn_empty, empty_feature=g["empty_feature"] if learn_empty else None)
+    o = O.query_points(_scene(g, feat, imgs, **kw), _mlp(g), pts, want_rgb=False)
+    inv = np.unpackbits(g["invalid_features" + tag])[:len(pts)].astype(bool)
+    assert np.array_equal(o["invalid_features"], inv)
+    assert_close(o["sigma"][sub], g["sigma" + tag], TOL_FP32, "sigma")
+    assert_close(o["dino"][sub], g["dino" + tag], TOL_FP32, "dino")
 
 
 def test_render_coarse(golden):
