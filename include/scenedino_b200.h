@@ -145,6 +145,15 @@ int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, 
                     float *sigma, float *dino, float *rgb, float *invalid,
                     unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same query when the points and the cameras have not changed since an earlier sd_query_points call that used this
+ * workspace (the SSC evaluation queries one fixed voxel grid frame after frame, sscbench/evaluate_model_sscbench.py:
+ * 270-279): the texel sort is reused, only the tile kernel runs -- on the scene's CURRENT feature map / projection.
+ * Needs a projected scene and SD_MLP_F16_TC.  The frustum mask (invalid_feat) of the earlier call stays valid and is
+ * not rewritten. */
+int sd_query_points_sorted(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                           float *sigma, float *dino, float *rgb, float *invalid, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
 /* ---- NeRFRenderer sampling (renderer/nerf.py:121-228) --------------------------------------- */
 /* sample_coarse (nerf.py:121-141).  u [R,Kc] = torch.rand_like draw, lin [Kc] = torch.linspace. */
 int sd_sample_coarse(const float *rays, long long R, int r_dim, const float *u, const float *lin,

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "sd_mlp_forward": (_I, [_ML, _P, _LL, _P, _P]),
     "sd_query_workspace_bytes": (_SZ, [_SC, _ML, _LL]),
     "sd_query_points": (_I, [_SC, _ML, _P, _LL, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "sd_query_points_sorted": (_I, [_SC, _ML, _P, _LL, _P, _P, _P, _P, _P, _SZ, _P]),
     "sd_sample_coarse": (_I, [_P, _LL, _I, _P, _P, _I, _I, _P, _P]),
     "sd_sample_fine": (_I, [_P, _LL, _I, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "sd_sample_fine_depth": (_I, [_P, _LL, _I, _P, _P, _I, _F, _P, _P]),

@@ -73,9 +73,28 @@ extern "C" size_t sd_query_workspace_bytes(const sd_scene *scene, const sd_mlp *
     return bin_workspace_bytes(scene->Hf, scene->Wf, N);
 }
 
+static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                             float *sigma, float *dino, float *rgb, float *invalid,
+                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted);
+
 extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                                float *sigma, float *dino, float *rgb, float *invalid,
                                unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream) {
+    return query_points_impl(scene, mlp, xyz, N, sigma, dino, rgb, invalid, invalid_feat, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int sd_query_points_sorted(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                                      float *sigma, float *dino, float *rgb, float *invalid, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+    SD_REQUIRE(scene && mlp && scene->feat_proj && mlp->precision == SD_MLP_F16_TC && workspace &&
+                   sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
+               "sd_query_points_sorted: needs a projected scene, SD_MLP_F16_TC and the workspace of an earlier sd_query_points call");
+    return query_points_impl(scene, mlp, xyz, N, sigma, dino, rgb, invalid, nullptr, workspace, workspace_bytes, stream, true);
+}
+
+static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
+                             float *sigma, float *dino, float *rgb, float *invalid,
+                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted) {
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
@@ -93,7 +112,9 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
             // leaves the per-point geometry (coordinates, bilinear weights, frustum mask) at the sorted positions
             const bool tile = scene->feat_proj && bin_kernel_supported(scene, mlp) &&
                               N >= 16ll * ((scene->Wf - 1) / SD_BIN + 1) * ((scene->Hf - 1) / SD_BIN + 1);
-            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream, tile, tile ? invalid_feat : nullptr);
+            SD_REQUIRE(tile || !reuse_sorted, "sd_query_points_sorted: this query does not take the sorted tile path");
+            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream, tile,
+                                   tile ? invalid_feat : nullptr, reuse_sorted);
             if (rc) return rc;
             if (tile && order.has_geo) return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
         }

@@ -218,7 +218,7 @@ size_t bin_workspace_bytes(int Hf, int Wf, long long N) {
 
 // Sorts the point indices by bin.  Fills `out` with device pointers into the workspace.
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      BinOrder *out, cudaStream_t st, bool want_geo, unsigned char *invalid_feat) {
+                      BinOrder *out, cudaStream_t st, bool want_geo, unsigned char *invalid_feat, bool reuse_sorted) {
     const size_t need = bin_workspace_bytes(fp.Hf, fp.Wf, N);
     if (need == 0 || workspace_bytes < need || !workspace) {
         set_error("binning: workspace of %zu B needed, %zu B given", need, workspace_bytes);
@@ -249,6 +249,15 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+    }
+    if (reuse_sorted) {
+        // the workspace still holds the sort of these points for these cameras (sd_query_points_sorted): only the tile
+        // counter has to start from zero again
+        SD_REQUIRE(want_geo && g.bw == SD_BIN, "binning: nothing to reuse for this map size");
+        SD_CUDA_OK(cudaMemsetAsync(meta, 0, 256, st));
+        out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
+        out->has_geo = true; out->rec = go.rec; out->tile_ctr = meta + 1; out->tiles = tiles;
+        return SD_OK;
     }
     const long long blocks_wanted = (N + 4 * BIN_THREADS - 1) / (4 * BIN_THREADS);
     const unsigned grid = (unsigned)(blocks_wanted < 4 * sm_count ? blocks_wanted : 4 * sm_count);

@@ -99,7 +99,8 @@ struct BinOrder {
 };
 size_t bin_workspace_bytes(int Hf, int Wf, long long N);
 int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void *workspace, size_t workspace_bytes,
-                      BinOrder *out, cudaStream_t st, bool want_geo = false, unsigned char *invalid_feat = nullptr);
+                      BinOrder *out, cudaStream_t st, bool want_geo = false, unsigned char *invalid_feat = nullptr,
+                      bool reuse_sorted = false);
 // ---- projected scene (field_proj.cu): blob layout -----------------------------------------------------------
 constexpr int PROJ_OFF_IDENT = 0;          // 2 x 16 KB: UMMA image of the 128 x 128 identity
 constexpr int PROJ_OFF_CODE = 32768;       // 16 KB: UMMA image of the code block of W_in (+ projected empty feature in column 47)

@@ -212,6 +212,22 @@ def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out
     return res
 
 
+def query_points_sorted(scene: Scene, mlp: Mlp, xyz, out: dict):
+    """The query again for unchanged points and cameras (sd_query_points_sorted): reuses the texel sort left in
+    ``out["_workspace"]`` by an earlier ``query_points(..., out=out)``; only the tile kernel runs."""
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    ws = out.get("_workspace")
+    if ws is None:
+        raise ValueError("query_points_sorted needs the `out` dict of an earlier query_points call (its workspace)")
+    sc, m = scene.c(), mlp.c(F16)
+    _abi.check(_abi.lib().sd_query_points_sorted(C.byref(sc), C.byref(m), _ptr(xyz), xyz.shape[0], _ptr(out["sigma"]),
+                                                 _ptr(out["dino"]), _ptr(out.get("rgb")), _ptr(out.get("invalid")),
+                                                 _ptr(ws), ws.numel(), _stream()), "sd_query_points_sorted")
+    res = {k: v for k, v in out.items() if not k.startswith("_")}
+    res["invalid_features"] = out["invalid_features"].view(torch.bool)
+    return res
+
+
 class QueryGraph:
     """One point query (fixed scene, head, points and output buffers) captured into a CUDA graph: replaying it costs one
     launch instead of seven (the sort's memset and four kernels, the field kernel) -- for callers that query the same

@@ -190,6 +190,31 @@ def test_tile_kernel_vs_reference_big(golden, tag, learn_empty):
     assert_close(g2n(q["dino"])[sub], g["dino" + tag], TOL_F16, "dino vs reference")
 
 
+def test_query_points_sorted_reuses_the_sort(golden):
+    """sd_query_points_sorted: same points and cameras, NEW feature map -- one launch (the tile kernel), the bits of a
+    full query on the new scene."""
+    from scenedino_b200 import _abi
+    g = golden("query")
+    _, dsc, _, dmlp = scenes_from_golden(g, feat_dtype=torch.float16)
+    pts = dev(syn.random_points(13, 70003))
+    out = None
+    scp = dsc.project(dmlp)
+    q1 = ops.query_points(scp, dmlp, pts, want_rgb=False, precision=ops.F16)
+    out = {k: v for k, v in q1.items()}
+    out["invalid_features"] = out["invalid_features"].view(torch.uint8)
+    ops.query_points(scp, dmlp, pts, want_rgb=False, precision=ops.F16, out=out)       # leaves the sort in out["_workspace"]
+    feat2 = syn.make_feature_map(77, *[int(v) for v in g["shape"][:3]])
+    scp2 = dsc.with_feat_dtype(feat2, torch.float16).project(dmlp)
+    ref = ops.query_points(scp2, dmlp, pts, want_rgb=False, precision=ops.F16)
+    assert not torch.equal(ref["dino"], q1["dino"])
+    n0 = _abi.launch_count()
+    q2 = ops.query_points_sorted(scp2, dmlp, pts, out)
+    assert _abi.launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    assert torch.equal(q2["sigma"], ref["sigma"]) and torch.equal(q2["dino"], ref["dino"])
+    assert torch.equal(q2["invalid_features"], ref["invalid_features"])
+
+
 def test_query_graph_replay_matches_direct_calls(golden):
     """ops.QueryGraph: the captured query gives the direct call's bits, and follows the CONTENTS of its input buffer."""
     g = golden("query")
