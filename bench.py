@@ -276,18 +276,16 @@ def main():
     # the copy engines (symmetric memory: peer pointers + a signal-pad barrier) -- no SM is taken from the persistent
     # field kernel, which an NCCL all-gather kernel does (measured at N = 4: 87 % of ideal with NCCL).  If the symmetric
     # rendezvous is not available on the box, NCCL's all-gather is used; the JSON line says which.
-    peer_views, symm_hdl, gather_how = None, None, "nccl all_gather_into_tensor"
+    peer, gather_how = None, "nccl all_gather_into_tensor"
     if world > 1 and os.environ.get("SD_BENCH_ALLGATHER", "p2p") == "p2p":
         try:
-            import torch.distributed._symmetric_memory as symm
-            bufs = [symm.empty((world * N * 5,), dtype=torch.uint8, device=dev) for _ in range(NB)]
-            symm_hdl = [symm.rendezvous(t, dist.group.WORLD) for t in bufs]
-            peer_views = [[symm_hdl[i].get_buffer(p, (world, N * 5), torch.uint8) for p in range(world)] for i in range(NB)]
-            gathered = [peer_views[i][rank] for i in range(NB)]
+            from scenedino_b200.sharding import PeerGather
+            peer = PeerGather(N * 5, dev, n_buffers=NB)
+            gathered = peer.gathered
             gather_how = "peer writes over NVLink by the copy engines (symmetric memory) + signal barrier"
         except Exception as exc:      # noqa: BLE001 -- any failure of the optional transport falls back to NCCL
             print(f"[bench rank {rank}] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
-            peer_views, symm_hdl = None, None
+            peer = None
     done_k = [torch.cuda.Event() for _ in range(NB)]      # kernel of the step using buffer b finished
     done_c = [torch.cuda.Event() for _ in range(NB)]      # all-gather reading buffer b finished
     state = {"i": 0}
@@ -316,11 +314,8 @@ def main():
             done_k[b].record()
             with torch.cuda.stream(comm):
                 comm.wait_event(done_k[b])
-                if peer_views is not None:
-                    for dp in range(world):                      # start with the neighbour: spreads the NVLink traffic
-                        p = (rank + dp) % world
-                        peer_views[b][p][rank].copy_(small[b], non_blocking=True)
-                    symm_hdl[b].barrier()                          # every shard of this step has landed everywhere
+                if peer is not None:
+                    peer.gather(b, small[b])
                 else:
                     dist.all_gather_into_tensor(gathered[b], small[b])
                 done_c[b].record()

@@ -56,6 +56,36 @@ def all_gather_ragged(local: torch.Tensor, n_total: int, dim: int = 0, group=Non
     return torch.cat(parts, 0).movedim(0, dim)
 
 
+class PeerGather:
+    """All-gather of equal-sized byte shards by PEER WRITES over NVLink with the copy engines.
+
+    The gathered buffers live in symmetric memory (``torch.distributed._symmetric_memory``): every rank copies its shard
+    into each peer's buffer (a device-to-device ``cudaMemcpyAsync`` on a peer pointer: DMA, no SM) and a signal-pad barrier
+    closes the step.  An NCCL all-gather kernel takes SMs away from the persistent field kernel instead (measured at 4
+    B200: 87 % of ideal weak scaling with NCCL, 96 % with peer writes).  ``n_buffers`` gathered buffers are kept so that the
+    gather of step i can overlap the work of step i + 1.  Raises if the symmetric rendezvous is not available: callers
+    fall back to :func:`torch.distributed.all_gather_into_tensor`."""
+
+    def __init__(self, shard_bytes: int, device, n_buffers: int = 2, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.shard_bytes = shard_bytes
+        bufs = [symm.empty((self.world * shard_bytes,), dtype=torch.uint8, device=device) for _ in range(n_buffers)]
+        self._hdl = [symm.rendezvous(t, group) for t in bufs]
+        self._views = [[h.get_buffer(p, (self.world, shard_bytes), torch.uint8) for p in range(self.world)] for h in self._hdl]
+        self.gathered = [v[self.rank] for v in self._views]       # [world, shard_bytes] on this rank, one per buffer
+
+    def gather(self, b: int, shard: torch.Tensor) -> torch.Tensor:
+        """Writes ``shard`` (uint8 [shard_bytes], on this device) into row ``rank`` of buffer ``b`` on every rank, on the
+        current stream; returns this rank's gathered buffer (complete once the barrier enqueued here has run)."""
+        for dp in range(self.world):                               # start with the neighbour: spreads the NVLink traffic
+            p = (self.rank + dp) % self.world
+            self._views[b][p][self.rank].copy_(shard, non_blocking=True)
+        self._hdl[b].barrier()                                     # every shard of this step has landed everywhere
+        return self.gathered[b]
+
+
 def render_rays_sharded(render_fn: Callable[[torch.Tensor], dict], rays: torch.Tensor, group=None,
                         keys: Sequence[str] = ("rgb", "depth", "dino_features")) -> dict:
     """rays [n, R, r_dim] -> each rank renders rays[:, shard] with ``render_fn`` (the wrapped renderer of
