@@ -480,11 +480,15 @@ def main():
 
     # ---- full-image render (122 880 rays x 64 samples), reported in the same line ---------------------
     if not args.no_render:
-        rays = torch.from_numpy(syn.image_rays(syn.view_pose_c2w(1), K[0])).to(dev)
+        # the view is 100 bytes (pose + intrinsics): its rays are generated on the device inside every step (sd_gen_rays)
+        view_c2w = torch.from_numpy(syn.view_pose_c2w(1).astype(np.float32)).to(dev)[None]
+        view_K = torch.from_numpy(np.asarray(K[0], np.float32)).to(dev)[None]
+        rays = torch.empty((RENDER_R, 11), device=dev)
         lin = torch.linspace(0, 1 - 1.0 / RENDER_K, RENDER_K, device=dev)
         u = torch.rand((RENDER_R, RENDER_K), device=dev, generator=g)
 
         def render_step():
+            ops.gen_rays(view_c2w, view_K, syn.IMG_H, syn.IMG_W, syn.Z_NEAR, syn.Z_FAR, out=rays)
             z = ops.sample_coarse(rays, u, lin, True)
             return ops.render_pass(scene_rgb, mlp, rays, z, per_sample=False)
 
@@ -498,7 +502,8 @@ def main():
         e1.record(); fence()
         r_ms = e0.elapsed_time(e1) / n_r
         if line is not None:
-            line["render"] = {"workload": "full 192x640 image from a stereo-offset view, 64 coarse samples/ray, "
+            line["render"] = {"workload": "full 192x640 image from a stereo-offset view (rays generated on the device from pose + "
+                                          "intrinsics every step), 64 coarse samples/ray, "
                                           "per-ray outputs depth+64-d+rgb"
                                           + (" (projected map: 128-channel gather)" if args.precision == "fp16" else ""),
                               "msamples_per_s": RENDER_R * RENDER_K / (r_ms * 1e-3) / 1e6, "ms": r_ms,

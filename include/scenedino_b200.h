@@ -195,6 +195,19 @@ int    sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_
 /* `mlp` packs linear_in / linear_out; out [N,d_out] is L2-normalised per row (F.normalize). */
 int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, void *stream);
 
+/* ---- section 8f-3: rays of whole views ------------------------------------------------------ */
+/* Replaces util.gen_rays / util.unproj_map (common/util.py:253-285, 113-158) and the ray half of
+ * ImageRaySampler.sample (common/ray_sampler.py:439-486) for ONE batch element:
+ *   c2w [V,4,4] camera-to-world poses, proj [V,3,3] normalised intrinsics (fx, fy, cx, cy are read from
+ *   [0][0], [1][1], [0][2], [1][2]), frame_ids [V] or NULL (then 0..V-1), all device pointers;
+ *   rays [V*H*W, 11] = origin(3) direction(3) z_near z_far frame-id pixel-x pixel-y, pixels row-major per view
+ *   (16-byte aligned).  norm_dir != 0 normalises the directions.  x_shift / y_shift are added to the
+ *   pixel-centre coordinates (the reference's xy_offset * pixel size, in NDC units; 0 = none).
+ * Bit-identical to torch's CPU result for the same inputs.  H, W >= 2. */
+int sd_gen_rays(const float *c2w, const float *proj, const float *frame_ids, int V, int H, int W,
+                float z_near, float z_far, int norm_dir, float x_shift, float y_shift, float *rays,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

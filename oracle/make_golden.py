@@ -280,12 +280,35 @@ def golden_superbatch(ref):
     print("render_superbatch.npz:", {k: v.shape for k, v in g.items()})
 
 
+def golden_rays(ref):
+    """ImageRaySampler.sample (ray_sampler.py:439-513) on two batch elements of two views, and on
+    odd image sizes with explicit frame ids and unnormalised directions."""
+    out = {}
+    K = syn.kitti360_K()
+    for tag, (n, v, H, W, ids, norm) in {"a": (2, 2, 24, 80, None, True), "b": (1, 3, 17, 37, [4, 7, 9], False)}.items():
+        c2w = np.stack([np.stack([syn.view_pose_c2w(j + 3 * i) for j in range(v)], 0) for i in range(n)], 0).astype(np.float32)
+        proj = np.broadcast_to(K, (n, v, 3, 3)).astype(np.float32).copy()
+        proj[:, 1:, 0, 2] += 0.03          # views with different principal points / focal lengths
+        proj[:, 1:, 1, 1] *= 1.1
+        imgs = np.stack([syn.make_images(IMG_SEED + i, v, H, W) for i in range(n)], 0)
+        s = ref.ImageRaySampler(3.0, 80.0, H, W, norm_dir=norm)
+        rays, rgb_gt = s.sample(t(imgs), t(c2w), t(proj), image_ids=ids)
+        assert rays.shape == (n, v * H * W, 11) and rgb_gt.shape == (n, v * H * W, 3)
+        out.update({f"{tag}_c2w": c2w, f"{tag}_proj": proj, f"{tag}_hw": np.array([H, W]), f"{tag}_norm_dir": np.array(norm),
+                    f"{tag}_ids": np.array(ids if ids is not None else [], np.float32), f"{tag}_rays": rays.numpy(),
+                    f"{tag}_img_sum": checksum(imgs), f"{tag}_rgb_gt_sum": checksum(rgb_gt.numpy())})
+    out["z"] = np.array([3.0, 80.0], np.float32)
+    np.savez_compressed(os.path.join(OUT, "rays.npz"), **out)
+    print("rays.npz", {k: v.shape for k, v in out.items() if k.endswith("rays")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = ref_shim.import_reference()
     only = sys.argv[1:]          # e.g. `python oracle/make_golden.py query_big` regenerates one fixture
-    jobs = {"query": golden_query, "query_big": golden_query_big, "render": golden_render, "superbatch": golden_superbatch}
+    jobs = {"query": golden_query, "query_big": golden_query_big, "render": golden_render, "superbatch": golden_superbatch,
+            "rays": golden_rays}
     for name, fn in jobs.items():
         if not only or name in only:
             fn(ref)

@@ -323,3 +323,15 @@ def expand_dim(f, w1, b1, w2, b2):
     lib().sdo_expand_dim(_p(f), C.c_int64(N), w1.shape[1], w1.shape[0], w2.shape[0], _p(w1), _p(b1),
                          _p(w2), _p(b2), _p(out))
     return out
+
+
+def gen_rays(c2w, proj, H, W, z_near, z_far, frame_ids=None, norm_dir=True, xy_shift=(0.0, 0.0)):
+    """ImageRaySampler.sample's rays for one batch element (ray_sampler.py:439-486, util.py:113-158,253-285):
+    c2w [V,4,4], proj [V,3,3] -> [V*H*W, 11]."""
+    c2w, proj = _f32(c2w), _f32(proj)
+    V = c2w.shape[0]
+    ids = None if frame_ids is None else _f32(frame_ids)
+    out = np.empty((V * H * W, 11), np.float32)
+    lib().sdo_gen_rays(_p(c2w), _p(proj), _p(ids) if ids is not None else None, V, H, W, C.c_float(z_near),
+                       C.c_float(z_far), int(bool(norm_dir)), C.c_float(xy_shift[0]), C.c_float(xy_shift[1]), _p(out))
+    return out

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "sd_render_pass": (_I, [_SC, _ML, _RC, _P, _LL, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             _P, _SZ, _P]),
     "sd_expand_dim": (_I, [_ML, _P, _LL, _P, _P]),
+    "sd_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _F, _P, _P]),
 }
 
 _lib = None

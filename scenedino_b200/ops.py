@@ -180,6 +180,28 @@ def mlp_forward(mlp: Mlp, x, precision=None):
     return out
 
 
+def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=None, norm_dir: bool = True,
+             xy_shift=(0.0, 0.0), out=None):
+    """c2w [V,4,4], proj [V,3,3] (CUDA) -> rays [V*H*W, 11] of one batch element (sd_gen_rays; util.gen_rays +
+    ImageRaySampler.sample's frame-id / pixel columns)."""
+    c2w = _f32c(c2w); require_cuda(c2w, "c2w")
+    proj = _dev(proj, c2w.device)
+    V = c2w.shape[0]
+    if c2w.shape[1:] != (4, 4) or proj.shape != (V, 3, 3):
+        raise ValueError(f"gen_rays: c2w {tuple(c2w.shape)} / proj {tuple(proj.shape)} are not [V,4,4] / [V,3,3]")
+    ids = None if frame_ids is None else _dev(frame_ids, c2w.device).reshape(-1)
+    if ids is not None and ids.numel() != V:
+        raise ValueError("gen_rays: one frame id per view")
+    if out is None:
+        out = _e((V * H * W, 11), c2w)
+    elif out.shape != (V * H * W, 11) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("gen_rays: out must be a contiguous float32 [V*H*W, 11] tensor")
+    _abi.check(_abi.lib().sd_gen_rays(_ptr(c2w), _ptr(proj), _ptr(ids) if ids is not None else None, V, H, W, z_near, z_far,
+                                      int(bool(norm_dir)), float(xy_shift[0]), float(xy_shift[1]), _ptr(out), _stream()),
+               "sd_gen_rays")
+    return out
+
+
 def expand_dim(mlp: Mlp, f):
     f = _f32c(f); require_cuda(f, "f")
     out = _e((f.shape[0], mlp.d_out), f)

@@ -18,6 +18,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+def sd_launches():
+    import scenedino_b200
+    return scenedino_b200.launch_count()
+
+
 def g2n(t):
     return t.detach().cpu().numpy()
 
@@ -494,3 +499,38 @@ def test_errors_are_loud(golden):
         ops.query_points(dsc, bad, torch.zeros(4, 3, device=DEV))
     with pytest.raises(SdError):
         ops.sort_rows(torch.zeros(2, 5000, device=DEV))
+
+
+# ---- rays of whole views on the device ------------------------------------------------------------------
+def test_gen_rays_matches_reference_and_oracle(golden):
+    """sd_gen_rays against the reference's ImageRaySampler.sample (tests/golden/rays.npz) and the oracle: bit-exact,
+    all eleven columns, odd image sizes / explicit frame ids / unnormalised directions included."""
+    g = golden("rays")
+    for tag in "ab":
+        H, W = (int(x) for x in g[f"{tag}_hw"])
+        ids = g[f"{tag}_ids"] if g[f"{tag}_ids"].size else None
+        norm = bool(g[f"{tag}_norm_dir"])
+        for i in range(g[f"{tag}_c2w"].shape[0]):
+            c2w, proj = g[f"{tag}_c2w"][i], g[f"{tag}_proj"][i]
+            r = g2n(ops.gen_rays(dev(c2w), dev(proj), H, W, 3.0, 80.0, frame_ids=None if ids is None else dev(ids), norm_dir=norm))
+            assert np.array_equal(r, g[f"{tag}_rays"][i]), (tag, i)
+            assert np.array_equal(r, O.gen_rays(c2w, proj, H, W, 3.0, 80.0, frame_ids=ids, norm_dir=norm))
+
+
+@pytest.mark.parametrize("V,H,W", [(1, 2, 2), (3, 7, 5), (2, 192, 640), (4, 376, 1408)])
+def test_gen_rays_shapes_and_shift(V, H, W):
+    """Ragged block tails (ray counts that are not multiples of 256 or 4), the full KITTI-360 image sizes, and the
+    sub-pixel shift, bit-exact against the oracle; the launch counter sees exactly one kernel."""
+    rng = np.random.default_rng(V * 1000 + H)
+    c2w = np.stack([syn.view_pose_c2w(v) for v in range(V)], 0).astype(np.float32)
+    proj = np.broadcast_to(syn.kitti360_K(), (V, 3, 3)).astype(np.float32).copy()
+    proj[:, 0, 2] += rng.uniform(-0.05, 0.05, V).astype(np.float32)
+    ids = rng.integers(0, 9, V).astype(np.float32)
+    for shift in ((0.0, 0.0), (0.25 * 2 / W, -0.5 * 2 / H)):
+        n0 = sd_launches()
+        r = ops.gen_rays(dev(c2w), dev(proj), H, W, 0.5, 120.0, frame_ids=dev(ids), xy_shift=shift)
+        assert sd_launches() - n0 == 1
+        want = O.gen_rays(c2w, proj, H, W, 0.5, 120.0, frame_ids=ids, xy_shift=shift)
+        assert np.array_equal(g2n(r), want)
+    assert np.allclose(np.linalg.norm(want[:, 3:6], axis=1), 1.0, atol=1e-6)
+    assert ops.gen_rays(dev(c2w[:0]), dev(proj[:0]), H, W, 0.5, 120.0).shape == (0, 11)

@@ -141,6 +141,49 @@ def test_format_outputs_shapes_and_quirk():
     assert d.a.b == 1 and d.toDict() == {"a": {"b": 1}, "c": 2}
 
 
+def test_gen_rays_argument_validation_without_gpu():
+    lib = _abi.lib()
+    buf = ctypes.create_string_buffer(64)
+    assert lib.sd_gen_rays(None, None, None, 0, 4, 4, 3.0, 80.0, 1, 0.0, 0.0, None, None) == 0       # no views: nothing to do
+    assert lib.sd_gen_rays(None, None, None, 1, 4, 4, 3.0, 80.0, 1, 0.0, 0.0, None, None) == -1 and "null" in _abi.last_error()
+    assert lib.sd_gen_rays(buf, buf, None, 1, 1, 4, 3.0, 80.0, 1, 0.0, 0.0, buf, None) == -1 and "2 x 2" in _abi.last_error()
+    assert lib.sd_gen_rays(buf, buf, None, -1, 4, 4, 3.0, 80.0, 1, 0.0, 0.0, buf, None) == -1
+    with pytest.raises(sd.SdError):          # host tensors are rejected: there is no CPU path
+        sd.ImageRaySampler(3.0, 80.0, 4, 4).sample(None, torch.eye(4).view(1, 1, 4, 4), torch.eye(3).view(1, 1, 3, 3))
+
+
+def test_image_ray_sampler_reconstruct_shapes():
+    """ImageRaySampler.reconstruct (ray_sampler.py:515-607): every per-ray entry becomes [n, v_in, H, W, ...] as a view
+    (checked against the reference's own reconstruct in the build container), ground truth included; the patch size
+    of the DINO ground truth is inferred from the element count as the reference does."""
+    n, v, H, W, K, vr, c, dd = 2, 2, 8, 12, 5, 3, 3, 16
+    R = v * H * W
+
+    def part():
+        return dict(rgb=torch.rand(n, R, vr * c), weights=torch.rand(n, R, K), depth=torch.rand(n, R), invalid=torch.rand(n, R, K, vr),
+                    invalid_features=torch.rand(n, R, K, vr) > 0.5, alphas=torch.rand(n, R, K), z_samps=torch.rand(n, R, K),
+                    rgb_samps=torch.rand(n, R, K, vr * c), ray_info=torch.rand(n, R, 3), extras=torch.rand(n, R, 4),
+                    dino_features=torch.rand(n, R, dd))
+
+    d = dict(coarse=part(), fine=part(), rgb_gt=torch.rand(n, R, c), dino_gt=torch.rand(n, v * (H // 4) * (W // 4), dd),
+             dino_artifacts=torch.rand(n, v * (H // 4) * (W // 4), dd), other=3)
+    flat = {k: t.clone() for k, t in d["coarse"].items()}
+    o = sd.ImageRaySampler(3.0, 80.0, H, W).reconstruct(d)
+    want = {"rgb": (vr, c), "weights": (K,), "depth": (), "invalid": (K, vr), "invalid_features": (K, vr), "alphas": (K,),
+            "z_samps": (K,), "rgb_samps": (K, vr, c), "ray_info": (3,), "extras": (4,), "dino_features": (1, dd)}
+    for lvl in ("coarse", "fine"):
+        for k, tail in want.items():
+            assert o[lvl][k].shape == (n, v, H, W) + tail, (lvl, k)
+    for k, t in flat.items():                       # same memory order: a view, not a permutation
+        assert torch.equal(o["coarse"][k].reshape(t.shape), t)
+    assert o["rgb_gt"].shape == (n, v, H, W, c) and o["other"] == 3
+    assert o["dino_gt"].shape == o["dino_artifacts"].shape == (n, v, H // 4, W // 4, dd)
+    o = sd.ImageRaySampler(3.0, 80.0, H, W, dino_upscaled=True).reconstruct(dict(coarse=part(), dino_gt=torch.rand(n, R, dd)))
+    assert o["dino_gt"].shape == (n, v, H, W, dd)
+    with pytest.raises(KeyError):                   # the reference needs weights / depth / invalid next to rgb as well
+        sd.ImageRaySampler(3.0, 80.0, H, W).reconstruct(dict(coarse=dict(rgb=torch.rand(n, R, 3))))
+
+
 def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):
         _net({"code_mode": "distance"})

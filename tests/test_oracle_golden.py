@@ -174,3 +174,37 @@ def test_composite_properties():
     o = O.composite(z, spike, feat, None)
     np.testing.assert_allclose(o["depth"], z[:, 7], rtol=1e-5)
     np.testing.assert_allclose(o["dino"], feat[:, 7], rtol=1e-5, atol=1e-6)
+
+
+def _ray_cases(g):
+    for tag in "ab":
+        H, W = (int(x) for x in g[f"{tag}_hw"])
+        ids = g[f"{tag}_ids"]
+        yield tag, H, W, (ids if ids.size else None), bool(g[f"{tag}_norm_dir"])
+
+
+def test_gen_rays_bit_exact(golden):
+    """ImageRaySampler.sample's rays (ray_sampler.py:439-486) -- every column bit-for-bit, including the
+    linspace pixel centres (odd sizes, explicit frame ids and unnormalised directions in case b)."""
+    g = golden("rays")
+    for tag, H, W, ids, norm in _ray_cases(g):
+        for i in range(g[f"{tag}_c2w"].shape[0]):
+            r = O.gen_rays(g[f"{tag}_c2w"][i], g[f"{tag}_proj"][i], H, W, float(g["z"][0]), float(g["z"][1]), frame_ids=ids,
+                           norm_dir=norm)
+            assert np.array_equal(r, g[f"{tag}_rays"][i]), (tag, i)
+
+
+def test_gen_rays_properties():
+    """Size-independent properties at the full 192 x 640 image: unit directions, pixel columns symmetric around 0,
+    and the projection of origin + t * direction lands back on the pixel."""
+    from scenedino_b200 import synthetic as syn
+    K = syn.kitti360_K().astype(np.float32)
+    c2w = np.stack([syn.view_pose_c2w(v) for v in range(2)], 0).astype(np.float32)
+    H, W = 192, 640
+    r = O.gen_rays(c2w, np.stack([K, K]), H, W, 3.0, 80.0).reshape(2, H, W, 11)
+    assert np.allclose(np.linalg.norm(r[..., 3:6], axis=-1), 1.0, atol=1e-6)
+    assert np.array_equal(r[0, 0, :, 9], -r[0, 0, ::-1, 9]) and np.array_equal(r[0, :, 0, 10], -r[0, ::-1, 0, 10])
+    assert np.array_equal(r[1, ..., 8], np.ones((H, W), np.float32)) and np.all(r[..., 6] == 3.0) and np.all(r[..., 7] == 80.0)
+    pts = (r[1, ..., :3] + 7.5 * r[1, ..., 3:6]).reshape(-1, 3)
+    xy, z, _ = O.project(K, _w2c(c2w[1:2])[0], pts)
+    assert np.allclose(xy, r[1, ..., 9:11].reshape(-1, 2), atol=2e-5) and np.all(z > 0)
