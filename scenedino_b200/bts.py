@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .heads import ResnetFC, _f32c, _ptr, _stream, require_cuda
+from .heads import ResnetFC, _f32c, _ptr, _stream, expand_precision, require_cuda
 
 PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
 
@@ -309,7 +309,8 @@ class BTSNet(nn.Module):
             invalid_features = invf.view(torch.bool)
 
         if predict_segmentation:  # bts.py:528-533, 584-592
-            dino_full = self.encoder.expand_dim(dino)
+            with expand_precision(prec):      # the expansion runs in the precision of the query that feeds it
+                dino_full = self.encoder.expand_dim(dino)
             seg = None
             if self.downstream_head is not None:
                 seg = self.downstream_head(dino_full, mode=prediction_mode)

@@ -87,6 +87,8 @@ struct MlpLayout {
     size_t off_w_in_h;   // fp16 UMMA K-major SW128 image of W_in:  [d_in_pad/64 blocks][d_hidden rows][64]
     size_t off_w_out_h;  // fp16 UMMA K-major SW128 image of W_out[1:]: [d_hidden/64 blocks][d_out_pad rows][64]
     size_t off_w_sigma;  // fp32 [d_hidden]  = W_out[0,:]  (density row, evaluated in fp32)
+    size_t off_x_w2;     // expand heads (64 -> 128 -> multiple of 128): fp16 K-major SW128 images of W_out in blocks of 128
+                         // outputs, [d_out/128][2 K blocks][128 rows][64] (expand_tc.cu); 0 = absent
     size_t total;
 };
 MlpLayout mlp_layout(int d_in, int d_hidden, int d_out);

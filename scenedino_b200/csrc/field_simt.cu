@@ -455,5 +455,8 @@ extern "C" int sd_sample_colors(const sd_scene *scene, const float *xyz, long lo
 }
 
 extern "C" int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, void *stream) {
+    // reduced precision: fp16 operands on the tensor cores (expand_tc.cu) for the shipped 64 -> 128 -> 768 shape
+    if (mlp && mlp->precision == SD_MLP_F16_TC && expand_tc_supported(mlp))
+        return launch_expand_tc(mlp, f, N, out, (cudaStream_t)stream);
     return launch_mlp_simt(mlp, f, N, out, true, (cudaStream_t)stream);
 }

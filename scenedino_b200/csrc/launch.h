@@ -116,5 +116,8 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
                      const BinOrder &order, const TcOut &out, cudaStream_t st);
 // ResnetFC.forward on explicit rows through the same tcgen05 pipeline (unit test of the MMA path)
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st);
+// expand_tc.cu: MlpDimReduction.transform_expand on the tensor cores (64 -> 128 -> ReLU -> d_out, L2-normalised rows)
+bool expand_tc_supported(const sd_mlp *mlp);
+int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out, cudaStream_t st);
 
 }  // namespace sd

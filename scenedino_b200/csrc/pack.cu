@@ -65,6 +65,10 @@ MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     const int n2 = (int)align_up((size_t)d_out, 16);
     L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden + 2, 64), 1024);
     L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
+    L.off_x_w2 = 0;
+    if (d_in == 64 && d_hidden == 128 && d_out >= 128 && d_out % 128 == 0) {   // MlpDimReduction.transform_expand
+        L.off_x_w2 = o; o = align_up(o + 2 * (size_t)d_out * d_hidden, 1024);
+    }
     L.total = o;
     return L;
 }
@@ -125,6 +129,13 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
         if (src >= 0 && k == H) v = b_out[src];
         if (src >= 0 && k == H + 1) v = b_out[src] - __half2float(__float2half_rn(b_out[src]));
         w_out_h[umma_sw128_offset(r, k, n2) / 2] = __float2half_rn(v);
+    }
+    if (L.off_x_w2) {   // blocks of 128 outputs in their natural order, each a complete B operand (K = 128) of 32 KB
+        __half *x_w2 = reinterpret_cast<__half *>(blob + L.off_x_w2);
+        for (int i = tid; i < L.d_out * H; i += nth) {
+            const int o = i / H, k = i - o * H;
+            x_w2[((size_t)(o >> 7) * 32768 + umma_sw128_offset(o & 127, k, 128)) / 2] = __float2half_rn(w_out[(size_t)o * H + k]);
+        }
     }
 }
 

@@ -11,8 +11,10 @@ field kernels).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
+import threading
 
 import torch
 from torch import nn
@@ -157,15 +159,44 @@ class PositionalEncoding(nn.Module):
         return cls(conf.get("num_freqs", 6), d_in, conf.get("freq_factor", math.pi), conf.get("include_input", True))
 
 
+_expand_precision = threading.local()
+
+
+@contextlib.contextmanager
+def expand_precision(precision: int):
+    """Precision of MlpDimReduction.transform_expand calls made inside the block (BTSNet.forward wraps
+    ``encoder.expand_dim`` in it so that the expansion follows the precision of the query that feeds it)."""
+    prev = getattr(_expand_precision, "value", None)
+    _expand_precision.value = precision
+    try:
+        yield
+    finally:
+        _expand_precision.value = prev
+
+
 class MlpDimReduction(nn.Module):
-    """dim_reduction.py:15-25; transform_expand = 64 -> 128 -> ReLU -> 768 -> L2 normalise."""
+    """dim_reduction.py:15-25; transform_expand = 64 -> 128 -> ReLU -> 768 -> L2 normalise.
+
+    ``precision``: "fp32" (CUDA cores, rel 1e-4), "fp16" (tensor cores, rel 2e-2; 64 -> 128 -> multiple-of-128 shapes)
+    or "auto" (default): what the enclosing BTSNet.forward runs in, else fp16 under torch autocast, else fp32."""
 
     def __init__(self, full_channels, reduced_channels, latent_channels):
         super().__init__()
         self.linear_in = nn.Linear(reduced_channels, latent_channels)
         self.linear_out = nn.Linear(latent_channels, full_channels)
         self.relu = nn.ReLU()
+        self.precision = "auto"
         self._packed = PackedMlp()
+
+    def _precision(self) -> int:
+        if self.precision == "auto":
+            ctx = getattr(_expand_precision, "value", None)
+            if ctx is not None:
+                return ctx
+            return _abi.SD_MLP_F16_TC if torch.is_autocast_enabled() else _abi.SD_MLP_FP32
+        if self.precision not in ("fp32", "fp16"):
+            raise ValueError(f"MlpDimReduction.precision must be 'auto', 'fp32' or 'fp16', got {self.precision!r}")
+        return _abi.SD_MLP_F16_TC if self.precision == "fp16" else _abi.SD_MLP_FP32
 
     def transform_expand(self, features):
         require_cuda(features, "transform_expand input")
@@ -173,6 +204,6 @@ class MlpDimReduction(nn.Module):
         d_full = self.linear_out.weight.shape[0]
         x = _f32c(features).reshape(-1, d_red)
         out = torch.empty(x.shape[0], d_full, dtype=torch.float32, device=x.device)
-        mlp = self._packed.get(self.linear_in, self.linear_out, _abi.SD_MLP_FP32)
+        mlp = self._packed.get(self.linear_in, self.linear_out, self._precision())
         _abi.check(_abi.lib().sd_expand_dim(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()), "sd_expand_dim")
         return out.reshape(*features.shape[:-1], d_full)

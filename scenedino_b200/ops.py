@@ -202,10 +202,11 @@ def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=N
     return out
 
 
-def expand_dim(mlp: Mlp, f):
+def expand_dim(mlp: Mlp, f, precision: int = FP32):
+    """MlpDimReduction.transform_expand; ``precision=F16`` takes the tensor-core kernel (64 -> 128 -> k*128 heads)."""
     f = _f32c(f); require_cuda(f, "f")
     out = _e((f.shape[0], mlp.d_out), f)
-    m = mlp.c(FP32)
+    m = mlp.c(precision)
     _abi.check(_abi.lib().sd_expand_dim(C.byref(m), _ptr(f), f.shape[0], _ptr(out), _stream()), "sd_expand_dim")
     return out
 

@@ -305,6 +305,47 @@ def test_expand_dim(golden):
     np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, rtol=1e-5)
 
 
+def test_expand_dim_tensor_cores_vs_reference(golden):
+    """The reference's own 768-d expansion of 256 queried features (tests/golden/query.npz), fp16-operand kernel."""
+    g = golden("query")
+    m = ops.Mlp(g["e_w1"], g["e_b1"], g["e_w2"], g["e_b2"], device=DEV)
+    n0 = sd_launches()
+    out = g2n(ops.expand_dim(m, dev(g["dino"][:256]), precision=ops.F16))
+    assert sd_launches() - n0 == 1
+    assert_close(out, g["dino_full"], TOL_F16, "expand_dim (tensor cores) vs reference")
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,d_full", [(1, 768), (127, 768), (129, 768), (1000, 128), (70001, 768), (19000, 1024)])
+def test_expand_dim_tensor_cores_shapes(N, d_full):
+    """Ragged tiles, several tiles per CTA (70 001 rows = 547 tiles on 148 CTAs), one to eight 128-column blocks;
+    rows that are exactly zero (norm clamp) and large inputs; against the oracle and the fp32 CUDA-core path."""
+    rs = np.random.RandomState(N + d_full)
+    w = [(rs.randn(128, 64) * 0.15).astype(np.float32), (rs.randn(128) * 0.1).astype(np.float32),
+         (rs.randn(d_full, 128) * 0.1).astype(np.float32), (rs.randn(d_full) * 0.05).astype(np.float32)]
+    f = (rs.randn(N, 64) * rs.choice([0.1, 1.0, 8.0], (N, 1))).astype(np.float32)
+    m = ops.Mlp(*w, device=DEV)
+    out = g2n(ops.expand_dim(m, dev(f), precision=ops.F16))
+    want = O.expand_dim(f, *w)
+    assert out.shape == (N, d_full) and np.isfinite(out).all()
+    assert_close(out, want, TOL_F16, "expand_dim (tensor cores) vs oracle")
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, rtol=1e-5)
+    assert_close(out, g2n(ops.expand_dim(m, dev(f))), TOL_F16, "expand_dim (tensor cores) vs fp32 path")
+    # a permuted batch returns the permuted result bit for bit (rows are independent of their tile position)
+    perm = rs.permutation(N)
+    assert np.array_equal(g2n(ops.expand_dim(m, dev(f[perm]), precision=ops.F16)), out[perm])
+    assert ops.expand_dim(m, dev(f[:0]), precision=ops.F16).shape == (0, d_full)
+
+
+def test_expand_dim_unsupported_shape_takes_the_fp32_path():
+    rs = np.random.RandomState(3)
+    w = [rs.randn(128, 32).astype(np.float32) * 0.1, np.zeros(128, np.float32), rs.randn(96, 128).astype(np.float32) * 0.1,
+         np.zeros(96, np.float32)]
+    f = rs.randn(300, 32).astype(np.float32)
+    m = ops.Mlp(*w, device=DEV)
+    assert np.array_equal(g2n(ops.expand_dim(m, dev(f), precision=ops.F16)), g2n(ops.expand_dim(m, dev(f))))
+
+
 # ---- sampling: all bit-exact -------------------------------------------------------------------
 @pytest.mark.parametrize("lindisp", [True, False])
 def test_sampling_bit_exact(lindisp):
