@@ -223,6 +223,9 @@ def test_btsnet_forward_large_fp16_uses_projected_map(golden):
     n = len(g["points"])
     assert_close(sigma16[0, :n, 0].cpu().numpy(), g["sigma_le"], TOL_F16, "sigma vs reference")
     assert dino_full.shape == (1, xyz.shape[1], 768) and sigma_seg.shape == (1, xyz.shape[1], 1)
+    # the expansion follows the query's precision (tensor-core expand kernel): two reduced-precision stages in a row
+    assert_close(dino_full[0, :256].cpu().numpy(), g["dino_full_le"], 5e-2, "dino_full (fp16 query + fp16 expansion) vs reference")
+    np.testing.assert_allclose(torch.linalg.norm(dino_full[0], dim=-1).cpu().numpy(), 1.0, rtol=1e-5)
 
 
 def test_image_ray_sampler_matches_reference(golden):
