@@ -192,7 +192,9 @@ int    sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_
                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- section 8f-1: MlpDimReduction.transform_expand (backbones/dino/dim_reduction.py:22-25) --- */
-/* `mlp` packs linear_in / linear_out; out [N,d_out] is L2-normalised per row (F.normalize). */
+/* `mlp` packs linear_in / linear_out; out [N,d_out] is L2-normalised per row (F.normalize).
+ * mlp->precision == SD_MLP_F16_TC and a 64 -> 128 -> k*128 (k <= 8) head: tcgen05 kernel (fp16 operands, fp32
+ * accumulation and normalisation, rel 2e-2; f and out 16-byte aligned); anything else: fp32 CUDA-core kernel (rel 1e-4). */
 int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, void *stream);
 
 /* ---- section 8f-3: rays of whole views ------------------------------------------------------ */
