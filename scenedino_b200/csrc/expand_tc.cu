@@ -154,27 +154,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                 mbar_wait(BAR(BAR_D2_FULL + b), (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
                 if (store) __syncwarp();      // the copy-out of the previous chunk has read the staging rows
-#pragma unroll 1
-                for (int qd = 0; qd < 4; ++qd) {
-                    uint32_t vr[32];
-                    tmem_ld32_issue(t_lane + D2_COL + b * 128 + qd * 32, vr);
+                {   // the whole 128-column chunk of this row in one batch of TMEM loads (one wait instead of four)
+                    uint32_t vr[128];
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) tmem_ld32_issue(t_lane + D2_COL + b * 128 + qd * 32, vr + qd * 32);
                     tmem_ld_wait();
-                    const float *bias = s_b2 + c * 128 + qd * 32;
+                    const float *bias = s_b2 + c * 128;
                     if (!store) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
+                        for (int e = 0; e < 128; ++e) {
                             const float v = __uint_as_float(vr[e]) + bias[e];
                             ss = fmaf(v, v, ss);
                         }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
+                        for (int e = 0; e < 32; ++e) {
                             float4 o;
                             o.x = (__uint_as_float(vr[4 * e + 0]) + bias[4 * e + 0]) * inv;
                             o.y = (__uint_as_float(vr[4 * e + 1]) + bias[4 * e + 1]) * inv;
                             o.z = (__uint_as_float(vr[4 * e + 2]) + bias[4 * e + 2]) * inv;
                             o.w = (__uint_as_float(vr[4 * e + 3]) + bias[4 * e + 3]) * inv;
-                            *reinterpret_cast<float4 *>(stage + lane * STAGE_ROW + qd * 128 + e * 16) = o;
+                            *reinterpret_cast<float4 *>(stage + lane * STAGE_ROW + e * 16) = o;
                         }
                     }
                 }
