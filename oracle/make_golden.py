@@ -302,13 +302,43 @@ def golden_rays(ref):
     print("rays.npz", {k: v.shape for k, v in out.items() if k.endswith("rays")})
 
 
+def golden_ssc_head(ref):
+    """SemanticHead.forward(mode="stego_kmeans") (downstream_head/semantic_head.py:107-112) on the 768-d
+    expansion of queried features.  SemanticHead's constructor allocates its training buffers on "cuda"
+    (semantic_head.py:69-70), so its own submodules (StegoClusterHead, KMeansParamHead) are composed here in the order
+    of its forward; eval mode (no dropout)."""
+    from scenedino.downstream_head.semantic_head import KMeansParamHead, StegoClusterHead, _norm
+    q = np.load(os.path.join(OUT, "query.npz"))
+    x = syn.ssc_head_inputs(q["dino_full"], q["dino_full_le"])             # [577, 768]; regenerated by the tests, not stored
+    w = syn.make_ssc_head(21)                                              # likewise (checksums stored)
+    n_cls, d_code = w["centres"].shape
+    d_in = w["wl"].shape[1]
+    stego = StegoClusterHead(d_in, d_code).eval()
+    km = KMeansParamHead(n_cls, 19, d_code).eval()
+    with torch.no_grad():
+        stego.linear_path[0].weight.copy_(t(w["wl"]).view(d_code, d_in, 1, 1)); stego.linear_path[0].bias.copy_(t(w["bl"]))
+        stego.nonlinear_path[0].weight.copy_(t(w["wn1"]).view(d_in, d_in, 1, 1)); stego.nonlinear_path[0].bias.copy_(t(w["bn1"]))
+        stego.nonlinear_path[2].weight.copy_(t(w["wn2"]).view(d_code, d_in, 1, 1)); stego.nonlinear_path[2].bias.copy_(t(w["bn2"]))
+        km.cluster_centers.copy_(t(w["centres"]))
+        km.pseudo_assignment.copy_(t(w["lut"]))
+        feats = _norm(t(x)[None])                                   # [1, N, 768] as BTSNet.forward hands it over (bts.py:586-589)
+        code = stego(feats)
+        res = km(code)
+        ip = torch.nn.functional.normalize(code.flatten(0, -2), dim=1) @ torch.nn.functional.normalize(km.cluster_centers, dim=1).t()
+    out = dict(seed=np.array(21), x_sum=checksum(x), w_sum=np.stack([checksum(w[k]) for k in sorted(w)]),
+               code=code[0].numpy(), seg=res["segs_pred"][0].numpy(), pseudo=res["pseudo_segs_pred"][0].numpy(), ip=ip.numpy())
+    assert out["seg"].dtype == np.int64 and out["seg"].shape == (x.shape[0],)
+    np.savez_compressed(os.path.join(OUT, "ssc_head.npz"), **out)
+    print("ssc_head.npz", {k: v.shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = ref_shim.import_reference()
     only = sys.argv[1:]          # e.g. `python oracle/make_golden.py query_big` regenerates one fixture
     jobs = {"query": golden_query, "query_big": golden_query_big, "render": golden_render, "superbatch": golden_superbatch,
-            "rays": golden_rays}
+            "rays": golden_rays, "ssc_head": golden_ssc_head}
     for name, fn in jobs.items():
         if not only or name in only:
             fn(ref)

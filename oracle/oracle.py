@@ -335,3 +335,19 @@ def gen_rays(c2w, proj, H, W, z_near, z_far, frame_ids=None, norm_dir=True, xy_s
     lib().sdo_gen_rays(_p(c2w), _p(proj), _p(ids) if ids is not None else None, V, H, W, C.c_float(z_near),
                        C.c_float(z_far), int(bool(norm_dir)), C.c_float(xy_shift[0]), C.c_float(xy_shift[1]), _p(out))
     return out
+
+
+def ssc_head(x, wl, bl, wn1, bn1, wn2, bn2, centres, lut):
+    """SemanticHead.forward(mode="stego_kmeans") (semantic_head.py:107-112, 285-305, 308-373):
+    x [N, d_in] -> (seg [N] int64, pseudo [N] int64, inner products [N, n_cls])."""
+    x, wl, bl, wn1, bn1, wn2, bn2, centres = (_f32(a) for a in (x, wl, bl, wn1, bn1, wn2, bn2, centres))
+    lut = np.ascontiguousarray(lut, dtype=np.int64)
+    N, d_in = x.shape
+    d_mid, d_code, n_cls = wn1.shape[0], wl.shape[0], centres.shape[0]
+    seg, pseudo = np.empty(N, np.int64), np.empty(N, np.int64)
+    ip = np.empty((N, n_cls), np.float32)
+    rc = lib().sdo_ssc_head(_p(x), C.c_int64(N), d_in, d_mid, d_code, n_cls, _p(wl), _p(bl), _p(wn1), _p(bn1), _p(wn2), _p(bn2),
+                            _p(centres), _p(lut), _p(seg), _p(pseudo), _p(ip))
+    if rc:
+        raise MemoryError("sdo_ssc_head")
+    return seg, pseudo, ip

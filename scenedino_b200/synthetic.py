@@ -135,3 +135,24 @@ def random_points(seed: int, n: int, box=((-30, 30), (-6, 6), (-5, 70))) -> np.n
     rs = np.random.RandomState(seed)
     lo = np.array([b[0] for b in box], np.float32); hi = np.array([b[1] for b in box], np.float32)
     return (rs.uniform(0, 1, (n, 3)).astype(np.float32) * (hi - lo) + lo).astype(np.float32)
+
+
+def make_ssc_head(seed: int, d_in: int = 768, d_code: int = 64, n_cls: int = 27, gt_cls: int = 19) -> dict:
+    """Seeded parameters of the unsupervised SSC head (downstream_head/semantic_head.py: StegoClusterHead 1x1-conv
+    weights at nn.Conv2d's default scale, KMeansParamHead centres and pseudo-label LUT)."""
+    rs = np.random.RandomState(seed)
+
+    def u(shape, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        return rs.uniform(-b, b, shape).astype(np.float32)
+
+    return dict(wl=u((d_code, d_in), d_in), bl=u((d_code,), d_in), wn1=u((d_in, d_in), d_in), bn1=u((d_in,), d_in),
+                wn2=u((d_code, d_in), d_in), bn2=u((d_code,), d_in), centres=rs.randn(n_cls, d_code).astype(np.float32),
+                lut=rs.randint(0, gt_cls, n_cls).astype(np.int64))
+
+
+def ssc_head_inputs(dino_full: np.ndarray, dino_full_le: np.ndarray) -> np.ndarray:
+    """Rows fed to the head in tests/golden/ssc_head.npz: the reference's own 768-d expansions (unit rows), some of them
+    scaled (the head re-normalises), and one all-zero row (norm clamp)."""
+    x = np.concatenate([dino_full, dino_full_le], 0).astype(np.float32)
+    return np.concatenate([x, (x[:64] * np.float32(3.5)).astype(np.float32), np.zeros((1, x.shape[1]), np.float32)], 0)

@@ -208,3 +208,28 @@ def test_gen_rays_properties():
     pts = (r[1, ..., :3] + 7.5 * r[1, ..., 3:6]).reshape(-1, 3)
     xy, z, _ = O.project(K, _w2c(c2w[1:2])[0], pts)
     assert np.allclose(xy, r[1, ..., 9:11].reshape(-1, 2), atol=2e-5) and np.all(z > 0)
+
+
+def test_ssc_head(golden):
+    """SURVEY 8f-2 (oracle only so far): SemanticHead.forward(mode="stego_kmeans") -- STEGO code, cosine scores against
+    the centres, argmax, pseudo-label LUT -- against the reference's own modules on the reference's 768-d expansions."""
+    from scenedino_b200 import synthetic as syn
+    g, q = golden("ssc_head"), golden("query")
+    x = syn.ssc_head_inputs(q["dino_full"], q["dino_full_le"])
+    w = syn.make_ssc_head(int(g["seed"]))
+
+    def checksum(a):
+        a = np.asarray(a, np.float64).ravel()
+        return np.array([a.sum(), np.abs(a).sum(), a[:: max(1, a.size // 97)].sum()], np.float64)
+
+    assert np.allclose(checksum(x), g["x_sum"], rtol=1e-12) and np.allclose([checksum(w[k]) for k in sorted(w)], g["w_sum"], rtol=1e-12)
+    seg, pseudo, ip = O.ssc_head(x, w["wl"], w["bl"], w["wn1"], w["bn1"], w["wn2"], w["bn2"], w["centres"], w["lut"])
+    assert seg.dtype == np.int64 and seg.shape == (len(x),)
+    assert np.abs(ip - g["ip"]).max() < 2e-5                      # cosine scores, |.| <= 1
+    top2 = np.sort(g["ip"], 1)[:, -2:]
+    clear = top2[:, 1] - top2[:, 0] > 1e-4                        # labels are compared where the reference's top-2 gap is clear
+    assert clear.mean() > 0.98
+    assert np.array_equal(pseudo[clear], g["pseudo"][clear]) and np.array_equal(seg[clear], g["seg"][clear])
+    assert np.array_equal(seg, w["lut"][pseudo])
+    # scaled copies of a row get the row's label (the head normalises its input); the all-zero row is finite
+    assert np.array_equal(pseudo[512:576], pseudo[:64]) and np.isfinite(ip[-1]).all()
