@@ -27,9 +27,9 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  try_wait is given a
-// suspend-time hint so that a waiting warp sleeps in hardware instead of spinning through the issue slots of the
-// warps that share its scheduler (without the hint ~90 five-instruction spins per tile and waiting role were measured).
+// Bounded wait: a protocol bug must surface as a trap (launch failure) within a second, never as a hung GPU.  Plain
+// try_wait spins: a suspend-time hint was measured and removed (slow wake-ups put the producer warps in lockstep with
+// the consumers they were supposed to run ahead of).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifdef SD_DEBUG_WAIT
     uint32_t done = 0;
