@@ -26,6 +26,21 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int device_once(DeviceOnce &seen, int *sm_count, bool *first) {
+    int dev = 0;
+    SD_CUDA_OK(cudaGetDevice(&dev));
+    SD_REQUIRE(dev >= 0 && dev < SD_MAX_DEVICES, "device ordinal %d is out of range (max %d devices per process)", dev, SD_MAX_DEVICES);
+    *first = seen.sm_count[dev] == 0;
+    if (*first) {
+        int n = 0;
+        SD_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        SD_REQUIRE(n > 0, "device %d reports no multiprocessors", dev);
+        seen.sm_count[dev] = n;
+    }
+    *sm_count = seen.sm_count[dev];
+    return SD_OK;
+}
+
 // sd_profile_next_kernel: a pair of caller-owned events recorded around the next launch of a field kernel
 static thread_local cudaEvent_t g_prof0 = nullptr, g_prof1 = nullptr;
 void profile_before(cudaStream_t st) {

@@ -240,11 +240,11 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     go.invalid_feat = invalid_feat;
     go.enc = fp.enc;
     go.learn_empty = fp.learn_empty;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        SD_CUDA_OK(cudaGetDevice(&dev));
-        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));

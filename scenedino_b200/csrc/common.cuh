@@ -20,6 +20,11 @@ namespace sd {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch(int n = 1);
+// One-time setup of a launcher PER DEVICE (kernel attributes such as the dynamic shared-memory limit belong to the device
+// the function was loaded on): SM count of the current device in *sm_count; *first says that `seen` had no entry for it.
+constexpr int SD_MAX_DEVICES = 64;
+struct DeviceOnce { int sm_count[SD_MAX_DEVICES]; };
+int device_once(DeviceOnce &seen, int *sm_count, bool *first);
 void profile_before(cudaStream_t st);   // sd_profile_next_kernel: events around the dominant (field) kernel
 void profile_after(cudaStream_t st);
 

@@ -274,11 +274,11 @@ int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out,
     P.b2 = reinterpret_cast<const float *>(blob + L.off_b_out);
     P.N = N; P.n_tiles = (N + ex::TM - 1) / ex::TM;
     P.d_out = mlp->d_out; P.nch = mlp->d_out / 128;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        SD_CUDA_OK(cudaGetDevice(&dev));
-        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(ex::expand_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);

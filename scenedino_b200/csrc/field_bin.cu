@@ -701,11 +701,11 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     const unsigned int box[3] = {64u, 8u, 8u};
     int rc = make_tmap_f16(&P.tmap, proj + PROJ_OFF_MAP, 3, dims, strides, box);
     if (rc) return rc;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        SD_CUDA_OK(cudaGetDevice(&dev));
-        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(tb::field_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);

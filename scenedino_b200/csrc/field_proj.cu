@@ -250,11 +250,11 @@ extern "C" int sd_field_project(const sd_scene *scene, const sd_mlp *mlp, void *
     const unsigned int box[2] = {64u, (unsigned)pj::TM};
     int rc = make_tmap_f16(&P.tmap, scene->feat, 2, dims, strides, box);
     if (rc) return rc;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        SD_CUDA_OK(cudaGetDevice(&dev));
-        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(pj::featmap_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pj::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);

@@ -859,11 +859,11 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st, const vo
     P.D = mlp->d_out - 1;
     P.cmma = proj && P.mode == tc::MODE_RENDER && P.D <= 64;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        SD_CUDA_OK(cudaGetDevice(&dev));
-        SD_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(tc::field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
