@@ -259,6 +259,35 @@ def golden_render(ref):
     print("render_from_dist.npz:", sorted(g.keys()))
 
 
+def golden_render_d768(ref):
+    """SURVEY 8d cfg 3 in small: the D = 768 head (d_out = 769), four colour views, Kc = 64 coarse + Kf = 32 importance
+    samples (n_fine_depth = 0) -> a 96-sample fine pass, training-shaped (hard_alpha_cap on)."""
+    nv_c, D = 4, 768
+    feat, imgs, K, c2w = scene_inputs(nv_c)
+    mlp = syn.make_mlp(MLP_SEED + 7, d_out=1 + D, bias_scale=0.1)
+    net = ref_shim.build_reference_net(ref, t(feat), *[t(w) for w in mlp], dino_dims=D)
+    encode(net, imgs, K, c2w, list(range(nv_c)))
+    rays = pick_rays([c2w[0, 0], syn.view_pose_c2w(3)], K[0, 0], 24, seed=9)[None]      # [1,48,11]
+    conf = {"n_coarse": 64, "n_fine": 32, "n_fine_depth": 0, "lindisp": True, "eval_batch_size": 100000, "hard_alpha_cap": True}
+    ren = ref.NeRFRenderer.from_conf(conf)
+    ren.hard_alpha_cap = True
+    wrapped = ren.bind_parallel(net, gpus=None).eval()
+    torch.manual_seed(103)
+    with DrawRecorder() as rec, torch.no_grad():
+        out = wrapped(t(rays), want_weights=True, want_alphas=True, want_z_samps=True)
+    kinds = [k for k, _ in rec.draws]
+    assert kinds == ["rand_like", "rand", "rand_like"], kinds
+    g = dict(K=K[0], c2w=c2w[0], w_in=mlp[0], b_in=mlp[1], w_out=mlp[2], b_out=mlp[3], feat_checksum=checksum(feat),
+             img_checksum=checksum(imgs), shape=np.array([C, HF, WF, HC, WC, nv_c]), rays=rays,
+             u_coarse=rec.draws[0][1].numpy(), u_fine0=rec.draws[1][1].numpy(), u_fine1=rec.draws[2][1].numpy(),
+             fine_inds=(rec.searches[0] - 1).clamp_min(0).numpy().astype(np.int32),
+             lin=torch.linspace(0, 1 - 1.0 / 64, 64).numpy(), conf=np.array([64, 32, 0, 1, 0]))
+    flat("", out, g)
+    assert g["fine.dino_features"].shape == (1, 48, D) and g["fine.z_samps"].shape == (1, 48, 96)
+    np.savez_compressed(os.path.join(OUT, "render_d768.npz"), **g)
+    print("render_d768.npz:", sorted(g.keys()))
+
+
 def golden_superbatch(ref):
     """sb = 2 scenes with different feature maps / cameras, 4 colour views (training-shaped)."""
     nv_c, n = 4, 2
@@ -338,7 +367,7 @@ def main():
     ref = ref_shim.import_reference()
     only = sys.argv[1:]          # e.g. `python oracle/make_golden.py query_big` regenerates one fixture
     jobs = {"query": golden_query, "query_big": golden_query_big, "render": golden_render, "superbatch": golden_superbatch,
-            "rays": golden_rays, "ssc_head": golden_ssc_head}
+            "rays": golden_rays, "ssc_head": golden_ssc_head, "render_d768": golden_render_d768}
     for name, fn in jobs.items():
         if not only or name in only:
             fn(ref)

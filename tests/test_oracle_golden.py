@@ -127,6 +127,26 @@ def test_render_fine(golden, name):
     _check_pass(o, g, "fine.")
 
 
+def test_render_d768(golden):
+    """SURVEY 8d cfg 3 in small: the 768-d head (d_out = 769), four colour views, 64 coarse + 32 importance samples
+    merged into a 96-sample fine pass, hard_alpha_cap on."""
+    g = golden("render_d768")
+    feat, imgs = golden_scene_arrays(g)
+    sc = _scene(g, feat, imgs)
+    rays = g["rays"][0]
+    assert g["w_out"].shape == (769, 128) and g["K"].shape[0] == 4
+    out = O.render_rays(sc, _mlp(g), rays, lin=g["lin"], u_coarse=g["u_coarse"], u_fine0=g["u_fine0"], u_fine1=g["u_fine1"],
+                        lindisp=True, hard_alpha_cap=True)
+    assert np.array_equal(out["coarse"]["z_samps"], g["coarse.z_samps"][0])
+    _check_pass(out["coarse"], g, "coarse.")
+    assert out["coarse"]["dino_features"].shape == (48, 768)
+    flips = (out["fine_inds"] != g["fine_inds"]).sum()
+    assert flips <= 1, f"{flips} index flips"
+    o = O.render_pass(sc, _mlp(g), rays, g["fine.z_samps"][0], hard_alpha_cap=True)
+    _check_pass(o, g, "fine.")
+    assert np.array_equal(o["invalid_features"].ravel(), g["fine.invalid_features"].ravel())
+
+
 def test_render_from_dist(golden):
     g = golden("render_from_dist")
     feat, imgs = golden_scene_arrays(g)
