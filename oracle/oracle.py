@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_ref", "libsd_oracle.so")
+_LIB_PATH = os.path.join(_HERE, "build", "libsd_oracle.so")
 _lib = None
 
 

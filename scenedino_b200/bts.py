@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .heads import ResnetFC, _f32c, _ptr, _stream, expand_precision, require_cuda
+from .heads import ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, require_cuda
 
 PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
 
@@ -141,6 +141,14 @@ class BTSNet(nn.Module):
         self._packed = {}
 
     # ---- C-ABI plumbing ----------------------------------------------------------------------------
+    def sd_tensors(self):
+        """Tensors whose device every call must share (heads.on_device)."""
+        head = self.heads[self.final_pred_head]
+        ts = [head.lin_in.weight]
+        if self.grid_f_features is not None:
+            ts.append(self.grid_f_features[self._scale])
+        return ts
+
     def _precision(self) -> int:
         p = self.precision
         if p == "auto":
@@ -182,8 +190,14 @@ class BTSNet(nn.Module):
     def _projection(self, st, b: int, mlp: _abi.SdMlp):
         """Blob of sd_field_project for batch element ``b`` and this head, made once per encode: the fp16 map pushed
         through the feature columns of the head's first layer, for the projected-map tile kernel."""
+        # the blob bakes in W_in[:, :C] and W_feat . empty_feature: key it on the pack generation of the head (a repack
+        # can land on a recycled allocator address) and on the identity / version of empty_feature
         cache = st.setdefault("proj", {})
-        key = (b, int(mlp.packed))
+        pm = self._packed_mlp()
+        ef = self.empty_feature if self.learn_empty else None
+        key = (b, id(pm), pm.generation, None if ef is None else (ef.data_ptr(), ef._version))
+        for k in [k for k in cache if k[0] == b and k != key]:
+            del cache[k]                      # stale projections of this batch element
         blob = cache.get(key)
         if blob is None:
             sc = self._scene(st, b)
@@ -220,14 +234,18 @@ class BTSNet(nn.Module):
             s.empty_feature = self._empty_f32.data_ptr()
         return s
 
-    def _mlp(self, precision: int) -> _abi.SdMlp:
+    def _packed_mlp(self):
         head = self.heads[self.final_pred_head]
         if isinstance(head, ResnetFC):
-            return head.packed(precision)
+            return head._packed
         if self._head_packed is None:
             from .heads import PackedMlp
             self._head_packed = PackedMlp()
-        return self._head_packed.get(head.lin_in, head.lin_out, precision)
+        return self._head_packed
+
+    def _mlp(self, precision: int) -> _abi.SdMlp:
+        head = self.heads[self.final_pred_head]
+        return self._packed_mlp().get(head.lin_in, head.lin_out, precision)
 
     def _check_points(self, xyz):
         require_cuda(xyz, "xyz")
@@ -238,6 +256,7 @@ class BTSNet(nn.Module):
         return _f32c(xyz)
 
     # ---- BTSNet.sample_features (bts.py:271-328) ---------------------------------------------------
+    @device_guard
     def sample_features(self, xyz):
         xyz = self._check_points(xyz)
         st = self._state(_abi.SD_MLP_FP32)
@@ -253,6 +272,7 @@ class BTSNet(nn.Module):
         return feat, inv.view(torch.bool)
 
     # ---- BTSNet.sample_colors (bts.py:330-441) -----------------------------------------------------
+    @device_guard
     def sample_colors(self, xyz, **kwargs):
         if kwargs.get("render_flow", False):
             raise NotImplementedError("render_flow is not implemented")
@@ -270,6 +290,7 @@ class BTSNet(nn.Module):
         return rgb.permute(0, 2, 1, 3), inv.view(torch.bool).permute(0, 2, 1).unsqueeze(-1)
 
     # ---- BTSNet.forward (bts.py:476-595) -----------------------------------------------------------
+    @device_guard
     def forward(self, xyz: torch.Tensor, **kwargs):
         only_density = kwargs.get("only_density", False)
         predict_segmentation = kwargs.get("predict_segmentation", False)

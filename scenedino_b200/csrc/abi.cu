@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "launch.h"
@@ -26,7 +28,15 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int debug_mask() {
+    static const int mask = [] { const char *e = getenv("SD_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    return mask;
+}
+
+static std::mutex g_once_mutex;
+
 int device_once(DeviceOnce &seen, int *sm_count, bool *first) {
+    std::lock_guard<std::mutex> lock(g_once_mutex);   // launchers may be entered from several host threads
     int dev = 0;
     SD_CUDA_OK(cudaGetDevice(&dev));
     SD_REQUIRE(dev >= 0 && dev < SD_MAX_DEVICES, "device ordinal %d is out of range (max %d devices per process)", dev, SD_MAX_DEVICES);
@@ -146,9 +156,15 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 extern "C" size_t sd_render_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long R, int K) {
     if (!scene || !mlp || R <= 0 || K <= 0) return 0;
     const size_t N = (size_t)R * K;
-    // fused kernel: only the per-sample colours make a round trip through memory (L2-sized tiles of it)
-    if (mlp->precision == SD_MLP_F16_TC && tc_supported(scene, mlp, K))
+    if (mlp->precision == SD_MLP_F16_TC && tc_supported(scene, mlp, K)) {
+        const int mode = tc_render_mode(scene, mlp);
+        // projected scene: the composite runs on the tensor cores and nothing per sample touches memory; with more than 64
+        // feature outputs the per-ray sums of the 128 hidden units (+ the sum of the weights) wait here for the head2 kernel
+        if (mode == 2) return align256((size_t)R * 128 * 4) + align256((size_t)R * 4);
+        if (mode == 1) return 0;
+        // unprojected scene: the per-sample colours make a round trip through memory (L2-sized tiles of it)
         return scene->nv_c > 0 ? align256(N * 3 * (size_t)scene->nv_c * 4) : 0;
+    }
     const int D = mlp->d_out - 1;
     // sigma [N], dino [N,D], rgb [N,3nv_c]
     return align256(N * 4) + align256(N * D * 4) + align256(N * 3 * (size_t)(scene->nv_c > 0 ? scene->nv_c : 1) * 4);
@@ -176,17 +192,26 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
         TcRender rr = {};
         rr.cfg = *cfg; rr.depth = depth; rr.dino = dino; rr.rgb_out = rgb_out; rr.weights = weights;
         rr.alphas = alphas; rr.rgb_samps = rgb_samps;
-        if (!rgb_samps && Crgb > 0 && rgb_out) {
-            const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);
-            if (workspace_bytes < need || !workspace) {
-                set_error("sd_render_pass: workspace of %zu B needed, %zu B given", need, workspace_bytes);
-                return SD_ERR_WORKSPACE;
-            }
+        rr.cmma = tc_render_mode(scene, mlp);
+        const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);
+        const bool use_ws = rr.cmma == 2 || (rr.cmma == 0 && !rgb_samps && Crgb > 0 && rgb_out);
+        if (use_ws && need && (workspace_bytes < need || !workspace)) {
+            set_error("sd_render_pass: workspace of %zu B needed, %zu B given", need, workspace_bytes);
+            return SD_ERR_WORKSPACE;
+        }
+        if (rr.cmma == 2) {
+            SD_REQUIRE(((uintptr_t)workspace & 15) == 0, "sd_render_pass: workspace must be 16-byte aligned");
+            rr.hsum = reinterpret_cast<float *>(workspace);
+            rr.wsum = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) + align256((size_t)R * 128 * 4));
+        } else if (use_ws) {
             rr.rgb_samps = reinterpret_cast<float *>(workspace);
         }
         TcOut o = {};
         o.sigma = sigma; o.invalid = invalid; o.invalid_feat = invalid_feat;
-        return launch_field_tc(fp, src, N, mlp, &rr, o, st, nullptr, scene->feat_proj);
+        rc = launch_field_tc(fp, src, N, mlp, &rr, o, st, nullptr, scene->feat_proj);
+        if (rc || rr.cmma != 2 || !dino) return rc;
+        // sum_k w_k (W h_k + b) = W (sum_k w_k h_k) + b sum_k w_k: the feature rows of W_out on the per-ray sums
+        return launch_head2(mlp, rr.hsum, rr.wsum, R, dino, st);
     }
 
     const size_t need = sd_render_workspace_bytes(scene, mlp, R, K);

@@ -25,6 +25,7 @@ void count_launch(int n = 1);
 constexpr int SD_MAX_DEVICES = 64;
 struct DeviceOnce { int sm_count[SD_MAX_DEVICES]; };
 int device_once(DeviceOnce &seen, int *sm_count, bool *first);
+int debug_mask();                       // SD_TC_DEBUG, read once per process (timing experiments; 0 in production)
 void profile_before(cudaStream_t st);   // sd_profile_next_kernel: events around the dominant (field) kernel
 void profile_after(cudaStream_t st);
 
@@ -92,6 +93,10 @@ struct MlpLayout {
     size_t off_w_in_h;   // fp16 UMMA K-major SW128 image of W_in:  [d_in_pad/64 blocks][d_hidden rows][64]
     size_t off_w_out_h;  // fp16 UMMA K-major SW128 image of W_out[1:]: [d_hidden/64 blocks][d_out_pad rows][64]
     size_t off_w_sigma;  // fp32 [d_hidden]  = W_out[0,:]  (density row, evaluated in fp32)
+    size_t off_w_sig_h;  // d_hidden == 128: fp16 K-major SW128 image [2 K blocks][16 rows][64] whose row 0 is the density row
+                         // W_out[0,:] (layer 2 of the hidden-composite render mode: only sigma is needed per sample)
+    size_t off_w_feat_blk;  // d_hidden == 128: W_out[1:] in blocks of 128 output rows, each a complete B operand
+                         // [2 K blocks][128 rows][64] (zero rows behind d_out - 1): head2 kernel (expand_tc.cu)
     size_t off_x_w2;     // expand heads (64 -> 128 -> multiple of 128): fp16 K-major SW128 images of W_out in blocks of 128
                          // outputs, [d_out/128][2 K blocks][128 rows][64] (expand_tc.cu); 0 = absent
     size_t total;

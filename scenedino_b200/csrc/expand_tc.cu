@@ -50,6 +50,9 @@ static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
 static_assert(STAGE_ROW % 16 == 0, "staging rows hold 16-byte accesses");
 
 struct Params {
+    int head2;                                // 1: second layer only, on explicit hidden rows (launch_head2)
+    const float *h;                           // head2: [N][128] fp32 hidden rows (per-ray sums of the hidden-composite render)
+    const float *scale;                       // head2: [N] factor of the bias (sum of the compositing weights) or NULL = 1
     const float *f;                           // [N][64]
     float *out;                               // [N][d_out]
     const unsigned char *w1_img;              // K-major SW128 image of W1 (first K block of the blob's W_in image)
@@ -81,9 +84,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
     }
     float *s_b1 = reinterpret_cast<float *>(sm + OFF_B1), *s_b2 = reinterpret_cast<float *>(sm + OFF_B2);
     for (int i = tid; i < 128; i += NTHREADS) s_b1[i] = __ldg(P.b1 + i);
-    for (int i = tid; i < P.d_out; i += NTHREADS) s_b2[i] = __ldg(P.b2 + i);
+    for (int i = tid; i < P.nch * 128; i += NTHREADS) s_b2[i] = i < P.d_out ? __ldg(P.b2 + i) : 0.0f;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !P.head2) {
         mbar_expect_tx(BAR(BAR_WLOAD), 16384);
         bulk_g2s(sm_u + OFF_W1, P.w1_img, 16384, BAR(BAR_WLOAD));
     }
@@ -93,7 +96,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
     const long long first = blockIdx.x, stride = gridDim.x;
     const long long my_tiles = P.n_tiles > first ? (P.n_tiles - first + stride - 1) / stride : 0;
-    const int nsteps = 2 * P.nch;             // chunk steps per tile: pass 0 (norm) and pass 1 (store)
+    // chunk steps per tile: pass 0 (norm) and pass 1 (store); head2 has no normalisation: one pass
+    const int nsteps = P.head2 ? P.nch : 2 * P.nch;
+    const int first_store = P.head2 ? 0 : P.nch;
 
     if (warp < 4) {
         const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -105,6 +110,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
         for (long long j = 0; j < my_tiles; ++j) {
             const long long tile = first + j * stride;
             const long long row = tile * TM + r_tile;
+            float bscale = 1.0f;
+            if (P.head2) {
+                // ---- hidden rows given: fp32 -> fp16 pairs straight into the TMEM columns layer 2 reads as its A operand
+                const uint4 *src = reinterpret_cast<const uint4 *>(P.h + row * 128);
+#pragma unroll 1
+                for (int kb = 0; kb < 4; ++kb) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+                        if (row < P.N) a = __ldg(src + kb * 8 + e);
+                        pk[2 * e] = pack_h2(__uint_as_float(a.x), __uint_as_float(a.y));
+                        pk[2 * e + 1] = pack_h2(__uint_as_float(a.z), __uint_as_float(a.w));
+                    }
+                    tmem_st16(t_lane + kb * 16, pk);
+                }
+                if (P.scale && row < P.N) bscale = __ldg(P.scale + row);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive_warp(BAR(BAR_H_FULL));
+            } else {
             // ---- A operand: this thread's row, fp32 -> fp16, 16-byte chunk q at position q ^ (row & 7) ----------
             {
                 const uint4 *src = reinterpret_cast<const uint4 *>(P.f + row * 64);
@@ -141,12 +167,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive_warp(BAR(BAR_H_FULL));
-            // ---- epilogue 2: two passes over the output chunks -------------------------------------------------
-            float ss = 0.0f, inv = 0.0f;
+            }
+            // ---- epilogue 2: two passes over the output chunks (head2: one) -------------------------------------
+            float ss = 0.0f, inv = 1.0f;
             for (int s = 0; s < nsteps; ++s, ++g) {
                 const int b = (int)(g & 1);
                 const int c = s < P.nch ? s : s - P.nch;
-                const bool store = s >= P.nch;
+                const bool store = s >= first_store;
                 if (s == P.nch) {
                     const float nrm = sqrtf(ss);
                     inv = 1.0f / (nrm > 1e-12f ? nrm : 1e-12f);
@@ -170,10 +197,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             float4 o;
-                            o.x = (__uint_as_float(vr[4 * e + 0]) + bias[4 * e + 0]) * inv;
-                            o.y = (__uint_as_float(vr[4 * e + 1]) + bias[4 * e + 1]) * inv;
-                            o.z = (__uint_as_float(vr[4 * e + 2]) + bias[4 * e + 2]) * inv;
-                            o.w = (__uint_as_float(vr[4 * e + 3]) + bias[4 * e + 3]) * inv;
+                            o.x = fmaf(bias[4 * e + 0], bscale, __uint_as_float(vr[4 * e + 0])) * inv;
+                            o.y = fmaf(bias[4 * e + 1], bscale, __uint_as_float(vr[4 * e + 1])) * inv;
+                            o.z = fmaf(bias[4 * e + 2], bscale, __uint_as_float(vr[4 * e + 2])) * inv;
+                            o.w = fmaf(bias[4 * e + 3], bscale, __uint_as_float(vr[4 * e + 3])) * inv;
                             *reinterpret_cast<float4 *>(stage + lane * STAGE_ROW + e * 16) = o;
                         }
                     }
@@ -184,14 +211,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                     // copy-out: row rr of the warp is one 512-byte STG.128 of the whole warp
                     const long long row0 = tile * TM + warp * 32;
                     float *dst = P.out + row0 * P.d_out + c * 128 + lane * 4;
+                    const int cols = P.d_out - (c * 128 + lane * 4);      // columns of this lane's quad inside the row
 #pragma unroll 1
                     for (int r0 = 0; r0 < 32; r0 += 8) {
                         float4 v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = lds128_ordered(stage_u + (r0 + i) * STAGE_ROW + lane * 16);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (row0 + r0 + i < P.N) stg128_ordered(dst + (long long)(r0 + i) * P.d_out, v[i]);
+                        for (int i = 0; i < 8; ++i) {
+                            if (row0 + r0 + i >= P.N) continue;
+                            float *d = dst + (long long)(r0 + i) * P.d_out;
+                            if (cols >= 4 && !(P.d_out & 3)) stg128_ordered(d, v[i]);
+                            else {                                   // ragged last chunk / rows that are not 16-byte aligned
+                                if (cols > 0) d[0] = v[i].x;
+                                if (cols > 1) d[1] = v[i].y;
+                                if (cols > 2) d[2] = v[i].z;
+                                if (cols > 3) d[3] = v[i].w;
+                            }
+                        }
                     }
                 }
             }
@@ -212,16 +249,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
         }
     } else {
         if (lane == 0) {
-            mbar_wait(BAR(BAR_WLOAD), 0);
+            if (!P.head2) mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc = umma_idesc(TM, 128);
             long long g = 0;
             for (long long j = 0; j < my_tiles; ++j) {
-                mbar_wait(BAR(BAR_A_FULL), (uint32_t)(j & 1));
-                tc_fence_after();
+                if (!P.head2) {
+                    mbar_wait(BAR(BAR_A_FULL), (uint32_t)(j & 1));
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
-                umma_commit(BAR(BAR_D1_FULL));
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
+                    umma_commit(BAR(BAR_D1_FULL));
+                }
                 mbar_wait(BAR(BAR_H_FULL), (uint32_t)(j & 1));
                 tc_fence_after();
                 for (int s = 0; s < nsteps; ++s, ++g) {
@@ -285,6 +324,36 @@ int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out,
     profile_before(st);
     ex::expand_tc_kernel<<<grid, ex::NTHREADS, ex::SMEM_ALLOC, st>>>(P);
     profile_after(st);
+    SD_LAUNCH_OK("expand_tc_kernel");
+    return SD_OK;
+}
+
+int launch_head2(const sd_mlp *mlp, const float *h, const float *scale, long long R, float *out, cudaStream_t st) {
+    SD_REQUIRE(mlp && mlp->packed && mlp->d_hidden == 128 && mlp->d_out >= 2 && mlp->d_out - 1 <= ex::MAX_DOUT,
+               "head2: needs a packed head with d_hidden = 128 and at most %d feature outputs", ex::MAX_DOUT);
+    if (R == 0) return SD_OK;
+    SD_REQUIRE(R > 0 && h && out, "head2: null pointer");
+    SD_REQUIRE(((uintptr_t)h & 15) == 0 && ((uintptr_t)out & 15) == 0, "head2: h and out must be 16-byte aligned");
+    const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
+    SD_REQUIRE(L.off_w_feat_blk != 0, "head2: the blob carries no feature-row images");
+    const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
+    SD_REQUIRE(((uintptr_t)blob & 15) == 0, "mlp: packed blob must be 16-byte aligned");
+    ex::Params P = {};
+    P.head2 = 1; P.h = h; P.scale = scale; P.out = out;
+    P.w2_img = blob + L.off_w_feat_blk;
+    P.b1 = reinterpret_cast<const float *>(blob + L.off_b_in);               // (unused)
+    P.b2 = reinterpret_cast<const float *>(blob + L.off_b_out) + 1;          // biases of the feature rows W_out[1:]
+    P.N = R; P.n_tiles = (R + ex::TM - 1) / ex::TM;
+    P.d_out = mlp->d_out - 1; P.nch = (P.d_out + 127) / 128;
+    static DeviceOnce once;
+    int sm_count = 0;
+    bool first_use = false;
+    if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
+    if (first_use) {
+        SD_CUDA_OK(cudaFuncSetAttribute(ex::expand_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ex::SMEM_ALLOC));
+    }
+    const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
+    ex::expand_tc_kernel<<<grid, ex::NTHREADS, ex::SMEM_ALLOC, st>>>(P);
     SD_LAUNCH_OK("expand_tc_kernel");
     return SD_OK;
 }

@@ -685,10 +685,7 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     P.tiles = order.tiles;
     P.tile_ctr = order.tile_ctr;
     P.N = N;
-    {
-        const char *e = getenv("SD_TC_DEBUG");
-        P.dbg = e ? atoi(e) : 0;
-    }
+    P.dbg = debug_mask();
     P.n_tiles = (N + tb::TM - 1) / tb::TM;
     P.D = mlp->d_out - 1;
     P.n2 = (mlp->d_out + 15) / 16 * 16;

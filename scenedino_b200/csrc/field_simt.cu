@@ -279,14 +279,19 @@ __global__ void __launch_bounds__(NTHREADS) mlp_simt_kernel(const float *__restr
     }
 }
 
-__global__ void __launch_bounds__(256) project_points_kernel(Camera cam, const float *__restrict__ xyz, long long N,
+// (camera matrices are read from device memory like everywhere else: no host round trip, graph-capturable)
+__global__ void __launch_bounds__(256) project_points_kernel(const float *__restrict__ Kd, const float *__restrict__ Wd,
+                                                             const float *__restrict__ xyz, long long N,
                                                              float *__restrict__ xy, float *__restrict__ z,
                                                              unsigned char *__restrict__ invalid) {
+    __shared__ float cam[21];
+    if (threadIdx.x < 21) cam[threadIdx.x] = threadIdx.x < 9 ? __ldg(Kd + threadIdx.x) : __ldg(Wd + (threadIdx.x - 9));
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float x, y, zz;
     bool inv;
-    project_point(cam.K, cam.w2c, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, zz, inv);
+    project_point(cam, cam + 9, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, zz, inv);
     if (xy) { xy[2 * i] = x; xy[2 * i + 1] = y; }
     if (z) z[i] = zz;
     if (invalid) invalid[i] = inv ? 1 : 0;
@@ -411,16 +416,8 @@ extern "C" int sd_project_points(const float *K, const float *w2c, const float *
     SD_REQUIRE(N >= 0, "sd_project_points: bad N");
     if (N == 0) return SD_OK;
     SD_REQUIRE(K && w2c && xyz, "sd_project_points: null pointer");
-    // camera matrices are tiny: fetch them synchronously w.r.t. the stream, then pass by value
-    Camera cam;
-    float hK[9], hW[16];
     cudaStream_t st = (cudaStream_t)stream;
-    SD_CUDA_OK(cudaMemcpyAsync(hK, K, sizeof(hK), cudaMemcpyDeviceToHost, st));
-    SD_CUDA_OK(cudaMemcpyAsync(hW, w2c, sizeof(hW), cudaMemcpyDeviceToHost, st));
-    SD_CUDA_OK(cudaStreamSynchronize(st));
-    for (int i = 0; i < 9; ++i) cam.K[i] = hK[i];
-    for (int i = 0; i < 12; ++i) cam.w2c[i] = hW[i];
-    project_points_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(cam, xyz, N, xy, z, invalid);
+    project_points_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(K, w2c, xyz, N, xy, z, invalid);
     SD_LAUNCH_OK("project_points_kernel");
     return SD_OK;
 }

@@ -40,6 +40,9 @@ constexpr int TMEM_COLS = 512;
 constexpr int D2_COL = 256;                  // layer-1 accumulators at columns 0 and 128, layer 2 (<= 80 columns) at 256
 constexpr int H_COL = 384;                   // fp16 hidden tile (A operand of layer 2): 64 columns, two halves per column
 constexpr int D3X_COL = 336, D3F_COL = 448;  // composite on the tensor cores: per-ray sums of (depth, sum w, colours) / of the 64 features
+// hidden-composite mode (cmma == 2): layer 2 is the density row alone (16 columns at D2_COL), the composite sums the 128
+// ReLU'd hidden units per ray (the feature rows of W_out are applied to the per-ray sums afterwards: both are linear)
+constexpr int D3X_COL2 = 272, H_COL2 = 288, D3H_COL2 = 352;
 constexpr int PART_STRIDE = 80;              // per (warp, segment) composite partial: 64 feat + depth + wsum + 12 rgb
 constexpr int MAX_NVC_TC = 4;
 constexpr int W2_BYTES = 2 * 80 * 128;       // [2 K blocks][<= 80 rows][128 B]
@@ -81,6 +84,16 @@ enum { BAR_FULL = 0, BAR_EMPTY = MAX_CHUNKS, BAR_D1 = 2 * MAX_CHUNKS, BAR_H = BA
 // field_bin.cu) in the output staging area, which render mode does not use.
 constexpr int OFF_A3 = OFF_W1 + 3 * CHUNK_BYTES;
 constexpr int OFF_B3 = OFF_H;
+constexpr int OFF_X3 = OFF_H + CHUNK_BYTES;          // (depth, 1, colours, depth lo) rows: B operand of the small composite MMA
+// cmma == 2: V = the tile's ReLU'd hidden rows as fp16, B operand [128 rows (K)][128 units (N)], MN-major, two 64-unit
+// halves of 16 KB in the two ring chunks a projected scene leaves unused; single buffered (the first epilogue of tile
+// j waits for the composite of tile j-1)
+constexpr int OFF_V = OFF_RING + 3 * CHUNK_BYTES;
+// per-sample colours of a tile as packed halves (12 values + padding = 32 B per row), handed from the point warps to the
+// epilogue next to the Geo slots: the composite takes them as fp16 anyway, so they never make a round trip through HBM
+constexpr int COL_SLOT = TM * 32;
+constexpr int OFF_COL1 = OFF_RING + 3 * CHUNK_BYTES, OFF_COL2 = OFF_H;   // cmma == 1 / cmma == 2
+static_assert(NGEO * COL_SLOT <= CHUNK_BYTES, "colour ring fits into one spare chunk");
 
 struct Params {
     int mode;
@@ -93,7 +106,10 @@ struct Params {
     int upt;                  // units per tile
     long long n_tiles;
     int nch;                  // K chunks of layer 1
-    int cmma;                 // render mode: composite on the tensor cores (projected scene)
+    int cmma;                 // render mode on a projected scene, composite on the tensor cores: 1 = of the <= 64 features,
+                              // 2 = of the 128 hidden units (any D; per-ray sums to hsum / wsum, W_out applied by the head2 kernel)
+    int sig_col;              // column of the density in the layer-2 accumulator
+    float *hsum, *wsum;       // cmma == 2: [rays][128] per-ray sums of w * relu(hidden), [rays] sums of w
     int n2;                   // layer-2 N: D feature rows + the density row, padded to 16
     int D;                    // feature outputs = d_out - 1
     const unsigned char *w1_img, *w2_img;
@@ -112,13 +128,12 @@ struct Params {
 };
 
 __device__ long long g_trace[4 * 64 * 8];   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
-__constant__ int c_dbg;   // copy of Params::dbg for the PTX wrappers (timing experiments)
 
 using namespace tcx;
 
 #define SD_TRACE(role, j, ev)                                                                    \
     do {                                                                                         \
-        if ((c_dbg & 8192) && blockIdx.x == 0 && (j) < 64 && (threadIdx.x & 31) == 0)             \
+        if ((P.dbg & 8192) && blockIdx.x == 0 && (j) < 64 && (threadIdx.x & 31) == 0)             \
             g_trace[((role) * 64 + (int)(j)) * 8 + (ev)] = clock64();                            \
     } while (0)
 
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
         for (int i = tid; i < 2 * CHUNK_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A3)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
         // the partial-sum area is free in this mode: keep the output bias of the features there
-        if (tid < 64) reinterpret_cast<float *>(sm + OFF_PART)[tid] = tid < P.D ? __ldg(P.b_out + 1 + tid) : 0.0f;
+        if (P.cmma == 1 && tid < 64) reinterpret_cast<float *>(sm + OFF_PART)[tid] = tid < P.D ? __ldg(P.b_out + 1 + tid) : 0.0f;
     }
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u + OFF_TMEM), "r"(TMEM_COLS) : "memory");
@@ -190,6 +205,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(sm + OFF_TMEM);
+    const uint32_t h_col = P.cmma == 2 ? H_COL2 : H_COL, d3x_col = P.cmma == 2 ? D3X_COL2 : D3X_COL;
+    const uint32_t d3f_col = P.cmma == 2 ? D3H_COL2 : D3F_COL;
+    const int off_col = P.cmma == 2 ? OFF_COL2 : OFF_COL1;
 
     const long long first = blockIdx.x, stride = gridDim.x;
     const long long my_tiles = P.n_tiles > first ? (P.n_tiles - first + stride - 1) / stride : 0;
@@ -214,6 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 
         float z_keep = 0.0f, zn_keep = 0.0f;
         long long grow_keep = -1;
+        uint32_t crgb_h[6] = {0u, 0u, 0u, 0u, 0u, 0u};           // this row's colours as packed halves (cmma)
         // composite on the tensor cores: the per-ray sums are read back and written out by point warp 3 (cm_output)
         long long cm_n = 0;          // composites handed to the MMA issuer so far
         for (long long j = 0; j <= my_tiles; ++j) {
@@ -223,20 +242,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 const int nrgb = 3 * P.fp.nv_c;
                 float crgb[3 * MAX_NVC_TC];
 #pragma unroll
-                for (int c = 0; c < 3 * MAX_NVC_TC; ++c)
-                    crgb[c] = (render && grow_keep >= 0 && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
+                for (int c = 0; c < 3 * MAX_NVC_TC; ++c)   // (cmma: the colours came through shared memory as halves, crgb_h)
+                    crgb[c] = (render && !P.cmma && grow_keep >= 0 && c < nrgb && P.rgb) ? __ldcg(P.rgb + grow_keep * nrgb + c) : 0.0f;
                 mbar_wait(BAR(BAR_D2), (uint32_t)((j - 1) & 1));
                 tc_fence_after();
                 if (warp == 0) SD_TRACE(0, j, 0);
                 const long long tile = first + (j - 1) * stride;
                 uint32_t vr[64], sr;
-                tmem_ld32_issue(t_lane + D2_COL, vr);
-                tmem_ld32_issue(t_lane + D2_COL + 32, vr + 32);
-                tmem_ld1_issue(t_lane + D2_COL + D, sr);                          // density column sits behind the features
+                if (P.cmma != 2) {
+                    tmem_ld32_issue(t_lane + D2_COL, vr);
+                    tmem_ld32_issue(t_lane + D2_COL + 32, vr + 32);
+                }
+                tmem_ld1_issue(t_lane + D2_COL + P.sig_col, sr);                  // density column (behind the features)
                 tmem_ld_wait();
                 float v[64];
 #pragma unroll
-                for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(vr[c]);
+                for (int c = 0; c < 64; ++c) v[c] = P.cmma != 2 ? __uint_as_float(vr[c]) : 0.0f;
                 const float sig = __uint_as_float(sr) + bo_sigma;
                 const float sg = P.mode == MODE_ROWS ? sig : softplus(sig);
                 const bool ok = grow_keep >= 0;
@@ -312,26 +333,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         //      out[ray][:] = sum_row Wt[ray][row] * V[row][:]; the MMA issuer does the rest ---------
                         if (warp == 0) SD_TRACE(0, j, 5);
                         // the previous composite has consumed the operands and its sums have been read from TMEM
+                        // (cmma == 2: the first epilogue of this tile waited already, before it wrote V)
                         if (cm_n > 0) mbar_wait(BAR(BAR_D3_READ), (uint32_t)((cm_n - 1) & 1));
                         if (warp == 0) SD_TRACE(0, j, 6);
-                        unsigned char *brow = sm + OFF_B3 + row * 128;
+                        if (P.cmma == 1) {
+                            unsigned char *brow = sm + OFF_B3 + row * 128;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {                  // 64 features (bias added at the output)
-                            uint4 o;
-                            o.x = ok ? pack_h2(v[8 * q + 0], v[8 * q + 1]) : 0u; o.y = ok ? pack_h2(v[8 * q + 2], v[8 * q + 3]) : 0u;
-                            o.z = ok ? pack_h2(v[8 * q + 4], v[8 * q + 5]) : 0u; o.w = ok ? pack_h2(v[8 * q + 6], v[8 * q + 7]) : 0u;
-                            *reinterpret_cast<uint4 *>(brow + ((q ^ (row & 7)) << 4)) = o;
+                            for (int q = 0; q < 8; ++q) {              // 64 features (bias added at the output)
+                                uint4 o;
+                                o.x = ok ? pack_h2(v[8 * q + 0], v[8 * q + 1]) : 0u; o.y = ok ? pack_h2(v[8 * q + 2], v[8 * q + 3]) : 0u;
+                                o.z = ok ? pack_h2(v[8 * q + 4], v[8 * q + 5]) : 0u; o.w = ok ? pack_h2(v[8 * q + 6], v[8 * q + 7]) : 0u;
+                                *reinterpret_cast<uint4 *>(brow + ((q ^ (row & 7)) << 4)) = o;
+                            }
                         }
-                        {                                              // depth, 1 (sum of weights), colours
-                            float x[16];
-                            x[0] = ok ? z_keep : 0.0f; x[1] = ok ? 1.0f : 0.0f;
-#pragma unroll
-                            for (int c = 0; c < 14; ++c) x[2 + c] = c < 3 * MAX_NVC_TC ? crgb[c] : 0.0f;
-                            unsigned char *xrow = brow + CHUNK_BYTES;
+                        {   // depth (hi), 1 (sum of weights), 12 colours, depth (lo): the depth keeps ~21 bits through fp16
+                            const float z_hi = __half2float(__float2half_rn(z_keep));
+                            unsigned char *xrow = sm + OFF_X3 + row * 128;
                             *reinterpret_cast<uint4 *>(xrow + ((0 ^ (row & 7)) << 4)) =
-                                make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
+                                ok ? make_uint4(pack_h2(z_hi, 1.0f), crgb_h[0], crgb_h[1], crgb_h[2]) : make_uint4(0u, 0u, 0u, 0u);
                             *reinterpret_cast<uint4 *>(xrow + ((1 ^ (row & 7)) << 4)) =
-                                make_uint4(pack_h2(x[8], x[9]), pack_h2(x[10], x[11]), pack_h2(x[12], x[13]), pack_h2(x[14], x[15]));
+                                ok ? make_uint4(crgb_h[3], crgb_h[4], crgb_h[5], pack_h2(z_keep - z_hi, 0.0f)) : make_uint4(0u, 0u, 0u, 0u);
                         }
                         const unsigned short wh = __half_as_ushort(__float2half_rn(wgt));
                         for (int u = 0; u < P.upt; ++u)                // weight matrix: column = this row, row = ray of the tile
@@ -426,9 +447,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 if (render) {
                     z_keep = s_geo[slot].z[row];
                     zn_keep = row + 1 < TM ? s_geo[slot].z[row + 1] : 0.0f;
+                    if (P.cmma) {
+                        const uint4 *cr = reinterpret_cast<const uint4 *>(sm + off_col + slot * COL_SLOT + row * 32);
+                        const uint4 c0 = cr[0], c1 = cr[1];
+                        crgb_h[0] = c0.x; crgb_h[1] = c0.y; crgb_h[2] = c0.z; crgb_h[3] = c0.w; crgb_h[4] = c1.x; crgb_h[5] = c1.y;
+                    }
                 }
                 mbar_arrive_warp(BAR(BAR_GEO_EMPTY + slot));
             }
+            // cmma == 2: V is single buffered -- the composite of the previous tile must have consumed it
+            if (P.cmma == 2 && cm_n > 0) mbar_wait(BAR(BAR_D3_READ), (uint32_t)((cm_n - 1) & 1));
             if (warp == 0) SD_TRACE(0, j, 2);
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));
@@ -443,7 +471,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
                     pk[e] = pack_h2(fmaxf(__uint_as_float(vr[2 * e]), 0.0f), fmaxf(__uint_as_float(vr[2 * e + 1]), 0.0f));
-                tmem_st32(t_lane + H_COL + kb * 32, pk);
+                tmem_st32(t_lane + h_col + kb * 32, pk);
+                if (P.cmma == 2) {                               // the same 64 units as one 128-byte row of V's half kb
+                    unsigned char *vrow = sm + OFF_V + kb * CHUNK_BYTES + row * 128;
+                    const bool live = grow_keep >= 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4 *>(vrow + ((q ^ (row & 7)) << 4)) =
+                            live ? make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]) : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -463,19 +499,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 SD_TRACE(1, jj + 1, 6);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts(tmem_base + D2_COL, tmem_base + H_COL + k * 8,
+                    umma_ts(tmem_base + D2_COL, tmem_base + h_col + k * 8,
                             umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
                 umma_commit(BAR(BAR_D2));
             };
-            const uint32_t idesc3f = umma_idesc(TM, 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
-            auto composite = [&](long long jj) {   // per-ray sums of tile jj: Wt [128 x 128 rows] . V [128 rows x (64 | 16)]
+            const uint32_t idesc3f = umma_idesc(TM, P.cmma == 2 ? 128 : 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
+            const uint32_t off_v3 = P.cmma == 2 ? OFF_V : OFF_B3;
+            auto composite = [&](long long jj) {   // per-ray sums of tile jj: Wt [128 x 128 rows] . V [128 rows x (64 | 128 | 16)]
                 mbar_wait(BAR(BAR_B3), (uint32_t)(jj & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t a = umma_desc(sm_u + OFF_A3 + (k >> 2) * CHUNK_BYTES + (k & 3) * 32);
-                    umma(tmem_base + D3F_COL, a, umma_desc_mn(sm_u + OFF_B3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
-                    umma(tmem_base + D3X_COL, a, umma_desc_mn(sm_u + OFF_B3 + CHUNK_BYTES + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
+                    umma(tmem_base + d3f_col, a, umma_desc_mn(sm_u + off_v3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
+                    umma(tmem_base + d3x_col, a, umma_desc_mn(sm_u + OFF_X3 + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
                 }
                 umma_commit(BAR(BAR_D3));
             };
@@ -485,22 +522,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 mbar_wait(BAR(BAR_D3), (uint32_t)(jj & 1));
                 tc_fence_after();
                 uint32_t xr[16], fr[64];
-                tmem_ld16_issue(tmem_base + D3X_COL, xr);
-                tmem_ld32_issue(tmem_base + D3F_COL, fr);
-                tmem_ld32_issue(tmem_base + D3F_COL + 32, fr + 32);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive_warp(BAR(BAR_D3_READ));                       // the accumulators may be overwritten
                 const int lane_ = lane;
                 const long long ray = (first + jj * stride) * P.upt + lane_;   // TMEM lane = ray of the tile
+                tmem_ld16_issue(tmem_base + d3x_col, xr);
+                if (P.cmma == 2) {
+                    // the 128 hidden sums of ray `lane` leave in two halves of 64 columns (a ray's row is 512 contiguous bytes)
+#pragma unroll 1
+                    for (int hq = 0; hq < 2; ++hq) {
+                        tmem_ld32_issue(tmem_base + d3f_col + hq * 64, fr);
+                        tmem_ld32_issue(tmem_base + d3f_col + hq * 64 + 32, fr + 32);
+                        tmem_ld_wait();
+                        if (lane_ < P.upt && ray < P.n_units) {
+                            float4 *o = reinterpret_cast<float4 *>(P.hsum + ray * 128 + hq * 64);
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                o[q] = make_float4(__uint_as_float(fr[4 * q]), __uint_as_float(fr[4 * q + 1]),
+                                                   __uint_as_float(fr[4 * q + 2]), __uint_as_float(fr[4 * q + 3]));
+                        }
+                    }
+                } else {
+                    tmem_ld32_issue(tmem_base + d3f_col, fr);
+                    tmem_ld32_issue(tmem_base + d3f_col + 32, fr + 32);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                mbar_arrive_warp(BAR(BAR_D3_READ));                       // the accumulators may be overwritten
                 if (lane_ < P.upt && ray < P.n_units) {
                     const float wsum = __uint_as_float(xr[1]);
                     const int nrgb = 3 * P.fp.nv_c;
-                    if (P.depth) P.depth[ray] = __uint_as_float(xr[0]);
+                    if (P.depth) P.depth[ray] = __uint_as_float(xr[0]) + __uint_as_float(xr[14]);
+                    if (P.cmma == 2 && P.wsum) P.wsum[ray] = wsum;
                     if (P.rgb_ray)
                         for (int c = 0; c < nrgb; ++c)
                             P.rgb_ray[ray * nrgb + c] = P.cfg.white_bkgd ? __uint_as_float(xr[2 + c]) + 1.0f - wsum : __uint_as_float(xr[2 + c]);
-                    if (P.dino_ray) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
+                    if (P.dino_ray && P.cmma == 1) {   // sum_k w_k (f_k + b) = sum_k w_k f_k + b * sum_k w_k
                         if (D == 64) {
                             float4 *o = reinterpret_cast<float4 *>(P.dino_ray + ray * 64);
 #pragma unroll
@@ -598,6 +653,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 const float zs = cur.zs;
                 int flags = 0, off = 0;
                 Tap t = {};
+                const bool ring_col = render && P.cmma;              // colours go to the epilogue through shared memory
+                float call[3 * MAX_NVC_TC];
+#pragma unroll
+                for (int c = 0; c < 3 * MAX_NVC_TC; ++c) call[c] = 0.0f;
                 if (ok) {
                     const float px = cur.px, py = cur.py, pz = cur.pz;
                     float zc;
@@ -614,21 +673,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     off = t.y0 * P.fp.Wf + t.x0;
                     flags = (inv ? 1 : 0) | 8;
                     if (P.invalid_feat) P.invalid_feat[grow] = inv ? 1 : 0;
-                    if (nv_c > 0 && (P.rgb || P.invalid)) {
-                        for (int v = 0; v < nv_c; ++v) {
+                    const bool want_col = P.rgb || (ring_col && P.rgb_ray);
+                    if (nv_c > 0 && (want_col || P.invalid)) {
+#pragma unroll
+                        for (int v = 0; v < MAX_NVC_TC; ++v) {
+                            if (v >= nv_c) break;
                             float cx, cy, cz;
                             bool cinv;
                             const float *c = s_cam + 21 * (1 + v);
                             project_point(c, c + 9, px, py, pz, cx, cy, cz, cinv);
-                            if (P.rgb) {
+                            if (want_col) {
                                 float c3[3];
                                 sample_color(P.fp.rgb + (size_t)v * 3 * P.fp.Hc * P.fp.Wc, P.fp.Hc, P.fp.Wc, cx, cy, c3);
-                                float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
-                                o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
+                                call[3 * v] = c3[0]; call[3 * v + 1] = c3[1]; call[3 * v + 2] = c3[2];
+                                if (P.rgb) {
+                                    float *o = P.rgb + (size_t)grow * 3 * nv_c + 3 * v;
+                                    o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2];
+                                }
                             }
                             if (P.invalid) P.invalid[(size_t)grow * nv_c + v] = (cinv || inv) ? 1.0f : 0.0f;
                         }
                     }
+                }
+                if (ring_col) {
+                    uint4 *cr = reinterpret_cast<uint4 *>(sm + off_col + slot * COL_SLOT + row * 32);
+                    cr[0] = make_uint4(pack_h2(call[0], call[1]), pack_h2(call[2], call[3]), pack_h2(call[4], call[5]), pack_h2(call[6], call[7]));
+                    cr[1] = make_uint4(pack_h2(call[8], call[9]), pack_h2(call[10], call[11]), 0u, 0u);
                 }
                 Geo &g = s_geo[slot];
                 {
@@ -815,18 +885,30 @@ extern "C" int sd_debug_read_trace(long long *host_out) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-static bool tc_head_ok(const sd_mlp *mlp) {
-    return mlp && mlp->packed && mlp->d_hidden == 128 && mlp->d_out >= 2 && mlp->d_out - 1 <= 64 && mlp->d_in >= 1 &&
+constexpr int TC_MAX_D = 64;      // feature outputs the kernel's own layer 2 produces; above: hidden-composite render (any D)
+static bool tc_head_ok(const sd_mlp *mlp, bool any_d = false) {
+    return mlp && mlp->packed && mlp->d_hidden == 128 && mlp->d_out >= 2 && (any_d || mlp->d_out - 1 <= TC_MAX_D) && mlp->d_in >= 1 &&
            mlp->d_in + 8 <= 64 * tc::MAX_CHUNKS;
 }
 
-static bool tc_scene_ok(const sd_scene *s, const sd_mlp *mlp) {
-    return s && s->feat_dtype == SD_F16 && s->C == 256 && s->Hf >= 2 && s->Wf >= 2 && s->nv_f == 1 && s->include_input && s->num_freqs == 6 &&
-           s->nv_c <= tc::MAX_NVC_TC && tc_head_ok(mlp) && mlp->d_in == s->C + 39;
+static bool tc_scene_ok(const sd_scene *s, const sd_mlp *mlp, bool any_d) {
+    return s && (s->feat_dtype == SD_F16 || s->feat_proj) && s->C == 256 && s->Hf >= 2 && s->Wf >= 2 && s->nv_f == 1 && s->include_input &&
+           s->num_freqs == 6 && s->nv_c <= tc::MAX_NVC_TC && tc_head_ok(mlp, any_d) && mlp->d_in == s->C + 39;
 }
 
+// Render mode.  A head with more than 64 feature outputs (the 768-d DINO variant) needs a projected scene: the composite
+// then sums the 128 hidden units per ray and the feature rows of W_out are applied to the sums (tc_render_mode() == 2).
 bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K) {
-    return tc_scene_ok(scene, mlp) && K >= 32 && K <= tc::TM;
+    const bool big = mlp && mlp->d_out - 1 > TC_MAX_D;
+    return tc_scene_ok(scene, mlp, big && scene && scene->feat_proj) && K >= 32 && K <= tc::TM;
+}
+
+// 0: composite in the epilogue (shuffles; unprojected scene), 1: tensor-core composite of the features, 2: of the hidden units
+int tc_render_mode(const sd_scene *scene, const sd_mlp *mlp) {
+    if (!scene || !mlp || !scene->feat_proj) return 0;
+    if (mlp->d_out - 1 > TC_MAX_D) return 2;
+    static const int forced = [] { const char *e = getenv("SD_TC_HCOMP"); return e ? atoi(e) : -1; }();
+    return forced == 1 ? 2 : 1;
 }
 
 static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st, const void *proj = nullptr) {
@@ -847,18 +929,19 @@ static int tc_launch(tc::Params &P, const sd_mlp *mlp, cudaStream_t st, const vo
     }
     P.w2_img = blob + L.off_w_out_h;
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
-    {
-        const char *e = getenv("SD_TC_DEBUG");
-        P.dbg = e ? atoi(e) : 0;
-    }
-    static int last_dbg = 0;
-    if (P.dbg != last_dbg) {
-        SD_CUDA_OK(cudaMemcpyToSymbol(tc::c_dbg, &P.dbg, sizeof(int)));
-        last_dbg = P.dbg;
-    }
+    P.dbg = debug_mask();
     P.D = mlp->d_out - 1;
-    P.cmma = proj && P.mode == tc::MODE_RENDER && P.D <= 64;
+    if (!(proj && P.mode == tc::MODE_RENDER)) P.cmma = 0;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
+    P.sig_col = P.D;
+    if (P.cmma == 2) {     // layer 2 = the density row alone
+        SD_REQUIRE(L.off_w_sig_h != 0 && P.hsum && P.wsum, "hidden-composite render: needs the density image and the per-ray scratch");
+        P.w2_img = blob + L.off_w_sig_h;
+        P.n2 = 16;
+        P.sig_col = 0;
+    } else {
+        SD_REQUIRE(P.D <= TC_MAX_D, "SD_MLP_F16_TC: more than %d feature outputs need the projected render path", TC_MAX_D);
+    }
     static DeviceOnce once;
     int sm_count = 0;
     bool first_use = false;
@@ -878,7 +961,8 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
                     const TcOut &out, cudaStream_t st, const unsigned int *perm, const void *proj) {
     if (N == 0) return SD_OK;
     SD_REQUIRE(N < (1ll << 31), "SD_MLP_F16_TC: at most 2^31 - 1 rows per call (got %lld)", N);
-    SD_REQUIRE(tc_head_ok(mlp), "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 and packed");
+    SD_REQUIRE(tc_head_ok(mlp, render && render->cmma == 2),
+               "SD_MLP_F16_TC: head must be d_in <= 312, d_hidden = 128, 2 <= d_out <= 65 (any d_out for renders of a projected scene) and packed");
     SD_REQUIRE(fp.feat_f16 || proj, "SD_MLP_F16_TC: the feature map must be packed as fp16 (sd_featmap_pack with SD_F16)");
     SD_REQUIRE(fp.C == 256 && fp.code_dim == 39 && fp.enc.include_input && mlp->d_in == fp.C + fp.code_dim,
                "SD_MLP_F16_TC: supports C = 256 with the 39-d positional code (got C=%d, code=%d, d_in=%d)", fp.C,
@@ -898,8 +982,10 @@ int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, con
         P.cfg = render->cfg;
         P.depth = render->depth; P.dino_ray = render->dino; P.rgb_ray = render->rgb_out;
         P.weights = render->weights; P.alphas = render->alphas;
-        P.rgb = render->rgb_samps;   // per-sample colours: the caller's buffer or workspace
-        SD_REQUIRE(fp.nv_c == 0 || !P.rgb_ray || P.rgb, "SD_MLP_F16_TC: rgb_out needs a per-sample colour buffer");
+        P.rgb = render->rgb_samps;   // per-sample colours: the caller's buffer (or, without the tensor-core composite, workspace)
+        P.cmma = proj ? render->cmma : 0;
+        P.hsum = render->hsum; P.wsum = render->wsum;
+        SD_REQUIRE(fp.nv_c == 0 || !P.rgb_ray || P.rgb || P.cmma, "SD_MLP_F16_TC: rgb_out needs a per-sample colour buffer");
     } else {
         P.mode = tc::MODE_POINTS;
         P.K = 1;

@@ -56,10 +56,13 @@ struct TcOut {            // per-point / per-sample outputs (any may be NULL)
 struct TcRender {         // per-ray outputs of the fused composite
     sd_render_cfg cfg;
     float *depth, *dino, *rgb_out, *weights, *alphas, *rgb_samps;
+    int cmma;             // tc_render_mode(): 0 composite in the epilogue, 1 / 2 on the tensor cores (features / hidden units)
+    float *hsum, *wsum;   // cmma == 2: [R,128] per-ray sums of w * relu(hidden) and [R] sums of w, input of launch_head2
 };
 
 // true when the fused kernel handles this (scene, head) in render mode with K samples per ray
 bool tc_supported(const sd_scene *scene, const sd_mlp *mlp, int K);
+int tc_render_mode(const sd_scene *scene, const sd_mlp *mlp);
 // `proj`: blob of sd_field_project or NULL.  With it the kernel gathers the 128 projected channels (half the bytes per
 // tap) and layer 1 is identity + code block (K 320 -> 192); without it the 256 feature channels and the full W_in.
 int launch_field_tc(const FieldParams &fp, const PointSrc &src, long long N, const sd_mlp *mlp,
@@ -118,6 +121,9 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
 int launch_mlp_tc(const sd_mlp *mlp, const float *x, long long N, float *out, cudaStream_t st);
 // expand_tc.cu: MlpDimReduction.transform_expand on the tensor cores (64 -> 128 -> ReLU -> d_out, L2-normalised rows)
 bool expand_tc_supported(const sd_mlp *mlp);
+// the feature rows of the head's second layer on explicit hidden rows: out[r, :D] = W_out[1:] . h[r] + b_out[1:] * scale[r]
+// (h [R,128] fp32, scale [R] or NULL = 1): second half of the hidden-composite render (field_tc.cu, cmma == 2)
+int launch_head2(const sd_mlp *mlp, const float *h, const float *scale, long long R, float *out, cudaStream_t st);
 int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out, cudaStream_t st);
 
 }  // namespace sd

@@ -65,6 +65,11 @@ MlpLayout mlp_layout(int d_in, int d_hidden, int d_out) {
     const int n2 = (int)align_up((size_t)d_out, 16);
     L.off_w_out_h = o; o = align_up(o + 2 * (size_t)n2 * align_up((size_t)d_hidden + 2, 64), 1024);
     L.off_w_sigma = o;  o = align_up(o + sizeof(float) * (size_t)d_hidden, 1024);
+    L.off_w_sig_h = L.off_w_feat_blk = 0;
+    if (d_hidden == 128) {
+        L.off_w_sig_h = o;     o = align_up(o + 2 * (size_t)16 * 128, 1024);
+        L.off_w_feat_blk = o;  o = align_up(o + (size_t)((d_out - 1 + 127) / 128) * 32768, 1024);
+    }
     L.off_x_w2 = 0;
     if (d_in == 64 && d_hidden == 128 && d_out >= 128 && d_out % 128 == 0) {   // MlpDimReduction.transform_expand
         L.off_x_w2 = o; o = align_up(o + 2 * (size_t)d_out * d_hidden, 1024);
@@ -129,6 +134,20 @@ __global__ void mlp_pack_kernel(const float *__restrict__ w_in, const float *__r
         if (src >= 0 && k == H) v = b_out[src];
         if (src >= 0 && k == H + 1) v = b_out[src] - __half2float(__float2half_rn(b_out[src]));
         w_out_h[umma_sw128_offset(r, k, n2) / 2] = __float2half_rn(v);
+    }
+    if (L.off_w_sig_h) {
+        __half *w_sig_h = reinterpret_cast<__half *>(blob + L.off_w_sig_h);
+        for (int i = tid; i < 16 * 128; i += nth) {
+            const int r = i >> 7, k = i & 127;
+            w_sig_h[umma_sw128_offset(r, k, 16) / 2] = __float2half_rn(r == 0 ? w_out[k] : 0.0f);
+        }
+        __half *w_fb = reinterpret_cast<__half *>(blob + L.off_w_feat_blk);
+        const int nblk = (L.d_out - 1 + 127) / 128;
+        for (int i = tid; i < nblk * 128 * 128; i += nth) {
+            const int o = i >> 7, k = i & 127;          // feature output o <-> W_out row o + 1
+            const float v = o < L.d_out - 1 ? w_out[(size_t)(o + 1) * H + k] : 0.0f;
+            w_fb[((size_t)(o >> 7) * 32768 + umma_sw128_offset(o & 127, k, 128)) / 2] = __float2half_rn(v);
+        }
     }
     if (L.off_x_w2) {   // blocks of 128 outputs in their natural order, each a complete B operand (K = 128) of 32 KB
         __half *x_w2 = reinterpret_cast<__half *>(blob + L.off_x_w2);

@@ -171,7 +171,9 @@ extern "C" int sd_sample_coarse(const float *rays, long long R, int r_dim, const
 extern "C" int sd_sample_fine(const float *rays, long long R, int r_dim, const float *weights, int Kc,
                               const float *u0, const float *u1, int Kf, int lindisp, float *z, int *inds,
                               void *stream) {
-    SD_REQUIRE(R >= 0 && r_dim >= 8 && Kc > 0 && Kf > 0 && Kc <= 4096, "sd_sample_fine: bad shape");
+    // 4 rays per block, (2 Kc + 2) floats each, inside the 48 KB a kernel gets without opting in
+    SD_REQUIRE(R >= 0 && r_dim >= 8 && Kc > 0 && Kf > 0, "sd_sample_fine: bad shape");
+    SD_REQUIRE(Kc <= 1534, "sd_sample_fine: at most 1534 coarse samples per ray (got %d)", Kc);
     if (R == 0) return SD_OK;
     SD_REQUIRE(rays && weights && u0 && u1 && z, "sd_sample_fine: null pointer");
     const size_t smem = 4 * (2 * (size_t)Kc + 2) * sizeof(float);
@@ -196,7 +198,9 @@ extern "C" int sd_sample_fine_depth(const float *rays, long long R, int r_dim, c
 extern "C" int sd_sample_coarse_from_dist(long long R, const float *weights, const float *z_samp, int Kp,
                                           const float *u0, const float *u1, int Kc, int lindisp, float *z,
                                           int *inds, void *stream) {
-    SD_REQUIRE(R >= 0 && Kp > 0 && Kc > 0 && Kp <= 2048, "sd_sample_coarse_from_dist: bad shape");
+    // 4 rays per block, (4 Kp + 4) floats each, inside the 48 KB a kernel gets without opting in
+    SD_REQUIRE(R >= 0 && Kp > 0 && Kc > 0, "sd_sample_coarse_from_dist: bad shape");
+    SD_REQUIRE(Kp <= 767, "sd_sample_coarse_from_dist: at most 767 proposal samples per ray (got %d)", Kp);
     if (R == 0) return SD_OK;
     SD_REQUIRE(weights && z_samp && u0 && u1 && z, "sd_sample_coarse_from_dist: null pointer");
     const size_t smem = 4 * (4 * (size_t)Kp + 4) * sizeof(float);

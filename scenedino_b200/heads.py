@@ -32,9 +32,53 @@ def _ptr(t: torch.Tensor | None):
 
 
 def _stream():
+    """Current stream of the CURRENT device: every entry point first makes the device of its tensors current
+    (``on_device``), because the library launches on the current device."""
     if not torch.cuda.is_available():
         raise _abi.SdError("no CUDA device available (scenedino_b200 has no CPU path)")
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _devices(objs, found):
+    for o in objs:
+        if torch.is_tensor(o):
+            if o.is_cuda:
+                found.add(o.device)
+        elif isinstance(o, (list, tuple)):
+            _devices(o, found)
+        elif hasattr(o, "sd_tensors"):          # ops.Scene / ops.Mlp
+            _devices(o.sd_tensors(), found)
+
+
+class on_device:
+    """Context manager: makes the device the given CUDA tensors live on the current one for the C-ABI calls inside.
+    The library launches its kernels on the current device and that device's current stream, and keeps per-device
+    kernel attributes; a model on cuda:1 while cuda:0 is current would otherwise run device-1 pointers on device 0.
+    All CUDA tensors passed must share one device."""
+
+    def __init__(self, *objs):
+        found = set()
+        _devices(objs, found)
+        if len(found) > 1:
+            raise _abi.SdError("all tensors of one call must live on ONE CUDA device, got " + ", ".join(sorted(map(str, found))))
+        self._ctx = torch.cuda.device(next(iter(found))) if found else contextlib.nullcontext()
+
+    def __enter__(self):
+        return self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
+
+
+def device_guard(fn):
+    """Decorator form of :class:`on_device` over every argument of ``fn``."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with on_device(*args, *kwargs.values()):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -56,6 +100,7 @@ class PackedMlp:
         self.blob = None
         self.key = None
         self.dims = None
+        self.generation = 0          # bumped on every (re)pack: caches derived from the blob key on it
 
     def get(self, lin_in: nn.Linear, lin_out: nn.Linear, precision: int) -> _abi.SdMlp:
         params = (lin_in.weight, lin_in.bias, lin_out.weight, lin_out.bias)
@@ -64,20 +109,25 @@ class PackedMlp:
         d_out = lin_out.weight.shape[0]
         if key != self.key:
             require_cuda(lin_in.weight, "MLP weights")
-            lib = _abi.lib()
-            nbytes = lib.sd_mlp_pack_bytes(d_in, d_hidden, d_out)
-            blob = torch.empty(nbytes + 1024, dtype=torch.uint8, device=lin_in.weight.device)
-            off = (-blob.data_ptr()) % 1024
-            blob = blob[off:off + nbytes]
-            ws = [_f32c(p) for p in params]
-            _abi.check(lib.sd_mlp_pack(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), d_in, d_hidden,
-                                       d_out, _ptr(blob), _stream()), "sd_mlp_pack")
-            self.blob, self.key, self.dims = blob, key, (d_in, d_hidden, d_out)
+            with on_device(*params):
+                self._pack(params, d_in, d_hidden, d_out, key)
         m = _abi.SdMlp()
         m.packed = self.blob.data_ptr()
         m.d_in, m.d_hidden, m.d_out = self.dims
         m.precision = precision
         return m
+
+    def _pack(self, params, d_in, d_hidden, d_out, key):
+        lib = _abi.lib()
+        nbytes = lib.sd_mlp_pack_bytes(d_in, d_hidden, d_out)
+        blob = torch.empty(nbytes + 1024, dtype=torch.uint8, device=params[0].device)
+        off = (-blob.data_ptr()) % 1024
+        blob = blob[off:off + nbytes]
+        ws = [_f32c(p) for p in params]
+        _abi.check(lib.sd_mlp_pack(_ptr(ws[0]), _ptr(ws[1]), _ptr(ws[2]), _ptr(ws[3]), d_in, d_hidden,
+                                   d_out, _ptr(blob), _stream()), "sd_mlp_pack")
+        self.blob, self.key, self.dims = blob, key, (d_in, d_hidden, d_out)
+        self.generation += 1
 
 
 class ResnetFC(nn.Module):
@@ -114,9 +164,10 @@ class ResnetFC(nn.Module):
         require_cuda(zx, "ResnetFC input")
         x = _f32c(zx).reshape(-1, self.d_in)
         out = torch.empty(x.shape[0], self.d_out, dtype=torch.float32, device=x.device)
-        mlp = self.packed(precision)
-        _abi.check(_abi.lib().sd_mlp_forward(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()),
-                   "sd_mlp_forward")
+        with on_device(x, self.lin_in.weight):
+            mlp = self.packed(precision)
+            _abi.check(_abi.lib().sd_mlp_forward(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()),
+                       "sd_mlp_forward")
         return out.reshape(*zx.shape[:-1], self.d_out)
 
     @classmethod
@@ -204,6 +255,7 @@ class MlpDimReduction(nn.Module):
         d_full = self.linear_out.weight.shape[0]
         x = _f32c(features).reshape(-1, d_red)
         out = torch.empty(x.shape[0], d_full, dtype=torch.float32, device=x.device)
-        mlp = self._packed.get(self.linear_in, self.linear_out, self._precision())
-        _abi.check(_abi.lib().sd_expand_dim(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()), "sd_expand_dim")
+        with on_device(x, self.linear_in.weight):
+            mlp = self._packed.get(self.linear_in, self.linear_out, self._precision())
+            _abi.check(_abi.lib().sd_expand_dim(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()), "sd_expand_dim")
         return out.reshape(*features.shape[:-1], d_full)

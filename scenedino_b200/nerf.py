@@ -20,7 +20,7 @@ import ctypes as C
 import torch
 
 from . import _abi
-from .heads import _f32c, _ptr, _stream, require_cuda
+from .heads import _f32c, _ptr, _stream, device_guard, require_cuda
 
 
 class DotMap(dict):
@@ -49,6 +49,7 @@ class _RenderWrapper(torch.nn.Module):
         self.renderer = renderer
         self.simple_output = simple_output
 
+    @device_guard
     def forward(self, rays, want_weights=False, want_alphas=False, want_z_samps=False, want_rgb_samps=False,
                 sample_from_dist=None):
         if rays.shape[0] == 0:
@@ -104,6 +105,7 @@ class NeRFRenderer(torch.nn.Module):
         return c
 
     # ---- sampling ------------------------------------------------------------------------------------
+    @device_guard
     def sample_coarse(self, rays):
         """nerf.py:121-141: stratified samples, (B, Kc)."""
         rays = self._rays2d(rays)
@@ -116,6 +118,7 @@ class NeRFRenderer(torch.nn.Module):
                                                int(bool(self.lindisp)), _ptr(z), _stream()), "sd_sample_coarse")
         return z
 
+    @device_guard
     def sample_coarse_from_dist(self, rays, weights, z_samp):
         """nerf.py:143-179: resampling of a proposal histogram, (B, Kc), unsorted."""
         rays = self._rays2d(rays)
@@ -130,6 +133,7 @@ class NeRFRenderer(torch.nn.Module):
                    "sd_sample_coarse_from_dist")
         return z
 
+    @device_guard
     def sample_fine(self, rays, weights):
         """nerf.py:181-212: importance samples, (B, Kf - Kfd)."""
         rays = self._rays2d(rays)
@@ -146,6 +150,7 @@ class NeRFRenderer(torch.nn.Module):
                                              int(bool(self.lindisp)), _ptr(z), None, _stream()), "sd_sample_fine")
         return z
 
+    @device_guard
     def sample_fine_depth(self, rays, depth):
         """nerf.py:214-228: samples around the expected depth, (B, Kfd)."""
         rays = self._rays2d(rays)
@@ -158,6 +163,7 @@ class NeRFRenderer(torch.nn.Module):
         return z
 
     @staticmethod
+    @device_guard
     def _sort_rows(z):
         z = z.contiguous()
         _abi.check(_abi.lib().sd_sort_rows(_ptr(z), z.shape[0], z.shape[1], _stream()), "sd_sort_rows")
@@ -169,6 +175,7 @@ class NeRFRenderer(torch.nn.Module):
         (weights, rgb, depth, alphas, invalid, z_samp, rgbs, ray_info, extras, state_dicts)."""
         return self._composite(model, rays, z_samp, coarse, sb, want_rgb_samps=True)
 
+    @device_guard
     def _composite(self, model, rays, z_samp, coarse, sb, want_rgb_samps):
         with torch.profiler.record_function("renderer_composite"):
             if self.render_mode != "volumetric":
@@ -212,8 +219,10 @@ class NeRFRenderer(torch.nn.Module):
         lib = _abi.lib()
         # reduced precision: render on the projected map (made once per encode and head): the gather reads 128 projected
         # channels per tap instead of 256 features and layer 1 shrinks to identity + code block
-        use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
-                    and Bp * K >= 65536)
+        # (a head with more than 64 feature outputs -- the 768-d variant -- always renders on the projected map: the
+        # composite then sums the 128 hidden units per ray and W_out is applied to the sums, whatever D is)
+        use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128
+                    and (D > 64 or Bp * K >= 65536))
         for b in range(sb):
             sc = net._scene(st, b, net._projection(st, b, mlp) if use_proj else None)
             sl = slice(b * Bp, (b + 1) * Bp)
@@ -266,6 +275,7 @@ class NeRFRenderer(torch.nn.Module):
         return weights, rgb, depth, alphas, invalid, rgbs, state
 
     # ---- forward -------------------------------------------------------------------------------------
+    @device_guard
     def forward(self, model, rays, want_weights=False, want_alphas=False, want_z_samps=False,
                 want_rgb_samps=False, sample_from_dist=None):
         """nerf.py:451-539: rays (SB, B, >=8) -> DotMap(coarse=..., [fine=...], state_dict=...)."""

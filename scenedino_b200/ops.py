@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _abi
-from .heads import _f32c, _ptr, _stream, require_cuda
+from .heads import _f32c, _ptr, _stream, device_guard, on_device, require_cuda
 
 FP32, F16 = _abi.SD_MLP_FP32, _abi.SD_MLP_F16_TC
 
@@ -23,6 +23,7 @@ def _dev(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+@device_guard
 def featmap_pack(nchw: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """[n, C, H, W] fp32 -> [n, H, W, C] fp32 | fp16 (sd_featmap_pack)."""
     require_cuda(nchw, "feature map")
@@ -46,11 +47,15 @@ class Mlp:
         self.precision = precision
         lib = _abi.lib()
         nbytes = lib.sd_mlp_pack_bytes(self.d_in, self.d_hidden, self.d_out)
-        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-        off = (-raw.data_ptr()) % 1024
-        self.blob = raw[off:off + nbytes]
-        _abi.check(lib.sd_mlp_pack(*[_ptr(t) for t in self.w], self.d_in, self.d_hidden, self.d_out, _ptr(self.blob),
-                                   _stream()), "sd_mlp_pack")
+        with on_device(self.w):
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.w[0].device)
+            off = (-raw.data_ptr()) % 1024
+            self.blob = raw[off:off + nbytes]
+            _abi.check(lib.sd_mlp_pack(*[_ptr(t) for t in self.w], self.d_in, self.d_hidden, self.d_out, _ptr(self.blob),
+                                       _stream()), "sd_mlp_pack")
+
+    def sd_tensors(self):
+        return [self.blob]
 
     def c(self, precision: int | None = None) -> _abi.SdMlp:
         m = _abi.SdMlp()
@@ -91,6 +96,10 @@ class Scene:
             s.empty_feature = _dev(s.empty_feature, device)
         return s
 
+    def sd_tensors(self):
+        return [t for t in (self.feat, self.K_f, self.w2c_f, self.rgb, self.K_c, self.w2c_c, self.empty_feature, self.proj)
+                if t is not None]
+
     def with_feat_dtype(self, feat_nchw, dtype):
         import dataclasses
         return dataclasses.replace(self, feat=featmap_pack(_dev(feat_nchw, self.feat.device), dtype)[0])
@@ -104,10 +113,11 @@ class Scene:
         sc, m = dataclasses.replace(self, proj=None).c(), mlp.c(F16)
         lib = _abi.lib()
         nbytes = lib.sd_field_project_bytes(C.byref(sc))
-        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.feat.device)
-        off = (-raw.data_ptr()) % 1024
-        blob = raw[off:off + nbytes]
-        _abi.check(lib.sd_field_project(C.byref(sc), C.byref(m), _ptr(blob), nbytes, _stream()), "sd_field_project")
+        with on_device(self, mlp):
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.feat.device)
+            off = (-raw.data_ptr()) % 1024
+            blob = raw[off:off + nbytes]
+            _abi.check(lib.sd_field_project(C.byref(sc), C.byref(m), _ptr(blob), nbytes, _stream()), "sd_field_project")
         return dataclasses.replace(self, proj=blob)
 
     @property
@@ -143,6 +153,7 @@ def _e(shape, ref, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=ref.device)
 
 
+@device_guard
 def project_points(K, w2c, xyz):
     xyz = _f32c(xyz); require_cuda(xyz, "xyz")
     N = xyz.shape[0]
@@ -152,6 +163,7 @@ def project_points(K, w2c, xyz):
     return xy, z, inv.view(torch.bool)
 
 
+@device_guard
 def sample_features(scene: Scene, xyz):
     xyz = _f32c(xyz); require_cuda(xyz, "xyz")
     N = xyz.shape[0]
@@ -163,6 +175,7 @@ def sample_features(scene: Scene, xyz):
     return feat, inv.view(torch.bool)
 
 
+@device_guard
 def sample_colors(scene: Scene, xyz):
     xyz = _f32c(xyz); require_cuda(xyz, "xyz")
     N = xyz.shape[0]
@@ -172,6 +185,7 @@ def sample_colors(scene: Scene, xyz):
     return rgb, inv.view(torch.bool)
 
 
+@device_guard
 def mlp_forward(mlp: Mlp, x, precision=None):
     x = _f32c(x); require_cuda(x, "x")
     out = _e((x.shape[0], mlp.d_out), x)
@@ -180,6 +194,7 @@ def mlp_forward(mlp: Mlp, x, precision=None):
     return out
 
 
+@device_guard
 def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=None, norm_dir: bool = True,
              xy_shift=(0.0, 0.0), out=None):
     """c2w [V,4,4], proj [V,3,3] (CUDA) -> rays [V*H*W, 11] of one batch element (sd_gen_rays; util.gen_rays +
@@ -202,6 +217,7 @@ def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=N
     return out
 
 
+@device_guard
 def expand_dim(mlp: Mlp, f, precision: int = FP32):
     """MlpDimReduction.transform_expand; ``precision=F16`` takes the tensor-core kernel (64 -> 128 -> k*128 heads)."""
     f = _f32c(f); require_cuda(f, "f")
@@ -211,6 +227,7 @@ def expand_dim(mlp: Mlp, f, precision: int = FP32):
     return out
 
 
+@device_guard
 def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out=None, binned=True):
     """BTSNet.forward for one scene -> dict(sigma[N], dino[N,D], rgb[N,3nv_c], invalid[N,nv_c],
     invalid_features[N] bool).  ``out`` lets bench.py reuse output buffers."""
@@ -235,6 +252,7 @@ def query_points(scene: Scene, mlp: Mlp, xyz, want_rgb=True, precision=None, out
     return res
 
 
+@device_guard
 def query_points_sorted(scene: Scene, mlp: Mlp, xyz, out: dict):
     """The query again for unchanged points and cameras (sd_query_points_sorted): reuses the texel sort left in
     ``out["_workspace"]`` by an earlier ``query_points(..., out=out)``; only the tile kernel runs."""
@@ -276,6 +294,7 @@ class QueryGraph:
         self.graph.replay()
 
 
+@device_guard
 def sample_coarse(rays, u, lin, lindisp=True):
     rays, u, lin = _f32c(rays), _f32c(u), _f32c(lin)
     R, Kc = u.shape
@@ -285,6 +304,7 @@ def sample_coarse(rays, u, lin, lindisp=True):
     return z
 
 
+@device_guard
 def sample_fine(rays, weights, u0, u1, lindisp=True):
     rays, weights, u0, u1 = _f32c(rays), _f32c(weights), _f32c(u0), _f32c(u1)
     R, Kc = weights.shape
@@ -295,6 +315,7 @@ def sample_fine(rays, weights, u0, u1, lindisp=True):
     return z, inds
 
 
+@device_guard
 def sample_fine_depth(rays, depth, noise, depth_std):
     rays, depth, noise = _f32c(rays), _f32c(depth), _f32c(noise)
     R, Kfd = noise.shape
@@ -304,6 +325,7 @@ def sample_fine_depth(rays, depth, noise, depth_std):
     return z
 
 
+@device_guard
 def sample_coarse_from_dist(weights, z_samp, u0, u1, lindisp=True):
     weights, z_samp, u0, u1 = _f32c(weights), _f32c(z_samp), _f32c(u0), _f32c(u1)
     R, Kp = weights.shape
@@ -315,6 +337,7 @@ def sample_coarse_from_dist(weights, z_samp, u0, u1, lindisp=True):
     return z, inds
 
 
+@device_guard
 def sort_rows(z):
     z = _f32c(z).clone()
     _abi.check(_abi.lib().sd_sort_rows(_ptr(z), z.shape[0], z.shape[1], _stream()), "sd_sort_rows")
@@ -327,6 +350,7 @@ def _cfg(lindisp=True, hard_alpha_cap=False, white_bkgd=False):
     return c
 
 
+@device_guard
 def composite(z, sigma, feat, rgb=None, hard_alpha_cap=False, white_bkgd=False):
     z, sigma, feat = _f32c(z), _f32c(sigma), _f32c(feat)
     R, K = z.shape
@@ -342,6 +366,7 @@ def composite(z, sigma, feat, rgb=None, hard_alpha_cap=False, white_bkgd=False):
     return out
 
 
+@device_guard
 def render_pass(scene: Scene, mlp: Mlp, rays, z, hard_alpha_cap=False, white_bkgd=False, want_rgb_samps=False,
                 want_sigma=True, per_sample=True, precision=None, out=None):
     """One NeRFRenderer.composite call for one scene (sd_render_pass)."""

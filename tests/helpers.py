@@ -17,6 +17,11 @@ def rel_err(a, b):
     return np.abs(a - b) / den
 
 
+#: element-wise bar on the entries that are not near zero (|b| > 0.1 rms): |a-b| <= ELEMENTWISE * tol * |b|.  The scale-relative
+#: measure above alone would let an entry of 0.1 rms be off by 10 tol of itself.
+ELEMENTWISE = 5.0
+
+
 def assert_close(a, b, tol, what=""):
     assert np.shape(a) == np.shape(b), f"{what}: shape {np.shape(a)} vs {np.shape(b)}"
     if np.size(b) == 0:
@@ -24,6 +29,13 @@ def assert_close(a, b, tol, what=""):
     e = rel_err(a, b)
     worst = float(e.max())
     assert worst <= tol, f"{what}: max rel err {worst:.3e} > {tol:.1e} at {np.unravel_index(e.argmax(), e.shape)}"
+    a64, b64 = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = np.sqrt(np.mean(b64 * b64))
+    big = np.abs(b64) > 0.1 * scale
+    if big.any():
+        ew = np.abs(a64 - b64)[big] / np.abs(b64)[big]
+        assert float(ew.max()) <= ELEMENTWISE * tol, \
+            f"{what}: element-wise rel err {float(ew.max()):.3e} > {ELEMENTWISE * tol:.1e} on an entry with |b| > 0.1 rms"
 
 
 def checksum(a):
