@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 2
+#define SD_ABI_VERSION 3
 
 typedef enum sd_status {
     SD_OK = 0,
@@ -197,6 +197,36 @@ int    sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_
  * accumulation and normalisation, rel 2e-2; f and out 16-byte aligned); anything else: fp32 CUDA-core kernel (rel 1e-4). */
 int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, void *stream);
 
+/* ---- section 8f-2: the unsupervised SSC head, fused with the expansion that feeds it ---------------------------------
+ * SemanticHead.forward(mode = "stego_kmeans") (downstream_head/semantic_head.py:107-112) on
+ * MlpDimReduction.transform_expand (dim_reduction.py:22-25) of the 64-d features of a field query -- what
+ * BTSNet.forward(predict_segmentation=True) does per voxel (models/bts.py:584-592) -- without ever forming the 768-d
+ * rows: everything between the two ReLUs is linear and is folded once per model by sd_ssc_head_pack (ssc_head.cu).
+ *   expand:  w1e [128,64], b1e [128], w2e [d_full,128], b2e [d_full]              (linear_in / linear_out)
+ *   STEGO:   wl [64,d_full], bl [64]; wn1 [d_mid,d_full], bn1 [d_mid]; wn2 [64,d_mid], bn2 [64]   (1x1-conv weights,
+ *            StegoClusterHead.linear_path / nonlinear_path, semantic_head.py:285-305; eval mode: no dropout)
+ *   k-means: centres [n_cls,64] (KMeansParamHead.cluster_centers), lut [n_cls] int64 (pseudo_assignment), :308-373
+ * all fp32 device pointers in nn.Module layout.  d_red = 64, d_lat = 128, d_code = 64, d_mid a multiple of 128 (<= 1024),
+ * n_cls <= 32.  `packed` must be 1024-byte aligned. */
+size_t sd_ssc_head_pack_bytes(int d_red, int d_lat, int d_full, int d_mid, int d_code, int n_cls);
+int    sd_ssc_head_pack(const float *w1e, const float *b1e, const float *w2e, const float *b2e, const float *wl,
+                        const float *bl, const float *wn1, const float *bn1, const float *wn2, const float *bn2,
+                        const float *centres, const long long *lut, int d_red, int d_lat, int d_full, int d_mid,
+                        int d_code, int n_cls, void *packed, void *stream);
+/* f [N,64] fp32 (16-byte aligned) -> seg [N] (labels after the pseudo-label LUT, what SemanticHead.forward returns),
+ * pseudo [N] (cluster ids), scores [N,n_cls] (cosine scores): any of the three may be NULL.  perm (or NULL): input row r
+ * stands for voxel perm[r], i.e. outputs are written at perm[r].  tcgen05 tensor cores, fp16 operands, fp32 accumulation:
+ * scores within 2e-2 of the reference (measured ~3e-4), labels equal wherever the top-2 gap exceeds that. */
+int    sd_ssc_head(const void *packed, int d_mid, int n_cls, const float *f, const unsigned int *perm, long long N,
+                   unsigned char *seg, unsigned char *pseudo, float *scores, void *stream);
+
+/* ---- PositionalEncoding.forward (common/positional_encoding.py:68-80) on its own --------------------------------------- */
+/* x [N,d_in] -> out [N, (include_input ? d_in : 0) + 2*num_freqs*d_in]: [x | per frequency k: sin(f_k x) (d_in), cos(f_k x)
+ * (d_in)], f_k = freq_factor * 2^k, cos evaluated as sin(. + pi/2) like the reference.  (Inside the field kernels the code
+ * is fused; this entry point is the 1:1 counterpart of the module's forward.) */
+int    sd_positional_encoding(const float *x, long long N, int d_in, int num_freqs, float freq_factor, int include_input,
+                              float *out, void *stream);
+
 /* ---- section 8f-3: rays of whole views ------------------------------------------------------ */
 /* Replaces util.gen_rays / util.unproj_map (common/util.py:253-285, 113-158) and the ray half of
  * ImageRaySampler.sample (common/ray_sampler.py:439-486) for ONE batch element:
@@ -209,6 +239,15 @@ int sd_expand_dim(const sd_mlp *mlp, const float *f, long long N, float *out, vo
 int sd_gen_rays(const float *c2w, const float *proj, const float *frame_ids, int V, int H, int W,
                 float z_near, float z_far, int norm_dir, float x_shift, float y_shift, float *rays,
                 void *stream);
+
+/* ---- diagnostics (timing experiments; not part of the data path) ----------------------------------------------------
+ * With the environment variable SD_TC_DEBUG & 8192 set when the library is loaded, CTA 0 of the tensor-core kernels
+ * records clock64 stamps per warp role and tile; these calls copy the trace of the last launch to HOST buffers:
+ * sd_debug_read_trace: field_tc_kernel, [4 roles][64 tiles][8 events] long long; sd_debug_read_trace_bin: field_bin_kernel,
+ * [8][64][8] long long; sd_debug_read_cta_ns: field_bin_kernel, [256 CTAs][start, end] %globaltimer. */
+int sd_debug_read_trace(long long *host_out);
+int sd_debug_read_trace_bin(long long *host_out);
+int sd_debug_read_cta_ns(unsigned long long *host_out);
 
 #ifdef __cplusplus
 }

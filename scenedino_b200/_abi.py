@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libscenedino_b200.so")
 
 SD_F32, SD_F16 = 0, 1
 SD_MLP_FP32, SD_MLP_F16_TC = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SdError(RuntimeError):
@@ -76,6 +76,13 @@ PROTOTYPES = {
                             _P, _SZ, _P]),
     "sd_expand_dim": (_I, [_ML, _P, _LL, _P, _P]),
     "sd_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _F, _P, _P]),
+    "sd_ssc_head_pack_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "sd_ssc_head_pack": (_I, [_P] * 12 + [_I] * 6 + [_P, _P]),
+    "sd_ssc_head": (_I, [_P, _I, _I, _P, _P, _LL, _P, _P, _P, _P]),
+    "sd_positional_encoding": (_I, [_P, _LL, _I, _I, _F, _I, _P, _P]),
+    "sd_debug_read_trace": (_I, [_P]),
+    "sd_debug_read_trace_bin": (_I, [_P]),
+    "sd_debug_read_cta_ns": (_I, [_P]),
 }
 
 _lib = None

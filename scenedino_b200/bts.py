@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .heads import ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, require_cuda
+from .heads import MlpDimReduction, ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, require_cuda
 
 PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
 
@@ -76,6 +76,9 @@ class BTSNet(nn.Module):
         #: "auto": fp16 under torch autocast (the dtype the reference runs the head in there), fp32 otherwise.
         self.precision = conf.get("sd_precision", "auto")
         self.encode_loss_features = True
+        #: forward(predict_segmentation=True) returns the 768-d expansion as its first element like the reference
+        #: (bts.py:585); False skips it (first element None) -- the SSC evaluation only keeps sigma and seg
+        self.materialize_dino_full = True
         self._packed = {}
         self._head_packed = None
         self.grid_f_features = None
@@ -330,11 +333,20 @@ class BTSNet(nn.Module):
             invalid_features = invf.view(torch.bool)
 
         if predict_segmentation:  # bts.py:528-533, 584-592
-            with expand_precision(prec):      # the expansion runs in the precision of the query that feeds it
-                dino_full = self.encoder.expand_dim(dino)
+            head = self.downstream_head
+            fused = head is not None and hasattr(head, "forward_reduced") and isinstance(
+                getattr(self.encoder, "dim_reduction", None), MlpDimReduction)
+            if self.materialize_dino_full or not fused:
+                with expand_precision(prec):      # the expansion runs in the precision of the query that feeds it
+                    dino_full = self.encoder.expand_dim(dino)
+            else:
+                dino_full = None                  # 3 KB per voxel (6.4 GB per SSC grid) nobody reads: sscbench keeps sigma + seg
             seg = None
-            if self.downstream_head is not None:
-                seg = self.downstream_head(dino_full, mode=prediction_mode)
+            if head is not None:
+                # scenedino_b200.SemanticHead: expansion + STEGO head + cosine argmax + pseudo-label LUT in ONE kernel
+                # (sd_ssc_head) starting from the 64-d features; any other head module is called like the reference does
+                seg = (head.forward_reduced(dino, self.encoder.dim_reduction, mode=prediction_mode) if fused
+                       else head(dino_full, mode=prediction_mode))
                 seg = torch.nn.functional.one_hot(seg, self.gt_classes)
             return dino_full, None, sigma, seg
         if only_density:  # bts.py:570-572

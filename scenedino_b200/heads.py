@@ -189,7 +189,7 @@ def make_head(conf, d_in: int, d_out: int):
 
 class PositionalEncoding(nn.Module):
     """common/positional_encoding.py:44-66: carries (num_freqs, freq_factor, include_input); the code
-    itself is evaluated inside the field kernels (sd_sample_features / sd_query_points)."""
+    is evaluated inside the field kernels (sd_sample_features / sd_query_points); ``forward`` is the stand-alone form."""
 
     def __init__(self, num_freqs=6, d_in=3, freq_factor=math.pi, include_input=True):
         super().__init__()
@@ -202,8 +202,19 @@ class PositionalEncoding(nn.Module):
         self.register_buffer("_phases", ph.view(1, -1, 1))
 
     def forward(self, x):
-        raise NotImplementedError(
-            "the positional code is fused into the field kernels; call BTSNet.sample_features")
+        """positional_encoding.py:68-80: x (batch, d_in) -> (batch, d_out) (sd_positional_encoding; inside the field
+        kernels the same code is fused and never materialised)."""
+        with torch.profiler.record_function("positional_enc"):
+            require_cuda(x, "PositionalEncoding input")
+            if x.dim() != 2 or x.shape[1] != self.d_in:
+                raise ValueError(f"PositionalEncoding.forward expects (batch, {self.d_in}), got {tuple(x.shape)}")
+            xs = _f32c(x)
+            out = torch.empty((xs.shape[0], self.d_out), dtype=torch.float32, device=xs.device)
+            with on_device(xs):
+                _abi.check(_abi.lib().sd_positional_encoding(_ptr(xs), xs.shape[0], self.d_in, self.num_freqs, self.freq_factor,
+                                                             int(bool(self.include_input)), _ptr(out), _stream()),
+                           "sd_positional_encoding")
+            return out.to(x.dtype)
 
     @classmethod
     def from_conf(cls, conf, d_in=3):
@@ -258,4 +269,8 @@ class MlpDimReduction(nn.Module):
         with on_device(x, self.linear_in.weight):
             mlp = self._packed.get(self.linear_in, self.linear_out, self._precision())
             _abi.check(_abi.lib().sd_expand_dim(C.byref(mlp), _ptr(x), x.shape[0], _ptr(out), _stream()), "sd_expand_dim")
-        return out.reshape(*features.shape[:-1], d_full)
+        out = out.reshape(*features.shape[:-1], d_full)
+        # the SSC head that follows (SemanticHead.forward, semantic_head.py) is evaluated fused with this expansion, starting
+        # from the 64-d features: the result carries them (a plain attribute on the tensor object the caller passes on)
+        out._sd_reduced = (features, self)
+        return out

@@ -396,3 +396,52 @@ def render_pass(scene: Scene, mlp: Mlp, rays, z, hard_alpha_cap=False, white_bkg
         res["invalid_features"] = res["invalid_features"].view(torch.bool)
     res["z_samps"] = z
     return res
+
+
+class SscHead:
+    """Folded weights of the expansion + unsupervised SSC head (sd_ssc_head_pack): ``expand`` = (w1 [128,64], b1, w2 [768,128],
+    b2) of MlpDimReduction, ``head`` = dict(wl, bl, wn1, bn1, wn2, bn2, centres, lut) as synthetic.make_ssc_head lays it out."""
+
+    def __init__(self, expand, head, device="cuda"):
+        w1, b1, w2, b2 = [_dev(t, device) for t in expand]
+        hs = [_dev(head[k], device) for k in ("wl", "bl", "wn1", "bn1", "wn2", "bn2", "centres")]
+        lut = torch.as_tensor(head["lut"]).to(device=device, dtype=torch.int64).contiguous()
+        self.d_mid, self.n_cls = hs[2].shape[0], hs[6].shape[0]
+        lib = _abi.lib()
+        nbytes = lib.sd_ssc_head_pack_bytes(w1.shape[1], w1.shape[0], w2.shape[0], self.d_mid, hs[0].shape[0], self.n_cls)
+        if nbytes == 0:
+            raise _abi.SdError("SscHead: unsupported head shape")
+        with on_device(w1, lut):
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=w1.device)
+            off = (-raw.data_ptr()) % 1024
+            self.blob = raw[off:off + nbytes]
+            _abi.check(lib.sd_ssc_head_pack(_ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), *[_ptr(h) for h in hs], _ptr(lut), w1.shape[1],
+                                            w1.shape[0], w2.shape[0], self.d_mid, hs[0].shape[0], self.n_cls, _ptr(self.blob),
+                                            _stream()), "sd_ssc_head_pack")
+
+    def sd_tensors(self):
+        return [self.blob]
+
+
+@device_guard
+def ssc_head(head: SscHead, f, want_scores=True, perm=None, out=None):
+    """f [N,64] -> dict(seg [N] uint8, pseudo [N] uint8, scores [N,n_cls]) (sd_ssc_head)."""
+    f = _f32c(f); require_cuda(f, "f")
+    N = f.shape[0]
+    if out is None:
+        out = dict(seg=_e((N,), f, torch.uint8))
+        if want_scores:
+            out.update(pseudo=_e((N,), f, torch.uint8), scores=_e((N, head.n_cls), f))
+    _abi.check(_abi.lib().sd_ssc_head(_ptr(head.blob), head.d_mid, head.n_cls, _ptr(f), _ptr(perm), N, _ptr(out["seg"]),
+                                      _ptr(out.get("pseudo")), _ptr(out.get("scores")), _stream()), "sd_ssc_head")
+    return out
+
+
+@device_guard
+def positional_encoding(x, num_freqs=6, freq_factor=1.5, include_input=True):
+    x = _f32c(x); require_cuda(x, "x")
+    N, d_in = x.shape
+    out = _e((N, (d_in if include_input else 0) + 2 * num_freqs * d_in), x)
+    _abi.check(_abi.lib().sd_positional_encoding(_ptr(x), N, d_in, num_freqs, float(freq_factor), int(bool(include_input)),
+                                                 _ptr(out), _stream()), "sd_positional_encoding")
+    return out

@@ -471,16 +471,20 @@ def test_render_superbatch_vs_reference(golden):
 
 
 # ---- BASELINE-size properties --------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol,feat_dtype,projected", [
-    (ops.FP32, TOL_FP32, torch.float32, False),
-    (ops.F16, TOL_F16, torch.float16, False),
-    (ops.F16, TOL_F16, torch.float16, True),
+@pytest.mark.parametrize("precision,tol,feat_dtype,projected,map_hw", [
+    (ops.FP32, TOL_FP32, torch.float32, False, (192, 640)),
+    (ops.F16, TOL_F16, torch.float16, False, (192, 640)),
+    (ops.F16, TOL_F16, torch.float16, True, (192, 640)),
+    # the map bench.py times (DINO ViT-B/8: 384 x 1280): TMA box coordinates, bin counts and the 16-bit compact bin ids of
+    # the sort all scale with it
+    (ops.F16, TOL_F16, torch.float16, True, (384, 1280)),
+    (ops.FP32, TOL_FP32, torch.float32, False, (384, 1280)),
 ])
-def test_ssc_grid_full_size(precision, tol, feat_dtype, projected):
-    """configs[1]: the 256x256x32 voxel grid against a DINOv2-sized map: masks bit-exact on all
+def test_ssc_grid_full_size(precision, tol, feat_dtype, projected, map_hw):
+    """configs[1]: the 256x256x32 voxel grid against a DINOv2-sized and a ViT-B/8-sized map: masks bit-exact on all
     2 097 152 voxels, values against the oracle on a strided subset, and batch-position independence
     (a permuted query returns the permuted result bit for bit)."""
-    C_, Hf, Wf = 256, 192, 640
+    C_, (Hf, Wf) = 256, map_hw
     feat = syn.make_feature_map(1, C_, Hf, Wf)
     K = syn.kitti360_K()[None]; w2c = np.eye(4, dtype=np.float32)[None]
     mlp_w = syn.make_mlp(0, bias_scale=0.05)
