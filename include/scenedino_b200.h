@@ -191,6 +191,34 @@ int    sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd_render_
                       float *invalid, unsigned char *invalid_feat, float *rgb_samps, float *sigma,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- NeRFRenderer.forward (renderer/nerf.py:451-539) for one scene, in ONE call ---------------------------------------
+ * Coarse sampling -> coarse pass -> (when n_fine > 0) importance + depth samples, merge, sort -> fine pass, launched back
+ * to back on `stream` without returning to the caller: sample_coarse kernel, fused field kernel, ONE kernel for
+ * sample_fine + sample_fine_depth + cat + sort (fine_merge_kernel), fused field kernel.  The random draws are inputs
+ * (u_coarse [R,n_coarse] and lin [n_coarse] as in sd_sample_coarse; u_fine0 / u_fine1 [R, n_fine - n_fine_depth] as in
+ * sd_sample_fine; n_depth [R, n_fine_depth] as in sd_sample_fine_depth), so a caller that draws them with the reference's
+ * torch calls in the reference's order reproduces its samples.  Results are those of the unfused entry points, bit for
+ * bit.  `fine` may be NULL when n_fine == 0.  Any pointer inside sd_render_out may be NULL. */
+typedef struct sd_render_out {
+    float *depth;                /* [R]           */
+    float *dino;                 /* [R, d_out-1]  */
+    float *rgb;                  /* [R, 3*nv_c]   */
+    float *weights, *alphas;     /* [R, K]        */
+    float *z_samps;              /* [R, K]        */
+    float *invalid;              /* [R, K, nv_c]  */
+    unsigned char *invalid_feat; /* [R, K]        */
+    float *rgb_samps;            /* [R, K, 3*nv_c] */
+} sd_render_out;
+typedef struct sd_sampling {
+    int   n_coarse, n_fine, n_fine_depth;
+    float depth_std;
+} sd_sampling;
+size_t sd_render_rays_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, const sd_sampling *samp, long long R);
+int    sd_render_rays(const sd_scene *scene, const sd_mlp *mlp, const sd_render_cfg *cfg, const sd_sampling *samp,
+                      const float *rays, long long R, int r_dim, const float *u_coarse, const float *lin,
+                      const float *u_fine0, const float *u_fine1, const float *n_depth, const sd_render_out *coarse,
+                      const sd_render_out *fine, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- section 8f-1: MlpDimReduction.transform_expand (backbones/dino/dim_reduction.py:22-25) --- */
 /* `mlp` packs linear_in / linear_out; out [N,d_out] is L2-normalised per row (F.normalize).
  * mlp->precision == SD_MLP_F16_TC and a 64 -> 128 -> k*128 (k <= 8) head: tcgen05 kernel (fp16 operands, fp32

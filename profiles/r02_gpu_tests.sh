@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round-2 GPU check: every test file in its own process (a trapped kernel poisons its CUDA context), logs to gpurun_out/.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+for f in test_gpu_zz_next test_gpu_ssc_head test_gpu_parity test_gpu_surface; do
+  timeout 900 python -m pytest tests/$f.py -m gpu -q --maxfail=25 -p no:cacheprovider > gpurun_out/$f.log 2>&1
+  echo "$f rc=$?"; tail -n 3 gpurun_out/$f.log
+done

@@ -43,6 +43,15 @@ class SdRenderCfg(C.Structure):
     _fields_ = [("lindisp", C.c_int), ("hard_alpha_cap", C.c_int), ("white_bkgd", C.c_int)]
 
 
+class SdRenderOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("depth", "dino", "rgb", "weights", "alphas", "z_samps", "invalid", "invalid_feat",
+                                          "rgb_samps")]
+
+
+class SdSampling(C.Structure):
+    _fields_ = [("n_coarse", C.c_int), ("n_fine", C.c_int), ("n_fine_depth", C.c_int), ("depth_std", C.c_float)]
+
+
 _P, _LL, _I, _F, _SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
 _SC, _ML, _RC = C.POINTER(SdScene), C.POINTER(SdMlp), C.POINTER(SdRenderCfg)
 
@@ -74,6 +83,9 @@ PROTOTYPES = {
     "sd_render_workspace_bytes": (_SZ, [_SC, _ML, _LL, _I]),
     "sd_render_pass": (_I, [_SC, _ML, _RC, _P, _LL, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             _P, _SZ, _P]),
+    "sd_render_rays_workspace_bytes": (_SZ, [_SC, _ML, C.POINTER(SdSampling), _LL]),
+    "sd_render_rays": (_I, [_SC, _ML, _RC, C.POINTER(SdSampling), _P, _LL, _I, _P, _P, _P, _P, _P, C.POINTER(SdRenderOut),
+                            C.POINTER(SdRenderOut), _P, _SZ, _P]),
     "sd_expand_dim": (_I, [_ML, _P, _LL, _P, _P]),
     "sd_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _F, _P, _P]),
     "sd_ssc_head_pack_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),

@@ -240,3 +240,58 @@ extern "C" int sd_render_pass(const sd_scene *scene, const sd_mlp *mlp, const sd
     return sd_composite(z, w_sigma, w_dino, Crgb ? w_rgb : nullptr, R, K, D, Crgb, cfg, weights, alphas, depth,
                         dino, rgb_out, stream);
 }
+
+// ---- NeRFRenderer.forward for one scene in one call (nerf.py:451-539) ---------------------------------------------------
+static size_t rays_ws_layout(const sd_scene *scene, const sd_mlp *mlp, const sd_sampling *sp, long long R, size_t *o_zc,
+                             size_t *o_wc, size_t *o_dc, size_t *o_za, size_t *o_pass) {
+    const int Kc = sp->n_coarse, K = sp->n_coarse + sp->n_fine;
+    size_t o = 0;
+    *o_zc = o; o += align256((size_t)R * Kc * 4);
+    *o_wc = o; o += align256((size_t)R * Kc * 4);
+    *o_dc = o; o += align256((size_t)R * 4);
+    *o_za = o; o += align256((size_t)R * K * 4);
+    *o_pass = o;
+    const size_t a = sd_render_workspace_bytes(scene, mlp, R, Kc), b = sp->n_fine > 0 ? sd_render_workspace_bytes(scene, mlp, R, K) : 0;
+    return o + (a > b ? a : b);
+}
+
+extern "C" size_t sd_render_rays_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, const sd_sampling *samp, long long R) {
+    if (!scene || !mlp || !samp || R <= 0 || samp->n_coarse <= 0 || samp->n_fine < 0) return 0;
+    size_t a, b, c, d, e;
+    return rays_ws_layout(scene, mlp, samp, R, &a, &b, &c, &d, &e);
+}
+
+extern "C" int sd_render_rays(const sd_scene *scene, const sd_mlp *mlp, const sd_render_cfg *cfg, const sd_sampling *samp,
+                              const float *rays, long long R, int r_dim, const float *u_coarse, const float *lin,
+                              const float *u_fine0, const float *u_fine1, const float *n_depth, const sd_render_out *coarse,
+                              const sd_render_out *fine, void *workspace, size_t workspace_bytes, void *stream) {
+    SD_REQUIRE(scene && mlp && cfg && samp && coarse, "sd_render_rays: null pointer");
+    const int Kc = samp->n_coarse, Kf = samp->n_fine, Kfd = samp->n_fine_depth, Kfi = Kf - Kfd;
+    SD_REQUIRE(Kc > 0 && Kf >= 0 && Kfd >= 0 && Kfi >= 0, "sd_render_rays: bad sample counts (%d coarse, %d fine, %d of them depth-guided)", Kc, Kf, Kfd);
+    SD_REQUIRE(Kf == 0 || fine, "sd_render_rays: n_fine > 0 needs the fine outputs");
+    SD_REQUIRE(R >= 0 && r_dim >= 8, "sd_render_rays: bad shape (rays need >= 8 columns)");
+    if (R == 0) return SD_OK;
+    size_t o_zc, o_wc, o_dc, o_za, o_pass;
+    const size_t need = rays_ws_layout(scene, mlp, samp, R, &o_zc, &o_wc, &o_dc, &o_za, &o_pass);
+    if (!workspace || workspace_bytes < need) {
+        set_error("sd_render_rays: workspace of %zu B needed, %zu B given", need, workspace_bytes);
+        return SD_ERR_WORKSPACE;
+    }
+    SD_REQUIRE(((uintptr_t)workspace & 255) == 0, "sd_render_rays: workspace must be 256-byte aligned");
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    float *z_c = coarse->z_samps ? coarse->z_samps : reinterpret_cast<float *>(ws + o_zc);
+    float *w_c = coarse->weights ? coarse->weights : reinterpret_cast<float *>(ws + o_wc);
+    float *d_c = coarse->depth ? coarse->depth : reinterpret_cast<float *>(ws + o_dc);
+    int rc = sd_sample_coarse(rays, R, r_dim, u_coarse, lin, Kc, cfg->lindisp, z_c, stream);
+    if (rc) return rc;
+    rc = sd_render_pass(scene, mlp, cfg, rays, R, r_dim, z_c, Kc, d_c, coarse->dino, coarse->rgb, Kf > 0 ? w_c : coarse->weights,
+                        coarse->alphas, coarse->invalid, coarse->invalid_feat, coarse->rgb_samps, nullptr, ws + o_pass,
+                        workspace_bytes - o_pass, stream);
+    if (rc || Kf == 0) return rc;
+    float *z_a = fine->z_samps ? fine->z_samps : reinterpret_cast<float *>(ws + o_za);
+    rc = launch_fine_merge(rays, R, r_dim, w_c, z_c, d_c, Kc, u_fine0, u_fine1, Kfi, n_depth, Kfd, samp->depth_std, cfg->lindisp, z_a,
+                           (cudaStream_t)stream);
+    if (rc) return rc;
+    return sd_render_pass(scene, mlp, cfg, rays, R, r_dim, z_a, Kc + Kf, fine->depth, fine->dino, fine->rgb, fine->weights, fine->alphas,
+                          fine->invalid, fine->invalid_feat, fine->rgb_samps, nullptr, ws + o_pass, workspace_bytes - o_pass, stream);
+}

@@ -126,4 +126,9 @@ bool expand_tc_supported(const sd_mlp *mlp);
 int launch_head2(const sd_mlp *mlp, const float *h, const float *scale, long long R, float *out, cudaStream_t st);
 int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out, cudaStream_t st);
 
+// sampling.cu: importance + depth samples of the fine pass, merged with the coarse depths and sorted, in one launch
+int launch_fine_merge(const float *rays, long long R, int r_dim, const float *weights, const float *z_coarse, const float *depth,
+                      int Kc, const float *u0, const float *u1, int Kfi, const float *noise, int Kfd, float depth_std,
+                      int lindisp, float *z_all, cudaStream_t st);
+
 }  // namespace sd

@@ -4,6 +4,7 @@
 // explicitly rounded intrinsic in the reference's eager-op order and the CDF accumulates
 // sequentially in double (torch CPU cumsum semantics), exactly like the oracle.
 #include "common.cuh"
+#include "launch.h"
 
 namespace sd {
 
@@ -149,6 +150,82 @@ __global__ void __launch_bounds__(128) sort_rows_kernel(float *__restrict__ z, l
         }
     }
     for (int k = lane; k < K; k += 32) z[r * K + k] = v[k];
+}
+
+// ---- a-2 + a-3 + a-5 in one launch: the fine pass's depths (nerf.py:511-529) --------------------------------------
+// One warp per ray: importance samples from the coarse weights (sample_fine), samples around the expected depth
+// (sample_fine_depth), concatenation with the coarse depths and the ascending sort -- the same arithmetic as the four
+// separate entry points, bit for bit, without the three intermediate tensors and four launches.
+__global__ void __launch_bounds__(128) fine_merge_kernel(const float *__restrict__ rays, long long R, int r_dim,
+                                                         const float *__restrict__ weights, const float *__restrict__ z_coarse,
+                                                         const float *__restrict__ depth, int Kc, const float *__restrict__ u0,
+                                                         const float *__restrict__ u1, int Kfi, const float *__restrict__ noise,
+                                                         int Kfd, float depth_std, int lindisp, int P, float *__restrict__ z_all) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 4 + warp;
+    if (r >= R) return;
+    const int K = Kc + Kfi + Kfd;
+    float *cdf = smem + warp * (2 * Kc + 2 + P);
+    float *w = cdf + Kc + 1;
+    float *v = w + Kc + 1;
+    for (int k = lane; k < Kc; k += 32) {
+        w[k] = __ldg(weights + r * Kc + k);
+        v[k] = __ldg(z_coarse + r * Kc + k);
+    }
+    for (int k = K + lane; k < P; k += 32) v[k] = __int_as_float(0x7f800000);
+    __syncwarp();
+    const float near = __ldg(rays + r * r_dim + 6), far = __ldg(rays + r * r_dim + 7);
+    if (Kfi > 0) {
+        if (lane == 0) build_cdf(w, Kc, cdf);
+        __syncwarp();
+        for (int j = lane; j < Kfi; j += 32) {
+            int ind = upper_bound(cdf, Kc + 1, __ldg(u0 + r * Kfi + j)) - 1;
+            ind = ind < 0 ? 0 : ind;
+            const float t = __fdiv_rn(__fadd_rn((float)ind, __ldg(u1 + r * Kfi + j)), (float)Kc);
+            v[Kc + j] = depth_from_t(near, far, t, lindisp);
+        }
+    }
+    if (Kfd > 0) {
+        const float d = __ldg(depth + r);
+        for (int j = lane; j < Kfd; j += 32) {
+            float x = __fadd_rn(d, __fmul_rn(__ldg(noise + r * Kfd + j), depth_std));
+            x = x < far ? x : far;
+            x = x > near ? x : near;
+            v[Kc + Kfi + j] = x;
+        }
+    }
+    __syncwarp();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < P / 2; i += 32) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const float a = v[lo], b2 = v[hi];
+                if ((a > b2) == up) { v[lo] = b2; v[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < K; k += 32) z_all[r * K + k] = v[k];
+}
+
+int launch_fine_merge(const float *rays, long long R, int r_dim, const float *weights, const float *z_coarse, const float *depth,
+                      int Kc, const float *u0, const float *u1, int Kfi, const float *noise, int Kfd, float depth_std,
+                      int lindisp, float *z_all, cudaStream_t st) {
+    const int K = Kc + Kfi + Kfd;
+    SD_REQUIRE(R >= 0 && r_dim >= 8 && Kc > 0 && Kfi >= 0 && Kfd >= 0 && Kfi + Kfd > 0, "fine pass: bad sample counts");
+    if (R == 0) return SD_OK;
+    SD_REQUIRE(rays && weights && z_coarse && z_all && (Kfi == 0 || (u0 && u1)) && (Kfd == 0 || (depth && noise)), "fine pass: null pointer");
+    int P = 2;
+    while (P < K) P <<= 1;
+    const size_t smem = 4 * (size_t)(2 * Kc + 2 + P) * sizeof(float);
+    SD_REQUIRE(smem <= 48 * 1024, "fine pass: %d + %d samples per ray do not fit the merge kernel's shared memory", Kc, Kfi + Kfd);
+    fine_merge_kernel<<<(unsigned)((R + 3) / 4), 128, smem, st>>>(rays, R, r_dim, weights, z_coarse, depth, Kc, u0, u1, Kfi, noise,
+                                                                  Kfd, depth_std, lindisp, P, z_all);
+    SD_LAUNCH_OK("fine_merge_kernel");
+    return SD_OK;
 }
 
 }  // namespace sd

@@ -191,20 +191,93 @@ class NeRFRenderer(torch.nn.Module):
                 out = self._composite_generic(model, rays, z_samp, coarse, sb)
             weights, rgb_final, depth, alphas, invalid, rgbs, state = out
             if self.nan_check:
-                bad = torch.isnan(depth).any() | torch.isnan(rgb_final).any() | torch.isnan(z_samp).any()
-                if bool(bad):
-                    raise FloatingPointError("NaN in rendered depth / rgb / z_samp (reference: nerf.py:428-432)")
+                self._nan_check(depth, rgb_final, z_samp)
             ray_info = rays[:, None, 8:] if rays.shape[-1] > 8 else None
             return weights, rgb_final, depth, alphas, invalid, z_samp, rgbs, ray_info, None, state
 
-    def _composite_native(self, net, rays, z, sb, want_rgb_samps):
-        if B_ := rays.shape[0] % sb:
-            raise ValueError(f"{rays.shape[0]} rays do not split into {sb} scenes ({B_} left over)")
+    @staticmethod
+    def _nan_check(*tensors):
+        """nerf.py:428-432 scans six tensors and exits the process; here NaN in the per-ray results raises.  One fused
+        reduction and ONE host sync for all tensors (a sum is NaN iff an element is -- or +inf meets -inf, equally bad)."""
+        total = sum(t.sum(dtype=torch.float32) for t in tensors if t is not None and t.numel())
+        if torch.is_tensor(total) and bool(torch.isnan(total)):
+            raise FloatingPointError("NaN in rendered depth / rgb / z_samp (reference: nerf.py:428-432)")
+
+    def _native_setup(self, net, sb, B):
+        if B_ := B % sb:
+            raise ValueError(f"{B} rays do not split into {sb} scenes ({B_} left over)")
         prec = net._precision()
         st = net._state(prec)
         mlp = net._mlp(prec)
         if st["n"] != sb:
             raise ValueError(f"super-batch {sb} but the field was encoded with batch {st['n']}")
+        return prec, st, mlp
+
+    def _forward_native(self, net, rays, sb, want_rgb_samps):
+        """NeRFRenderer.forward for a native BTSNet: ONE library call per scene (sd_render_rays: coarse sampling, coarse pass,
+        importance + depth samples, merge, sort, fine pass launched back to back, no Python in between).  The random draws
+        are made here with the reference's torch calls in the reference's order (nerf.py:134, 193-203, 221)."""
+        if self.render_mode != "volumetric":
+            raise NotImplementedError(f"render_mode={self.render_mode!r}: only 'volumetric' is implemented")
+        if self.training and self.noise_std > 0.0:
+            raise NotImplementedError("noise_std > 0 in training mode is not implemented")
+        rays = self._rays2d(rays)
+        B = rays.shape[0]
+        prec, st, mlp = self._native_setup(net, max(sb, 1), B)
+        sb = max(sb, 1)
+        Bp = B // sb
+        Kc, Kf, Kfd = self.n_coarse, (self.n_fine if self.using_fine else 0), (self.n_fine_depth if self.using_fine else 0)
+        Kfi = Kf - Kfd
+        dev = rays.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        lin = torch.linspace(0, 1 - 1.0 / Kc, Kc, device=dev)
+        u_c = torch.rand_like(torch.empty((B, Kc), **f32))
+        u0 = torch.rand(B, Kfi, **f32) if Kfi > 0 else None
+        u1 = torch.rand_like(u0) if Kfi > 0 else None
+        noise = torch.randn_like(torch.empty((B, Kfd), **f32)) if Kfd > 0 else None
+        nv_c, D = st["rgb"].shape[1], mlp.d_out - 1
+
+        def alloc(K):
+            return dict(weights=torch.empty((B, K), **f32), alphas=torch.empty((B, K), **f32), depth=torch.empty((B,), **f32),
+                        dino=torch.empty((B, D), **f32), rgb=torch.empty((B, 3 * nv_c), **f32), z=torch.empty((B, K), **f32),
+                        invalid=torch.empty((B, K, nv_c), **f32), invf=torch.empty((B, K, 1), dtype=torch.uint8, device=dev),
+                        rgbs=torch.empty((B, K, 3 * nv_c), **f32) if want_rgb_samps else None)
+
+        passes = [alloc(Kc)] + ([alloc(Kc + Kf)] if Kf > 0 else [])
+        use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128
+                    and (D > 64 or Bp * Kc >= 65536))
+        cfg = self._cfg()
+        sp = _abi.SdSampling()
+        sp.n_coarse, sp.n_fine, sp.n_fine_depth, sp.depth_std = Kc, Kf, Kfd, float(self.depth_std)
+        lib = _abi.lib()
+        for b in range(sb):
+            sc = net._scene(st, b, net._projection(st, b, mlp) if use_proj else None)
+            sl = slice(b * Bp, (b + 1) * Bp)
+            outs = []
+            for o in passes:
+                ro = _abi.SdRenderOut()
+                ro.depth, ro.dino, ro.rgb = o["depth"][sl].data_ptr(), o["dino"][sl].data_ptr(), o["rgb"][sl].data_ptr()
+                ro.weights, ro.alphas, ro.z_samps = o["weights"][sl].data_ptr(), o["alphas"][sl].data_ptr(), o["z"][sl].data_ptr()
+                ro.invalid, ro.invalid_feat = o["invalid"][sl].data_ptr(), o["invf"][sl].data_ptr()
+                ro.rgb_samps = o["rgbs"][sl].data_ptr() if want_rgb_samps else None
+                outs.append(ro)
+            need = lib.sd_render_rays_workspace_bytes(C.byref(sc), C.byref(mlp), C.byref(sp), Bp)
+            ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            _abi.check(lib.sd_render_rays(
+                C.byref(sc), C.byref(mlp), C.byref(cfg), C.byref(sp), _ptr(rays[sl]), Bp, rays.shape[1], _ptr(u_c[sl]), _ptr(lin),
+                _ptr(u0[sl]) if Kfi > 0 else None, _ptr(u1[sl]) if Kfi > 0 else None, _ptr(noise[sl]) if Kfd > 0 else None,
+                C.byref(outs[0]), C.byref(outs[1]) if Kf > 0 else None, _ptr(ws), need, _stream()), "sd_render_rays")
+        ray_info = rays[:, None, 8:] if rays.shape[-1] > 8 else None
+        res = []
+        for o in passes:
+            if self.nan_check:
+                self._nan_check(o["depth"], o["rgb"], o["z"])
+            state = {"invalid_features": o["invf"].view(torch.bool), "dino_features": o["dino"]}
+            res.append((o["weights"], o["rgb"], o["depth"], o["alphas"], o["invalid"], o["z"], o["rgbs"], ray_info, None, state))
+        return res
+
+    def _composite_native(self, net, rays, z, sb, want_rgb_samps):
+        prec, st, mlp = self._native_setup(net, sb, rays.shape[0])
         B, K = z.shape
         Bp = B // sb
         nv_c, D = st["rgb"].shape[1], mlp.d_out - 1
@@ -286,6 +359,15 @@ class NeRFRenderer(torch.nn.Module):
             assert len(rays.shape) == 3
             sb = rays.shape[0]
             rays = rays.reshape(-1, rays.shape[-1])
+            if sample_from_dist is None and (hasattr(model, "_sd_render_pass") or hasattr(model, "_scene")):
+                passes = self._forward_native(model, rays, sb, want_rgb_samps)
+                fmt = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
+                           want_rgb_samps=want_rgb_samps)
+                outputs = DotMap(coarse=self._format_outputs(passes[0], sb, **fmt))
+                outputs.state_dict = passes[0][-1]
+                if len(passes) > 1:
+                    outputs.fine = self._format_outputs(passes[1], sb, **fmt)
+                return outputs
             if sample_from_dist is None:
                 z_coarse = self.sample_coarse(rays)
             else:

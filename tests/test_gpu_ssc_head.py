@@ -43,7 +43,8 @@ def test_ssc_head_vs_reference(golden):
     golden query's 64-d features: the fused kernel starts from those 64-d features."""
     g, q = golden("ssc_head"), golden("query")
     w = syn.make_ssc_head(int(g["seed"]))
-    f = np.concatenate([q["dino"], q["dino_le"]], 0).astype(np.float32)
+    nq = len(q["dino_full"])                       # the fixture expands the first 256 points of each variant
+    f = np.concatenate([q["dino"][:nq], q["dino_le"][:nq]], 0).astype(np.float32)
     n = len(f)
     expand = (q["e_w1"], q["e_b1"], q["e_w2"], q["e_b2"])
     # the fixture's first rows are the reference's expansions of exactly these features
