@@ -305,7 +305,7 @@ int launch_expand_tc(const sd_mlp *mlp, const float *f, long long N, float *out,
     SD_REQUIRE(L.off_x_w2 != 0, "sd_expand_dim: the blob carries no expand images");
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
     SD_REQUIRE(((uintptr_t)blob & 15) == 0, "mlp: packed blob must be 16-byte aligned");
-    ex::Params P;
+    ex::Params P = {};
     P.f = f; P.out = out;
     P.w1_img = blob + L.off_w_in_h;
     P.w2_img = blob + L.off_x_w2;
