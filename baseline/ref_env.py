@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CANDIDATES = [os.environ.get("SCENEDINO_REFERENCE", ""), "/root/reference", os.path.join(HERE, "_ref")]
 
 STUB_PACKAGES = {"hydra", "ignite", "matplotlib", "lpips", "kornia", "timm", "pykeops", "pydensecrf", "plyfile", "skimage",
-                 "open3d", "gradio", "optuna", "dotdict", "tensorboardX", "wandb", "seaborn", "PIL_stub", "moviepy", "imageio"}
+                 "open3d", "gradio", "optuna", "dotdict", "pulp", "tensorboardX", "wandb", "seaborn", "PIL_stub", "moviepy", "imageio"}
 
 
 def reference_root():

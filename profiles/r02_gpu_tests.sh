@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-for f in test_gpu_zz_next test_gpu_ssc_head test_gpu_parity test_gpu_surface; do
+for f in ${SD_R02_FILES:-test_gpu_zz_next test_gpu_ssc_head test_gpu_parity test_gpu_surface}; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --maxfail=25 -p no:cacheprovider > gpurun_out/$f.log 2>&1
   echo "$f rc=$?"; tail -n 3 gpurun_out/$f.log
 done

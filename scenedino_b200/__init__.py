@@ -11,6 +11,7 @@ from .heads import MlpDimReduction, PositionalEncoding, ResnetFC, make_head  # n
 from .nerf import DotMap, NeRFRenderer, _RenderWrapper  # noqa: F401
 from .ray_sampler import ImageRaySampler, RaySampler  # noqa: F401
 from .semantic_head import SemanticHead, make_downstream_head  # noqa: F401
+from .install import install  # noqa: F401
 
-__all__ = ["BTSNet", "NeRFRenderer", "ResnetFC", "make_head", "PositionalEncoding", "MlpDimReduction", "ImageRaySampler", "RaySampler", "SemanticHead", "make_downstream_head",
+__all__ = ["BTSNet", "NeRFRenderer", "ResnetFC", "make_head", "PositionalEncoding", "MlpDimReduction", "ImageRaySampler", "RaySampler", "SemanticHead", "make_downstream_head", "install",
            "DotMap", "SdError", "launch_count", "lib"]

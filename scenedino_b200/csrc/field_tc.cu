@@ -333,7 +333,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         //      out[ray][:] = sum_row Wt[ray][row] * V[row][:]; the MMA issuer does the rest ---------
                         if (warp == 0) SD_TRACE(0, j, 5);
                         // the previous composite has consumed the operands and its sums have been read from TMEM
-                        // (cmma == 2: the first epilogue of this tile waited already, before it wrote V)
                         if (cm_n > 0) mbar_wait(BAR(BAR_D3_READ), (uint32_t)((cm_n - 1) & 1));
                         if (warp == 0) SD_TRACE(0, j, 6);
                         if (P.cmma == 1) {
@@ -455,8 +454,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 }
                 mbar_arrive_warp(BAR(BAR_GEO_EMPTY + slot));
             }
-            // cmma == 2: V is single buffered -- the composite of the previous tile must have consumed it
-            if (P.cmma == 2 && cm_n > 0) mbar_wait(BAR(BAR_D3_READ), (uint32_t)((cm_n - 1) & 1));
+            // cmma == 2: V is single buffered -- the composite MMAs of the previous tile must have consumed it.  (Their
+            // completion, BAR_D3, not the read-out of their sums, BAR_D3_READ: the issuer reads the sums out only behind
+            // layer 2 of THIS tile, which waits for this epilogue -- that wait would close a cycle.)
+            if (P.cmma == 2 && cm_n > 0) mbar_wait(BAR(BAR_D3), (uint32_t)((cm_n - 1) & 1));
             if (warp == 0) SD_TRACE(0, j, 2);
             const int b = (int)(j & 1);
             mbar_wait(BAR(BAR_D1 + b), (uint32_t)((j >> 1) & 1));

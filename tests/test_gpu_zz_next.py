@@ -67,3 +67,37 @@ def test_render_d64_hidden_composite_matches_feature_composite(golden):
     _check_pass({**b, "dino_features": b["dino_features"][:, :64]}, g, "coarse.", TOL_F16)
     scale = float(a["dino_features"].abs().mean())
     assert float((a["dino_features"] - b["dino_features"][:, :64]).abs().max()) < 2e-2 * scale * 10
+
+
+@pytest.mark.parametrize("K,D,nv", [(64, 200, 2), (96, 768, 4), (32, 64, 1)])
+def test_render_big_heads_many_tiles_vs_oracle(K, D, nv):
+    """Several tiles per CTA (the fixtures above give every CTA at most one): 2 600 rays of a rotated view against the
+    oracle, D > 64 on the hidden-composite path incl. a ragged last block of W_out (D = 200), D = 64 on the feature composite."""
+    from oracle import oracle as O
+    from scenedino_b200 import synthetic as syn
+    from helpers import assert_close
+    C_, Hf, Wf = 256, 48, 160
+    feat = syn.make_feature_map(5, C_, Hf, Wf)
+    imgs = syn.make_images(6, nv, 24, 80)
+    Km = np.broadcast_to(syn.kitti360_K(), (nv, 3, 3)).copy()
+    c2w = np.stack([syn.view_pose_c2w(v) for v in range(nv)])
+    w2c = np.linalg.inv(c2w.astype(np.float64)).astype(np.float32)
+    mlp_w = syn.make_mlp(2, d_out=D + 1, bias_scale=0.05)
+    R = 2600
+    rays = syn.image_rays(syn.view_pose_c2w(3), Km[0])[:: (syn.IMG_H * syn.IMG_W) // R][:R]
+    rs = np.random.RandomState(K)
+    z = np.sort(rs.uniform(3, 80, (R, K)).astype(np.float32), 1)
+    osc = O.Scene(feat=feat, K_f=Km[:1], w2c_f=w2c[:1], rgb=imgs, K_c=Km, w2c_c=w2c)
+    oo = O.render_pass(osc, O.Mlp(*mlp_w), rays, z, hard_alpha_cap=True)
+    dsc = ops.Scene.from_arrays(feat, Km[:1], w2c[:1], imgs, Km, w2c, device="cuda", feat_dtype=torch.float16)
+    dmlp = ops.Mlp(*mlp_w, device="cuda")
+    dsc = dsc.project(dmlp)
+    o = ops.render_pass(dsc, dmlp, dev(rays), dev(z), hard_alpha_cap=True, precision=ops.F16)
+    for k in ("weights", "alphas", "depth", "dino_features", "rgb"):
+        assert_close(g2n(o[k]), oo[k], TOL_F16, k)
+    assert np.array_equal(g2n(o["invalid"]), oo["invalid"]) and np.array_equal(g2n(o["invalid_features"]), oo["invalid_features"])
+    # depth keeps a hi/lo pair through the fp16 composite operands: far tighter than the bar
+    assert_close(g2n(o["depth"]), oo["depth"], 2e-3, "depth (hi/lo split)")
+    o2 = ops.render_pass(dsc, dmlp, dev(rays), dev(z), hard_alpha_cap=True, precision=ops.F16, per_sample=False)
+    for k in ("depth", "dino_features", "rgb"):
+        assert torch.equal(o2[k], o[k]), k
