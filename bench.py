@@ -3,19 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|fp32] [--impl reference]
 
-Headline workload (BASELINE.json configs[1]): the SSCBench voxel-grid query -- 256 x 256 x 32 voxels
-@ 0.2 m projected into one 192 x 640 view whose DINO ViT-B/8 feature map is 256 x 384 x 1280, MLP head
-295 -> 128 -> 65.  One "step" = one pass of the hot path over the whole grid (2 097 152 voxels):
-sd_query_points -> sigma [N] + 64-d features [N,64] + frustum mask [N].  Synthetic data: seeded random
-feature map and random-init (kaiming) head weights.  The same line also carries a full-image render
-(122 880 rays x 64 samples) as ``render``.
+Headline workload (BASELINE.json configs[1]): the SSCBench voxel-grid query -- 256 x 256 x 32 voxels @ 0.2 m projected
+into one 192 x 640 view whose DINO ViT-B/8 feature map is 256 x 384 x 1280, MLP head 295 -> 128 -> 65.  One "step" = one
+pass of the hot path over the whole grid (2 097 152 voxels): sd_query_points -> sigma [N] + 64-d features [N,64] + frustum
+mask [N].  Synthetic data: seeded random feature map and random-init (kaiming) head weights.
 
-N > 1 (torchrun, one rank per GPU): every rank queries one full grid against its own replica of the
-map (weak scaling: voxel slabs / frames are independent), then all ranks all-gather the density grid
-and the frustum mask over NCCL; time = max over ranks.
+The one JSON line carries, besides the contract's keys (value, e2e, roofline, cpu_baseline, clocks, gpu_launches):
+  e2e            the same query through the reference-shaped API, ``BTSNet.forward(xyz)``, with the points coming from
+                 pinned host memory and sigma + mask going back to it every step
+  per_frame      what ONE FRAME of the SSC evaluation costs (sscbench/evaluate_model_sscbench.py:690-756): a NEW feature
+                 map every step -> pack + project (BTSNet.encode) -> query of the (fixed) grid -> expansion + SSC head ->
+                 sigma + label back on the host; through ``BTSNet.forward(predict_segmentation=True)``
+  renders        BASELINE configs 1, 3 and 4 through ``NeRFRenderer`` (sd_render_rays): Msamples/s, tensor roofline, e2e
+  fp32           the rel-1e-4 mode (CUDA-core parity path) on a slab of the grid
+  strong_scaling (N > 1) ONE grid split into x-slabs across the ranks + all-gather of sigma and mask
 
-``--impl reference``: the CPU restatement of the reference algorithm (oracle/, the reference is pure
-Python and cannot travel to the GPU box) on all host cores, rank 0 only, on a bounded sample.
+N > 1 (torchrun, one rank per GPU): ``value`` is weak scaling -- every rank queries one full grid against its own replica
+of the map (frames are independent), then all ranks all-gather the density grid and the frustum mask; time = max over
+ranks.
+
+``--impl reference``: the reference's own PyTorch CPU path (baseline/_ref, the unmodified reference tree; the C/OpenMP
+oracle port when that tree is absent) on all host cores, rank 0 only, on a bounded sample.
 """
 from __future__ import annotations
 
@@ -36,13 +44,17 @@ from scenedino_b200 import synthetic as syn  # noqa: E402
 
 GRID = (256, 256, 32)
 C_FEAT, HF, WF = 256, 384, 1280          # DINO ViT-B/8 + DPT head at 192 x 640
+HF2, WF2 = 192, 640                      # DINOv2 ViT-B/14 variant
 D_IN, D_HID, D_OUT = 295, 128, 65
-FLOP_PER_POINT = 2 * (D_IN * D_HID + D_HID * D_OUT)   # 92 160
-RENDER_R, RENDER_K = syn.IMG_H * syn.IMG_W, 64
+FLOP_PER_POINT = 2 * (D_IN * D_HID + D_HID * D_OUT)        # 92 160
+FLOP_PER_POINT_768 = 2 * (D_IN * D_HID + D_HID * 769)      # 272 384
+FLOP_EXPAND = 2 * (64 * 128 + 128 * 768)                   # 212 992 per vector
+FLOP_SSC_HEAD = 2 * (768 * 64 + 768 * 768 + 768 * 64)      # 1 376 256 per voxel ("1.38 MFLOP")
 
 
 def measured_traffic(kernel):
-    """dram bytes per launch of `kernel` from the latest committed ncu summary (profiles/*_traffic.json), or None."""
+    """dram bytes per launch of `kernel` from the latest committed ncu summary (profiles/*_traffic.json) and the commit
+    it was profiled at -- a constant read from a file, NOT a measurement of this run -- or None."""
     import glob
     best = None
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
@@ -51,7 +63,7 @@ def measured_traffic(kernel):
         except (OSError, ValueError):
             continue
         if kernel in d:
-            best = d[kernel]
+            best = (d[kernel], d.get("commit", "unknown"), os.path.basename(f))
     return best
 
 
@@ -125,8 +137,8 @@ def unique_texels(pts, K, Hf, Wf):
     return int(np.unique(ids).size)
 
 
-def cpu_reference_voxels(feat_nchw, mlp_w, pts, budget_s=12.0):
-    """Times the CPU oracle (OpenMP, all host cores) on a strided sample of the grid."""
+def cpu_port_voxels(feat_nchw, mlp_w, pts, budget_s=12.0):
+    """Times the CPU oracle (C / OpenMP restatement, all host cores) on a strided sample of the grid."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     O.set_num_threads(cores)
@@ -145,6 +157,20 @@ def cpu_reference_voxels(feat_nchw, mlp_w, pts, budget_s=12.0):
                 sample=f"{len(sub)} voxels strided over the 256x256x32 grid, oracle/sd_oracle.c (OpenMP), {dt:.2f} s")
 
 
+def cpu_reference_voxels(feat_nchw, mlp_w, pts, budget_s=12.0, net_cache={}):
+    """The reference's own CPU path where its tree travelled with the snapshot (kind "reference": the unmodified PyTorch code,
+    baseline/ref_bench.py), else the oracle port (kind "port")."""
+    try:
+        from baseline import ref_bench
+        if ref_bench.available():
+            if "net" not in net_cache:
+                net_cache["net"] = ref_bench.build_net(feat_nchw, mlp_w, syn.kitti360_K())
+            return ref_bench.time_voxel_query(net_cache["net"], pts, budget_s)
+    except Exception as exc:          # noqa: BLE001 -- the baseline must not take the benchmark down
+        print(f"[bench] reference CPU path unavailable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+    return cpu_port_voxels(feat_nchw, mlp_w, pts, budget_s)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,14 +179,17 @@ def run_reference(args):
     mlp_w = syn.make_mlp(0)
     pts = syn.ssc_voxel_grid(GRID)
     vals, last = [], None
+    per = max(2.0, 40.0 / (args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_voxels(feat, mlp_w, pts, budget_s=max(2.0, 40.0 / (args.warmup + args.steps)))
+        last = cpu_reference_voxels(feat, mlp_w, pts, budget_s=per)
         if i >= args.warmup:
             vals.append(last["value"])
     v = float(np.mean(vals))
     last["value"] = v
+    n_sample = int(last["sample"].split()[0])
     line = {"impl": "reference", "metric": "ssc_voxel_query_throughput", "value": v, "unit": "voxels/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": GRID[0] * GRID[1] * GRID[2] / v * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_sample / v * 1e3,
+            "step_unit": f"one step = {n_sample} voxels (a bounded strided sample of the grid), not the whole grid",
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config("fp16"), "cpu_baseline": last,
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,6 +208,47 @@ def workload_config(precision):
             "launch": "one CUDA-graph replay per step (memset + 4 sort kernels + field kernel)" if precision == "fp16" else "direct calls"}
 
 
+def build_net(sd, torch, feat_holder, dev, precision, d_out=D_OUT, with_head=True, seed=0):
+    """scenedino_b200.BTSNet the way a caller builds it: encoder (a module that hands out the current feature map: the ViT
+    is out of scope), positional code, ResnetFC head, SemanticHead; weights by state-dict key."""
+    class Encoder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.latent_size, self.extra_outs = C_FEAT, 0
+            self.dim_reduction = sd.MlpDimReduction(768, 64, 128)
+
+        def forward(self, x, ground_truth=False):
+            return [feat_holder["map"]]
+
+        def expand_dim(self, f):
+            return self.dim_reduction.transform_expand(f)
+
+    conf = {"predict_dino": True, "dino_dims": d_out - 1, "inv_z": True, "learn_empty": False, "code_mode": "z",
+            "sd_precision": precision}
+    code = sd.PositionalEncoding.from_conf({"num_freqs": 6, "freq_factor": 1.5, "include_input": True}, d_in=3)
+    head = sd.make_head({"type": "resnet", "name": "normal_head", "args": {"n_blocks": 0, "d_hidden": 128}}, C_FEAT + code.d_out, d_out)
+    down = sd.SemanticHead.from_conf({"n_classes": 27, "gt_classes": 19, "input_dim": 768, "code_dim": 64}) if with_head else None
+    net = sd.BTSNet(conf, Encoder(), code, {"normal_head": head}, None, downstream_head=down)
+    net.encode_loss_features = False
+    mlp_w, ex = syn.make_mlp(seed, d_out=d_out), syn.make_expand(3)
+    state = {"heads.normal_head.lin_in.weight": mlp_w[0], "heads.normal_head.lin_in.bias": mlp_w[1],
+             "heads.normal_head.lin_out.weight": mlp_w[2], "heads.normal_head.lin_out.bias": mlp_w[3],
+             "encoder.dim_reduction.linear_in.weight": ex[0], "encoder.dim_reduction.linear_in.bias": ex[1],
+             "encoder.dim_reduction.linear_out.weight": ex[2], "encoder.dim_reduction.linear_out.bias": ex[3]}
+    if with_head:
+        hw = syn.make_ssc_head(21)
+        state.update({"downstream_head.stego_head.linear_path.0.weight": hw["wl"].reshape(64, 768, 1, 1),
+                      "downstream_head.stego_head.linear_path.0.bias": hw["bl"],
+                      "downstream_head.stego_head.nonlinear_path.0.weight": hw["wn1"].reshape(768, 768, 1, 1),
+                      "downstream_head.stego_head.nonlinear_path.0.bias": hw["bn1"],
+                      "downstream_head.stego_head.nonlinear_path.2.weight": hw["wn2"].reshape(64, 768, 1, 1),
+                      "downstream_head.stego_head.nonlinear_path.2.bias": hw["bn2"],
+                      "downstream_head.stego_cluster_head.cluster_centers": hw["centres"],
+                      "downstream_head.stego_cluster_head.pseudo_assignment": hw["lut"]})
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=False)
+    return net.to(dev).eval()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +258,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_frame / fp32 / strong-scaling objects")
     ap.add_argument("--no-graph", action="store_true", help="time direct library calls instead of CUDA-graph replays")
     args = ap.parse_args()
     # a run that takes absurdly long dumps its Python stacks and exits instead of hanging its caller (seconds;
@@ -202,6 +273,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import scenedino_b200 as sd
     from scenedino_b200 import _abi, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,39 +297,42 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     pk = peaks()
-    prec = ops.F16 if args.precision == "fp16" else ops.FP32
-    fdt = torch.float16 if args.precision == "fp16" else torch.float32
+    f16 = args.precision == "fp16"
+    prec = ops.F16 if f16 else ops.FP32
+    fdt = torch.float16 if f16 else torch.float32
 
     # ---- scene: seeded random map (encoder stand-in), camera, head -----------------------------------
     g = torch.Generator(device=dev).manual_seed(1)
     feat_nchw = torch.randn((1, C_FEAT, HF, WF), device=dev, generator=g)
     K = syn.kitti360_K()[None]; w2c = np.eye(4, dtype=np.float32)[None]
-    imgs = syn.make_images(2, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    feat = ops.featmap_pack(feat_nchw, fdt)            # first call also pays the module load; time the second
-    torch.cuda.synchronize()
-    e0.record()
-    feat = ops.featmap_pack(feat_nchw, fdt)
-    e1.record(); torch.cuda.synchronize()
-    pack_ms = e0.elapsed_time(e1)
+
+    def timed_ms(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    feat = ops.featmap_pack(feat_nchw, fdt)            # first call also pays the module load
+    pack_ms = timed_ms(lambda: ops.featmap_pack(feat_nchw, fdt), n=3, warm=1)
     scene = ops.Scene(feat=feat[0], K_f=torch.from_numpy(K).to(dev), w2c_f=torch.from_numpy(w2c).to(dev))
-    scene_rgb = ops.Scene(feat=feat[0], K_f=scene.K_f, w2c_f=scene.w2c_f, rgb=torch.from_numpy(imgs).to(dev),
-                          K_c=scene.K_f, w2c_c=scene.w2c_f)
     mlp_w = syn.make_mlp(0)
     mlp = ops.Mlp(*mlp_w, device=dev, precision=prec)
     project_ms = None
-    if args.precision == "fp16":
+    if f16:
         # once per encode (like the pack above): the map pushed through the feature columns of the head's first layer;
         # the voxel query then interpolates 128 hidden pre-activations on the tensor cores (field_proj.cu, field_bin.cu)
-        for _ in range(2):                 # (the second call lets the caching allocator settle: no cudaMalloc in the timed one)
-            scene = scene.project(mlp)
-        torch.cuda.synchronize()
-        e0.record()
         scene = scene.project(mlp)
-        e1.record(); torch.cuda.synchronize()
-        project_ms = e0.elapsed_time(e1)
-        import dataclasses
-        scene_rgb = dataclasses.replace(scene_rgb, proj=scene.proj)     # the render runs on the projected map too
+        state_p = {}
+
+        def proj_step():
+            state_p["s"] = scene.project(mlp)
+        project_ms = timed_ms(proj_step, n=3, warm=2)
+        scene = state_p["s"]
     pts_np = syn.ssc_voxel_grid(GRID)
     N = len(pts_np)
     pts_host = torch.from_numpy(pts_np).pin_memory()
@@ -269,7 +344,6 @@ def main():
     small = [torch.empty(N * 5, dtype=torch.uint8, device=dev) for _ in range(NB)]
     outs = [dict(sigma=small[i][:N * 4].view(torch.float32), invalid_features=small[i][N * 4:],
                  dino=torch.empty((N, D_OUT - 1), device=dev)) for i in range(NB)]
-    out = outs[0]
     gathered = [torch.empty((world, N * 5), dtype=torch.uint8, device=dev) for _ in range(NB)] if world > 1 else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     # All-gather of the small outputs.  Preferred: every rank WRITES its shard into its peers' buffers over NVLink with
@@ -294,7 +368,7 @@ def main():
     # the timed region give the kernel's own duration for the roofline
     k_events = []
     # the timed steps replay a CUDA graph of the query (one launch instead of seven per step), one graph per output buffer
-    graphs = [ops.QueryGraph(scene, mlp, pts, outs[i]) for i in range(NB)] if args.precision == "fp16" and not args.no_graph else None
+    graphs = [ops.QueryGraph(scene, mlp, pts, outs[i]) for i in range(NB)] if f16 and not args.no_graph else None
 
     def step(timed=False):
         b = state["i"] % NB
@@ -330,6 +404,13 @@ def main():
         if os.environ.get("SD_BENCH_VERBOSE"):
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     note("setup done")
     for _ in range(args.warmup):
         step()
@@ -354,10 +435,7 @@ def main():
         launches = _abi.launch_count() - n0
         if graphs is not None:         # kernels inside the replayed graphs (the library counts launches at capture time only)
             launches += (state["i"] - replays0) * graphs[0].launches
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms)
         # keep the sampler alive long enough to see the load on very short runs.  The number of extra steps comes from
         # the agreed (max-over-ranks) time, so that every rank issues the same number of all-gathers: a time-based loop
         # here made ranks disagree and hang now and then.
@@ -372,7 +450,7 @@ def main():
     # ---- the same query with the texel sort reused (fixed grid and cameras, new feature map every frame: what the SSC
     #      evaluation loop does).  Reported beside `value`, which always includes the sort. -----------------------------
     sorted_reuse = None
-    if args.precision == "fp16":
+    if f16:
         ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[0])
         for _ in range(3):
             ops.query_points_sorted(scene, mlp, pts, outs[0])
@@ -384,14 +462,28 @@ def main():
         sr_ms = e0.elapsed_time(e1) / args.steps
         sorted_reuse = {"value": world * N / (sr_ms * 1e-3), "unit": "voxels/s", "ms_per_step": sr_ms,
                         "note": "sd_query_points_sorted: tile kernel only, the sort of the (unchanged) points is reused"}
+    del graphs
+    torch.cuda.empty_cache()
 
-    # ---- end to end: pinned host points -> device -> query -> density grid + mask back to the host ------
-    # Every step moves ITS OWN inputs host->device and its results device->host; the three legs run on three
-    # streams with double buffers, so the copy of step i+1 overlaps the kernel of step i (PCIe is full duplex).
+    # ---- end to end through the reference-shaped API: pinned host points -> device -> BTSNet.forward(xyz) -> density
+    #      grid + mask back to the host.  Every step moves ITS OWN inputs host->device and its results device->host; the
+    #      three legs run on three streams with double buffers (PCIe is full duplex). ----------------------------------
+    holder = {"map": feat_nchw}
+    net = build_net(sd, torch, holder, dev, args.precision)
+    Kt = torch.from_numpy(K).to(dev)[None]
+    eye = torch.eye(4, device=dev)[None, None]
+    dummy_img = torch.zeros(1, 1, 3, 8, 8, device=dev)
+
+    def encode():
+        net.encode(dummy_img, Kt, eye, ids_encoder=[0], ids_render=[0], images_alt=dummy_img)
+        net.set_scale(0)
+
+    encode()
     h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream()
-    pts_in = [torch.empty_like(pts) for _ in range(NB)]
+    main_s = torch.cuda.current_stream()
+    pts_in = [torch.empty((1, N, 3), device=dev) for _ in range(NB)]
     res_host = [torch.empty(N * 5, dtype=torch.uint8).pin_memory() for _ in range(NB)]
+    res_dev = [torch.empty(N * 5, dtype=torch.uint8, device=dev) for _ in range(NB)]
     ev_in = [torch.cuda.Event() for _ in range(NB)]
     ev_k = [torch.cuda.Event() for _ in range(NB)]
     ev_out = [torch.cuda.Event() for _ in range(NB)]
@@ -402,19 +494,22 @@ def main():
         e2e_state["i"] += 1
         with torch.cuda.stream(h2d):
             h2d.wait_event(ev_k[b])                       # the kernel that last read pts_in[b] is done
-            pts_in[b].copy_(pts_host, non_blocking=True)
+            pts_in[b][0].copy_(pts_host, non_blocking=True)
             ev_in[b].record()
-        main.wait_event(ev_in[b])
-        main.wait_event(ev_out[b])                        # the read-back of the step that last used outs[b] is done
-        ops.query_points(scene, mlp, pts_in[b], want_rgb=False, out=outs[b])
+        main_s.wait_event(ev_in[b])
+        main_s.wait_event(ev_out[b])                      # the read-back of the step that last used res_dev[b] is done
+        with torch.no_grad():
+            _, invalid, sigma, _, _ = net(pts_in[b], only_density=True)
+        res_dev[b][:N * 4].view(torch.float32).copy_(sigma.reshape(-1))
+        res_dev[b][N * 4:].copy_(invalid.reshape(-1))     # (only_density: invalid = the frustum mask as floats, bts.py:570-572)
         ev_k[b].record()
         with torch.cuda.stream(d2h):
             d2h.wait_event(ev_k[b])
-            res_host[b].copy_(small[b], non_blocking=True)
+            res_host[b].copy_(res_dev[b], non_blocking=True)
             ev_out[b].record()
 
     def e2e_fence():
-        main.wait_stream(h2d); main.wait_stream(d2h)
+        main_s.wait_stream(h2d); main_s.wait_stream(d2h)
         fence()
 
     for _ in range(3):
@@ -424,90 +519,256 @@ def main():
     e0.record()
     for _ in range(args.steps):
         e2e_step()
-    main.wait_stream(d2h)
+    main_s.wait_stream(d2h)
     e1.record()
     e2e_fence()
     wall_ms = (time.perf_counter() - t0) * 1e3
     note("end-to-end done")
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
     e2e_value = world * N / (e2e_ms / args.steps * 1e-3)
+    del pts_in, res_dev
+    torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
         ntex = unique_texels(pts_np, K[0], HF, WF)
-        # Algorithmic bytes of the dominant kernel per launch: per voxel its 32-byte record in,
-        # density + 64 features out (the frustum mask is written by the sort); per touched texel its row of the map
-        # the kernel reads -- fp16, 128 projected channels on the tensor-core path (fp32, 256 channels on the fp32 path).
-        if args.precision == "fp16":
-            algo_bytes = N * (32 + 4 + 4 * (D_OUT - 1)) + ntex * 128 * 2
+        # Algorithmic bytes of the dominant kernel per launch: per voxel its 12-byte
+        # point in, density + 64 features out (the frustum mask is written by the sort); per touched texel its row of the
+        # map the kernel reads -- fp16, 128 projected channels on the tensor-core path (fp32, 256 channels on the fp32 path).
+        if f16:
+            algo_bytes = N * (12 + 4 + 4 * (D_OUT - 1)) + ntex * 128 * 2
             dom = "field_bin_kernel"
         else:
             algo_bytes = N * (12 + 4 + 4 * (D_OUT - 1) + 1) + ntex * C_FEAT * 4
             dom = "field_simt_kernel"
-        t_kernel = kernel_ms * 1e-3 if args.precision == "fp16" else ms_step * 1e-3
+        t_kernel = kernel_ms * 1e-3 if f16 else ms_step * 1e-3
         hbm_ach = algo_bytes / t_kernel / 1e9
         tc_ach = N * FLOP_PER_POINT / t_kernel / 1e12
-        traffic = measured_traffic(dom)
+        tr = measured_traffic(dom)
+        traffic = tr[0] if tr else None
         roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_ach / pk["hbm"],
-                    "traffic": traffic, "algorithmic_bytes": algo_bytes, "unique_texels": ntex, "peak_source": pk["src"]}
+                    "traffic": traffic,
+                    "traffic_source": (f"constant from profiles/{tr[2]} (ncu --set full at commit {tr[1]}), not a measurement of this run"
+                                       if tr else None),
+                    "algorithmic_bytes": algo_bytes, "unique_texels": ntex, "peak_source": pk["src"],
+                    "step_frac": algo_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm"],
+                    "step_frac_note": "the same bytes over the whole step (texel sort + tile kernel): what a caller waits for"}
         roof_tc = {"bound": "tensor", "achieved": tc_ach, "peak": pk["tc_burst"], "unit": "TFLOP/s",
                    "frac": tc_ach / pk["tc_burst"], "traffic": traffic, "algorithmic_flops": N * FLOP_PER_POINT,
                    "peak_source": pk["src"] + " (burst: kernel timed alone)"}
         # The tile kernel is bound by memory-side work (records in, 260 B/voxel out, map tiles through L2): its tensor
         # work is ~1/3 of the reference's 92 160 FLOP/voxel because the map is pre-projected once per encode, so the HBM
         # roof is the honest one; the tensor fraction (reference FLOPs over the same time) is reported beside it.
-        primary = roof_hbm
         roof_hbm["kernel"] = roof_tc["kernel"] = dom
         roof_hbm["kernel_ms"] = roof_tc["kernel_ms"] = t_kernel * 1e3
         roof_tc["note"] = "reference-algorithm FLOPs (2*(295*128+128*65) per voxel) over the kernel time"
         line = {"metric": "ssc_voxel_query_throughput", "value": value, "unit": "voxels/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16" if f16 else "f32",
                 "data": "synthetic", "config": workload_config(args.precision),
                 "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12,
                         "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,
-                        "note": "every step: pinned xyz host->device, query, density grid + frustum mask device->host "
+                        "api": "scenedino_b200.BTSNet.forward(xyz, only_density=True) (models/bts.py:476-595), fresh outputs and "
+                               "workspace per call, full texel sort per call",
+                        "note": "every step: pinned xyz host->device, BTSNet.forward, density grid + frustum mask device->host "
                                 "(the 64-d features stay on the device for expand_dim / the SSC head, as in the reference); "
                                 "copies and kernels of consecutive steps overlap on three streams"},
                 "gpu_launches": int(launches), "clocks": clk.summary(),
                 "all_gather": gather_how if world > 1 else None,
-                "roofline": primary, "roofline_hbm": roof_hbm, "roofline_tensor": roof_tc,
+                "roofline": roof_hbm, "roofline_hbm": roof_hbm, "roofline_tensor": roof_tc,
                 "featmap_pack_ms": pack_ms, "featmap_project_ms": project_ms, "sorted_reuse": sorted_reuse}
 
-    # ---- full-image render (122 880 rays x 64 samples), reported in the same line ---------------------
-    if not args.no_render:
-        # the view is 100 bytes (pose + intrinsics): its rays are generated on the device inside every step (sd_gen_rays)
-        view_c2w = torch.from_numpy(syn.view_pose_c2w(1).astype(np.float32)).to(dev)[None]
-        view_K = torch.from_numpy(np.asarray(K[0], np.float32)).to(dev)[None]
-        rays = torch.empty((RENDER_R, 11), device=dev)
-        lin = torch.linspace(0, 1 - 1.0 / RENDER_K, RENDER_K, device=dev)
-        u = torch.rand((RENDER_R, RENDER_K), device=dev, generator=g)
+    # ---- one frame of the SSC evaluation: NEW map -> encode (pack + project) -> query of the fixed grid -> expansion +
+    #      SSC head -> sigma + label on the host.  Through BTSNet.encode / BTSNet.forward(predict_segmentation=True). -----
+    if f16 and not args.no_extras:
+        maps = [feat_nchw, torch.randn((1, C_FEAT, HF, WF), device=dev, generator=g)]
+        net.static_query, net.materialize_dino_full, net.one_hot_seg = True, False, False
+        xyz_dev = pts[None]
+        out_host = torch.empty(N * 5, dtype=torch.uint8).pin_memory()
+        out_dev = torch.empty(N * 5, dtype=torch.uint8, device=dev)
+        fstate = {"i": 0}
 
-        def render_step():
-            ops.gen_rays(view_c2w, view_K, syn.IMG_H, syn.IMG_W, syn.Z_NEAR, syn.Z_FAR, out=rays)
-            z = ops.sample_coarse(rays, u, lin, True)
-            return ops.render_pass(scene_rgb, mlp, rays, z, per_sample=False)
+        def frame():
+            holder["map"] = maps[fstate["i"] % 2]
+            fstate["i"] += 1
+            encode()
+            with torch.no_grad():
+                _, _, sigma, seg = net(xyz_dev, predict_segmentation=True, prediction_mode="stego_kmeans")
+            out_dev[:N * 4].view(torch.float32).copy_(sigma.reshape(-1))
+            out_dev[N * 4:].copy_(seg.reshape(-1))          # (labels as uint8: one_hot_seg = False; the reference returns them one-hot)
+            out_host.copy_(out_dev, non_blocking=True)
+
+        frame(); frame(); fence()
+        nl0 = _abi.launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            frame()
+        e1.record(); fence()
+        pf_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+        pf_ms = max_over_ranks(max(e0.elapsed_time(e1) / args.steps, pf_wall))
+        pf_launch = (_abi.launch_count() - nl0) / args.steps
+        # breakdown with the functional layer (same kernels), kernel-only
+        hd = ops.SscHead(syn.make_expand(3), syn.make_ssc_head(21), device=dev)
+        seg_o = dict(seg=torch.empty((N,), dtype=torch.uint8, device=dev))
+        ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[0])
+        q_ms = timed_ms(lambda: ops.query_points_sorted(scene, mlp, pts, outs[0]))
+        h_ms = timed_ms(lambda: ops.ssc_head(hd, outs[0]["dino"], want_scores=False, out=seg_o))
+        ex_mlp = ops.Mlp(*syn.make_expand(3), device=dev)
+        ex_ms = timed_ms(lambda: ops.expand_dim(ex_mlp, outs[0]["dino"][: N // 4], precision=ops.F16), n=3, warm=1) * 4
+        if line is not None:
+            dev_sum = pack_ms + project_ms + q_ms + h_ms
+            line["per_frame"] = {
+                "what": "one SSC frame: new 256x384x1280 map -> BTSNet.encode (pack fp32 planar -> fp16 channels-last, project "
+                        "through lin_in) -> BTSNet.forward(grid, predict_segmentation=True) on the fixed 2 097 152-voxel grid (texel "
+                        "sort kept: static_query) -> fused expansion + STEGO head + cosine argmax + LUT -> sigma fp32 + label u8 to "
+                        "pinned host memory",
+                "ms": pf_ms, "voxels_per_s": world * N / (pf_ms * 1e-3), "launches_per_frame": pf_launch,
+                "d2h_bytes": N * 5, "h2d_bytes": 0,
+                "note_ms": "max(device time, host wall time) per frame: includes torch glue (one-hot + argmax of the labels, output "
+                           "allocation) around the library calls",
+                "kernels_ms": {"featmap_pack": pack_ms, "field_project": project_ms, "query_sorted(field_bin)": q_ms,
+                               "expand+ssc_head(ssc_head_kernel)": h_ms, "sum": dev_sum},
+                "ssc_head": {"ms": h_ms, "executed_tflops": N * 364544 / (h_ms * 1e-3) / 1e12,
+                             "reference_algorithm_tflops": N * (FLOP_EXPAND + FLOP_SSC_HEAD) / (h_ms * 1e-3) / 1e12,
+                             "tensor_frac_executed": N * 364544 / (h_ms * 1e-3) / 1e12 / pk["tc_burst"],
+                             "note": "the folded head executes 0.36 MFLOP/voxel of the reference's 1.59 (expansion + head); "
+                                     "fraction of the measured bf16 cuBLAS peak on the executed FLOPs"},
+                "unfused_expand_dim_ms": ex_ms,
+                "headline_ratio_uses": "the driver's e2e ratio uses `e2e` (plain query through BTSNet.forward), not this object"}
+        net.static_query, net.materialize_dino_full, net.one_hot_seg = False, True, True
+        net.reset_static_query()
+        del maps, hd, seg_o, ex_mlp
+        torch.cuda.empty_cache()
+        note("per-frame done")
+
+    # ---- the rel-1e-4 mode (fp32 map, CUDA-core head) on one 32-voxel-thick x-slab -------------------------------------
+    if f16 and not args.no_extras:
+        n32 = N // 8
+        feat32 = ops.featmap_pack(feat_nchw, torch.float32)
+        sc32 = ops.Scene(feat=feat32[0], K_f=scene.K_f, w2c_f=scene.w2c_f)
+        o32 = None
+
+        def q32():
+            nonlocal o32
+            o32 = ops.query_points(sc32, mlp, pts[:n32], want_rgb=False, precision=ops.FP32, out=o32)
+        ms32 = timed_ms(q32, n=2, warm=1)
+        if line is not None:
+            line["fp32"] = {"what": "rel-1e-4 parity mode: fp32 channels-last map, FFMA head (field_simt_kernel), one x-slab of 262 144 voxels",
+                            "voxels_per_s": n32 / (ms32 * 1e-3), "ms": ms32, "ffma_tflops": n32 * FLOP_PER_POINT / (ms32 * 1e-3) / 1e12}
+        del feat32, sc32, o32
+        torch.cuda.empty_cache()
+
+    # ---- strong scaling: ONE grid split into x-slabs (what north_star's partition names), all-gather of sigma + mask ----
+    if world > 1 and f16 and not args.no_extras:
+        from scenedino_b200.sharding import shard_slice
+        sx = shard_slice(GRID[0], rank, world)
+        n_loc = (sx.stop - sx.start) * GRID[1] * GRID[2]
+        loc = pts[sx.start * GRID[1] * GRID[2]: sx.stop * GRID[1] * GRID[2]].contiguous()
+        small_l = torch.empty(n_loc * 5, dtype=torch.uint8, device=dev)
+        out_l = dict(sigma=small_l[:n_loc * 4].view(torch.float32), invalid_features=small_l[n_loc * 4:],
+                     dino=torch.empty((n_loc, D_OUT - 1), device=dev))
+        gath = torch.empty((world, n_loc * 5), dtype=torch.uint8, device=dev)
+        qg = ops.QueryGraph(scene, mlp, loc, out_l)
+
+        def sstep():
+            qg.replay()
+            dist.all_gather_into_tensor(gath, small_l)
 
         for _ in range(3):
-            render_step()
+            sstep()
         fence()
-        n_r = max(3, args.steps // 2)
         e0.record()
-        for _ in range(n_r):
-            render_step()
+        for _ in range(args.steps):
+            sstep()
         e1.record(); fence()
-        r_ms = e0.elapsed_time(e1) / n_r
+        s_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         if line is not None:
-            line["render"] = {"workload": "full 192x640 image from a stereo-offset view (rays generated on the device from pose + "
-                                          "intrinsics every step), 64 coarse samples/ray, "
-                                          "per-ray outputs depth+64-d+rgb"
-                                          + (" (projected map: 128-channel gather)" if args.precision == "fp16" else ""),
-                              "msamples_per_s": RENDER_R * RENDER_K / (r_ms * 1e-3) / 1e6, "ms": r_ms,
-                              "tensor_frac": RENDER_R * RENDER_K * FLOP_PER_POINT / (r_ms * 1e-3) / 1e12 / pk["tc_burst"]}
+            line["strong_scaling"] = {"what": f"ONE 256x256x32 grid in {world} x-slabs of {sx.stop - sx.start} (sort + tile kernel per slab, "
+                                              "graph replay) + NCCL all-gather of sigma + mask (5 B/voxel); max over ranks",
+                                      "ms_per_grid": s_ms, "voxels_per_s": N / (s_ms * 1e-3),
+                                      "speedup_vs_one_gpu_step": ms_step / s_ms if world == 1 else None,
+                                      "one_gpu_ms_reference": "compare with ms_per_step of the N=1 run"}
+        del qg, out_l, gath, small_l, loc
+        torch.cuda.empty_cache()
+
+    # ---- renders: BASELINE configs 1, 4, 3 through NeRFRenderer (one sd_render_rays call per scene) --------------------
+    if not args.no_render and f16:
+        renders = {}
+        ray_sampler = sd.ImageRaySampler(z_near=syn.Z_NEAR, z_far=syn.Z_FAR, height=syn.IMG_H, width=syn.IMG_W)
+
+        def render_cfg(tag, what, Hf_, Wf_, views, n_coarse, n_fine, d_out, nv_c, ray_subset=None, expand=False):
+            hold = {"map": feat_nchw if (Hf_, Wf_) == (HF, WF) else torch.randn((1, C_FEAT, Hf_, Wf_), device=dev, generator=g)}
+            rnet = build_net(sd, torch, hold, dev, "fp16", d_out=d_out, with_head=False, seed=0)
+            ren = sd.NeRFRenderer.from_conf({"n_coarse": n_coarse, "n_fine": n_fine, "n_fine_depth": 0, "lindisp": True,
+                                             "hard_alpha_cap": n_fine > 0})
+            ren.nan_check = False                       # (one host sync per pass; the throughput configuration skips it)
+            wrapped = ren.bind_parallel(rnet, gpus=None).eval()
+            imgs = torch.from_numpy(syn.make_images(2, nv_c)).to(dev)[None]
+            Kc = torch.from_numpy(np.broadcast_to(syn.kitti360_K(), (nv_c, 3, 3)).copy()).to(dev)[None]
+            c2w = torch.from_numpy(np.stack([syn.view_pose_c2w(v) for v in range(nv_c)])).to(dev)[None]
+            rnet.encode(imgs * 2 - 1, Kc, c2w, ids_encoder=[0], ids_render=list(range(nv_c)), images_alt=imgs)
+            rnet.set_scale(0)
+            vposes_host = torch.from_numpy(np.stack([syn.view_pose_c2w(v) for v in views])).pin_memory()
+            vK = torch.from_numpy(np.broadcast_to(syn.kitti360_K(), (len(views), 3, 3)).copy()).to(dev)[None]
+            R_full = len(views) * syn.IMG_H * syn.IMG_W
+            sel = None
+            if ray_subset is not None:
+                sel = torch.randperm(R_full, device=dev, generator=g)[:ray_subset]
+            R = R_full if sel is None else ray_subset
+            res = {}
+            host_out = torch.empty(R * (1 + 3 * nv_c), dtype=torch.float32).pin_memory()
+
+            def rstep(e2e=False):
+                vp = vposes_host.to(dev, non_blocking=True)[None] if e2e else rstep.vp
+                rays, _ = ray_sampler.sample(None, vp, vK)             # rays of whole views generated on the device
+                if sel is not None:
+                    rays = rays[:, sel].contiguous()
+                with torch.no_grad():
+                    out = wrapped(rays)
+                lvl = out["fine"] if n_fine > 0 else out["coarse"]
+                if expand:
+                    res["full"] = rnet.encoder.expand_dim(lvl["dino_features"])
+                if e2e:
+                    host_out[:R].copy_(lvl["depth"].reshape(-1), non_blocking=True)
+                    host_out[R:].copy_(lvl["rgb"].reshape(-1), non_blocking=True)
+                return lvl
+
+            rstep.vp = vposes_host.to(dev)[None]
+            n_r = max(3, args.steps // 4)
+            nl = _abi.launch_count()
+            ms_k = timed_ms(rstep, n=n_r, warm=2)
+            nl = (_abi.launch_count() - nl) / (n_r + 2)
+            ms_e = timed_ms(lambda: rstep(True), n=n_r, warm=1)
+            samples = R * (n_coarse + ((n_coarse + n_fine) if n_fine > 0 else 0))
+            flop = FLOP_PER_POINT_768 if d_out == 769 else FLOP_PER_POINT
+            ach = samples * flop / (ms_k * 1e-3) / 1e12
+            renders[tag] = {"workload": what, "rays": R, "samples_per_step": samples, "ms": ms_k,
+                            "msamples_per_s": samples / (ms_k * 1e-3) / 1e6, "launches_per_step": nl,
+                            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                                         "frac": ach / pk["tc_burst"], "traffic": None,
+                                         "note": f"reference-algorithm FLOPs ({flop} per sample, SURVEY.md 8d) over the step time "
+                                                 "(sampling, field kernel, head2 / expand kernels); the field kernel executes fewer: "
+                                                 "the map is pre-projected and, for D > 64, W_out is applied to per-ray sums"},
+                            "e2e": {"ms": ms_e, "msamples_per_s": samples / (ms_e * 1e-3) / 1e6,
+                                    "h2d_bytes_per_step": len(views) * 64, "d2h_bytes_per_step": R * (1 + 3 * nv_c) * 4,
+                                    "note": "poses from pinned host memory, rays generated on the device, depth + rgb images back to the "
+                                            "host (the rendered features stay on the device for the loss / expansion)"}}
+            del rnet, wrapped, hold
+            torch.cuda.empty_cache()
+
+        render_cfg("cfg1", "BASELINE configs[0]: 4096 random rays of the input view x 64 coarse samples, ViT-B/8 map, D=64 "
+                           "(~20 us of B200 work: launch-bound, reported for completeness)", HF, WF, [0], 64, 0, D_OUT, 1, ray_subset=4096)
+        render_cfg("cfg4", "BASELINE configs[3]: DINOv2 map 256x192x640, full 192x640 image of a stereo-offset view x 32 coarse samples, "
+                           "D=64, then expand_dim 64->128->768 + L2 norm of the 122 880 rendered vectors", HF2, WF2, [1], 32, 0, D_OUT, 1,
+                   expand=True)
+        render_cfg("cfg3", "BASELINE configs[2]: 4 views x 192x640 rays against the view-0 ViT-B/8 map, 64 coarse + 32 fine samples "
+                           "(coarse pass 64, fine pass 96), 768-d feature composite, 4 colour views", HF, WF, [0, 1, 2, 3], 64, 32, 769, 4)
+        if line is not None:
+            line["renders"] = renders
+            line["render"] = {"msamples_per_s": renders["cfg4"]["msamples_per_s"], "ms": renders["cfg4"]["ms"],
+                              "tensor_frac": renders["cfg4"]["roofline"]["frac"], "workload": "see renders.cfg4"}
+        note("renders done")
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_voxels(feat_nchw.cpu().numpy(), mlp_w, pts_np)

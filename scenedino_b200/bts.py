@@ -79,6 +79,15 @@ class BTSNet(nn.Module):
         #: forward(predict_segmentation=True) returns the 768-d expansion as its first element like the reference
         #: (bts.py:585); False skips it (first element None) -- the SSC evaluation only keeps sigma and seg
         self.materialize_dino_full = True
+        #: forward(predict_segmentation=True) returns the labels one-hot [n, N, gt_classes] int64 like the reference
+        #: (bts.py:588: 152 B per voxel); False returns them as they leave the kernel: uint8 [n, N]
+        self.one_hot_seg = True
+        #: the caller queries the SAME points tensor (same storage, unchanged contents) against the SAME encoder camera
+        #: frame after frame -- the SSC evaluation does (sscbench/evaluate_model_sscbench.py:270-279 builds the grid
+        #: once) --: the texel sort of the points is then kept across encode() calls and only the tile kernel runs
+        #: (sd_query_points_sorted).  Off by default: the library cannot see in-place edits of the points.
+        self.static_query = False
+        self._static_cache = {}
         self._packed = {}
         self._head_packed = None
         self.grid_f_features = None
@@ -92,6 +101,10 @@ class BTSNet(nn.Module):
 
     def compute_grid_transforms(self, *args, **kwargs):
         pass
+
+    def reset_static_query(self):
+        """Drops the point sorts kept under ``static_query``."""
+        self._static_cache.clear()
 
     # ---- encode (bts.py:112-259) -----------------------------------------------------------------
     def encode(self, images, Ks, poses_c2w, ids_encoder=None, ids_render=None, ids_loss=None, images_alt=None,
@@ -187,6 +200,8 @@ class BTSNet(nn.Module):
             )
             if st["rgb"].shape[2] != 3:
                 raise NotImplementedError("colour views must have 3 channels")
+            if self.static_query:   # one small read-back per encode: the kept sort is only valid for this camera
+                st["cam_sig"] = bytes(torch.cat([st["K_f"].reshape(-1), st["w2c_f"].reshape(-1)]).cpu().numpy().tobytes())
             self._packed[key] = st
         return st
 
@@ -325,11 +340,25 @@ class BTSNet(nn.Module):
             for b in range(n):
                 sc = self._scene(st, b, self._projection(st, b, mlp) if use_proj else None)
                 need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(mlp), N)
+                skey = (b, xyz.data_ptr(), xyz._version, N, need, st.get("cam_sig")) if (self.static_query and use_proj and need) else None
+                kept = self._static_cache.get(skey) if skey else None
+                if kept is not None:         # same points, same camera: the sort (and the frustum mask) of the first call
+                    ws, mask = kept
+                    _abi.check(lib.sd_query_points_sorted(
+                        C.byref(sc), C.byref(mlp), _ptr(xyz[b]), N, _ptr(sigma[b]), _ptr(dino[b]),
+                        _ptr(rgb[b]) if want_colors else None, _ptr(invalid[b]) if want_colors else None,
+                        _ptr(ws), need, _stream()), "sd_query_points_sorted")
+                    invf[b].copy_(mask)
+                    continue
                 ws = torch.empty((need,), dtype=torch.uint8, device=dev) if need else None
                 _abi.check(lib.sd_query_points(
                     C.byref(sc), C.byref(mlp), _ptr(xyz[b]), N, _ptr(sigma[b]), _ptr(dino[b]),
                     _ptr(rgb[b]) if want_colors else None, _ptr(invalid[b]) if want_colors else None,
                     _ptr(invf[b]), _ptr(ws), need, _stream()), "sd_query_points")
+                if skey:
+                    if len(self._static_cache) >= 8:
+                        self._static_cache.clear()
+                    self._static_cache[skey] = (ws, invf[b].clone())
             invalid_features = invf.view(torch.bool)
 
         if predict_segmentation:  # bts.py:528-533, 584-592
@@ -345,9 +374,13 @@ class BTSNet(nn.Module):
             if head is not None:
                 # scenedino_b200.SemanticHead: expansion + STEGO head + cosine argmax + pseudo-label LUT in ONE kernel
                 # (sd_ssc_head) starting from the 64-d features; any other head module is called like the reference does
-                seg = (head.forward_reduced(dino, self.encoder.dim_reduction, mode=prediction_mode) if fused
-                       else head(dino_full, mode=prediction_mode))
-                seg = torch.nn.functional.one_hot(seg, self.gt_classes)
+                if fused and not self.one_hot_seg:
+                    seg = head.forward_reduced(dino, self.encoder.dim_reduction, mode=prediction_mode,
+                                               out=torch.empty((n * N,), dtype=torch.uint8, device=dev)).view(n, N)
+                else:
+                    seg = (head.forward_reduced(dino, self.encoder.dim_reduction, mode=prediction_mode) if fused
+                           else head(dino_full, mode=prediction_mode))
+                    seg = torch.nn.functional.one_hot(seg, self.gt_classes)
             return dino_full, None, sigma, seg
         if only_density:  # bts.py:570-572
             rgb = torch.zeros((n, N, nv_c * 3), device=dev)
