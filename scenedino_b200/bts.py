@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .heads import MlpDimReduction, ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, require_cuda
+from .heads import (MlpDimReduction, ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, note_field_precision,
+                    require_cuda)
 
 PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
 
@@ -85,7 +86,8 @@ class BTSNet(nn.Module):
         #: the caller queries the SAME points tensor (same storage, unchanged contents) against the SAME encoder camera
         #: frame after frame -- the SSC evaluation does (sscbench/evaluate_model_sscbench.py:270-279 builds the grid
         #: once) --: the texel sort of the points is then kept across encode() calls and only the tile kernel runs
-        #: (sd_query_points_sorted).  Off by default: the library cannot see in-place edits of the points.
+        #: (sd_query_points_sorted).  Off by default: the library cannot see in-place edits of the points.  True trusts the
+        #: caller on the camera too; "check" compares the encoder camera at every encode (one small device->host read-back).
         self.static_query = False
         self._static_cache = {}
         self._packed = {}
@@ -171,6 +173,7 @@ class BTSNet(nn.Module):
             p = "fp16" if torch.is_autocast_enabled() else "fp32"
         if p not in PRECISIONS:
             raise ValueError(f"precision must be one of fp32|fp16|auto, got {self.precision!r}")
+        note_field_precision(PRECISIONS[p])
         return PRECISIONS[p]
 
     def _state(self, precision: int):
@@ -200,7 +203,7 @@ class BTSNet(nn.Module):
             )
             if st["rgb"].shape[2] != 3:
                 raise NotImplementedError("colour views must have 3 channels")
-            if self.static_query:   # one small read-back per encode: the kept sort is only valid for this camera
+            if self.static_query == "check":   # one small read-back (a host sync) per encode: the kept sort is only valid for this camera
                 st["cam_sig"] = bytes(torch.cat([st["K_f"].reshape(-1), st["w2c_f"].reshape(-1)]).cpu().numpy().tobytes())
             self._packed[key] = st
         return st

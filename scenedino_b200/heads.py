@@ -224,6 +224,13 @@ class PositionalEncoding(nn.Module):
 _expand_precision = threading.local()
 
 
+def note_field_precision(precision: int) -> None:
+    """Remembers the precision of this thread's latest field query / render: an ``MlpDimReduction`` in "auto" mode
+    follows it when it is called outside BTSNet.forward -- the demo expands the rendered features right after the
+    render (demo_utils/utils.py:223-229) and should not drop from the tensor cores to the fp32 CUDA-core path there."""
+    _expand_precision.last = precision
+
+
 @contextlib.contextmanager
 def expand_precision(precision: int):
     """Precision of MlpDimReduction.transform_expand calls made inside the block (BTSNet.forward wraps
@@ -240,7 +247,8 @@ class MlpDimReduction(nn.Module):
     """dim_reduction.py:15-25; transform_expand = 64 -> 128 -> ReLU -> 768 -> L2 normalise.
 
     ``precision``: "fp32" (CUDA cores, rel 1e-4), "fp16" (tensor cores, rel 2e-2; 64 -> 128 -> multiple-of-128 shapes)
-    or "auto" (default): what the enclosing BTSNet.forward runs in, else fp16 under torch autocast, else fp32."""
+    or "auto" (default): what the enclosing BTSNet.forward runs in, else fp16 under torch autocast, else the precision of
+    this thread's latest field query / render (the features being expanded came from it), else fp32."""
 
     def __init__(self, full_channels, reduced_channels, latent_channels):
         super().__init__()
@@ -255,7 +263,10 @@ class MlpDimReduction(nn.Module):
             ctx = getattr(_expand_precision, "value", None)
             if ctx is not None:
                 return ctx
-            return _abi.SD_MLP_F16_TC if torch.is_autocast_enabled() else _abi.SD_MLP_FP32
+            if torch.is_autocast_enabled():
+                return _abi.SD_MLP_F16_TC
+            last = getattr(_expand_precision, "last", None)
+            return last if last is not None else _abi.SD_MLP_FP32
         if self.precision not in ("fp32", "fp16"):
             raise ValueError(f"MlpDimReduction.precision must be 'auto', 'fp32' or 'fp16', got {self.precision!r}")
         return _abi.SD_MLP_F16_TC if self.precision == "fp16" else _abi.SD_MLP_FP32
