@@ -445,8 +445,45 @@ class NeRFRenderer(torch.nn.Module):
             normalize_dino=conf.get("normalize_dino", False))
 
     def bind_parallel(self, net, gpus=None, simple_output=False):
-        """nerf.py:641-658.  Multi-GPU here is one process per GPU (scenedino_b200.sharding), not
-        nn.DataParallel, so ``gpus`` with more than one entry is rejected."""
-        if gpus is not None and len(gpus) > 1:
-            raise NotImplementedError("use scenedino_b200.sharding (one process per GPU) instead of DataParallel")
-        return _RenderWrapper(net, self, simple_output=simple_output)
+        """nerf.py:641-658.  The reference wraps the renderer in ``nn.DataParallel(dim=1)`` when ``gpus`` has more than one
+        entry -- one process, rays split along dim 1.  Here multi-GPU is one process PER GPU (torch.distributed): with an
+        initialised process group whose size equals ``len(gpus)`` the returned module renders this rank's contiguous tile of
+        the rays and all-gathers the per-ray outputs (scenedino_b200.sharding.render_rays_sharded), so that every rank gets
+        the full result like DataParallel's caller does; without a process group the request is an error."""
+        wrapped = _RenderWrapper(net, self, simple_output=simple_output)
+        if gpus is None or len(gpus) <= 1:
+            return wrapped
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == len(gpus)):
+            raise NotImplementedError(
+                f"bind_parallel(gpus={list(gpus)}): scenedino_b200 runs one process per GPU -- launch {len(gpus)} ranks with "
+                "torchrun and call bind_parallel on each (rays are sharded by scenedino_b200.sharding), not nn.DataParallel")
+        return _ShardedRenderWrapper(wrapped)
+
+
+class _ShardedRenderWrapper(torch.nn.Module):
+    """The multi-process counterpart of ``DataParallel(_RenderWrapper, dim=1)`` (nerf.py:654-658): every rank renders its
+    contiguous tile of rays [n, R/world, .] and the outputs are all-gathered along the ray dimension."""
+
+    def __init__(self, wrapped: _RenderWrapper):
+        super().__init__()
+        self.module = wrapped
+        self.net, self.renderer = wrapped.net, wrapped.renderer
+
+    def forward(self, rays, **kwargs):
+        from .sharding import all_gather_ragged, shard_slice
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        R = rays.shape[1]
+        sl = shard_slice(R, rank, world)
+        local = self.module(rays[:, sl].contiguous(), **kwargs)
+        if isinstance(local, tuple):                       # simple_output: (rgb, depth)
+            return tuple(all_gather_ragged(t, R, dim=1) for t in local)
+        out = {}
+        for level, part in local.items():
+            if level == "state_dict":
+                out[level] = part                            # per-sample state stays sharded, like the 64-d voxel features
+                continue
+            out[level] = {k: (all_gather_ragged(v, R, dim=1) if torch.is_tensor(v) and v.dim() >= 2 and v.shape[1] == sl.stop - sl.start
+                              else v) for k, v in part.items()}
+        return out

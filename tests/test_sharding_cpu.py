@@ -64,6 +64,21 @@ def _worker(rank, world, port, n_rays, grid, q):
         t = torch.arange(2 * 7 * 3, dtype=torch.float32).reshape(2, 7, 3)
         sl = sh.shard_slice(7, rank, world)
         ok = ok and torch.equal(sh.all_gather_ragged(t[:, sl].contiguous(), 7, dim=1), t)
+        # NeRFRenderer.bind_parallel(gpus=[...]) under a process group: the reference's DataParallel(dim=1) wrapper
+        # (renderer/nerf.py:654-658) as one process per GPU -- each rank renders its tile, per-ray outputs are gathered
+        import scenedino_b200 as sd
+        ren = sd.NeRFRenderer(n_coarse=4)
+        wrapped = ren.bind_parallel(torch.nn.Identity(), gpus=list(range(world)))
+        assert type(wrapped).__name__ == "_ShardedRenderWrapper" and wrapped.renderer is ren
+        wrapped.module.forward = lambda r, **kw: {**_fake_render(r), "state_dict": {"x": r[..., 0]}}
+        got = wrapped(rays, want_weights=True)
+        ok = ok and all(torch.equal(got["coarse"][k], full["coarse"][k]) for k in ("rgb", "depth", "dino_features", "weights"))
+        ok = ok and got["state_dict"]["x"].shape[1] == sh.shard_slice(n_rays, rank, world).stop - sh.shard_slice(n_rays, rank, world).start
+        try:
+            ren.bind_parallel(torch.nn.Identity(), gpus=list(range(world + 1)))
+            ok = False
+        except NotImplementedError:
+            pass
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
