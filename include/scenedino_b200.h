@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 3
+#define SD_ABI_VERSION 4
 
 typedef enum sd_status {
     SD_OK = 0,
@@ -153,6 +153,19 @@ int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, 
 int sd_query_points_sorted(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                            float *sigma, float *dino, float *rgb, float *invalid, void *workspace,
                            size_t workspace_bytes, void *stream);
+
+/* The same query with the 64-d features left in TEXEL-BIN ORDER (the order the tile kernel walks the points in) for a
+ * consumer that takes a permutation (sd_ssc_head): dino_binned [N,64], row r holds the features of
+ * point perm[r]; sigma [N] and invalid_feat [N] stay in the caller's order.  The rows of a tile are consecutive rows of
+ * dino_binned, so they leave the SM as TMA tile stores (cp.async.bulk.tensor, 32 rows x 128 B each) instead of one
+ * scattered 16-byte store per thread and piece: the reference's chunk loop (sscbench/evaluate_model_sscbench.py:711-717)
+ * only ever hands these rows to encoder.expand_dim + the downstream head (models/bts.py:584-592), row by row.
+ * reuse_sorted != 0: like sd_query_points_sorted (the workspace holds the sort of the same points and cameras;
+ * invalid_feat is not rewritten).  Needs a projected scene, SD_MLP_F16_TC, a 64-d head, dino_binned 16-byte aligned, and
+ * enough points for the sorted tile path (16 per texel bin of the map). */
+int sd_query_points_binned(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N, float *sigma,
+                           float *dino_binned, unsigned int *perm, unsigned char *invalid_feat, void *workspace,
+                           size_t workspace_bytes, int reuse_sorted, void *stream);
 
 /* ---- NeRFRenderer sampling (renderer/nerf.py:121-228) --------------------------------------- */
 /* sample_coarse (nerf.py:121-141).  u [R,Kc] = torch.rand_like draw, lin [Kc] = torch.linspace. */

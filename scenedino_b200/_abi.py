@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libscenedino_b200.so")
 
 SD_F32, SD_F16 = 0, 1
 SD_MLP_FP32, SD_MLP_F16_TC = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SdError(RuntimeError):
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "sd_query_workspace_bytes": (_SZ, [_SC, _ML, _LL]),
     "sd_query_points": (_I, [_SC, _ML, _P, _LL, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sd_query_points_sorted": (_I, [_SC, _ML, _P, _LL, _P, _P, _P, _P, _P, _SZ, _P]),
+    "sd_query_points_binned": (_I, [_SC, _ML, _P, _LL, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "sd_sample_coarse": (_I, [_P, _LL, _I, _P, _P, _I, _I, _P, _P]),
     "sd_sample_fine": (_I, [_P, _LL, _I, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "sd_sample_fine_depth": (_I, [_P, _LL, _I, _P, _P, _I, _F, _P, _P]),

@@ -100,7 +100,8 @@ extern "C" size_t sd_query_workspace_bytes(const sd_scene *scene, const sd_mlp *
 
 static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                              float *sigma, float *dino, float *rgb, float *invalid,
-                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted);
+                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted,
+                             float *dino_binned = nullptr, unsigned int *perm_out = nullptr);
 
 extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                                float *sigma, float *dino, float *rgb, float *invalid,
@@ -117,9 +118,22 @@ extern "C" int sd_query_points_sorted(const sd_scene *scene, const sd_mlp *mlp, 
     return query_points_impl(scene, mlp, xyz, N, sigma, dino, rgb, invalid, nullptr, workspace, workspace_bytes, stream, true);
 }
 
+extern "C" int sd_query_points_binned(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N, float *sigma,
+                                      float *dino_binned, unsigned int *perm, unsigned char *invalid_feat, void *workspace,
+                                      size_t workspace_bytes, int reuse_sorted, void *stream) {
+    SD_REQUIRE(scene && mlp && scene->feat_proj && mlp->precision == SD_MLP_F16_TC && workspace &&
+                   sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
+               "sd_query_points_binned: needs a projected scene, SD_MLP_F16_TC and a workspace of sd_query_workspace_bytes");
+    SD_REQUIRE(dino_binned && mlp->d_out == 65, "sd_query_points_binned: needs dino_binned and a 64-d feature head");
+    if (N == 0) return SD_OK;
+    return query_points_impl(scene, mlp, xyz, N, sigma, nullptr, nullptr, nullptr, reuse_sorted ? nullptr : invalid_feat, workspace,
+                             workspace_bytes, stream, reuse_sorted != 0, dino_binned, perm);
+}
+
 static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                              float *sigma, float *dino, float *rgb, float *invalid,
-                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted) {
+                             unsigned char *invalid_feat, void *workspace, size_t workspace_bytes, void *stream, bool reuse_sorted,
+                             float *dino_binned, unsigned int *perm_out) {
     FieldParams fp;
     int rc = make_field_params(scene, &fp);
     if (rc) return rc;
@@ -129,6 +143,7 @@ static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const flo
     if (mlp->precision == SD_MLP_F16_TC) {
         TcOut o = {};
         o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
+        o.dino_binned = dino_binned; o.perm_out = perm_out;
         BinOrder order = {};
         const size_t need = sd_query_workspace_bytes(scene, mlp, N);
         if (need && workspace && workspace_bytes >= need) {   // walk the points bin by bin of the feature map
@@ -143,6 +158,7 @@ static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const flo
             if (rc) return rc;
             if (tile && order.has_geo) return launch_field_bin(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
         }
+        SD_REQUIRE(!dino_binned, "sd_query_points_binned: this query does not take the sorted tile path (too few points for the map)");
         return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm, scene->feat_proj);
     }
     SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);

@@ -78,7 +78,9 @@ constexpr int BATCH = 4;                                  // tiles claimed per a
 constexpr int OFF_TAB = OFF_HDR + NREC * 16;              // two batches of table entries, fetched by bulk copies
 constexpr int OFF_MINFO = OFF_TAB + 2 * BATCH * 16;       // per weight-ring entry: chunks of the tile whose first chunk sits there
 constexpr int OFF_NTILES = OFF_MINFO + 16;      // tiles this CTA processed, published by the MMA issuer at the end
-constexpr int OFF_DIRTY = OFF_NTILES + 8;
+constexpr int OFF_TIDX = OFF_NTILES + 8;      // per record-ring entry: the tile's index in sorted order (binned output)
+constexpr int OFF_PTILE = OFF_TIDX + 16;       // per perm-ring entry: the same, handed on to epilogue 2 by the point warps
+constexpr int OFF_DIRTY = OFF_PTILE + NPERM * 4;
 constexpr int OFF_CAM = OFF_DIRTY + NRA * TM;
 constexpr int OFF_BAR = OFF_CAM + 448;
 enum { BAR_FULL_A = 0, BAR_EMPTY_A = NRA, BAR_FULL_B = 2 * NRA, BAR_EMPTY_B = 2 * NRA + NRB, BAR_FULL_C = 2 * NRA + 2 * NRB,
@@ -91,7 +93,7 @@ constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_ALLOC = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 1024 == 0 && OFF_BAR % 8 == 0 && NREC * 4 <= 16, "alignment");
 
 #ifndef TB_T0
 #define TB_T0 40   // first traced tile of CTA 0 (SD_TC_DEBUG & 8192): tiles TB_T0 .. TB_T0 + 63
@@ -106,6 +108,7 @@ __device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globalt
 
 struct Params {
     CUtensorMap tmap;          // P as [Hf][Wf][128] fp16, box 8 x 8 x 64 channels, SWIZZLE_128B
+    CUtensorMap tmap_out;      // binned output: dino as [N][64] fp32, box 32 rows x 32 columns, SWIZZLE_128B
     FieldParams fp;
     const float *xyz;
     unsigned int *tile_ctr;    // next unclaimed tile (zeroed by the sort): CTAs claim tiles dynamically
@@ -120,7 +123,14 @@ struct Params {
     const float *b_out;
     float *sigma, *dino, *rgb, *invalid;
     unsigned char *invalid_feat;
+    int binned;                // feature rows leave in SORTED order (row r of tile t -> dino[t * 128 + r]) by TMA tile stores
+    unsigned int *perm_out;    // binned: [N] sorted position -> point index (or NULL)
 };
+
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -242,7 +252,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             const int grow_keep = s_perm[(int)(j % NPERM) * TM + row];       // point this thread's row of tile j stands for
             const uint32_t t_d2 = t_lane + D2_COL + b1 * D2_STRIDE;
             const bool ok = grow_keep >= 0;
-            if (P.dino && D == 64) {
+            if (P.binned) {
+                // Binned output: the tile's rows are consecutive rows of dino, so the features leave as four TMA tile stores
+                // per warp-quadrant pair (32 rows x 128 B each) straight from the staging buffer -- written once, swizzled
+                // the way the tensor map expects (16-byte piece q of row r at q ^ (r & 7)), never read back, no address per
+                // row: nothing of the output queues in the load/store unit besides these 16 shared-memory stores per thread.
+                // Rows past N (ragged last tile) fall outside the tensor map and are clipped by the copy engine.
+                const int t = reinterpret_cast<const volatile int *>(sm + OFF_PTILE)[(int)(j % NPERM)];
+                uint32_t sr;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t vr[32];
+                    tmem_ld32_issue(t_d2 + hf * 32, vr);
+                    if (hf == 1) tmem_ld1_issue(t_d2 + D, sr);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
+                    }
+                    if (lane == 0) bulk_wait_read<1>();        // the store that last read this half (a tile ago) has left
+                    __syncwarp();
+                    unsigned char *stage = hf ? stage1 : stage0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4 *>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                            make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(P.dbg & 1)) {
+                        tma_store_2d(&P.tmap_out, smem_u32(stage), hf * 32, t * TM + wq * 32);
+                        bulk_commit();
+                    }
+                }
+                if (ok) {
+                    if (P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
+                    if (P.perm_out) P.perm_out[(long long)t * TM + row] = (unsigned int)grow_keep;
+                }
+            } else if (P.dino && D == 64) {
                 // Two halves of 32 columns (registers).  Transpose through shared memory: lane = row writes its 8 chunks
                 // of a half (XOR-swizzled, conflict free), then 8 lanes read one row back and the warp stores four
                 // 128-byte row halves per request.  (One 256-byte bulk copy per row was measured instead: ~22 cycles
@@ -418,6 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             if (lane == 0) {
                 mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
                 s_hdr[r].c0m = ti.c0m; s_hdr[r].b01 = ti.b01; s_hdr[r].b23 = ti.b23; s_hdr[r].rows = ti.rows;
+                reinterpret_cast<volatile int *>(sm + OFF_TIDX)[r] = (int)(P.n_tiles - 1 - v);
                 if (ti.rows == 0) {
                     mbar_arrive(BAR(BAR_REC_FULL + r));             // no more tiles: a header alone
                 } else {
@@ -489,6 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 break;
             }
             const GeoRec *rr = rec_ptr(j);
+            const int tile_idx = reinterpret_cast<const volatile int *>(sm + OFF_TIDX)[(int)(j % NREC)];
             cur.c0 = (int)(rr[0].cs & 0xFFFFu);            // compact bins the tile touches: first, last
             cur.c1 = (int)(rr[rows - 1].cs & 0xFFFFu);
             const bool mine = (int)(j % N_PT_GROUPS) == grp;
@@ -557,6 +605,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             mbar_wait(BAR(BAR_EMPTY_C + cs), (uint32_t)(((j / NCODE) & 1) ^ 1));
             TB_TRACE(pt_role, j, 5);
             reinterpret_cast<int *>(sm + OFF_PERM)[(int)(j % NPERM) * TM + row] = ok ? cur.grow : -1;
+            if (row == 0) reinterpret_cast<volatile int *>(sm + OFF_PTILE)[(int)(j % NPERM)] = tile_idx;
             unsigned char *crow = sm + OFF_CODE + cs * CHUNK + row * 128;
 #pragma unroll
             for (int qq = 0; qq < 6; ++qq)
@@ -693,6 +742,14 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     P.w2_img = blob + L.off_w_out_h;
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
     P.sigma = out.sigma; P.dino = out.dino; P.rgb = out.rgb; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;
+    if (out.dino_binned) {
+        SD_REQUIRE(P.D == 64 && !out.dino, "field_bin: binned output needs a 64-d head and no caller-order dino");
+        SD_REQUIRE(((uintptr_t)out.dino_binned & 15) == 0, "field_bin: dino_binned must be 16-byte aligned");
+        P.binned = 1; P.dino = out.dino_binned; P.perm_out = out.perm_out;
+        const unsigned long long odims[2] = {64ull, (unsigned long long)N}, ostrides[1] = {256ull};
+        const unsigned int obox[2] = {32u, 32u};
+        if (int rc_o = make_tmap(&P.tmap_out, out.dino_binned, 4, 2, odims, ostrides, obox)) return rc_o;
+    }
     const unsigned long long dims[3] = {128ull, (unsigned long long)fp.Wf, (unsigned long long)fp.Hf};
     const unsigned long long strides[2] = {256ull, 256ull * (unsigned long long)fp.Wf};
     const unsigned int box[3] = {64u, 8u, 8u};

@@ -38,6 +38,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,
                   const unsigned long long *strides_bytes, const unsigned int *box) {
+    return make_tmap(tmap_out, base, 2, rank, dims, strides_bytes, box);
+}
+
+int make_tmap(void *tmap_out, const void *base, int elem_bytes, int rank, const unsigned long long *dims,
+              const unsigned long long *strides_bytes, const unsigned int *box) {
+    SD_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "make_tmap: fp16 or fp32 elements");
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -50,7 +56,8 @@ int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned lon
     cuuint32_t b[5], es[5];
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-    const CUresult r = fn(reinterpret_cast<CUtensorMap *>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+    const CUresult r = fn(reinterpret_cast<CUtensorMap *>(tmap_out),
+                          elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                           const_cast<void *>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);

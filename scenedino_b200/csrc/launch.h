@@ -51,6 +51,10 @@ struct TcOut {            // per-point / per-sample outputs (any may be NULL)
     float *rgb;           // [N, 3*nv_c]   (point mode: BTSNet.forward rgb; render mode: rgb_samps)
     float *invalid;       // [N, nv_c]
     unsigned char *invalid_feat;  // [N]
+    // projected-map tile kernel only (field_bin.cu): the 64-d rows in texel-bin (sorted) order, written by TMA tile stores,
+    // and the sorted position -> point index map that goes with them
+    float *dino_binned;           // [N, 64]
+    unsigned int *perm_out;       // [N]
 };
 
 struct TcRender {         // per-ray outputs of the fused composite
@@ -112,6 +116,8 @@ constexpr int PROJ_OFF_MAP = 50176;        // P [Hf*Wf][128] fp16
 
 // ---- projected-map tile kernel (field_proj.cu, field_bin.cu) ---------------------------------------------
 // encodes a tiled fp16 tensor map (SWIZZLE_128B) into the 128 bytes at tmap_out (64-byte aligned)
+int make_tmap(void *tmap_out, const void *base, int elem_bytes, int rank, const unsigned long long *dims,
+              const unsigned long long *strides_bytes, const unsigned int *box);   // elem_bytes: 2 = fp16, 4 = fp32
 int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,
                   const unsigned long long *strides_bytes, const unsigned int *box);
 bool bin_kernel_supported(const sd_scene *scene, const sd_mlp *mlp);

@@ -269,25 +269,56 @@ def query_points_sorted(scene: Scene, mlp: Mlp, xyz, out: dict):
     return res
 
 
+@device_guard
+def query_points_binned(scene: Scene, mlp: Mlp, xyz, out=None, reuse_sorted=False):
+    """The point query with the 64-d features left in texel-bin order (sd_query_points_binned): dict(sigma [N],
+    invalid_features [N] -- caller's order --, dino_binned [N,64], perm [N] int32: row r of dino_binned belongs to point
+    perm[r]).  ``dino_binned[argsort(perm)]`` is bit-identical to ``query_points(...)["dino"]``.  ``reuse_sorted``: the
+    workspace in ``out`` holds the sort of the same points and cameras (only the tile kernel runs)."""
+    xyz = _f32c(xyz); require_cuda(xyz, "xyz")
+    N = xyz.shape[0]
+    if out is None:
+        out = dict(sigma=_e((N,), xyz), dino_binned=_e((N, 64), xyz), perm=_e((N,), xyz, torch.int32),
+                   invalid_features=_e((N,), xyz, torch.uint8))
+    sc, m = scene.c(), mlp.c(F16)
+    lib = _abi.lib()
+    need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(m), N)
+    ws = out.get("_workspace")
+    if need and (ws is None or ws.numel() < need):
+        if reuse_sorted:
+            raise ValueError("query_points_binned(reuse_sorted=True) needs the `out` dict of an earlier call (its workspace)")
+        ws = out["_workspace"] = torch.empty((need,), dtype=torch.uint8, device=xyz.device)
+    _abi.check(lib.sd_query_points_binned(C.byref(sc), C.byref(m), _ptr(xyz), N, _ptr(out["sigma"]), _ptr(out["dino_binned"]),
+                                          _ptr(out.get("perm")), _ptr(out["invalid_features"]), _ptr(ws) if need else None,
+                                          need, int(bool(reuse_sorted)), _stream()), "sd_query_points_binned")
+    res = {k: v for k, v in out.items() if not k.startswith("_")}
+    res["invalid_features"] = out["invalid_features"].view(torch.bool)
+    return res
+
+
 class QueryGraph:
     """One point query (fixed scene, head, points and output buffers) captured into a CUDA graph: replaying it costs one
     launch instead of seven (the sort's memset and four kernels, the field kernel) -- for callers that query the same
     grid frame after frame, like the SSC evaluation (sscbench/evaluate_model_sscbench.py:270-279 builds the grid once).
     The scene tensors, ``xyz`` and ``out`` must stay alive and in place; their CONTENTS may change between replays."""
 
-    def __init__(self, scene: Scene, mlp: Mlp, xyz, out: dict, want_rgb: bool = False, precision=None):
+    def __init__(self, scene: Scene, mlp: Mlp, xyz, out: dict, want_rgb: bool = False, precision=None, binned_out: bool = False):
         self._keep = (scene, mlp, xyz, out)
+        if binned_out:       # features in texel-bin order + perm (query_points_binned); ``out`` holds dino_binned / perm
+            call = lambda: query_points_binned(scene, mlp, xyz, out=out)
+        else:
+            call = lambda: query_points(scene, mlp, xyz, want_rgb=want_rgb, precision=precision, out=out)
         side = torch.cuda.Stream(device=xyz.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):            # first calls: module load, function attributes, workspace allocation
             for _ in range(2):
-                query_points(scene, mlp, xyz, want_rgb=want_rgb, precision=precision, out=out)
+                call()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = _abi.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            query_points(scene, mlp, xyz, want_rgb=want_rgb, precision=precision, out=out)
+            call()
         self.launches = _abi.launch_count() - n0     # kernels inside one replay
 
     def replay(self):
