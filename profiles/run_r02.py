@@ -1,5 +1,5 @@
 """Small single-purpose workloads for the round-2 ncu captures (one mode per process, a handful of launches each):
-    python profiles/run_r02.py query|ssc|render64|render768|expand [n_iter]"""
+    python profiles/run_r02.py query|binned|ssc|render64|render768|expand [n_iter]"""
 import os
 import sys
 
@@ -17,7 +17,7 @@ def main():
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(1)
     Kc = syn.kitti360_K()
-    if mode in ("query", "ssc"):
+    if mode in ("query", "ssc", "binned"):
         N = 1 << 21
         if mode == "ssc":
             f = torch.randn((N, 64), device=dev, generator=g) * 0.5
@@ -33,7 +33,12 @@ def main():
             pts = torch.from_numpy(syn.ssc_voxel_grid()).to(dev)
             out = None
             for _ in range(n_iter):
-                out = ops.query_points(sc, mlp, pts, want_rgb=False, out=out)
+                if mode == "binned":
+                    r = ops.query_points_binned(sc, mlp, pts, out=out)
+                    if out is None:
+                        out = dict(r); out["invalid_features"] = out["invalid_features"].view(torch.uint8)
+                else:
+                    out = ops.query_points(sc, mlp, pts, want_rgb=False, out=out)
     elif mode == "expand":
         N = 1 << 19
         f = torch.randn((N, 64), device=dev, generator=g) * 0.5

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscenedino_b200.so")
+LIB_PATH = os.environ.get("SD_B200_LIB") or os.path.join(HERE, "libscenedino_b200.so")   # (override: kernel experiments)
 
 SD_F32, SD_F16 = 0, 1
 SD_MLP_FP32, SD_MLP_F16_TC = 0, 1

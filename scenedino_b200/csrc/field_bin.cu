@@ -49,7 +49,22 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #ifndef SD_TB_PT_GROUPS
 #define SD_TB_PT_GROUPS 1
 #endif
-constexpr int NRA = 2, NRB = 4, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
+#ifndef SD_TB_NRA
+#define SD_TB_NRA 2
+#endif
+#ifndef SD_TB_NRB
+#define SD_TB_NRB 4
+#endif
+#ifndef SD_TB_STAGE
+#define SD_TB_STAGE 8192      // staging bytes per epilogue-2 warp (4096: binned output only, one half reused)
+#endif
+#ifndef SD_TB_ABLATE
+#define SD_TB_ABLATE 0        // timing experiments only (results are garbage): 1 no code computation, 2 no output path in epilogue 2,
+#endif                        // 4 no box loads, 8 no layer-2 MMAs, 16 no chunk MMAs, 32 no epilogue-1 conversion
+#ifndef SD_TB_BOX_AHEAD
+#define SD_TB_BOX_AHEAD 0     // the producer issues the boxes of tile j + BOX_AHEAD while it publishes the records of tile j + 2
+#endif
+constexpr int NRA = SD_TB_NRA, NRB = SD_TB_NRB, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
 constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_PT_GROUPS = SD_TB_PT_GROUPS;
 constexpr int WARP_EPI2 = N_EPI_WARPS, WARP_MMA = 2 * N_EPI_WARPS, WARP_MMA2 = WARP_MMA + 1, WARP_TMA = WARP_MMA2 + 1,
               WARP_PT0 = WARP_TMA + 1;
@@ -71,7 +86,7 @@ constexpr int OFF_STAGE = OFF_W2 + W2_BYTES;
 constexpr int NREC = 3;                      // ring of per-tile record blocks (128 x 32 B), filled by bulk copies
 constexpr int REC_BYTES = TM * 32;
 constexpr int NPERM = 8;                     // ring of per-tile point indices handed from the point warps to epilogue 2
-constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * 8192;
+constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * SD_TB_STAGE;
 constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
 constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: the tile's table entry (TileInfo, 16 B)
 constexpr int BATCH = 4;                                  // tiles claimed per atomic
@@ -93,12 +108,14 @@ constexpr int REC_CONSUMERS = N_PT_GROUPS * N_PT_WARPS;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_ALLOC = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget");
+static_assert(SD_TB_BOX_AHEAD >= 0 && SD_TB_BOX_AHEAD <= 2, "headers live in a ring of NREC = 3");
 static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 1024 == 0 && OFF_BAR % 8 == 0 && NREC * 4 <= 16, "alignment");
 
 #ifndef TB_T0
 #define TB_T0 40   // first traced tile of CTA 0 (SD_TC_DEBUG & 8192): tiles TB_T0 .. TB_T0 + 63
 #endif
 __device__ long long g_trace[8 * 64 * 8];
+__device__ long long g_tiles[4 * 2 * 512];          // [cta 0..3][tile][clock64 at the layer-1 issuer's tile start, chunks] (SD_TC_DEBUG & 8192)
 __device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globaltimer (SD_TC_DEBUG & 8192)   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
 #define TB_TRACE(role, j, ev)                                                                    \
     do {                                                                                         \
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     float *s_cam = reinterpret_cast<float *>(sm + OFF_CAM);
@@ -148,6 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_cta_ns[2 * blockIdx.x] = t; g_cta_ns[2 * blockIdx.x + 1] = 0;
     }
+    if ((P.dbg & 8192) && blockIdx.x < 4 && tid == 0) g_tiles[(blockIdx.x * 512 + 510) * 2] = clock64();
     if (tid == 0) {
         for (int e = 0; e < NRA; ++e) { mbar_init(BAR(BAR_FULL_A + e), N_PT_WARPS); mbar_init(BAR(BAR_EMPTY_A + e), 1); }
         for (int e = 0; e < NRB; ++e) { mbar_init(BAR(BAR_FULL_B + e), 1); mbar_init(BAR(BAR_EMPTY_B + e), 1); }
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             tc_fence_after();
             if (warp == 0) TB_TRACE(0, j, 2);
 #pragma unroll 1
-            for (int kb = 0; kb < 4; ++kb) {      // 32 hidden units -> 16 packed columns, written over columns already read
+            for (int kb = (SD_TB_ABLATE & 32) ? 4 : 0; kb < 4; ++kb) {      // 32 hidden units -> 16 packed columns, written over columns already read
                 uint32_t vr[32];
                 tmem_ld32_issue(t_lane + b * 128 + kb * 32, vr);
                 tmem_ld_wait();
@@ -237,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         const int row = wq * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
         const int D = P.D;
-        unsigned char *stage0 = sm + OFF_STAGE + wq * 8192, *stage1 = stage0 + 4096;
+        unsigned char *stage0 = sm + OFF_STAGE + wq * SD_TB_STAGE, *stage1 = stage0 + (SD_TB_STAGE == 8192 ? 4096 : 0);
         // The point index of this thread's row was left in the perm ring by the point warps when they processed the tile.
         // No barrier of its own: the write is ordered before this read by the chain FULL_C -> MMA -> D1 -> H -> D2, and
         // an entry is rewritten 8 tiles later, while the point warps can be at most 5 tiles ahead of this role (two
@@ -270,7 +288,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                         tc_fence_before();
                         mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
                     }
-                    if (lane == 0) bulk_wait_read<1>();        // the store that last read this half (a tile ago) has left
+                    if (SD_TB_ABLATE & 2) continue;
+                    if (lane == 0) bulk_wait_read<(SD_TB_STAGE == 8192 ? 1 : 0)>();        // the store that last read this half (a tile ago) has left
                     __syncwarp();
                     unsigned char *stage = hf ? stage1 : stage0;
 #pragma unroll
@@ -284,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                         bulk_commit();
                     }
                 }
-                if (ok) {
+                if (ok && !(SD_TB_ABLATE & 2)) {
                     if (P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
                     if (P.perm_out) P.perm_out[(long long)t * TM + row] = (unsigned int)grow_keep;
                 }
@@ -351,9 +370,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         }
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
-        // Layer 1.  (Layer 2 is issued by a second thread, warp WARP_MMA2: every barrier test is a round trip through the
-        // load/store unit, ~250 cycles behind the epilogue's stores, and one thread doing all of them was the critical path.)
-        if (lane == 0) {
+        // Layer 1, issued by the whole warp in lockstep (tc_common.cuh: "elected" forms -- one lane issues, nothing
+        // diverges, the tcgen05 instructions come out back to back).  Layer 2 has a warp of its own (WARP_MMA2): every
+        // barrier test is a round trip through the load/store unit and one warp doing all of them was the critical path.
+        {
             mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc_k = umma_idesc(TM, 128), idesc_mn = idesc_k | UMMA_B_MN_MAJOR;
             int e = 0, eb = 0;                       // ring positions: weight chunks, box chunks
@@ -364,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 // The tile's first weight chunk carries its chunk count (0: no more tiles) and stands for the code operand
                 // too: one barrier test where there were three.
                 mbar_wait(BAR(BAR_FULL_A + e), ph);
-                const int m = s_minfo[e];
+                const int m = __shfl_sync(0xffffffffu, s_minfo[e], 0);
                 // the accumulator (its first 64 columns held the hidden tile of tile j-2) is free once layer 2 of j-2 has run.
                 // (Also before the closing arrival below: nobody may complete two phases of a barrier ahead of its waiter.)
                 mbar_wait(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
@@ -372,6 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
+                if ((P.dbg & 8192) && blockIdx.x < 4 && j < 500 && lane == 0) { g_tiles[(blockIdx.x * 512 + j) * 2] = clock64(); g_tiles[(blockIdx.x * 512 + j) * 2 + 1] = m; }
                 for (int i = 0; i < m; ++i) {
                     if (i > 0) mbar_wait(BAR(BAR_FULL_A + e), ph);
                     if (i == 0) TB_TRACE(1, j, 1);
@@ -379,13 +400,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     tc_fence_after();
                     if (i == 0) TB_TRACE(1, j, 2);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {    // 16 texel slots per instruction
-                        umma(d1, umma_desc(sm_u + OFF_A + e * CHUNK + k * 32),
-                             umma_desc_mn(sm_u + OFF_B + eb * CHUNK + k * 2048, CHUNK / 2, 1024), idesc_mn, acc);
+                    for (int k = (SD_TB_ABLATE & 16) ? 4 : 0; k < 4; ++k) {    // 16 texel slots per instruction
+                        umma_e(d1, umma_desc(sm_u + OFF_A + e * CHUNK + k * 32),
+                               umma_desc_mn(sm_u + OFF_B + eb * CHUNK + k * 2048, CHUNK / 2, 1024), idesc_mn, acc);
                         acc = 1;
                     }
-                    umma_commit(BAR(BAR_EMPTY_A + e));
-                    umma_commit(BAR(BAR_EMPTY_B + eb));
+                    umma_commit_e(BAR(BAR_EMPTY_A + e));
+                    umma_commit_e(BAR(BAR_EMPTY_B + eb));
                     if (++e == NRA) { e = 0; ph ^= 1; }
                     if (++eb == NRB) { eb = 0; phb ^= 1; }
                 }
@@ -393,19 +414,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 TB_TRACE(1, j, 4);
 #pragma unroll
                 for (int k = 0; k < KCODE; ++k)
-                    umma(d1, umma_desc(sm_u + OFF_CODE + cs * CHUNK + k * 32), umma_desc(sm_u + OFF_WC + k * 32), idesc_k, 1);
-                umma_commit(BAR(BAR_EMPTY_C + cs));
-                umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                    umma_e(d1, umma_desc(sm_u + OFF_CODE + cs * CHUNK + k * 32), umma_desc(sm_u + OFF_WC + k * 32), idesc_k, 1);
+                umma_commit_e(BAR(BAR_EMPTY_C + cs));
+                umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
                 TB_TRACE(1, j, 6);
             }
             // closing: tell everybody downstream how many tiles there were and complete the phase the first epilogue waits
             // on; it passes the arrival on to the layer-2 issuer, which passes it on to the second epilogue
-            *s_ntiles = (int)j;
-            mbar_arrive(BAR(BAR_D1 + (int)(j & 1)));
+            if (lane == 0) *s_ntiles = (int)j;
+            __syncwarp();
+            mbar_arrive_e(BAR(BAR_D1 + (int)(j & 1)));
         }
     } else if (warp == WARP_MMA2) {
         // =================================== MMA ISSUER, LAYER 2 ======================================
-        if (lane == 0) {
+        {   // (whole warp, elected forms: see the layer-1 issuer)
             mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc2 = umma_idesc(TM, P.n2);
             for (long long j = 0;; ++j) {
@@ -414,16 +436,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 // (the accumulator drained -- also before the closing arrival: nobody may complete two phases of a barrier
                 // ahead of its waiter)
                 mbar_wait(BAR(BAR_D2_EMPTY + b), (uint32_t)(((j >> 1) & 1) ^ 1));
-                if (j >= *s_ntiles) { mbar_arrive(BAR(BAR_D2 + b)); break; }
+                const int nt = __shfl_sync(0xffffffffu, *s_ntiles, 0);
+                if (j >= nt) { mbar_arrive_e(BAR(BAR_D2 + b)); break; }
                 tc_fence_after();
                 TB_TRACE(1, j + 1, 5);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
-                            umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
-                umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
-                umma_commit(BAR(BAR_D2 + b));
-                umma_commit(BAR(BAR_D1_FREE + b));
+                for (int k = (SD_TB_ABLATE & 8) ? 8 : 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                    umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
+                              umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
+                umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
+                umma_commit_e(BAR(BAR_D2 + b));
+                umma_commit_e(BAR(BAR_D1_FREE + b));
             }
         }
     } else if (warp == WARP_TMA) {
@@ -483,12 +506,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         };
         publish_next(0);
         publish_next(1);
-        for (long long j = 0;; ++j) {
-            publish_next(j + 2);
-            __syncwarp();
+        // boxes of tile j: from the header published for it (false: past the end)
+        auto issue_boxes = [&](long long j) -> bool {
             const int r = (int)(j % NREC);
             const unsigned int rows = s_hdr[r].rows, c0m = s_hdr[r].c0m, b01 = s_hdr[r].b01, b23 = s_hdr[r].b23;
-            if (rows == 0) break;
+            if (rows == 0) return false;
             const int c0 = (int)(c0m & 0xFFFFu), m = (int)(c0m >> 16);
             if (lane == 0) {
                 for (int i = 0; i < m; ++i) {
@@ -498,16 +520,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     if (i == 0) TB_TRACE(6, j, 0);
                     mbar_wait(BAR(BAR_EMPTY_B + e), ph ^ 1);
                     if (i == 0) TB_TRACE(6, j, 1);
+                    if (SD_TB_ABLATE & 4) {
+                        mbar_arrive(BAR(BAR_FULL_B + e));
+                    } else {
                     mbar_expect_tx(BAR(BAR_FULL_B + e), CHUNK);
                     const uint32_t dst = sm_u + OFF_B + e * CHUNK;
                     tma_load_3d(dst, &P.tmap, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
                     tma_load_3d(dst + CHUNK / 2, &P.tmap, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                    }
                     if (++e == NRB) { e = 0; ph ^= 1; }
                 }
                 TB_TRACE(6, j, 2);
                 if ((P.dbg & 8192) && blockIdx.x == 0 && j >= TB_T0 && j < TB_T0 + 64) g_trace[(6 * 64 + (int)j - TB_T0) * 8 + 7] = m;
             }
             __syncwarp();
+            return true;
+        };
+        // Per iteration: the records of tile j + 2 (the point warps run ahead of the MMAs), then the boxes of tile
+        // j + BOX_AHEAD from the header published for it earlier.
+        bool more = true;
+        for (int a = 0; a < SD_TB_BOX_AHEAD && more; ++a) { __syncwarp(); more = issue_boxes(a); }
+        for (long long j = 0; more; ++j) {
+            publish_next(j + 2);
+            __syncwarp();
+            more = issue_boxes(j + SD_TB_BOX_AHEAD);
         }
     } else {
         // =================================== POINT WARPS ================================================
@@ -569,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             uint32_t pk[24];
 #pragma unroll
             for (int i = 0; i < 24; ++i) pk[i] = 0u;
-            if (ok) {
+            if (ok && !(SD_TB_ABLATE & 1)) {
                 float code[48];
                 code[0] = x; code[1] = y; code[2] = zp;
                 code[45] = 1.0f; code[46] = 1.0f;                      // layer-1 bias (hi, lo) comes out of the MMA
@@ -682,6 +718,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     bulk_wait<0>();            // output rows still in flight (epilogue threads)
     tc_fence_before();
     __syncthreads();
+    if ((P.dbg & 8192) && blockIdx.x < 4 && tid == 0) g_tiles[(blockIdx.x * 512 + 511) * 2] = clock64();
     if (warp == WARP_MMA) {
         __syncwarp();
         tc_fence_after();
@@ -694,6 +731,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
 // debug: clock64 trace of the last launch made with SD_TC_DEBUG & 8192 (not part of the public header)
 extern "C" int sd_debug_read_cta_ns(unsigned long long *host_out) {
     SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_cta_ns, sizeof(unsigned long long) * 512));
+    return SD_OK;
+}
+extern "C" int sd_debug_read_tiles_bin(long long *host_out) {
+    SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_tiles, sizeof(long long) * 4 * 2 * 512));
     return SD_OK;
 }
 extern "C" int sd_debug_read_trace_bin(long long *host_out) {

@@ -100,6 +100,38 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// ---- whole-warp ("elected") forms ------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / TMA copies are uniform-datapath instructions.  Issued under `if (lane == 0)` they sit in
+// divergent control flow and ptxas wraps EVERY one of them in an ELECT / BRA.U.ANY loop with its operands rebuilt in
+// uniform registers first (~90 cycles of dependent scalar work per instruction: a single-chunk tile's 16 MMAs and 6
+// commits were ~2 000 cycles of pure issue, the critical path of the tile kernel).  Run by all 32 lanes of a warp whose
+// index the compiler KNOWS to be uniform (warp_uniform()), with the single issuing lane chosen inside the asm by
+// elect.sync, the same instructions come out back to back.  elect.sync with a full mask always elects the same lane, so
+// MMAs and the commits that track them are issued by one thread, as tcgen05.commit requires.
+__device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// one arrival (elected lane) of a converged warp
+__device__ __forceinline__ void mbar_arrive_e(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
