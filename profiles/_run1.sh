@@ -1,2 +1,4 @@
-python -m pytest tests/test_gpu_binned.py tests/test_gpu_parity.py -x -q -k "binned or tile or ssc_grid or projected or sorted or graph" 2>&1 | tail -3
-python profiles/time_bin.py 2>&1 | tail -1
+for v in a0 a1 a2 a2b5; do
+  SD_B200_LIB=$PWD/scenedino_b200/build/variants/lib_$v.so timeout 60 python profiles/time_bin_k.py 2>&1 | tail -1 | cut -c1-200
+done
+SD_B200_LIB=$PWD/scenedino_b200/build/variants/lib_a2.so python profiles/time_bin.py 2>&1 | tail -1

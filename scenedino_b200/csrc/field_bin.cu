@@ -62,7 +62,7 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #define SD_TB_ABLATE 0        // timing experiments only (results are garbage): 1 no code computation, 2 no output path in epilogue 2,
 #endif                        // 4 no box loads, 8 no layer-2 MMAs, 16 no chunk MMAs, 32 no epilogue-1 conversion
 #ifndef SD_TB_BOX_AHEAD
-#define SD_TB_BOX_AHEAD 0     // the producer issues the boxes of tile j + BOX_AHEAD while it publishes the records of tile j + 2
+#define SD_TB_BOX_AHEAD 1     // the producer issues the boxes of tile j + BOX_AHEAD while it publishes the records of tile j + 2
 #endif
 constexpr int NRA = SD_TB_NRA, NRB = SD_TB_NRB, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
 constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_PT_GROUPS = SD_TB_PT_GROUPS;
@@ -143,11 +143,6 @@ struct Params {
     int binned;                // feature rows leave in SORTED order (row r of tile t -> dino[t * 128 + r]) by TMA tile stores
     unsigned int *perm_out;    // binned: [N] sorted position -> point index (or NULL)
 };
-
-__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -289,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                         mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
                     }
                     if (SD_TB_ABLATE & 2) continue;
-                    if (lane == 0) bulk_wait_read<(SD_TB_STAGE == 8192 ? 1 : 0)>();        // the store that last read this half (a tile ago) has left
+                    bulk_wait_read_e<(SD_TB_STAGE == 8192 ? 1 : 0)>();     // the store that last read this half (a tile ago) has left
                     __syncwarp();
                     unsigned char *stage = hf ? stage1 : stage0;
 #pragma unroll
@@ -298,10 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                             make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && !(P.dbg & 1)) {
-                        tma_store_2d(&P.tmap_out, smem_u32(stage), hf * 32, t * TM + wq * 32);
-                        bulk_commit();
-                    }
+                    tma_store_2d_commit_e(&P.tmap_out, smem_u32(stage), hf * 32, t * TM + wq * 32);
                 }
                 if (ok && !(SD_TB_ABLATE & 2)) {
                     if (P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
@@ -451,21 +443,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         }
     } else if (warp == WARP_TMA) {
         // =================================== TMA PRODUCER =============================================
+        // The whole warp runs the role in lockstep and the copies are issued in their "elected" forms (tc_common.cuh): no
+        // per-instruction ELECT loop.
         if (lane == 0) tma_prefetch_desc(&P.tmap);
+        __syncwarp();
         int e = 0;
         uint32_t ph = 0;
         // Tiles are claimed BATCH at a time with one atomic; the table entries of a batch (rows, chunk span, first bins: all
         // the producer needs to know about a tile) arrive by a bulk copy.  In steady state this warp issues no load through
-        // the load/store unit, whose queue is full of the epilogue's stores: a claim and a table fetch have a whole batch
-        // of tiles to complete.  Per tile: publish header + records of slot j+2 (the point warps run ahead of the MMAs),
-        // then issue the boxes of slot j from the header written two iterations ago.
+        // the load/store unit: a claim and a table fetch have a whole batch of tiles to complete.  Per iteration: publish
+        // header + records of tile j+2 (the point warps run ahead of the MMAs), then issue the boxes of tile j + BOX_AHEAD
+        // (a box takes ~2 400 cycles to arrive -- a tile period -- so they are requested as far ahead as the ring allows).
         const TileInfo *s_tab = reinterpret_cast<const TileInfo *>(sm + OFF_TAB);
         auto claim = [&]() -> long long { return lane == 0 ? (long long)atomicAdd(P.tile_ctr, (unsigned)BATCH) : 0; };
         auto bcast = [&](long long v) { return __shfl_sync(0xffffffffu, v, 0); };
         auto fetch_tab = [&](long long k, long long base) {        // batch k -> table slot k & 1
-            if (lane != 0 || base >= P.n_tiles) return;
-            mbar_expect_tx(BAR(BAR_TAB + (int)(k & 1)), BATCH * 16);
-            bulk_g2s(sm_u + OFF_TAB + (int)(k & 1) * BATCH * 16, P.tiles + base, BATCH * 16, BAR(BAR_TAB + (int)(k & 1)));
+            if (base >= P.n_tiles) return;
+            if (elect_one()) {
+                mbar_expect_tx(BAR(BAR_TAB + (int)(k & 1)), BATCH * 16);
+                bulk_g2s(sm_u + OFF_TAB + (int)(k & 1) * BATCH * 16, P.tiles + base, BATCH * 16, BAR(BAR_TAB + (int)(k & 1)));
+            }
+            __syncwarp();
         };
         // stream of this CTA's tiles: batch k, entry i
         long long k = 0, base = bcast(claim()), base_n;
@@ -481,22 +479,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             long long v = -1;                                       // position in claim order
             if (base < P.n_tiles) {
                 if (!tab_ready) { mbar_wait(BAR(BAR_TAB + (int)(k & 1)), (uint32_t)((k >> 1) & 1)); tab_ready = true; }
-                ti = s_tab[(int)(k & 1) * BATCH + bi];
+                const TileInfo tl = s_tab[(int)(k & 1) * BATCH + bi];      // (broadcasts: the compiler must SEE that the
+                ti.c0m = __shfl_sync(0xffffffffu, tl.c0m, 0);               // control flow below is uniform, or every copy gets
+                ti.b01 = __shfl_sync(0xffffffffu, tl.b01, 0);               // its ELECT loop back)
+                ti.b23 = __shfl_sync(0xffffffffu, tl.b23, 0);
+                ti.rows = __shfl_sync(0xffffffffu, tl.rows, 0);
                 v = base + bi;
             }
+            mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
             if (lane == 0) {
-                mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
                 s_hdr[r].c0m = ti.c0m; s_hdr[r].b01 = ti.b01; s_hdr[r].b23 = ti.b23; s_hdr[r].rows = ti.rows;
                 reinterpret_cast<volatile int *>(sm + OFF_TIDX)[r] = (int)(P.n_tiles - 1 - v);
-                if (ti.rows == 0) {
-                    mbar_arrive(BAR(BAR_REC_FULL + r));             // no more tiles: a header alone
-                } else {
-                    const long long t = P.n_tiles - 1 - v;          // claim order runs from the last tile down
-                    mbar_expect_tx(BAR(BAR_REC_FULL + r), ti.rows * 32u);
-                    bulk_g2s(sm_u + OFF_REC + r * REC_BYTES, P.rec + t * TM, ti.rows * 32u, BAR(BAR_REC_FULL + r));
-                }
             }
-            if (ti.rows == 0) { ended = true; return; }
+            __syncwarp();                                           // (the header is written before whichever lane arrives)
+            if (ti.rows == 0) {
+                mbar_arrive_e(BAR(BAR_REC_FULL + r));               // no more tiles: a header alone
+                ended = true;
+                return;
+            }
+            const long long t = P.n_tiles - 1 - v;                  // claim order runs from the last tile down
+            if (elect_one()) {
+                mbar_expect_tx(BAR(BAR_REC_FULL + r), ti.rows * 32u);
+                bulk_g2s(sm_u + OFF_REC + r * REC_BYTES, P.rec + t * TM, ti.rows * 32u, BAR(BAR_REC_FULL + r));
+            }
+            __syncwarp();
             if (++bi == BATCH) {                                    // next batch: its claim was made a batch ago
                 bi = 0; ++k; tab_ready = false;
                 base = bcast(base_n);
@@ -509,40 +515,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         // boxes of tile j: from the header published for it (false: past the end)
         auto issue_boxes = [&](long long j) -> bool {
             const int r = (int)(j % NREC);
-            const unsigned int rows = s_hdr[r].rows, c0m = s_hdr[r].c0m, b01 = s_hdr[r].b01, b23 = s_hdr[r].b23;
+            const unsigned int rows = __shfl_sync(0xffffffffu, s_hdr[r].rows, 0), c0m = __shfl_sync(0xffffffffu, s_hdr[r].c0m, 0),
+                               b01 = __shfl_sync(0xffffffffu, s_hdr[r].b01, 0), b23 = __shfl_sync(0xffffffffu, s_hdr[r].b23, 0);
             if (rows == 0) return false;
             const int c0 = (int)(c0m & 0xFFFFu), m = (int)(c0m >> 16);
-            if (lane == 0) {
-                for (int i = 0; i < m; ++i) {
-                    unsigned int b = i == 0 ? (b01 & 0xFFFFu) : i == 1 ? (b01 >> 16) : i == 2 ? (b23 & 0xFFFFu) : (b23 >> 16);
-                    if (i >= 4) b = __ldg(P.cbin + c0 + i);          // a tile that touches more than four bins (rare)
-                    const int by = (int)(b / (unsigned)P.nbx), bx = (int)(b - (unsigned)by * (unsigned)P.nbx);
-                    if (i == 0) TB_TRACE(6, j, 0);
-                    mbar_wait(BAR(BAR_EMPTY_B + e), ph ^ 1);
-                    if (i == 0) TB_TRACE(6, j, 1);
-                    if (SD_TB_ABLATE & 4) {
-                        mbar_arrive(BAR(BAR_FULL_B + e));
-                    } else {
+            for (int i = 0; i < m; ++i) {
+                unsigned int b = i == 0 ? (b01 & 0xFFFFu) : i == 1 ? (b01 >> 16) : i == 2 ? (b23 & 0xFFFFu) : (b23 >> 16);
+                if (i >= 4) b = __shfl_sync(0xffffffffu, __ldg(P.cbin + c0 + i), 0);   // a tile that touches more than four bins (rare)
+                const int by = (int)(b / (unsigned)P.nbx), bx = (int)(b - (unsigned)by * (unsigned)P.nbx);
+                if (i == 0) TB_TRACE(6, j, 0);
+                mbar_wait(BAR(BAR_EMPTY_B + e), ph ^ 1);
+                if (i == 0) TB_TRACE(6, j, 1);
+                if (SD_TB_ABLATE & 4) {
+                    mbar_arrive_e(BAR(BAR_FULL_B + e));
+                } else if (elect_one()) {
                     mbar_expect_tx(BAR(BAR_FULL_B + e), CHUNK);
                     const uint32_t dst = sm_u + OFF_B + e * CHUNK;
                     tma_load_3d(dst, &P.tmap, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
                     tma_load_3d(dst + CHUNK / 2, &P.tmap, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
-                    }
-                    if (++e == NRB) { e = 0; ph ^= 1; }
                 }
-                TB_TRACE(6, j, 2);
-                if ((P.dbg & 8192) && blockIdx.x == 0 && j >= TB_T0 && j < TB_T0 + 64) g_trace[(6 * 64 + (int)j - TB_T0) * 8 + 7] = m;
+                __syncwarp();
+                if (++e == NRB) { e = 0; ph ^= 1; }
             }
-            __syncwarp();
+            TB_TRACE(6, j, 2);
+            if ((P.dbg & 8192) && blockIdx.x == 0 && j >= TB_T0 && j < TB_T0 + 64 && lane == 0) g_trace[(6 * 64 + (int)j - TB_T0) * 8 + 7] = m;
             return true;
         };
-        // Per iteration: the records of tile j + 2 (the point warps run ahead of the MMAs), then the boxes of tile
-        // j + BOX_AHEAD from the header published for it earlier.
         bool more = true;
-        for (int a = 0; a < SD_TB_BOX_AHEAD && more; ++a) { __syncwarp(); more = issue_boxes(a); }
+        for (int a = 0; a < SD_TB_BOX_AHEAD && more; ++a) more = issue_boxes(a);
         for (long long j = 0; more; ++j) {
             publish_next(j + 2);
-            __syncwarp();
             more = issue_boxes(j + SD_TB_BOX_AHEAD);
         }
     } else {

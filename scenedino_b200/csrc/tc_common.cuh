@@ -108,6 +108,13 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 // index the compiler KNOWS to be uniform (warp_uniform()), with the single issuing lane chosen inside the asm by
 // elect.sync, the same instructions come out back to back.  elect.sync with a full mask always elects the same lane, so
 // MMAs and the commits that track them are issued by one thread, as tcgen05.commit requires.
+// elect.sync as a C++ predicate: `if (elect_one()) { ... }` in a converged warp is the form ptxas recognises as a
+// single-thread region for TMA / bulk copies (clean UTMALDG / UBLKCP; predicating them INSIDE the asm still loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -125,6 +132,24 @@ __device__ __forceinline__ void umma_commit_e(uint32_t bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// tile store shared -> global + its bulk group, and the wait for the smem reads of all but the last N groups: issued,
+// committed and waited for by the SAME (elected) lane of a converged warp (bulk groups are per thread)
+__device__ __forceinline__ void tma_store_2d_commit_e(const void *tmap, uint32_t src, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+        "@q cp.async.bulk.commit_group;\n\t}"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_e() {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N) : "memory");
 }
 // one arrival (elected lane) of a converged warp
 __device__ __forceinline__ void mbar_arrive_e(uint32_t bar) {
