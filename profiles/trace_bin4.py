@@ -28,7 +28,7 @@ raw.sd_debug_read_trace_bin(buf)
 a = np.array(buf[:]).reshape(8, 64, 8)
 t0 = a[1, 10, 0]
 f = lambda v: f"{int(v - t0):6d}"
-print("tile m | tma: start gotB issued | pt: start code EMPTY_C sts EMPTY_A done | mma1: start A B chunks commit | epi1: start end | mma2 issue | epi2: start end")
+print("tile m | publish: begin gotREC end | tma: start gotB issued | pt: start code EMPTY_C sts EMPTY_A done | mma1: start A B chunks commit | epi1: start end | mma2 issue | epi2: start end")
 for j in range(10, 26):
-    print(f"{j:3d} {a[6, j, 7]:2d} | {f(a[6,j,0])} {f(a[6,j,1])} {f(a[6,j,2])} | {f(a[2,j,0])} {f(a[2,j,4])} {f(a[2,j,5])} {f(a[2,j,1])} {f(a[2,j,2])} {f(a[2,j,3])} |"
+    print(f"{j:3d} {a[6, j, 7]:2d} | {f(a[6,j,3])} {f(a[6,j,4])} {f(a[6,j,5])} | {f(a[6,j,0])} {f(a[6,j,1])} {f(a[6,j,2])} | {f(a[2,j,0])} {f(a[2,j,4])} {f(a[2,j,5])} {f(a[2,j,1])} {f(a[2,j,2])} {f(a[2,j,3])} |"
           f" {f(a[1,j,0])} {f(a[1,j,1])} {f(a[1,j,2])} {f(a[1,j,4])} {f(a[1,j,6])} | {f(a[0,j,2])} {f(a[0,j,3])} | {f(a[1,j+1,5])} | {f(a[0,j,0])} {f(a[0,j,1])}")

@@ -89,7 +89,10 @@ constexpr int NPERM = 8;                     // ring of per-tile point indices h
 constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * SD_TB_STAGE;
 constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
 constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: the tile's table entry (TileInfo, 16 B)
-constexpr int BATCH = 4;                                  // tiles claimed per atomic
+#ifndef SD_TB_BATCH
+#define SD_TB_BATCH 4
+#endif
+constexpr int BATCH = SD_TB_BATCH;                        // tiles claimed per atomic
 constexpr int OFF_TAB = OFF_HDR + NREC * 16;              // two batches of table entries, fetched by bulk copies
 constexpr int OFF_MINFO = OFF_TAB + 2 * BATCH * 16;       // per weight-ring entry: chunks of the tile whose first chunk sits there
 constexpr int OFF_NTILES = OFF_MINFO + 16;      // tiles this CTA processed, published by the MMA issuer at the end
