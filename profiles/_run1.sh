@@ -1,3 +1,3 @@
-for v in base b1 b2 b8; do
-  SD_B200_LIB=$PWD/scenedino_b200/build/variants/lib_$v.so timeout 60 python profiles/time_bin_k.py 2>&1 | tail -1 | cut -c1-200
-done
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+python profiles/time_r02.py > gpurun_out/time_r02c.json 2> gpurun_out/time_r02c.err; cat gpurun_out/time_r02c.json; tail -2 gpurun_out/time_r02c.err
+python profiles/time_bin.py 2>&1 | tail -1

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;   // (warp index the compiler knows to be uniform)
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     if (tid == 0) {
@@ -234,21 +234,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
             }
         }
     } else if (warp == 4) {
-        if (lane == 0) {
-            long long g = 0;
-            for (long long j = 0; j < my_tiles; ++j)
-                for (int s = 0; s < nsteps; ++s, ++g) {
-                    const int slot = (int)(g % NW2);
-                    const int c = s < P.nch ? s : s - P.nch;
-                    mbar_wait(BAR(BAR_W_EMPTY + slot), (uint32_t)(((g / NW2) & 1) ^ 1));
+        // (whole warp in lockstep; copies inside an elect_one() branch, MMAs / commits in their elected forms: tc_common.cuh)
+        long long g = 0;
+        for (long long j = 0; j < my_tiles; ++j)
+            for (int s = 0; s < nsteps; ++s, ++g) {
+                const int slot = (int)(g % NW2);
+                const int c = s < P.nch ? s : s - P.nch;
+                mbar_wait(BAR(BAR_W_EMPTY + slot), (uint32_t)(((g / NW2) & 1) ^ 1));
+                if (elect_one()) {
                     mbar_expect_tx(BAR(BAR_W_FULL + slot), W2_BYTES);
                     const unsigned char *src = P.w2_img + (size_t)c * W2_BYTES;
                     bulk_g2s(sm_u + OFF_W2 + slot * W2_BYTES, src, 16384, BAR(BAR_W_FULL + slot));
                     bulk_g2s(sm_u + OFF_W2 + slot * W2_BYTES + 16384, src + 16384, 16384, BAR(BAR_W_FULL + slot));
                 }
-        }
+                __syncwarp();
+            }
     } else {
-        if (lane == 0) {
+        {
             if (!P.head2) mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc = umma_idesc(TM, 128);
             long long g = 0;
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
-                    umma_commit(BAR(BAR_D1_FULL));
+                        umma_e(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
+                    umma_commit_e(BAR(BAR_D1_FULL));
                 }
                 mbar_wait(BAR(BAR_H_FULL), (uint32_t)(j & 1));
                 tc_fence_after();
@@ -271,10 +273,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                     const uint32_t w2 = sm_u + OFF_W2 + slot * W2_BYTES;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                        umma_ts(tmem_base + D2_COL + b * 128, tmem_base + k * 8, umma_desc(w2 + (k >> 2) * 16384 + (k & 3) * 32),
-                                idesc, k != 0);
-                    umma_commit(BAR(BAR_W_EMPTY + slot));
-                    umma_commit(BAR(BAR_D2_FULL + b));
+                        umma_ts_e(tmem_base + D2_COL + b * 128, tmem_base + k * 8, umma_desc(w2 + (k >> 2) * 16384 + (k & 3) * 32),
+                                  idesc, k != 0);
+                    umma_commit_e(BAR(BAR_W_EMPTY + slot));
+                    umma_commit_e(BAR(BAR_D2_FULL + b));
                 }
             }
         }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;   // (warp index the compiler knows to be uniform)
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     if (tid == 0) {
@@ -158,19 +158,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
         }
         if (lane == 0) bulk_wait<0>();
     } else if (warp == 4) {
-        if (lane == 0) {
-            tma_prefetch_desc(&P.tmap);
-            for (long long j = 0; j < my_tiles; ++j) {
-                const long long tile = first + j * stride;
-                const int s = (int)(j & 1);
-                mbar_wait(BAR(BAR_EMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
+        // (whole warp in lockstep; copies inside an elect_one() branch, MMAs / commits in their elected forms: tc_common.cuh)
+        if (lane == 0) tma_prefetch_desc(&P.tmap);
+        __syncwarp();
+        for (long long j = 0; j < my_tiles; ++j) {
+            const long long tile = first + j * stride;
+            const int s = (int)(j & 1);
+            mbar_wait(BAR(BAR_EMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
+            if (elect_one()) {
                 mbar_expect_tx(BAR(BAR_FULL + s), A_BYTES);
                 for (int c = 0; c < 4; ++c)
                     tma_load_2d(sm_u + OFF_A + s * A_BYTES + c * CHUNK, &P.tmap, c * 64, (int)(tile * TM), BAR(BAR_FULL + s));
             }
+            __syncwarp();
         }
     } else {
-        if (lane == 0) {
+        {
             mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc = umma_idesc(TM, 128);
             for (long long j = 0; j < my_tiles; ++j) {
@@ -180,10 +183,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    umma(tmem_base + s * 128, umma_desc(sm_u + OFF_A + s * A_BYTES + (k >> 2) * CHUNK + (k & 3) * 32),
-                         umma_desc(sm_u + OFF_W + (k >> 2) * CHUNK + (k & 3) * 32), idesc, k != 0);
-                umma_commit(BAR(BAR_EMPTY + s));
-                umma_commit(BAR(BAR_DFULL + s));
+                    umma_e(tmem_base + s * 128, umma_desc(sm_u + OFF_A + s * A_BYTES + (k >> 2) * CHUNK + (k & 3) * 32),
+                           umma_desc(sm_u + OFF_W + (k >> 2) * CHUNK + (k & 3) * 32), idesc, k != 0);
+                umma_commit_e(BAR(BAR_EMPTY + s));
+                umma_commit_e(BAR(BAR_DFULL + s));
             }
         }
     }

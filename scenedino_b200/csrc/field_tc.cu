@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
     // an integer would make every shared access of the kernel a generic LD/ST
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;   // (warp index the compiler knows to be uniform)
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     float *s_cam = reinterpret_cast<float *>(sm + OFF_CAM);
@@ -489,10 +489,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
         }
     } else if (warp == WARP_MMA) {
         // =================================== MMA ISSUER ===============================================
-        // Lane 0 issues the MMAs.  In render mode on a projected scene the whole warp (its TMEM lanes are 0..31 = the rays
+        // The whole warp runs the issue loop in lockstep and one elected lane issues (tc_common.cuh, "elected" forms: under
+        // `if (lane == 0)` every tcgen05 instruction was wrapped in an ELECT loop, ~90 cycles each).  In render mode on a projected scene the whole warp (its TMEM lanes are 0..31 = the rays
         // of a tile) also reads the per-ray sums the composite MMAs leave in TMEM and writes them out.
         {
-            if (lane == 0) mbar_wait(BAR(BAR_WLOAD), 0);
+            mbar_wait(BAR(BAR_WLOAD), 0);
             const uint32_t idesc1 = umma_idesc(TM, 128), idesc2 = umma_idesc(TM, P.n2);
             auto layer2 = [&](long long jj) {
                 mbar_wait(BAR(BAR_H), (uint32_t)(jj & 1));
@@ -500,9 +501,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 SD_TRACE(1, jj + 1, 6);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts(tmem_base + D2_COL, tmem_base + h_col + k * 8,
+                    umma_ts_e(tmem_base + D2_COL, tmem_base + h_col + k * 8,
                             umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
-                umma_commit(BAR(BAR_D2));
+                umma_commit_e(BAR(BAR_D2));
             };
             const uint32_t idesc3f = umma_idesc(TM, P.cmma == 2 ? 128 : 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
             const uint32_t off_v3 = P.cmma == 2 ? OFF_V : OFF_B3;
@@ -512,10 +513,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t a = umma_desc(sm_u + OFF_A3 + (k >> 2) * CHUNK_BYTES + (k & 3) * 32);
-                    umma(tmem_base + d3f_col, a, umma_desc_mn(sm_u + off_v3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
-                    umma(tmem_base + d3x_col, a, umma_desc_mn(sm_u + OFF_X3 + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
+                    umma_e(tmem_base + d3f_col, a, umma_desc_mn(sm_u + off_v3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
+                    umma_e(tmem_base + d3x_col, a, umma_desc_mn(sm_u + OFF_X3 + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
                 }
-                umma_commit(BAR(BAR_D3));
+                umma_commit_e(BAR(BAR_D3));
             };
             auto cm_output = [&](long long jj) {
                 const float *s_bo = reinterpret_cast<const float *>(sm + OFF_PART);
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 }
             };
             for (long long j = 0; j < my_tiles; ++j) {
-                if (lane == 0) {
+                {
                     const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                     // the gather warps fence and arrive once per tile (FULL[0]) for all the chunks they fill -- every
                     // fence.proxy.async / mbarrier round trip queues behind their loads in the LSU --, the point warps
@@ -588,11 +589,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
+                            umma_e(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
                                  umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
-                        umma_commit(BAR(BAR_EMPTY + c));
+                        umma_commit_e(BAR(BAR_EMPTY + c));
                     }
-                    umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                    umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
                     SD_TRACE(1, j, 5);
                     if (P.cmma && j > 1) composite(j - 2);     // its operands were written a tile ago
                     if (j > 0) layer2(j - 1);
@@ -601,14 +602,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 __syncwarp();
                 if (P.cmma && j > 1) cm_output(j - 2);
             }
-            if (lane == 0) {
-                if (P.cmma && my_tiles > 1) composite(my_tiles - 2);
-                if (my_tiles > 0) layer2(my_tiles - 1);
-            }
+            if (P.cmma && my_tiles > 1) composite(my_tiles - 2);
+            if (my_tiles > 0) layer2(my_tiles - 1);
             __syncwarp();
             if (P.cmma && my_tiles > 1) cm_output(my_tiles - 2);
             if (P.cmma && my_tiles > 0) {
-                if (lane == 0) composite(my_tiles - 1);
+                composite(my_tiles - 1);
                 __syncwarp();
                 cm_output(my_tiles - 1);
             }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_u = smem_u32(sm);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;   // (warp index the compiler knows to be uniform)
     const uint32_t bar0 = sm_u + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     const int dmid = P.nch * 128;
@@ -266,19 +266,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
             epi_done();
         }
     } else if (warp == WARP_TMA) {
-        if (lane == 0) {
-            long long g = 0;
-            for (long long p = 0; p < n_pairs; ++p)
-                for (int s = 0; s < nsteps; ++s, ++g) {
-                    const int slot = (int)(g % NSLOT);
-                    mbar_wait(BAR(BAR_RING_EMPTY + slot), (uint32_t)(((g / NSLOT) & 1) ^ 1));
+        // (whole warp in lockstep, the copy inside an elect_one() branch: tc_common.cuh, "elected" forms)
+        long long g = 0;
+        for (long long p = 0; p < n_pairs; ++p)
+            for (int s = 0; s < nsteps; ++s, ++g) {
+                const int slot = (int)(g % NSLOT);
+                mbar_wait(BAR(BAR_RING_EMPTY + slot), (uint32_t)(((g / NSLOT) & 1) ^ 1));
+                if (elect_one()) {
                     mbar_expect_tx(BAR(BAR_RING_FULL + slot), CHUNK_BYTES);
                     bulk_g2s(sm_u + OFF_RING + slot * CHUNK_BYTES, P.blob + (size_t)s * CHUNK_BYTES, CHUNK_BYTES, BAR(BAR_RING_FULL + slot));
                 }
-        }
+                __syncwarp();
+            }
     } else {
         // =================================== MMA ISSUER ===============================================
-        if (lane == 0) {
+        // The whole warp runs the issue loop in lockstep; one elected lane issues (tc_common.cuh: under `if (lane == 0)` every
+        // tcgen05 instruction was wrapped in an ELECT loop, ~90 cycles each -- ~240 MMAs per pair of tiles: the issue rate,
+        // not the tensor pipe, bounded this kernel).
+        {
             mbar_wait(BAR(BAR_RES), 0);
             const uint32_t id128 = umma_idesc(TM, 128), id64 = umma_idesc(TM, 64), id32 = umma_idesc(TM, 32);
             uint32_t pe[2] = {0u, 0u};                       // phase of EPI_DONE[l] to wait for next
@@ -295,22 +300,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
                     wait_epi(l);                             // operand built, accumulator drained
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma(tmem_base + ACC_COL + l * 128, umma_desc(sm_u + OFF_A + l * 16384 + k * 32), umma_desc(ring + k * 32), id128, k != 0);
-                    umma_commit(BAR(BAR_MMA_DONE + l));
+                        umma_e(tmem_base + ACC_COL + l * 128, umma_desc(sm_u + OFF_A + l * 16384 + k * 32), umma_desc(ring + k * 32), id128, k != 0);
+                    umma_commit_e(BAR(BAR_MMA_DONE + l));
                 }
                 for (int l = 0; l < nl; ++l) {               // q = G h (-> |v|) and the linear path ML h -> code accumulator
                     wait_epi(l);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
+                        umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
                                 umma_desc(ring + 16384 + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
-                    umma_commit(BAR(BAR_MMA_DONE + l));
+                    umma_commit_e(BAR(BAR_MMA_DONE + l));
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_ts(tmem_base + CODE_COL + l * 64, tmem_base + HE_COL + l * 64 + k * 8,
+                        umma_ts_e(tmem_base + CODE_COL + l * 64, tmem_base + HE_COL + l * 64 + k * 8,
                                 umma_desc(sm_u + OFF_ML + (k >> 2) * 8192 + (k & 3) * 32), id64, k != 0);
                 }
-                umma_commit(BAR(BAR_RING_EMPTY + slot));
+                umma_commit_e(BAR(BAR_RING_EMPTY + slot));
                 ++g;
                 // ---- chunks 1..nch: [M1 block c | Wn2 K-slice c]
                 for (int c = 0; c < P.nch; ++c, ++g) {
@@ -323,26 +328,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
                                                              // runs this thread's MMAs in order, behind the Wn2 slice that read it)
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
+                            umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
                                     umma_desc(ring + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
-                        umma_commit(BAR(BAR_MMA_DONE + l));
+                        umma_commit_e(BAR(BAR_MMA_DONE + l));
                     }
                     for (int l = 0; l < nl; ++l) {
                         wait_epi(l);                         // the block's hidden units are in the accumulator's columns as fp16
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            umma_ts(tmem_base + CODE_COL + l * 64, tmem_base + ACC_COL + l * 128 + k * 8,
+                            umma_ts_e(tmem_base + CODE_COL + l * 64, tmem_base + ACC_COL + l * 128 + k * 8,
                                     umma_desc(ring + 32768 + (k >> 2) * 8192 + (k & 3) * 32), id64, 1);
                     }
-                    umma_commit(BAR(BAR_RING_EMPTY + slot));
+                    umma_commit_e(BAR(BAR_RING_EMPTY + slot));
                 }
-                for (int l = 0; l < nl; ++l) umma_commit(BAR(BAR_MMA_DONE + l));     // code accumulators complete
+                for (int l = 0; l < nl; ++l) umma_commit_e(BAR(BAR_MMA_DONE + l));     // code accumulators complete
                 for (int l = 0; l < nl; ++l) {               // cosine scores against the centres
                     wait_epi(l);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8, umma_desc(sm_u + OFF_CEN + k * 32), id32, k != 0);
-                    umma_commit(BAR(BAR_MMA_DONE + l));
+                        umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8, umma_desc(sm_u + OFF_CEN + k * 32), id32, k != 0);
+                    umma_commit_e(BAR(BAR_MMA_DONE + l));
                 }
             }
         }
