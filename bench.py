@@ -197,8 +197,11 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(precision):
-    return {"workload": "SSC voxel-grid query 256x256x32 @0.2m (51.2 m), DINO ViT-B/8 map 256x384x1280, "
+def workload_config(precision, binned=False):
+    return {"output_layout": ("sigma + frustum mask in the caller's order; 64-d feature rows in texel-bin order + perm[] (row r belongs "
+                              "to point perm[r]) -- the layout the fused SSC head (sd_ssc_head) consumes; `other_layout` has the "
+                              "caller-order variant" if binned else "everything in the caller's order"),
+            "workload": "SSC voxel-grid query 256x256x32 @0.2m (51.2 m), DINO ViT-B/8 map 256x384x1280, "
                         "MLP 295->128->65, outputs sigma+64-d features+mask",
             "path": ("texel sort + projected-map tile kernel (tcgen05 interpolation from TMA tiles)" if precision == "fp16"
                      else "fp32 CUDA-core parity path"),
@@ -260,6 +263,9 @@ def main():
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per_frame / fp32 / strong-scaling objects")
     ap.add_argument("--no-graph", action="store_true", help="time direct library calls instead of CUDA-graph replays")
+    ap.add_argument("--layout", default="binned", choices=["binned", "caller"],
+                    help="fp16 value step: 64-d rows in texel-bin order + perm (sd_query_points_binned, what the fused SSC head "
+                         "consumes) or scattered to the caller's order (sd_query_points); the other one is reported beside it")
     args = ap.parse_args()
     # a run that takes absurdly long dumps its Python stacks and exits instead of hanging its caller (seconds;
     # SD_BENCH_WATCHDOG=0 switches it off)
@@ -344,6 +350,11 @@ def main():
     small = [torch.empty(N * 5, dtype=torch.uint8, device=dev) for _ in range(NB)]
     outs = [dict(sigma=small[i][:N * 4].view(torch.float32), invalid_features=small[i][N * 4:],
                  dino=torch.empty((N, D_OUT - 1), device=dev)) for i in range(NB)]
+    binned = f16 and args.layout == "binned"
+    perm_bufs = [torch.empty((N,), dtype=torch.int32, device=dev) for _ in range(NB)] if f16 else None
+    # the same buffers seen as the outputs of sd_query_points_binned: rows of `dino` in texel-bin order + the permutation
+    outs_b = [dict(sigma=outs[i]["sigma"], invalid_features=outs[i]["invalid_features"], dino_binned=outs[i]["dino"],
+                   perm=perm_bufs[i]) for i in range(NB)] if f16 else None
     gathered = [torch.empty((world, N * 5), dtype=torch.uint8, device=dev) for _ in range(NB)] if world > 1 else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     # All-gather of the small outputs.  Preferred: every rank WRITES its shard into its peers' buffers over NVLink with
@@ -368,7 +379,13 @@ def main():
     # the timed region give the kernel's own duration for the roofline
     k_events = []
     # the timed steps replay a CUDA graph of the query (one launch instead of seven per step), one graph per output buffer
-    graphs = [ops.QueryGraph(scene, mlp, pts, outs[i]) for i in range(NB)] if f16 and not args.no_graph else None
+    def make_graphs(bin_layout):
+        if not f16 or args.no_graph:
+            return None
+        return [ops.QueryGraph(scene, mlp, pts, outs_b[i] if bin_layout else outs[i], binned_out=bin_layout) for i in range(NB)]
+
+    graphs = make_graphs(binned)
+    mode = {"binned": binned}
 
     def step(timed=False):
         b = state["i"] % NB
@@ -382,6 +399,8 @@ def main():
             k_events.append((ka, kb))
         if graphs is not None and not timed:
             graphs[b].replay()
+        elif mode["binned"]:
+            ops.query_points_binned(scene, mlp, pts, out=outs_b[b])
         else:
             ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[b])
         if world > 1:
@@ -450,18 +469,46 @@ def main():
     # ---- the same query with the texel sort reused (fixed grid and cameras, new feature map every frame: what the SSC
     #      evaluation loop does).  Reported beside `value`, which always includes the sort. -----------------------------
     sorted_reuse = None
+    other_layout = None
     if f16:
-        ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[0])
+        def reuse_call():
+            if binned:
+                ops.query_points_binned(scene, mlp, pts, out=outs_b[0], reuse_sorted=True)
+            else:
+                ops.query_points_sorted(scene, mlp, pts, outs[0])
+        step(timed=False) if graphs is None else (ops.query_points_binned(scene, mlp, pts, out=outs_b[0]) if binned
+                                                  else ops.query_points(scene, mlp, pts, want_rgb=False, out=outs[0]))
         for _ in range(3):
-            ops.query_points_sorted(scene, mlp, pts, outs[0])
+            reuse_call()
         fence()
         e0.record()
         for _ in range(args.steps):
-            ops.query_points_sorted(scene, mlp, pts, outs[0])
+            reuse_call()
         e1.record(); fence()
         sr_ms = e0.elapsed_time(e1) / args.steps
         sorted_reuse = {"value": world * N / (sr_ms * 1e-3), "unit": "voxels/s", "ms_per_step": sr_ms,
-                        "note": "sd_query_points_sorted: tile kernel only, the sort of the (unchanged) points is reused"}
+                        "note": "tile kernel only, the sort of the (unchanged) points is reused "
+                                "(sd_query_points_binned(reuse_sorted) / sd_query_points_sorted)"}
+        # ---- the other output layout, same timing recipe (graph replays for the step, library events for the kernel) --
+        if world == 1 and not args.no_extras:
+            del graphs
+            mode["binned"] = not binned
+            graphs = make_graphs(not binned)
+            k_events.clear()
+            for _ in range(3):
+                step()
+            for _ in range(5):
+                step(timed=True)
+            fence()
+            ok_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in k_events]))
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record(); fence()
+            o_ms = e0.elapsed_time(e1) / args.steps
+            other_layout = {"layout": "binned" if not binned else "caller", "ms_per_step": o_ms, "value": N / (o_ms * 1e-3),
+                            "unit": "voxels/s", "kernel_ms": ok_ms}
+            mode["binned"] = binned
     del graphs
     torch.cuda.empty_cache()
 
@@ -544,7 +591,7 @@ def main():
         t_kernel = kernel_ms * 1e-3 if f16 else ms_step * 1e-3
         hbm_ach = algo_bytes / t_kernel / 1e9
         tc_ach = N * FLOP_PER_POINT / t_kernel / 1e12
-        tr = measured_traffic(dom)
+        tr = measured_traffic(dom + ("_binned" if f16 and binned else ""))
         traffic = tr[0] if tr else None
         roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_ach / pk["hbm"],
                     "traffic": traffic,
@@ -559,13 +606,19 @@ def main():
         # The tile kernel is bound by memory-side work (records in, 260 B/voxel out, map tiles through L2): its tensor
         # work is ~1/3 of the reference's 92 160 FLOP/voxel because the map is pre-projected once per encode, so the HBM
         # roof is the honest one; the tensor fraction (reference FLOPs over the same time) is reported beside it.
+        if f16:
+            roof_hbm["layout"] = ("binned: 64-d rows in texel-bin order by TMA tile stores + perm (sd_query_points_binned)" if binned
+                                  else "caller order: scattered 16-byte stores (sd_query_points)")
+            if other_layout is not None:       # the other output layout of the same kernel, same bytes, same recipe
+                other_layout["roofline_frac"] = algo_bytes / (other_layout["kernel_ms"] * 1e-3) / 1e9 / pk["hbm"]
+                other_layout["step_frac"] = algo_bytes / (other_layout["ms_per_step"] * 1e-3) / 1e9 / pk["hbm"]
         roof_hbm["kernel"] = roof_tc["kernel"] = dom
         roof_hbm["kernel_ms"] = roof_tc["kernel_ms"] = t_kernel * 1e3
         roof_tc["note"] = "reference-algorithm FLOPs (2*(295*128+128*65) per voxel) over the kernel time"
         line = {"metric": "ssc_voxel_query_throughput", "value": value, "unit": "voxels/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16" if f16 else "f32",
-                "data": "synthetic", "config": workload_config(args.precision),
+                "data": "synthetic", "config": workload_config(args.precision, binned),
                 "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12,
                         "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,
                         "api": "scenedino_b200.BTSNet.forward(xyz, only_density=True) (models/bts.py:476-595), fresh outputs and "
@@ -576,7 +629,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clk.summary(),
                 "all_gather": gather_how if world > 1 else None,
                 "roofline": roof_hbm, "roofline_hbm": roof_hbm, "roofline_tensor": roof_tc,
-                "featmap_pack_ms": pack_ms, "featmap_project_ms": project_ms, "sorted_reuse": sorted_reuse}
+                "featmap_pack_ms": pack_ms, "featmap_project_ms": project_ms, "sorted_reuse": sorted_reuse,
+                "other_layout": other_layout}
 
     # ---- one frame of the SSC evaluation: NEW map -> encode (pack + project) -> query of the fixed grid -> expansion +
     #      SSC head -> sigma + label on the host.  Through BTSNet.encode / BTSNet.forward(predict_segmentation=True). -----

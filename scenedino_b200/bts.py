@@ -340,11 +340,34 @@ class BTSNet(nn.Module):
             hf, wf = st["Hf"], st["Wf"]
             use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
                         and N >= 16 * ((hf + 5) // 7 + 1) * ((wf + 5) // 7 + 1))
+            # predict_segmentation with the fused head: the 64-d rows only feed sd_ssc_head, which takes a permutation --
+            # they stay in the tile kernel's own (texel-bin) order and leave the SM by TMA tile stores
+            # (sd_query_points_binned); nothing caller-visible changes, seg / sigma come back in the caller's order
+            head = self.downstream_head
+            fused = (predict_segmentation and head is not None and hasattr(head, "forward_reduced")
+                     and isinstance(getattr(self.encoder, "dim_reduction", None), MlpDimReduction))
+            binned = fused and use_proj and D == 64 and not self.materialize_dino_full
+            perm = torch.empty((n, N), dtype=torch.int32, device=dev) if binned else None
             for b in range(n):
                 sc = self._scene(st, b, self._projection(st, b, mlp) if use_proj else None)
                 need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(mlp), N)
                 skey = (b, xyz.data_ptr(), xyz._version, N, need, st.get("cam_sig")) if (self.static_query and use_proj and need) else None
                 kept = self._static_cache.get(skey) if skey else None
+                if binned and need:
+                    ws, mask = kept if kept is not None else (torch.empty((need,), dtype=torch.uint8, device=dev), None)
+                    _abi.check(lib.sd_query_points_binned(
+                        C.byref(sc), C.byref(mlp), _ptr(xyz[b]), N, _ptr(sigma[b]), _ptr(dino[b]), _ptr(perm[b]),
+                        _ptr(invf[b]), _ptr(ws), need, int(kept is not None), _stream()), "sd_query_points_binned")
+                    if kept is not None:
+                        invf[b].copy_(mask)
+                    elif skey:
+                        if len(self._static_cache) >= 8:
+                            self._static_cache.clear()
+                        self._static_cache[skey] = (ws, invf[b].clone())
+                    continue
+                if binned:          # (too few points for the sorted tile path: plain query, identity order)
+                    perm = None
+                    binned = False
                 if kept is not None:         # same points, same camera: the sort (and the frustum mask) of the first call
                     ws, mask = kept
                     _abi.check(lib.sd_query_points_sorted(
@@ -365,9 +388,6 @@ class BTSNet(nn.Module):
             invalid_features = invf.view(torch.bool)
 
         if predict_segmentation:  # bts.py:528-533, 584-592
-            head = self.downstream_head
-            fused = head is not None and hasattr(head, "forward_reduced") and isinstance(
-                getattr(self.encoder, "dim_reduction", None), MlpDimReduction)
             if self.materialize_dino_full or not fused:
                 with expand_precision(prec):      # the expansion runs in the precision of the query that feeds it
                     dino_full = self.encoder.expand_dim(dino)
@@ -377,7 +397,12 @@ class BTSNet(nn.Module):
             if head is not None:
                 # scenedino_b200.SemanticHead: expansion + STEGO head + cosine argmax + pseudo-label LUT in ONE kernel
                 # (sd_ssc_head) starting from the 64-d features; any other head module is called like the reference does
-                if fused and not self.one_hot_seg:
+                if fused and binned:            # rows in texel-bin order: one launch per scene, labels land at perm[r]
+                    seg8 = torch.empty((n, N), dtype=torch.uint8, device=dev)
+                    for b in range(n):
+                        head.forward_reduced(dino[b], self.encoder.dim_reduction, mode=prediction_mode, perm=perm[b], out=seg8[b])
+                    seg = seg8 if not self.one_hot_seg else torch.nn.functional.one_hot(seg8.to(torch.int64), self.gt_classes)
+                elif fused and not self.one_hot_seg:
                     seg = head.forward_reduced(dino, self.encoder.dim_reduction, mode=prediction_mode,
                                                out=torch.empty((n * N,), dtype=torch.uint8, device=dev)).view(n, N)
                 else:

@@ -86,3 +86,36 @@ def test_binned_errors_are_loud(golden):
     dscp = dsc.project(dmlp)
     with pytest.raises(SdError):
         few(dscp, dmlp, pts[:5].contiguous())
+
+
+def test_btsnet_forward_segmentation_takes_the_binned_path():
+    """BTSNet.forward(grid, predict_segmentation=True) (models/bts.py:584-592): with the fused head the 64-d rows stay in
+    texel-bin order between the query and sd_ssc_head (launches: 4 sort + tile kernel + head = 6, then tile + head = 2 on
+    the next frame of a static grid); labels / sigma equal the caller-order route (materialize_dino_full) wherever the
+    head's top-2 gap is clear -- here: bit for bit, both routes feed the head the same rows."""
+    import bench
+    import scenedino_b200 as sd
+    from scenedino_b200 import _abi
+    hold = {"map": dev(syn.make_feature_map(1, 256, 96, 320))}
+    net = bench.build_net(sd, torch, hold, DEV, "fp16")
+    imgs = dev(syn.make_images(2, 1))[None]
+    Kc = dev(syn.kitti360_K()[None])[None]
+    c2w = dev(np.eye(4, dtype=np.float32)[None])[None]
+    net.encode(imgs * 2 - 1, Kc, c2w, ids_encoder=[0], ids_render=[0], images_alt=imgs)
+    net.set_scale(0)
+    grid = dev(syn.ssc_voxel_grid()[::5].copy())[None]
+    net.static_query, net.one_hot_seg = True, False
+    with torch.no_grad():
+        net.materialize_dino_full = True
+        full, _, sig_a, seg_a = net(grid, predict_segmentation=True)
+        net._static_cache.clear()
+        net.materialize_dino_full = False
+        n0 = _abi.launch_count()
+        none, _, sig_b, seg_b = net(grid, predict_segmentation=True)
+        n1 = _abi.launch_count()
+        _, _, sig_c, seg_c = net(grid, predict_segmentation=True)          # static grid: the sort is reused
+        n2 = _abi.launch_count()
+    assert none is None and full is not None
+    assert n1 - n0 == 6 and n2 - n1 == 2, (n1 - n0, n2 - n1)
+    assert torch.equal(sig_a, sig_b) and torch.equal(sig_b, sig_c)
+    assert torch.equal(seg_a.reshape(-1).to(torch.int64), seg_b.reshape(-1).to(torch.int64)) and torch.equal(seg_b, seg_c)
