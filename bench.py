@@ -263,6 +263,8 @@ def main():
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip per_frame / fp32 / strong-scaling objects")
     ap.add_argument("--no-graph", action="store_true", help="time direct library calls instead of CUDA-graph replays")
+    ap.add_argument("--e2e-input", default="device-grid", choices=["device-grid", "upload"],
+                    help="e2e step input: frame spec (128 B) + voxel grid made on the device, or the 25 MB of points uploaded")
     ap.add_argument("--layout", default="binned", choices=["binned", "caller"],
                     help="fp16 value step: 64-d rows in texel-bin order + perm (sd_query_points_binned, what the fused SSC head "
                          "consumes) or scattered to the caller's order (sd_query_points); the other one is reported beside it")
@@ -536,14 +538,31 @@ def main():
     ev_out = [torch.cuda.Event() for _ in range(NB)]
     e2e_state = {"i": 0}
 
+    # The step's inputs.  "device-grid" (default): what changes from frame to frame in the SSC loop is the camera, not the
+    # grid -- the frame's spec (lidar -> camera matrix, origin, voxel size: 128 B) goes host -> device from pinned memory and
+    # the 2 097 152 voxel centres are made on the device (sd_gen_voxel_grid, bit-identical to the host construction of
+    # sscbench/evaluate_model_sscbench.py:270-278).  "upload": the 25 MB of points travel over PCIe every step (round 1's
+    # e2e; eight ranks doing that saturate the host's memory system: 30 % scaling efficiency at N = 8).
+    T_v2c = syn.velo_to_cam()
+    spec_host = torch.zeros(16, dtype=torch.float64).pin_memory()
+    spec_host[:12] = torch.from_numpy(np.ascontiguousarray(T_v2c[:3, :4]).reshape(-1))
+    spec_host[12:15] = torch.tensor([0.0, -25.6, -2.0], dtype=torch.float64)
+    spec_host[15] = 0.2
+    spec_dev = torch.empty(16, dtype=torch.float64, device=dev)
+    upload = args.e2e_input == "upload"
+
     def e2e_step():
         b = e2e_state["i"] % NB
         e2e_state["i"] += 1
-        with torch.cuda.stream(h2d):
-            h2d.wait_event(ev_k[b])                       # the kernel that last read pts_in[b] is done
-            pts_in[b][0].copy_(pts_host, non_blocking=True)
-            ev_in[b].record()
-        main_s.wait_event(ev_in[b])
+        if upload:
+            with torch.cuda.stream(h2d):
+                h2d.wait_event(ev_k[b])                   # the kernel that last read pts_in[b] is done
+                pts_in[b][0].copy_(pts_host, non_blocking=True)
+                ev_in[b].record()
+            main_s.wait_event(ev_in[b])
+        else:
+            spec_dev.copy_(spec_host, non_blocking=True)
+            ops.gen_voxel_grid(T_v2c, dims=GRID, out=pts_in[b][0])
         main_s.wait_event(ev_out[b])                      # the read-back of the step that last used res_dev[b] is done
         with torch.no_grad():
             _, invalid, sigma, _, _ = net(pts_in[b], only_density=True)
@@ -619,11 +638,14 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16" if f16 else "f32",
                 "data": "synthetic", "config": workload_config(args.precision, binned),
-                "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12,
+                "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": N * 12 if upload else 128,
+                        "input": ("xyz [N,3] fp32 uploaded from pinned host memory every step" if upload else
+                                  "frame spec (lidar->camera matrix, origin, voxel size: 128 B) from pinned host memory; the voxel "
+                                  "centres are generated on the device (sd_gen_voxel_grid, bit-identical to the host grid)"),
                         "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,
                         "api": "scenedino_b200.BTSNet.forward(xyz, only_density=True) (models/bts.py:476-595), fresh outputs and "
                                "workspace per call, full texel sort per call",
-                        "note": "every step: pinned xyz host->device, BTSNet.forward, density grid + frustum mask device->host "
+                        "note": "every step: inputs host->device (see `input`), BTSNet.forward, density grid + frustum mask device->host "
                                 "(the 64-d features stay on the device for expand_dim / the SSC head, as in the reference); "
                                 "copies and kernels of consecutive steps overlap on three streams"},
                 "gpu_launches": int(launches), "clocks": clk.summary(),

@@ -281,6 +281,16 @@ int sd_gen_rays(const float *c2w, const float *proj, const float *frame_ids, int
                 float z_near, float z_far, int norm_dir, float x_shift, float y_shift, float *rays,
                 void *stream);
 
+/* Voxel centres of an SSC grid in the camera frame: what sscbench/evaluate_model_sscbench.py:270-278 builds on the host
+ * once (generate_point_grid, sscbench/point_utils.py:46-67) and uploads -- 25 MB for 256 x 256 x 32 -- made on the device
+ * instead.  origin [3] (voxel (0,0,0) corner, lidar frame) and T [3][4] (row-major float64 lidar -> camera, the
+ * calibration's T_velo_2_cam) are HOST pointers read before the call returns.  xyz [(x1-x0)*ny*nz, 3] fp32, flattened
+ * 'ij' order (x slowest); [x0, x1) selects a slab of x indices (voxel-slab sharding).  centre = origin + size*idx + size/2
+ * in fp32 (TSDFVolume.vox2world, sscbench/fusion.py:205-219), then the rigid transform as a float64 dot product rounded
+ * once (rigid_transform, fusion.py:407-411): bit-identical to scenedino_b200.synthetic.ssc_voxel_grid. */
+int sd_gen_voxel_grid(const float *origin, float voxel_size, int nx, int ny, int nz, int x0, int x1,
+                      const double *T, float *xyz, void *stream);
+
 /* ---- diagnostics (timing experiments; not part of the data path) ----------------------------------------------------
  * With the environment variable SD_TC_DEBUG & 8192 set when the library is loaded, CTA 0 of the tensor-core kernels
  * records clock64 stamps per warp role and tile; these calls copy the trace of the last launch to HOST buffers:

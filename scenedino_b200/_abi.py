@@ -89,6 +89,7 @@ PROTOTYPES = {
                             C.POINTER(SdRenderOut), _P, _SZ, _P]),
     "sd_expand_dim": (_I, [_ML, _P, _LL, _P, _P]),
     "sd_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _F, _P, _P]),
+    "sd_gen_voxel_grid": (_I, [_P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
     "sd_ssc_head_pack_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
     "sd_ssc_head_pack": (_I, [_P] * 12 + [_I] * 6 + [_P, _P]),
     "sd_ssc_head": (_I, [_P, _I, _I, _P, _P, _LL, _P, _P, _P, _P]),

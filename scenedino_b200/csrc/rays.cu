@@ -74,9 +74,53 @@ __global__ void __launch_bounds__(RAYS_PER_BLOCK) gen_rays_kernel(RayGrid g, con
     for (int k = (nv4 << 2) + threadIdx.x; k < nfl; k += RAYS_PER_BLOCK) dst[k] = s_ray[k];
 }
 
+// ---- voxel centres of an SSC grid in the camera frame (sscbench/point_utils.py:46-67 generate_point_grid) ---------------
+// centre = origin + size * idx + size * 0.5 per axis (TSDFVolume.vox2world, sscbench/fusion.py:205-219; evaluated in fp32,
+// left to right, as scenedino_b200.synthetic.ssc_voxel_grid does), then rigid_transform (fusion.py:407-411) with the
+// calibration's float64 matrix: a double-precision dot product rounded once to fp32.  Flattened 'ij' order (x slowest).
+struct VoxGrid {
+    float ox, oy, oz, vs;
+    int ny, nz, x0;
+    long long n;
+    double T[12];
+};
+
+__global__ void __launch_bounds__(256) gen_voxel_grid_kernel(VoxGrid g, float *__restrict__ xyz) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= g.n) return;
+    const int iz = (int)(i % g.nz);
+    const long long t = i / g.nz;
+    const int iy = (int)(t % g.ny), ix = (int)(t / g.ny) + g.x0;
+    const float half = __fmul_rn(g.vs, 0.5f);
+    const float px = __fadd_rn(__fadd_rn(g.ox, __fmul_rn(g.vs, (float)ix)), half);
+    const float py = __fadd_rn(__fadd_rn(g.oy, __fmul_rn(g.vs, (float)iy)), half);
+    const float pz = __fadd_rn(__fadd_rn(g.oz, __fmul_rn(g.vs, (float)iz)), half);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double v = fma(g.T[4 * r], (double)px, fma(g.T[4 * r + 1], (double)py, fma(g.T[4 * r + 2], (double)pz, g.T[4 * r + 3])));
+        xyz[3 * i + r] = (float)v;
+    }
+}
+
 }  // namespace sd
 
 using namespace sd;
+
+extern "C" int sd_gen_voxel_grid(const float *origin, float voxel_size, int nx, int ny, int nz, int x0, int x1,
+                                 const double *T_host, float *xyz, void *stream) {
+    SD_REQUIRE(origin && T_host, "sd_gen_voxel_grid: origin / T are host pointers and must not be NULL");
+    SD_REQUIRE(nx > 0 && ny > 0 && nz > 0 && 0 <= x0 && x0 <= x1 && x1 <= nx, "sd_gen_voxel_grid: bad grid (%d x %d x %d, slab %d..%d)", nx, ny, nz, x0, x1);
+    VoxGrid g;
+    g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2]; g.vs = voxel_size;
+    g.ny = ny; g.nz = nz; g.x0 = x0;
+    g.n = (long long)(x1 - x0) * ny * nz;
+    for (int i = 0; i < 12; ++i) g.T[i] = T_host[i];
+    if (g.n == 0) return SD_OK;
+    SD_REQUIRE(xyz, "sd_gen_voxel_grid: null output");
+    gen_voxel_grid_kernel<<<(unsigned)((g.n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, xyz);
+    SD_LAUNCH_OK("gen_voxel_grid_kernel");
+    return SD_OK;
+}
 
 extern "C" int sd_gen_rays(const float *c2w, const float *proj, const float *frame_ids, int V, int H, int W,
                            float z_near, float z_far, int norm_dir, float x_shift, float y_shift, float *rays,

@@ -217,6 +217,22 @@ def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=N
     return out
 
 
+def gen_voxel_grid(T, dims=(256, 256, 32), voxel_size=0.2, origin=(0.0, -25.6, -2.0), x_range=None, device="cuda", out=None):
+    """Voxel centres of an SSC grid in the camera frame, made on the device (sd_gen_voxel_grid): [N,3] fp32, bit-identical
+    to ``synthetic.ssc_voxel_grid``.  ``T``: [3..4, 4] float64 lidar -> camera (host array)."""
+    import numpy as np
+    x0, x1 = (0, dims[0]) if x_range is None else x_range
+    Th = np.ascontiguousarray(np.asarray(T, np.float64)[:3, :4])
+    org = np.ascontiguousarray(np.asarray(origin, np.float32))
+    n = (x1 - x0) * dims[1] * dims[2]
+    if out is None:
+        out = torch.empty((n, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _abi.check(_abi.lib().sd_gen_voxel_grid(org.ctypes.data, float(voxel_size), dims[0], dims[1], dims[2], x0, x1,
+                                                Th.ctypes.data, _ptr(out), _stream()), "sd_gen_voxel_grid")
+    return out
+
+
 @device_guard
 def expand_dim(mlp: Mlp, f, precision: int = FP32):
     """MlpDimReduction.transform_expand; ``precision=F16`` takes the tensor-core kernel (64 -> 128 -> k*128 heads)."""
