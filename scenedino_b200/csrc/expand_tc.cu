@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
             for (int s = 0; s < nsteps; ++s, ++g) {
                 const int slot = (int)(g % NW2);
                 const int c = s < P.nch ? s : s - P.nch;
-                mbar_wait(BAR(BAR_W_EMPTY + slot), (uint32_t)(((g / NW2) & 1) ^ 1));
+                mbar_wait_warp(BAR(BAR_W_EMPTY + slot), (uint32_t)(((g / NW2) & 1) ^ 1));
                 if (elect_one()) {
                     mbar_expect_tx(BAR(BAR_W_FULL + slot), W2_BYTES);
                     const unsigned char *src = P.w2_img + (size_t)c * W2_BYTES;
@@ -251,24 +251,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
             }
     } else {
         {
-            if (!P.head2) mbar_wait(BAR(BAR_WLOAD), 0);
+            if (!P.head2) mbar_wait_warp(BAR(BAR_WLOAD), 0);
             const uint32_t idesc = umma_idesc(TM, 128);
             long long g = 0;
             for (long long j = 0; j < my_tiles; ++j) {
                 if (!P.head2) {
-                    mbar_wait(BAR(BAR_A_FULL), (uint32_t)(j & 1));
+                    mbar_wait_warp(BAR(BAR_A_FULL), (uint32_t)(j & 1));
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_e(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
                     umma_commit_e(BAR(BAR_D1_FULL));
                 }
-                mbar_wait(BAR(BAR_H_FULL), (uint32_t)(j & 1));
+                mbar_wait_warp(BAR(BAR_H_FULL), (uint32_t)(j & 1));
                 tc_fence_after();
                 for (int s = 0; s < nsteps; ++s, ++g) {
                     const int slot = (int)(g % NW2), b = (int)(g & 1);
-                    mbar_wait(BAR(BAR_W_FULL + slot), (uint32_t)((g / NW2) & 1));
-                    mbar_wait(BAR(BAR_D2_FREE + b), (uint32_t)(((g >> 1) & 1) ^ 1));
+                    mbar_wait_warp(BAR(BAR_W_FULL + slot), (uint32_t)((g / NW2) & 1));
+                    mbar_wait_warp(BAR(BAR_D2_FREE + b), (uint32_t)(((g >> 1) & 1) ^ 1));
                     tc_fence_after();
                     const uint32_t w2 = sm_u + OFF_W2 + slot * W2_BYTES;
 #pragma unroll

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         // diverges, the tcgen05 instructions come out back to back).  Layer 2 has a warp of its own (WARP_MMA2): every
         // barrier test is a round trip through the load/store unit and one warp doing all of them was the critical path.
         {
-            mbar_wait(BAR(BAR_WLOAD), 0);
+            mbar_wait_warp(BAR(BAR_WLOAD), 0);
             const uint32_t idesc_k = umma_idesc(TM, 128), idesc_mn = idesc_k | UMMA_B_MN_MAJOR;
             int e = 0, eb = 0;                       // ring positions: weight chunks, box chunks
             uint32_t ph = 0, phb = 0;
@@ -378,20 +378,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             for (;; ++j) {
                 // The tile's first weight chunk carries its chunk count (0: no more tiles) and stands for the code operand
                 // too: one barrier test where there were three.
-                mbar_wait(BAR(BAR_FULL_A + e), ph);
+                mbar_wait_warp(BAR(BAR_FULL_A + e), ph);
                 const int m = __shfl_sync(0xffffffffu, s_minfo[e], 0);
                 // the accumulator (its first 64 columns held the hidden tile of tile j-2) is free once layer 2 of j-2 has run.
                 // (Also before the closing arrival below: nobody may complete two phases of a barrier ahead of its waiter.)
-                mbar_wait(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
+                mbar_wait_warp(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
                 if (m == 0) break;
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
                 if ((P.dbg & 8192) && blockIdx.x < 4 && j < 500 && lane == 0) { g_tiles[(blockIdx.x * 512 + j) * 2] = clock64(); g_tiles[(blockIdx.x * 512 + j) * 2 + 1] = m; }
                 for (int i = 0; i < m; ++i) {
-                    if (i > 0) mbar_wait(BAR(BAR_FULL_A + e), ph);
+                    if (i > 0) mbar_wait_warp(BAR(BAR_FULL_A + e), ph);
                     if (i == 0) TB_TRACE(1, j, 1);
-                    mbar_wait(BAR(BAR_FULL_B + eb), phb);
+                    mbar_wait_warp(BAR(BAR_FULL_B + eb), phb);
                     tc_fence_after();
                     if (i == 0) TB_TRACE(1, j, 2);
 #pragma unroll
@@ -423,14 +423,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     } else if (warp == WARP_MMA2) {
         // =================================== MMA ISSUER, LAYER 2 ======================================
         {   // (whole warp, elected forms: see the layer-1 issuer)
-            mbar_wait(BAR(BAR_WLOAD), 0);
+            mbar_wait_warp(BAR(BAR_WLOAD), 0);
             const uint32_t idesc2 = umma_idesc(TM, P.n2);
             for (long long j = 0;; ++j) {
                 const int b = (int)(j & 1);
-                mbar_wait(BAR(BAR_H + b), (uint32_t)((j >> 1) & 1));
+                mbar_wait_warp(BAR(BAR_H + b), (uint32_t)((j >> 1) & 1));
                 // (the accumulator drained -- also before the closing arrival: nobody may complete two phases of a barrier
                 // ahead of its waiter)
-                mbar_wait(BAR(BAR_D2_EMPTY + b), (uint32_t)(((j >> 1) & 1) ^ 1));
+                mbar_wait_warp(BAR(BAR_D2_EMPTY + b), (uint32_t)(((j >> 1) & 1) ^ 1));
                 const int nt = __shfl_sync(0xffffffffu, *s_ntiles, 0);
                 if (j >= nt) { mbar_arrive_e(BAR(BAR_D2 + b)); break; }
                 tc_fence_after();
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             ti.c0m = 0; ti.b01 = 0; ti.b23 = 0; ti.rows = 0;
             long long v = -1;                                       // position in claim order
             if (base < P.n_tiles) {
-                if (!tab_ready) { mbar_wait(BAR(BAR_TAB + (int)(k & 1)), (uint32_t)((k >> 1) & 1)); tab_ready = true; }
+                if (!tab_ready) { mbar_wait_warp(BAR(BAR_TAB + (int)(k & 1)), (uint32_t)((k >> 1) & 1)); tab_ready = true; }
                 const TileInfo tl = s_tab[(int)(k & 1) * BATCH + bi];      // (broadcasts: the compiler must SEE that the
                 ti.c0m = __shfl_sync(0xffffffffu, tl.c0m, 0);               // control flow below is uniform, or every copy gets
                 ti.b01 = __shfl_sync(0xffffffffu, tl.b01, 0);               // its ELECT loop back)
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 ti.rows = __shfl_sync(0xffffffffu, tl.rows, 0);
                 v = base + bi;
             }
-            mbar_wait(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
+            mbar_wait_warp(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
             if (lane == 0) {
                 s_hdr[r].c0m = ti.c0m; s_hdr[r].b01 = ti.b01; s_hdr[r].b23 = ti.b23; s_hdr[r].rows = ti.rows;
                 reinterpret_cast<volatile int *>(sm + OFF_TIDX)[r] = (int)(P.n_tiles - 1 - v);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 if (i >= 4) b = __shfl_sync(0xffffffffu, __ldg(P.cbin + c0 + i), 0);   // a tile that touches more than four bins (rare)
                 const int by = (int)(b / (unsigned)P.nbx), bx = (int)(b - (unsigned)by * (unsigned)P.nbx);
                 if (i == 0) TB_TRACE(6, j, 0);
-                mbar_wait(BAR(BAR_EMPTY_B + e), ph ^ 1);
+                mbar_wait_warp(BAR(BAR_EMPTY_B + e), ph ^ 1);
                 if (i == 0) TB_TRACE(6, j, 1);
                 if (SD_TB_ABLATE & 4) {
                     mbar_arrive_e(BAR(BAR_FULL_B + e));

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
         for (long long j = 0; j < my_tiles; ++j) {
             const long long tile = first + j * stride;
             const int s = (int)(j & 1);
-            mbar_wait(BAR(BAR_EMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
+            mbar_wait_warp(BAR(BAR_EMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
             if (elect_one()) {
                 mbar_expect_tx(BAR(BAR_FULL + s), A_BYTES);
                 for (int c = 0; c < 4; ++c)
@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
         }
     } else {
         {
-            mbar_wait(BAR(BAR_WLOAD), 0);
+            mbar_wait_warp(BAR(BAR_WLOAD), 0);
             const uint32_t idesc = umma_idesc(TM, 128);
             for (long long j = 0; j < my_tiles; ++j) {
                 const int s = (int)(j & 1);
-                mbar_wait(BAR(BAR_FULL + s), (uint32_t)((j >> 1) & 1));
-                mbar_wait(BAR(BAR_DEMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
+                mbar_wait_warp(BAR(BAR_FULL + s), (uint32_t)((j >> 1) & 1));
+                mbar_wait_warp(BAR(BAR_DEMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 16; ++k)

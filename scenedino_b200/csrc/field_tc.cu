@@ -493,10 +493,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
         // `if (lane == 0)` every tcgen05 instruction was wrapped in an ELECT loop, ~90 cycles each).  In render mode on a projected scene the whole warp (its TMEM lanes are 0..31 = the rays
         // of a tile) also reads the per-ray sums the composite MMAs leave in TMEM and writes them out.
         {
-            mbar_wait(BAR(BAR_WLOAD), 0);
+            mbar_wait_warp(BAR(BAR_WLOAD), 0);
             const uint32_t idesc1 = umma_idesc(TM, 128), idesc2 = umma_idesc(TM, P.n2);
             auto layer2 = [&](long long jj) {
-                mbar_wait(BAR(BAR_H), (uint32_t)(jj & 1));
+                mbar_wait_warp(BAR(BAR_H), (uint32_t)(jj & 1));
                 tc_fence_after();
                 SD_TRACE(1, jj + 1, 6);
 #pragma unroll
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             const uint32_t idesc3f = umma_idesc(TM, P.cmma == 2 ? 128 : 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
             const uint32_t off_v3 = P.cmma == 2 ? OFF_V : OFF_B3;
             auto composite = [&](long long jj) {   // per-ray sums of tile jj: Wt [128 x 128 rows] . V [128 rows x (64 | 128 | 16)]
-                mbar_wait(BAR(BAR_B3), (uint32_t)(jj & 1));
+                mbar_wait_warp(BAR(BAR_B3), (uint32_t)(jj & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             auto cm_output = [&](long long jj) {
                 const float *s_bo = reinterpret_cast<const float *>(sm + OFF_PART);
                 const int D = P.D;
-                mbar_wait(BAR(BAR_D3), (uint32_t)(jj & 1));
+                mbar_wait_warp(BAR(BAR_D3), (uint32_t)(jj & 1));
                 tc_fence_after();
                 uint32_t xr[16], fr[64];
                 const int lane_ = lane;
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                     const int ngath = field ? P.nch - 1 : P.nch;
                     for (int c = 0; c < P.nch; ++c) {
                         if (c == 0 || c == ngath) {
-                            mbar_wait(BAR(BAR_FULL + c), (uint32_t)(j & 1));
+                            mbar_wait_warp(BAR(BAR_FULL + c), (uint32_t)(j & 1));
                             tc_fence_after();
                             SD_TRACE(1, j, c == 0 ? 0 : 4);
                         }

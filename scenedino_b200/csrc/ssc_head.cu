@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
         for (long long p = 0; p < n_pairs; ++p)
             for (int s = 0; s < nsteps; ++s, ++g) {
                 const int slot = (int)(g % NSLOT);
-                mbar_wait(BAR(BAR_RING_EMPTY + slot), (uint32_t)(((g / NSLOT) & 1) ^ 1));
+                mbar_wait_warp(BAR(BAR_RING_EMPTY + slot), (uint32_t)(((g / NSLOT) & 1) ^ 1));
                 if (elect_one()) {
                     mbar_expect_tx(BAR(BAR_RING_FULL + slot), CHUNK_BYTES);
                     bulk_g2s(sm_u + OFF_RING + slot * CHUNK_BYTES, P.blob + (size_t)s * CHUNK_BYTES, CHUNK_BYTES, BAR(BAR_RING_FULL + slot));
@@ -284,17 +284,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
         // tcgen05 instruction was wrapped in an ELECT loop, ~90 cycles each -- ~240 MMAs per pair of tiles: the issue rate,
         // not the tensor pipe, bounded this kernel).
         {
-            mbar_wait(BAR(BAR_RES), 0);
+            mbar_wait_warp(BAR(BAR_RES), 0);
             const uint32_t id128 = umma_idesc(TM, 128), id64 = umma_idesc(TM, 64), id32 = umma_idesc(TM, 32);
             uint32_t pe[2] = {0u, 0u};                       // phase of EPI_DONE[l] to wait for next
-            auto wait_epi = [&](int l) { mbar_wait(BAR(BAR_EPI_DONE + l), pe[l]); pe[l] ^= 1; tc_fence_after(); };
+            auto wait_epi = [&](int l) { mbar_wait_warp(BAR(BAR_EPI_DONE + l), pe[l]); pe[l] ^= 1; tc_fence_after(); };
             long long g = 0;
             for (long long p = 0; p < n_pairs; ++p) {
                 const int nl = (2 * p + 1 < my_tiles) ? 2 : 1;
                 // ---- chunk 0: [W1e | G]
                 int slot = (int)(g % NSLOT);
                 uint32_t ring = sm_u + OFF_RING + slot * CHUNK_BYTES;
-                mbar_wait(BAR(BAR_RING_FULL + slot), (uint32_t)((g / NSLOT) & 1));
+                mbar_wait_warp(BAR(BAR_RING_FULL + slot), (uint32_t)((g / NSLOT) & 1));
                 tc_fence_after();
                 for (int l = 0; l < nl; ++l) {               // layer 1 of the expansion: A from shared memory
                     wait_epi(l);                             // operand built, accumulator drained
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
                 for (int c = 0; c < P.nch; ++c, ++g) {
                     slot = (int)(g % NSLOT);
                     ring = sm_u + OFF_RING + slot * CHUNK_BYTES;
-                    mbar_wait(BAR(BAR_RING_FULL + slot), (uint32_t)((g / NSLOT) & 1));
+                    mbar_wait_warp(BAR(BAR_RING_FULL + slot), (uint32_t)((g / NSLOT) & 1));
                     tc_fence_after();
                     for (int l = 0; l < nl; ++l) {
                         if (c == 0) wait_epi(l);             // |v| taken: the accumulator is free (later blocks: the tensor pipe

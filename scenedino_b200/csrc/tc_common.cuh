@@ -66,6 +66,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 #endif
 }
+// The wait of a role that a whole warp runs in lockstep (elected issue forms below): every lane polls, then the warp is
+// reconverged EXPLICITLY.  Lanes can leave the polling loop in different iterations; a uniform-datapath instruction
+// (tcgen05.mma / commit, TMA) reached by two halves of a diverged warp would be issued twice -- a commit that arrives
+// twice skews the barrier's phase and the pipeline deadlocks many tiles later (seen once per few thousand launches, under
+// the timing of a second GPU's peer traffic only).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    mbar_wait(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
