@@ -44,8 +44,11 @@ typedef enum sd_dtype { SD_F32 = 0, SD_F16 = 1 } sd_dtype;
  * SD_MLP_F16_TC: 16-bit operands on tcgen05 tensor cores (kind::f16) with fp32 accumulation in TMEM
  * (reduced-precision mode, rel 2e-2).  The operands are IEEE half, the dtype the reference itself runs
  * the head in under torch autocast (training/base_trainer.py:223): same tensor-core rate as bf16, 8x
- * smaller rounding error -- single-pass bf16 sits AT the 2e-2 bar for a 295-term contraction. */
-typedef enum sd_precision { SD_MLP_FP32 = 0, SD_MLP_F16_TC = 1 } sd_precision;
+ * smaller rounding error -- single-pass bf16 sits AT the 2e-2 bar for a 295-term contraction.
+ * SD_MLP_F32_TC: the rel-1e-4 bar ON the tensor cores (point queries on a scene projected by sd_field_project_x3): every
+ * operand is an fp16 pair hi + lo (~22 significant bits), every product the three kind::f16 products hi.hi + lo.hi + hi.lo,
+ * fp32 accumulation in TMEM, fp32 biases / softplus in the epilogues.  Other entry points treat it like SD_MLP_FP32. */
+typedef enum sd_precision { SD_MLP_FP32 = 0, SD_MLP_F16_TC = 1, SD_MLP_F32_TC = 2 } sd_precision;
 
 /* What BTSNet.encode stashes for ONE batch element (models/bts.py:246-257), with the feature map
  * re-laid out channels-last by sd_featmap_pack. */
@@ -68,6 +71,7 @@ typedef struct sd_scene {
     const float *empty_feature; /* [C] or NULL                                             */
     const void  *feat_proj;     /* optional: blob written by sd_field_project for the head these queries
                                    will use (NULL = absent); enables the projected-map tile kernel */
+    const void  *feat_proj_x3;  /* optional: blob written by sd_field_project_x3 (SD_MLP_F32_TC queries) */
 } sd_scene;
 
 /* ResnetFC head with n_blocks = 0 (models/prediction_heads/resnetfc.py:90-96,162-199).
@@ -117,6 +121,12 @@ int    sd_mlp_pack(const float *w_in, const float *b_in, const float *w_out, con
  * tied to `mlp` (and to empty_feature when learn_empty); `proj` must be 1024-byte aligned. */
 size_t sd_field_project_bytes(const sd_scene *scene);
 int    sd_field_project(const sd_scene *scene, const sd_mlp *mlp, void *proj, size_t proj_bytes, void *stream);
+
+/* The same once-per-encode projection for SD_MLP_F32_TC queries: P = W_in[:, :C] . F in fp32 (CUDA cores) from the fp32
+ * channels-last map, stored as an fp16 (hi, lo) pair of maps behind (hi, lo) UMMA images of the code block of W_in and of
+ * W_out.  Set scene->feat_proj_x3 to the result.  proj 1024-byte aligned, sd_field_project_x3_bytes(scene) bytes. */
+size_t sd_field_project_x3_bytes(const sd_scene *scene);
+int    sd_field_project_x3(const sd_scene *scene, const sd_mlp *mlp, void *proj, size_t proj_bytes, void *stream);
 
 /* ---- point ops, one per reference function (unfused; for 1:1 parity tests) -------------------- */
 /* pts_into_camera + project_to_image + outside_frustum (common/cameras/pinhole.py:40-112) for one

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SD_B200_LIB") or os.path.join(HERE, "libscenedino_b200.so")   # (override: kernel experiments)
 
 SD_F32, SD_F16 = 0, 1
-SD_MLP_FP32, SD_MLP_F16_TC = 0, 1
+SD_MLP_FP32, SD_MLP_F16_TC, SD_MLP_F32_TC = 0, 1, 2
 ABI_VERSION = 4
 
 
@@ -31,6 +31,7 @@ class SdScene(C.Structure):
         ("num_freqs", C.c_int), ("freq_factor", C.c_float), ("include_input", C.c_int),
         ("learn_empty", C.c_int), ("empty_feature", C.c_void_p),
         ("feat_proj", C.c_void_p),
+        ("feat_proj_x3", C.c_void_p),
     ]
 
 
@@ -67,6 +68,8 @@ PROTOTYPES = {
     "sd_mlp_pack": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "sd_field_project_bytes": (_SZ, [_SC]),
     "sd_field_project": (_I, [_SC, _ML, _P, _SZ, _P]),
+    "sd_field_project_x3_bytes": (_SZ, [_SC]),
+    "sd_field_project_x3": (_I, [_SC, _ML, _P, _SZ, _P]),
     "sd_project_points": (_I, [_P, _P, _P, _LL, _P, _P, _P, _P]),
     "sd_sample_features": (_I, [_SC, _P, _LL, _P, _P, _P]),
     "sd_sample_colors": (_I, [_SC, _P, _LL, _P, _P, _P]),

@@ -94,7 +94,7 @@ extern "C" int sd_mlp_forward(const sd_mlp *mlp, const float *x, long long N, fl
 extern "C" size_t sd_query_workspace_bytes(const sd_scene *scene, const sd_mlp *mlp, long long N) {
     if (!scene || !mlp || N <= 0) return 0;
     // only the tensor-core path reorders the points; below a few tiles per SM it is not worth three launches
-    if (mlp->precision != SD_MLP_F16_TC || N < 65536) return 0;
+    if ((mlp->precision != SD_MLP_F16_TC && mlp->precision != SD_MLP_F32_TC) || N < 65536) return 0;
     return bin_workspace_bytes(scene->Hf, scene->Wf, N);
 }
 
@@ -112,18 +112,18 @@ extern "C" int sd_query_points(const sd_scene *scene, const sd_mlp *mlp, const f
 extern "C" int sd_query_points_sorted(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N,
                                       float *sigma, float *dino, float *rgb, float *invalid, void *workspace,
                                       size_t workspace_bytes, void *stream) {
-    SD_REQUIRE(scene && mlp && scene->feat_proj && mlp->precision == SD_MLP_F16_TC && workspace &&
-                   sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
-               "sd_query_points_sorted: needs a projected scene, SD_MLP_F16_TC and the workspace of an earlier sd_query_points call");
+    SD_REQUIRE(scene && mlp && ((scene->feat_proj && mlp->precision == SD_MLP_F16_TC) || (scene->feat_proj_x3 && mlp->precision == SD_MLP_F32_TC)) &&
+                   workspace && sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
+               "sd_query_points_sorted: needs a projected scene, SD_MLP_F16_TC / SD_MLP_F32_TC and the workspace of an earlier sd_query_points call");
     return query_points_impl(scene, mlp, xyz, N, sigma, dino, rgb, invalid, nullptr, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int sd_query_points_binned(const sd_scene *scene, const sd_mlp *mlp, const float *xyz, long long N, float *sigma,
                                       float *dino_binned, unsigned int *perm, unsigned char *invalid_feat, void *workspace,
                                       size_t workspace_bytes, int reuse_sorted, void *stream) {
-    SD_REQUIRE(scene && mlp && scene->feat_proj && mlp->precision == SD_MLP_F16_TC && workspace &&
-                   sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
-               "sd_query_points_binned: needs a projected scene, SD_MLP_F16_TC and a workspace of sd_query_workspace_bytes");
+    SD_REQUIRE(scene && mlp && ((scene->feat_proj && mlp->precision == SD_MLP_F16_TC) || (scene->feat_proj_x3 && mlp->precision == SD_MLP_F32_TC)) &&
+                   workspace && sd_query_workspace_bytes(scene, mlp, N) > 0 && workspace_bytes >= sd_query_workspace_bytes(scene, mlp, N),
+               "sd_query_points_binned: needs a projected scene, SD_MLP_F16_TC / SD_MLP_F32_TC and a workspace of sd_query_workspace_bytes");
     SD_REQUIRE(dino_binned && mlp->d_out == 65, "sd_query_points_binned: needs dino_binned and a 64-d feature head");
     if (N == 0) return SD_OK;
     return query_points_impl(scene, mlp, xyz, N, sigma, nullptr, nullptr, nullptr, reuse_sorted ? nullptr : invalid_feat, workspace,
@@ -161,7 +161,26 @@ static int query_points_impl(const sd_scene *scene, const sd_mlp *mlp, const flo
         SD_REQUIRE(!dino_binned, "sd_query_points_binned: this query does not take the sorted tile path (too few points for the map)");
         return launch_field_tc(fp, src, N, mlp, nullptr, o, (cudaStream_t)stream, order.perm, scene->feat_proj);
     }
-    SD_REQUIRE(mlp->precision == SD_MLP_FP32, "sd_query_points: unknown precision %d", mlp->precision);
+    if (mlp->precision == SD_MLP_F32_TC) {
+        // rel-1e-4 on the tensor cores: the same texel sort + tile kernel with every operand as an fp16 (hi, lo) pair
+        // (field_bin_x3.cu).  Queries too small for the sorted tile path take the fp32 CUDA-core kernel below -- same bar.
+        const size_t need = sd_query_workspace_bytes(scene, mlp, N);
+        const bool tile = need && workspace && workspace_bytes >= need && scene->feat_proj_x3 && bin_kernel_supported_x3(scene, mlp) &&
+                          N >= 16ll * ((scene->Wf - 1) / SD_BIN + 1) * ((scene->Hf - 1) / SD_BIN + 1);
+        SD_REQUIRE(tile || (!reuse_sorted && !dino_binned), "sd_query_points: this SD_MLP_F32_TC query does not take the sorted tile path");
+        if (tile) {
+            TcOut o = {};
+            o.sigma = sigma; o.dino = dino; o.rgb = rgb; o.invalid = invalid; o.invalid_feat = invalid_feat;
+            o.dino_binned = dino_binned; o.perm_out = perm_out;
+            BinOrder order = {};
+            rc = launch_bin_points(fp, xyz, N, workspace, workspace_bytes, &order, (cudaStream_t)stream, true, invalid_feat, reuse_sorted);
+            if (rc) return rc;
+            SD_REQUIRE(order.has_geo, "sd_query_points: the texel sort left no geometry records");
+            return launch_field_bin_x3(scene, fp, xyz, N, mlp, order, o, (cudaStream_t)stream);
+        }
+        SD_REQUIRE(scene->feat_dtype == SD_F32, "sd_query_points: SD_MLP_F32_TC below the tile-path size needs the fp32 map");
+    }
+    SD_REQUIRE(mlp->precision == SD_MLP_FP32 || mlp->precision == SD_MLP_F32_TC, "sd_query_points: unknown precision %d", mlp->precision);
     SimtOut out = {};
     out.sigma = sigma; out.dino = dino; out.rgb = rgb; out.invalid = invalid; out.invalid_feat = invalid_feat;
     return launch_field_simt(MODE_QUERY_, fp, src, N, mlp, out, (cudaStream_t)stream);

@@ -40,9 +40,26 @@
 #include "launch.h"
 #include "tc_common.cuh"
 
+// SD_TB_X3 = 1 (field_bin_x3.cu compiles this file a second time): the rel-1e-4 variant of the same kernel.  Every operand
+// of every contraction is carried as an fp16 pair hi + lo (hi = half(v), lo = half(v - hi): ~22 significant bits) and every
+// product as the three tensor-core products hi.hi + lo.hi + hi.lo, accumulated in fp32 in TMEM: bilinear weights x
+// projected map (two maps P_hi / P_lo, sd_field_project_x3), positional code x code block of W_in, hidden x W_out.  The
+// biases are added in fp32 in the epilogues, sin / cos start from an accurate sincosf, sigma uses the accurate softplus.
+// Single-slot weight / code rings (shared memory: 2 x 16 KB per operand), rows leave by direct 16-byte stores.
+#ifndef SD_TB_X3
+#define SD_TB_X3 0
+#endif
+#if SD_TB_X3
+#define TB_NS tbx
+#else
+#define TB_NS tb
+#endif
+
 namespace sd {
-namespace tb {
+namespace TB_NS {
 using namespace tcx;
+constexpr bool X3 = SD_TB_X3 != 0;
+constexpr int XK = X3 ? 2 : 1;                // operand images per ring entry: hi (+ lo)
 
 constexpr int TM = 128;
 constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp16 = B chunk [2 halves][64 slots][64 ch] fp16
@@ -64,7 +81,7 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #ifndef SD_TB_BOX_AHEAD
 #define SD_TB_BOX_AHEAD 1     // the producer issues the boxes of tile j + BOX_AHEAD while it publishes the records of tile j + 2
 #endif
-constexpr int NRA = SD_TB_NRA, NRB = SD_TB_NRB, NCODE = 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
+constexpr int NRA = X3 ? 1 : SD_TB_NRA, NRB = X3 ? 2 : SD_TB_NRB, NCODE = X3 ? 1 : 2;    // ring depths: weight (A) chunks, box (B) chunks, code operands
 constexpr int N_EPI_WARPS = 4, N_PT_WARPS = 4, N_PT_GROUPS = SD_TB_PT_GROUPS;
 constexpr int WARP_EPI2 = N_EPI_WARPS, WARP_MMA = 2 * N_EPI_WARPS, WARP_MMA2 = WARP_MMA + 1, WARP_TMA = WARP_MMA2 + 1,
               WARP_PT0 = WARP_TMA + 1;
@@ -73,20 +90,21 @@ static_assert(NCODE % N_PT_GROUPS == 0, "a code operand is always filled by the 
 constexpr int TMEM_COLS = 512;
 constexpr int D2_COL = 256, D2_STRIDE = 128;  // layer-1 accumulators at columns 0 / 128, layer-2 at 256 / 384
 constexpr int MAX_NVC_TB = 4;
-constexpr int W2_BYTES = 3 * 80 * 128;     // W_out: two K blocks + the bias block
+constexpr int W2_BYTES = X3 ? 2 * 2 * 80 * 128 : 3 * 80 * 128;     // W_out: two K blocks + the bias block (x3: hi and lo images, no bias block)
 constexpr int ONE_COL = 496;                 // 8 TMEM columns holding the constant (1, 1, 0, ...): A operand of the bias K step
 constexpr int KCODE = 3;                     // K steps of the code block (48 columns)
 
 constexpr int OFF_WC = 0;
-constexpr int OFF_A = OFF_WC + CHUNK;
-constexpr int OFF_B = OFF_A + NRA * CHUNK;
-constexpr int OFF_CODE = OFF_B + NRB * CHUNK;
-constexpr int OFF_W2 = OFF_CODE + NCODE * CHUNK;
+constexpr int OFF_A = OFF_WC + XK * CHUNK;
+constexpr int OFF_B = OFF_A + NRA * XK * CHUNK;
+constexpr int OFF_CODE = OFF_B + NRB * XK * CHUNK;
+constexpr int OFF_W2 = OFF_CODE + NCODE * XK * CHUNK;
 constexpr int OFF_STAGE = OFF_W2 + W2_BYTES;
+constexpr int STAGE_PER_WARP = X3 ? 0 : SD_TB_STAGE;
 constexpr int NREC = 3;                      // ring of per-tile record blocks (128 x 32 B), filled by bulk copies
 constexpr int REC_BYTES = TM * 32;
 constexpr int NPERM = 8;                     // ring of per-tile point indices handed from the point warps to epilogue 2
-constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * SD_TB_STAGE;
+constexpr int OFF_REC = OFF_STAGE + N_EPI_WARPS * STAGE_PER_WARP;
 constexpr int OFF_PERM = OFF_REC + NREC * REC_BYTES;
 constexpr int OFF_HDR = OFF_PERM + NPERM * TM * 4;        // per record-ring entry: the tile's table entry (TileInfo, 16 B)
 #ifndef SD_TB_BATCH
@@ -99,8 +117,9 @@ constexpr int OFF_NTILES = OFF_MINFO + 16;      // tiles this CTA processed, pub
 constexpr int OFF_TIDX = OFF_NTILES + 8;      // per record-ring entry: the tile's index in sorted order (binned output)
 constexpr int OFF_PTILE = OFF_TIDX + 16;       // per perm-ring entry: the same, handed on to epilogue 2 by the point warps
 constexpr int OFF_DIRTY = OFF_PTILE + NPERM * 4;
-constexpr int OFF_CAM = OFF_DIRTY + NRA * TM;
-constexpr int OFF_BAR = OFF_CAM + 448;
+constexpr int OFF_CAM = OFF_DIRTY + NRA * TM + (NRA * TM % 8 ? 8 - NRA * TM % 8 : 0);
+constexpr int OFF_BIAS = OFF_CAM + 448;            // x3: b_in [128] + b_out [80] fp32
+constexpr int OFF_BAR = OFF_BIAS + (X3 ? 832 : 0);
 enum { BAR_FULL_A = 0, BAR_EMPTY_A = NRA, BAR_FULL_B = 2 * NRA, BAR_EMPTY_B = 2 * NRA + NRB, BAR_FULL_C = 2 * NRA + 2 * NRB,
        BAR_EMPTY_C = BAR_FULL_C + NCODE,
        BAR_D1 = BAR_EMPTY_C + NCODE, BAR_H = BAR_D1 + 2, BAR_D2 = BAR_H + 2, BAR_D2_EMPTY = BAR_D2 + 2,
@@ -129,6 +148,8 @@ __device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globalt
 struct Params {
     CUtensorMap tmap;          // P as [Hf][Wf][128] fp16, box 8 x 8 x 64 channels, SWIZZLE_128B
     CUtensorMap tmap_out;      // binned output: dino as [N][64] fp32, box 32 rows x 32 columns, SWIZZLE_128B
+    CUtensorMap tmap_lo;       // x3: the lo half of the projected map
+    const float *b_in;         // x3: fp32 biases, added in the epilogues
     FieldParams fp;
     const float *xyz;
     unsigned int *tile_ctr;    // next unclaimed tile (zeroed by the sort): CTAs claim tiles dynamically
@@ -185,7 +206,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         s_cam[i] = e < 9 ? __ldg(K + e) : __ldg(W + (e - 9));
     }
     // the weight operands start out all zero and are kept so by the undo log of the point warps
-    for (int i = tid; i < NRA * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NRA * XK * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_A)[i] = make_uint4(0, 0, 0, 0);
+    if (X3) {   // fp32 biases for the epilogues; the code operands start out zero (their unused columns stay zero)
+        float *s_bias = reinterpret_cast<float *>(sm + OFF_BIAS);
+        for (int i = tid; i < 128 + 80; i += NTHREADS) s_bias[i] = i < 128 ? __ldg(P.b_in + i) : (i - 128 <= P.D ? __ldg(P.b_out + (i - 128)) : 0.0f);
+        for (int i = tid; i < NCODE * XK * CHUNK / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + OFF_CODE)[i] = make_uint4(0, 0, 0, 0);
+    }
     for (int i = tid; i < NRA * TM; i += NTHREADS) s_dirty[i] = 0xFF;
     if (tid == 0) *reinterpret_cast<volatile int *>(sm + OFF_NTILES) = 0x7FFFFFFF;
     fence_proxy_async();
@@ -195,9 +221,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t w2b = 3u * (uint32_t)P.n2 * 128u;
-        mbar_expect_tx(BAR(BAR_WLOAD), CHUNK + w2b);
-        bulk_g2s(sm_u + OFF_WC, P.wc_img, CHUNK, BAR(BAR_WLOAD));
+        const uint32_t w2b = (X3 ? 4u : 3u) * (uint32_t)P.n2 * 128u;
+        mbar_expect_tx(BAR(BAR_WLOAD), XK * CHUNK + w2b);
+        bulk_g2s(sm_u + OFF_WC, P.wc_img, XK * CHUNK, BAR(BAR_WLOAD));
         bulk_g2s(sm_u + OFF_W2, P.w2_img, w2b, BAR(BAR_WLOAD));
     }
     tc_fence_before();
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         // =================================== EPILOGUE 1 ==============================================
         // layer-1 accumulator -> ReLU -> fp16 -> the same TMEM columns, A operand of layer 2
         const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        {   // constant-1 columns (k = 128, 129 of layer 2): the output bias comes out of the MMA
+        if (!X3) {   // constant-1 columns (k = 128, 129 of layer 2): the output bias comes out of the MMA
             uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             tmem_st8(t_lane + ONE_COL, one);
         }
@@ -236,6 +262,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 tmem_ld32_issue(t_lane + b * 128 + kb * 32, vr);
                 tmem_ld_wait();
                 uint32_t pk[16];
+                if (X3) {
+                    // h = relu(acc + b_in) in fp32 -> (hi, lo) halves: hi pairs over columns 32 kb .. +15, lo pairs over
+                    // 32 kb + 16 .. +31 (both inside the 32 columns just read)
+                    const float *s_b1 = reinterpret_cast<const float *>(sm + OFF_BIAS) + kb * 32;
+                    uint32_t pl[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float h0 = fmaxf(__uint_as_float(vr[2 * e]) + s_b1[2 * e], 0.0f), h1 = fmaxf(__uint_as_float(vr[2 * e + 1]) + s_b1[2 * e + 1], 0.0f);
+                        const __half2 hi = __floats2half2_rn(h0, h1);
+                        const float2 hf = __half22float2(hi);
+                        pk[e] = as_u32(hi);
+                        pl[e] = pack_h2(h0 - hf.x, h1 - hf.y);
+                    }
+                    tmem_st16(t_lane + b * 128 + kb * 32, pk);
+                    tmem_st16(t_lane + b * 128 + kb * 32 + 16, pl);
+                    continue;
+                }
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     pk[e] = pack_h2_relu(__uint_as_float(vr[2 * e]), __uint_as_float(vr[2 * e + 1]));
@@ -253,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         const int row = wq * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
         const int D = P.D;
-        unsigned char *stage0 = sm + OFF_STAGE + wq * SD_TB_STAGE, *stage1 = stage0 + (SD_TB_STAGE == 8192 ? 4096 : 0);
+        unsigned char *stage0 = sm + OFF_STAGE + wq * STAGE_PER_WARP, *stage1 = stage0 + (STAGE_PER_WARP == 8192 ? 4096 : 0);
         // The point index of this thread's row was left in the perm ring by the point warps when they processed the tile.
         // No barrier of its own: the write is ordered before this read by the chain FULL_C -> MMA -> D1 -> H -> D2, and
         // an entry is rewritten 8 tiles later, while the point warps can be at most 5 tiles ahead of this role (two
@@ -268,7 +311,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             const int grow_keep = s_perm[(int)(j % NPERM) * TM + row];       // point this thread's row of tile j stands for
             const uint32_t t_d2 = t_lane + D2_COL + b1 * D2_STRIDE;
             const bool ok = grow_keep >= 0;
-            if (P.binned) {
+            if (X3) {
+                // fp32 biases, accurate softplus; the row leaves by direct 16-byte stores (its own row of dino, in the
+                // caller's order or -- binned -- at its sorted position)
+                const float *s_b2 = reinterpret_cast<const float *>(sm + OFF_BIAS) + 128;    // b_out in nn.Linear order: [sigma, f0 ...]
+                const int t = reinterpret_cast<const volatile int *>(sm + OFF_PTILE)[(int)(j % NPERM)];
+                uint32_t vr[64], sr;
+                tmem_ld32_issue(t_d2, vr);
+                tmem_ld32_issue(t_d2 + 32, vr + 32);
+                tmem_ld1_issue(t_d2 + D, sr);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
+                if (ok) {
+                    if (P.sigma) P.sigma[grow_keep] = softplus(__uint_as_float(sr) + s_b2[0]);
+                    if (P.binned && P.perm_out) P.perm_out[(long long)t * TM + row] = (unsigned int)grow_keep;
+                    if (P.dino) {
+                        float *o = P.dino + (P.binned ? (long long)t * TM + row : (long long)grow_keep) * D;
+                        if (D == 64) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                reinterpret_cast<float4 *>(o)[q] = make_float4(__uint_as_float(vr[4 * q]) + s_b2[1 + 4 * q], __uint_as_float(vr[4 * q + 1]) + s_b2[2 + 4 * q],
+                                                                               __uint_as_float(vr[4 * q + 2]) + s_b2[3 + 4 * q], __uint_as_float(vr[4 * q + 3]) + s_b2[4 + 4 * q]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 64; ++c)
+                                if (c < D) o[c] = __uint_as_float(vr[c]) + s_b2[1 + c];
+                        }
+                    }
+                }
+            } else if (P.binned) {
                 // Binned output: the tile's rows are consecutive rows of dino, so the features leave as four TMA tile stores
                 // per warp-quadrant pair (32 rows x 128 B each) straight from the staging buffer -- written once, swizzled
                 // the way the tensor map expects (16-byte piece q of row r at q ^ (r & 7)), never read back, no address per
@@ -396,9 +468,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     if (i == 0) TB_TRACE(1, j, 2);
 #pragma unroll
                     for (int k = (SD_TB_ABLATE & 16) ? 4 : 0; k < 4; ++k) {    // 16 texel slots per instruction
-                        umma_e(d1, umma_desc(sm_u + OFF_A + e * CHUNK + k * 32),
-                               umma_desc_mn(sm_u + OFF_B + eb * CHUNK + k * 2048, CHUNK / 2, 1024), idesc_mn, acc);
+                        const uint32_t a_h = sm_u + OFF_A + e * XK * CHUNK + k * 32, b_h = sm_u + OFF_B + eb * XK * CHUNK + k * 2048;
+                        umma_e(d1, umma_desc(a_h), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, acc);
                         acc = 1;
+                        if (X3) {       // + w_lo . P_hi + w_hi . P_lo
+                            umma_e(d1, umma_desc(a_h + CHUNK), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, 1);
+                            umma_e(d1, umma_desc(a_h), umma_desc_mn(b_h + CHUNK, CHUNK / 2, 1024), idesc_mn, 1);
+                        }
                     }
                     umma_commit_e(BAR(BAR_EMPTY_A + e));
                     umma_commit_e(BAR(BAR_EMPTY_B + eb));
@@ -408,8 +484,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 const int cs = (int)(j % NCODE);
                 TB_TRACE(1, j, 4);
 #pragma unroll
-                for (int k = 0; k < KCODE; ++k)
-                    umma_e(d1, umma_desc(sm_u + OFF_CODE + cs * CHUNK + k * 32), umma_desc(sm_u + OFF_WC + k * 32), idesc_k, 1);
+                for (int k = 0; k < KCODE; ++k) {
+                    const uint32_t c_h = sm_u + OFF_CODE + cs * XK * CHUNK + k * 32, w_h = sm_u + OFF_WC + k * 32;
+                    umma_e(d1, umma_desc(c_h), umma_desc(w_h), idesc_k, 1);
+                    if (X3) {
+                        umma_e(d1, umma_desc(c_h + CHUNK), umma_desc(w_h), idesc_k, 1);
+                        umma_e(d1, umma_desc(c_h), umma_desc(w_h + CHUNK), idesc_k, 1);
+                    }
+                }
                 umma_commit_e(BAR(BAR_EMPTY_C + cs));
                 umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
                 TB_TRACE(1, j, 6);
@@ -435,11 +517,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 if (j >= nt) { mbar_arrive_e(BAR(BAR_D2 + b)); break; }
                 tc_fence_after();
                 TB_TRACE(1, j + 1, 5);
+                if (X3) {
+                    // hidden (hi, lo) pairs sit in blocks of 16 columns per 32 units (epilogue 1): k-step k reads hi at
+                    // 32 (k / 2) + 8 (k % 2), lo 16 columns further; W_out hi image, then the lo image 2 n2 128 bytes behind
+                    const uint32_t w2l = 2u * (uint32_t)P.n2 * 128u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t a_h = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
+                        const uint32_t w_h = sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32;
+                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h), idesc2, k != 0);
+                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h + 16, umma_desc(w_h), idesc2, 1);
+                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h + w2l), idesc2, 1);
+                    }
+                } else {
 #pragma unroll
                 for (int k = (SD_TB_ABLATE & 8) ? 8 : 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
                     umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
                               umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
                 umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
+                }
                 umma_commit_e(BAR(BAR_D2 + b));
                 umma_commit_e(BAR(BAR_D1_FREE + b));
             }
@@ -448,7 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
         // =================================== TMA PRODUCER =============================================
         // The whole warp runs the role in lockstep and the copies are issued in their "elected" forms (tc_common.cuh): no
         // per-instruction ELECT loop.
-        if (lane == 0) tma_prefetch_desc(&P.tmap);
+        if (lane == 0) { tma_prefetch_desc(&P.tmap); if (X3) tma_prefetch_desc(&P.tmap_lo); }
         __syncwarp();
         int e = 0;
         uint32_t ph = 0;
@@ -532,10 +628,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 if (SD_TB_ABLATE & 4) {
                     mbar_arrive_e(BAR(BAR_FULL_B + e));
                 } else if (elect_one()) {
-                    mbar_expect_tx(BAR(BAR_FULL_B + e), CHUNK);
-                    const uint32_t dst = sm_u + OFF_B + e * CHUNK;
+                    mbar_expect_tx(BAR(BAR_FULL_B + e), XK * CHUNK);
+                    const uint32_t dst = sm_u + OFF_B + e * XK * CHUNK;
                     tma_load_3d(dst, &P.tmap, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
                     tma_load_3d(dst + CHUNK / 2, &P.tmap, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                    if (X3) {
+                        tma_load_3d(dst + CHUNK, &P.tmap_lo, 0, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                        tma_load_3d(dst + CHUNK + CHUNK / 2, &P.tmap_lo, 64, bx * SD_BIN, by * SD_BIN, BAR(BAR_FULL_B + e));
+                    }
                 }
                 __syncwarp();
                 if (++e == NRB) { e = 0; ph ^= 1; }
@@ -607,23 +707,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             const bool plain = ok && cur.slot != 0xFF;     // bilinear taps (else: the learned empty feature, bts.py:311-319)
             // ---- positional code -> code operand (positional_encoding.py:68-80; sin/cos of 1.5*2^k*v by angle
             //      doubling from one accurate sincosf per coordinate) -------------------------------------------
-            uint32_t pk[24];
+            uint32_t pk[24], pl[X3 ? 24 : 1];
 #pragma unroll
             for (int i = 0; i < 24; ++i) pk[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < (X3 ? 24 : 1); ++i) pl[i] = 0u;
             if (ok && !(SD_TB_ABLATE & 1)) {
                 float code[48];
-                code[0] = x; code[1] = y; code[2] = zp;
-                code[45] = 1.0f; code[46] = 1.0f;                      // layer-1 bias (hi, lo) comes out of the MMA
-                code[47] = plain ? 0.0f : 1.0f;                        // learn_empty: W_feat . empty_feature (bts.py:311-319)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {                          // hi/lo split of the raw coordinates (see mlp_pack_kernel)
-                    const float hi = __half2float(__float2half_rn(code[d]));
-                    code[39 + d] = code[d] - hi;
-                    code[42 + d] = hi;
+                for (int i = 39; i < 48; ++i) code[i] = 0.0f;
+                code[0] = x; code[1] = y; code[2] = zp;
+                if (X3) {
+                    code[39] = plain ? 0.0f : 1.0f;                    // learn_empty: W_feat . empty_feature (column 39 of the x3 code block)
+                } else {
+                    code[45] = 1.0f; code[46] = 1.0f;                  // layer-1 bias (hi, lo) comes out of the MMA
+                    code[47] = plain ? 0.0f : 1.0f;                    // learn_empty: W_feat . empty_feature (bts.py:311-319)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {                      // hi/lo split of the raw coordinates (see mlp_pack_kernel)
+                        const float hi = __half2float(__float2half_rn(code[d]));
+                        code[39 + d] = code[d] - hi;
+                        code[42 + d] = hi;
+                    }
                 }
                 float s[3], c[3];
                 const float a0 = x * P.fp.enc.freq_factor, a1 = y * P.fp.enc.freq_factor, a2 = zp * P.fp.enc.freq_factor;
-                if (fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(a2)) <= 3.2f) {    // the usual case: hardware sin / cos
+                if (!X3 && fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(a2)) <= 3.2f) {    // the usual case: hardware sin / cos
                     s[0] = __sinf(a0); c[0] = __cosf(a0); s[1] = __sinf(a1); c[1] = __cosf(a1); s[2] = __sinf(a2); c[2] = __cosf(a2);
                 } else {                                                         // next to / behind the camera: |z'| is large
                     sincosf(a0, &s[0], &c[0]); sincosf(a1, &s[1], &c[1]); sincosf(a2, &s[2], &c[2]);
@@ -639,7 +747,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 24; ++i) pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
+                for (int i = 0; i < 24; ++i) {
+                    if (X3) {
+                        const __half2 hi = __floats2half2_rn(code[2 * i], code[2 * i + 1]);
+                        const float2 hf = __half22float2(hi);
+                        pk[i] = as_u32(hi);
+                        pl[i] = pack_h2(code[2 * i] - hf.x, code[2 * i + 1] - hf.y);
+                    } else {
+                        pk[i] = pack_h2(code[2 * i], code[2 * i + 1]);
+                    }
+                }
             }
             const int cs = (int)(j % NCODE);
             TB_TRACE(pt_role, j, 4);
@@ -647,17 +764,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             TB_TRACE(pt_role, j, 5);
             reinterpret_cast<int *>(sm + OFF_PERM)[(int)(j % NPERM) * TM + row] = ok ? cur.grow : -1;
             if (row == 0) reinterpret_cast<volatile int *>(sm + OFF_PTILE)[(int)(j % NPERM)] = tile_idx;
-            unsigned char *crow = sm + OFF_CODE + cs * CHUNK + row * 128;
+            unsigned char *crow = sm + OFF_CODE + cs * XK * CHUNK + row * 128;
 #pragma unroll
-            for (int qq = 0; qq < 6; ++qq)
+            for (int qq = 0; qq < 6; ++qq) {
                 *reinterpret_cast<uint4 *>(crow + ((qq ^ (row & 7)) << 4)) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+                if (X3) *reinterpret_cast<uint4 *>(crow + CHUNK + ((qq ^ (row & 7)) << 4)) = make_uint4(pl[4 * qq], pl[4 * qq + 1], pl[4 * qq + 2], pl[4 * qq + 3]);
+            }
             // (made visible to the tensor cores by the fence + arrival of the tile's first weight chunk below)
             // ---- bilinear weights -> this row's 4 slots of its bin's chunk; every other slot of the row stays zero.
             //      Slots (nw, ne) = (s, s+1) share one 16-byte piece of the row (lx <= 6), (sw, se) the next one:
             //      the dirty byte keeps (ly << 3 | lx) and the undo clears the same two pairs.
             const int lx = cur.slot & 7, ly = (cur.slot >> 3) & 7;
             const int q = cur.cr - cur.c0;
-            const uint32_t w_top = cur.w01, w_bot = cur.w23;
+            uint32_t w_top = cur.w01, w_bot = cur.w23, w_top_l = 0u, w_bot_l = 0u;
+            if (X3 && plain) {      // the fp32 weights again (the sort made them from the same x, y: binning.cu) -> (hi, lo) halves
+                Tap t = bilinear_tap(x, y, P.fp.Hf, P.fp.Wf);
+                clamp_footprint(t, P.fp.Hf, P.fp.Wf);
+                const __half2 th = __floats2half2_rn(t.wnw, t.wne), bh = __floats2half2_rn(t.wsw, t.wse);
+                const float2 tf = __half22float2(th), bf = __half22float2(bh);
+                w_top = as_u32(th); w_bot = as_u32(bh);
+                w_top_l = pack_h2(t.wnw - tf.x, t.wne - tf.y); w_bot_l = pack_h2(t.wsw - bf.x, t.wse - bf.y);
+            }
             auto pair_off = [&](int lyy, int lxx) {      // byte offset of slot (lyy, lxx) inside the row
                 return (uint32_t)(((lyy ^ (row & 7)) << 4) + lxx * 2);
             };
@@ -666,18 +793,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             for (int i = 0; i < m; ++i) {
                 mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
                 if (i == 0) TB_TRACE(pt_role, j, 2);
-                unsigned char *arow = sm + OFF_A + e * CHUNK + row * 128;
+                unsigned char *arow = sm + OFF_A + e * XK * CHUNK + row * 128;
                 const int d = s_dirty[e * TM + row];
                 if (d != 0xFF) {
                     unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(d >> 3, d & 7));
                     unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off((d >> 3) + 1, d & 7));
                     p0[0] = 0; p0[1] = 0; p1[0] = 0; p1[1] = 0;
+                    if (X3) {
+                        p0 += CHUNK / 2; p1 += CHUNK / 2;
+                        p0[0] = 0; p0[1] = 0; p1[0] = 0; p1[1] = 0;
+                    }
                 }
                 if (plain && i == q) {
                     unsigned short *p0 = reinterpret_cast<unsigned short *>(arow + pair_off(ly, lx));
                     unsigned short *p1 = reinterpret_cast<unsigned short *>(arow + pair_off(ly + 1, lx));
                     p0[0] = (unsigned short)w_top; p0[1] = (unsigned short)(w_top >> 16);
                     p1[0] = (unsigned short)w_bot; p1[1] = (unsigned short)(w_bot >> 16);
+                    if (X3) {
+                        p0 += CHUNK / 2; p1 += CHUNK / 2;
+                        p0[0] = (unsigned short)w_top_l; p0[1] = (unsigned short)(w_top_l >> 16);
+                        p1[0] = (unsigned short)w_bot_l; p1[1] = (unsigned short)(w_bot_l >> 16);
+                    }
                     s_dirty[e * TM + row] = (unsigned char)cur.slot;
                 } else if (d != 0xFF) {
                     s_dirty[e * TM + row] = 0xFF;
@@ -731,8 +867,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
     }
 }
 
-}  // namespace tb
+}  // namespace TB_NS
 
+#if !SD_TB_X3
 // debug: clock64 trace of the last launch made with SD_TC_DEBUG & 8192 (not part of the public header)
 extern "C" int sd_debug_read_cta_ns(unsigned long long *host_out) {
     SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_cta_ns, sizeof(unsigned long long) * 512));
@@ -754,24 +891,37 @@ extern "C" int sd_debug_read_timeout(unsigned int *host_out) {
 }
 #endif
 
+#endif  // !SD_TB_X3
+
+#if SD_TB_X3
+bool bin_kernel_supported_x3(const sd_scene *s, const sd_mlp *mlp) {
+    return s && mlp && s->feat_proj_x3 && mlp->packed && mlp->precision == SD_MLP_F32_TC && s->C == 256 && s->nv_f == 1 &&
+           s->include_input && s->num_freqs == 6 && s->Hf >= 2 && s->Wf >= 2 && s->nv_c <= TB_NS::MAX_NVC_TB &&
+           mlp->d_hidden == 128 && mlp->d_in == s->C + 39 && mlp->d_out >= 2 && mlp->d_out - 1 <= 64;
+}
+#define TB_SUPPORTED bin_kernel_supported_x3
+int launch_field_bin_x3(const sd_scene *scene, const FieldParams &fp, const float *xyz, long long N, const sd_mlp *mlp,
+                        const BinOrder &order, const TcOut &out, cudaStream_t st) {
+#else
 bool bin_kernel_supported(const sd_scene *s, const sd_mlp *mlp) {
     return s && mlp && s->feat_proj && mlp->packed && mlp->precision == SD_MLP_F16_TC && s->C == 256 && s->nv_f == 1 &&
            s->include_input && s->num_freqs == 6 && s->Hf >= 2 && s->Wf >= 2 && s->nv_c <= tb::MAX_NVC_TB &&
            mlp->d_hidden == 128 && mlp->d_in == s->C + 39 && mlp->d_out >= 2 && mlp->d_out - 1 <= 64;
 }
-
+#define TB_SUPPORTED bin_kernel_supported
 int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *xyz, long long N, const sd_mlp *mlp,
                      const BinOrder &order, const TcOut &out, cudaStream_t st) {
+#endif
     if (N == 0) return SD_OK;
-    SD_REQUIRE(bin_kernel_supported(scene, mlp), "field_bin: unsupported scene / head for the projected-map kernel");
+    SD_REQUIRE(TB_SUPPORTED(scene, mlp), "field_bin: unsupported scene / head for the projected-map kernel");
     SD_REQUIRE(order.bw == SD_BIN, "field_bin: the feature map is too large for %d x %d bins", SD_BIN, SD_BIN);
     SD_REQUIRE(N < (1ll << 31), "field_bin: at most 2^31 - 1 points per call (got %lld)", N);
     const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
     const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
-    const unsigned char *proj = reinterpret_cast<const unsigned char *>(scene->feat_proj);
+    const unsigned char *proj = reinterpret_cast<const unsigned char *>(SD_TB_X3 ? scene->feat_proj_x3 : scene->feat_proj);
     SD_REQUIRE(((uintptr_t)blob & 15) == 0 && ((uintptr_t)proj & 15) == 0, "field_bin: packed blobs must be 16-byte aligned");
     SD_REQUIRE(((uintptr_t)out.dino & 15) == 0, "field_bin: dino must be 16-byte aligned");
-    tb::Params P = {};
+    TB_NS::Params P = {};
     P.fp = fp;
     P.xyz = xyz;
     P.cbin = order.cbin; P.nbx = order.nbx;
@@ -781,38 +931,55 @@ int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *
     P.tile_ctr = order.tile_ctr;
     P.N = N;
     P.dbg = debug_mask();
-    P.n_tiles = (N + tb::TM - 1) / tb::TM;
+    P.n_tiles = (N + TB_NS::TM - 1) / TB_NS::TM;
     P.D = mlp->d_out - 1;
     P.n2 = (mlp->d_out + 15) / 16 * 16;
+#if SD_TB_X3
+    SD_REQUIRE(P.n2 == 80 || P.n2 * 4 * 128 <= PROJX_W2_BYTES, "field_bin_x3: d_out too large");
+    P.wc_img = proj + PROJX_OFF_WC;
+    P.w2_img = proj + PROJX_OFF_W2;
+    P.b_in = reinterpret_cast<const float *>(blob + L.off_b_in);
+#else
     P.wc_img = proj + PROJ_OFF_CODE;
     P.w2_img = blob + L.off_w_out_h;
+#endif
     P.b_out = reinterpret_cast<const float *>(blob + L.off_b_out);
     P.sigma = out.sigma; P.dino = out.dino; P.rgb = out.rgb; P.invalid = out.invalid; P.invalid_feat = out.invalid_feat;
     if (out.dino_binned) {
         SD_REQUIRE(P.D == 64 && !out.dino, "field_bin: binned output needs a 64-d head and no caller-order dino");
         SD_REQUIRE(((uintptr_t)out.dino_binned & 15) == 0, "field_bin: dino_binned must be 16-byte aligned");
         P.binned = 1; P.dino = out.dino_binned; P.perm_out = out.perm_out;
+#if !SD_TB_X3
         const unsigned long long odims[2] = {64ull, (unsigned long long)N}, ostrides[1] = {256ull};
         const unsigned int obox[2] = {32u, 32u};
         if (int rc_o = make_tmap(&P.tmap_out, out.dino_binned, 4, 2, odims, ostrides, obox)) return rc_o;
+#endif
     }
     const unsigned long long dims[3] = {128ull, (unsigned long long)fp.Wf, (unsigned long long)fp.Hf};
     const unsigned long long strides[2] = {256ull, 256ull * (unsigned long long)fp.Wf};
     const unsigned int box[3] = {64u, 8u, 8u};
+#if SD_TB_X3
+    const size_t map_bytes = (size_t)fp.Hf * fp.Wf * 256;
+    int rc = make_tmap_f16(&P.tmap, proj + PROJX_OFF_MAP, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_f16(&P.tmap_lo, proj + PROJX_OFF_MAP + map_bytes, 3, dims, strides, box);
+    if (rc) return rc;
+#else
     int rc = make_tmap_f16(&P.tmap, proj + PROJ_OFF_MAP, 3, dims, strides, box);
     if (rc) return rc;
+#endif
     static DeviceOnce once;
     int sm_count = 0;
     bool first_use = false;
     if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
     if (first_use) {
-        SD_CUDA_OK(cudaFuncSetAttribute(tb::field_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb::SMEM_ALLOC));
+        SD_CUDA_OK(cudaFuncSetAttribute(TB_NS::field_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_NS::SMEM_ALLOC));
     }
     const unsigned grid = (unsigned)(P.n_tiles < sm_count ? P.n_tiles : sm_count);
     profile_before(st);
-    tb::field_bin_kernel<<<grid, tb::NTHREADS, tb::SMEM_ALLOC, st>>>(P);
+    TB_NS::field_bin_kernel<<<grid, TB_NS::NTHREADS, TB_NS::SMEM_ALLOC, st>>>(P);
     profile_after(st);
-    SD_LAUNCH_OK("field_bin_kernel");
+    SD_LAUNCH_OK(SD_TB_X3 ? "field_bin_kernel (x3)" : "field_bin_kernel");
     return SD_OK;
 }
 

@@ -221,10 +221,130 @@ __global__ void __launch_bounds__(128) proj_code_image_kernel(const unsigned cha
     reinterpret_cast<__half *>(wc_img + PROJ_OFF_EMPTY)[n] = __float2half_rn(pe);
 }
 
+
+// ---- rel-1e-4 variant (sd_field_project_x3): P = W_in[:, :C] . F in fp32 on the CUDA cores, stored as an fp16 (hi, lo) pair
+// of maps.  Once per encode; a 64-texel x 128-unit block tile, K in slices of 32 channels through shared memory, each
+// thread 4 texels x 8 units.  (fp32 FFMA like the reference's own F.linear; the sum runs over the channels in order.)
+constexpr int X3_TEX = 64, X3_KS = 32;
+__global__ void __launch_bounds__(256) proj_x3_kernel(const float *__restrict__ F, const float *__restrict__ w_in_t, int C,
+                                                      long long n_texels, __half *__restrict__ P_hi, __half *__restrict__ P_lo) {
+    __shared__ float sF[X3_TEX][X3_KS + 1];
+    __shared__ __align__(16) float sW[X3_KS][128];
+    const long long t0 = (long long)blockIdx.x * X3_TEX;
+    const int tid = threadIdx.x, ug = tid & 15, tg = tid >> 4;        // units 8 ug .. +7, texels 4 tg .. +3
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+    for (int k0 = 0; k0 < C; k0 += X3_KS) {
+        for (int i = tid; i < X3_TEX * X3_KS; i += 256) {
+            const int tx = i / X3_KS, k = i - tx * X3_KS;
+            sF[tx][k] = (t0 + tx < n_texels && k0 + k < C) ? __ldg(F + (size_t)(t0 + tx) * C + k0 + k) : 0.0f;
+        }
+        for (int i = tid; i < X3_KS * 128; i += 256) {
+            const int k = i >> 7, n = i & 127;
+            sW[k][n] = k0 + k < C ? __ldg(w_in_t + (size_t)(k0 + k) * 128 + n) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < X3_KS; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(&sW[k][8 * ug]), w1 = *reinterpret_cast<const float4 *>(&sW[k][8 * ug + 4]);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float f = sF[4 * tg + a][k];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(f, w[b], acc[a][b]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const long long t = t0 + 4 * tg + a;
+        if (t >= n_texels) continue;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const __half2 h = __floats2half2_rn(acc[a][2 * b], acc[a][2 * b + 1]);
+            const float2 hf = __half22float2(h);
+            hi[b] = tcx::as_u32(h);
+            lo[b] = tcx::pack_h2(acc[a][2 * b] - hf.x, acc[a][2 * b + 1] - hf.y);
+        }
+        *reinterpret_cast<uint4 *>(P_hi + (size_t)t * 128 + 8 * ug) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(P_lo + (size_t)t * 128 + 8 * ug) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// (hi, lo) UMMA images of the code block of W_in (column 39: W_feat . empty_feature) and of W_out (feature rows first, the
+// density row last, as field_bin.cu expects them); one block of 128 threads
+__global__ void __launch_bounds__(128) x3_weights_kernel(const float *__restrict__ w_in_t, const float *__restrict__ w_out_t, int C,
+                                                         int d_out, int d_out_pad, int n2, const float *__restrict__ empty_feature,
+                                                         int learn_empty, unsigned char *__restrict__ out) {
+    const int n = threadIdx.x;
+    auto put = [](unsigned char *img_hi, unsigned char *img_lo, size_t off, float v) {
+        const __half h = __float2half_rn(v);
+        reinterpret_cast<__half *>(img_hi)[off / 2] = h;
+        reinterpret_cast<__half *>(img_lo)[off / 2] = __float2half_rn(v - __half2float(h));
+    };
+    float pe = 0.0f;
+    if (learn_empty)
+        for (int c = 0; c < C; ++c) pe = fmaf(__ldg(w_in_t + (size_t)c * 128 + n), __ldg(empty_feature + c), pe);
+    unsigned char *wc_hi = out + PROJX_OFF_WC, *wc_lo = wc_hi + 16384;
+    for (int k = 0; k < 64; ++k)
+        put(wc_hi, wc_lo, umma_sw128_offset(n, k, 128), k < 39 ? __ldg(w_in_t + (size_t)(C + k) * 128 + n) : (k == 39 ? pe : 0.0f));
+    // W_out: image row r = feature r (nn.Linear row 1 + r) for r < d_out - 1, the density (row 0) at r = d_out - 1; K = hidden unit
+    unsigned char *w2_hi = out + PROJX_OFF_W2, *w2_lo = w2_hi + 2 * (size_t)n2 * 128;
+    for (int r = 0; r < n2; ++r) {
+        const int o = r < d_out - 1 ? r + 1 : (r == d_out - 1 ? 0 : -1);
+        const float v = o >= 0 ? __ldg(w_out_t + (size_t)n * d_out_pad + o) : 0.0f;
+        put(w2_hi, w2_lo, (size_t)(n >> 6) * n2 * 128 + umma_sw128_offset(r, n & 63, n2), v);
+    }
+}
+
 }  // namespace pj
 }  // namespace sd
 
 using namespace sd;
+
+extern "C" size_t sd_field_project_x3_bytes(const sd_scene *scene) {
+    if (!scene || scene->Hf <= 0 || scene->Wf <= 0) return 0;
+    return (size_t)PROJX_OFF_MAP + 2 * (size_t)scene->Hf * scene->Wf * 128 * sizeof(__half);
+}
+
+extern "C" int sd_field_project_x3(const sd_scene *scene, const sd_mlp *mlp, void *proj, size_t proj_bytes, void *stream) {
+    SD_REQUIRE(scene && mlp && proj, "sd_field_project_x3: null pointer");
+    SD_REQUIRE(scene->feat && scene->feat_dtype == SD_F32 && scene->C == 256 && scene->nv_f == 1,
+               "sd_field_project_x3: needs the fp32 channels-last map with C = 256 and one encoder view");
+    SD_REQUIRE(mlp->packed && mlp->d_hidden == 128 && mlp->d_in == scene->C + 39 && scene->include_input && scene->num_freqs == 6 &&
+                   mlp->d_out >= 2 && mlp->d_out <= 65,
+               "sd_field_project_x3: head must be packed, d_hidden = 128, d_in = C + 39, d_out <= 65 (got d_in=%d d_out=%d)", mlp->d_in, mlp->d_out);
+    SD_REQUIRE(!scene->learn_empty || scene->empty_feature, "sd_field_project_x3: learn_empty without empty_feature");
+    SD_REQUIRE(((uintptr_t)proj & 1023) == 0, "sd_field_project_x3: proj must be 1024-byte aligned");
+    const size_t need = sd_field_project_x3_bytes(scene);
+    if (proj_bytes < need) {
+        set_error("sd_field_project_x3: %zu B needed, %zu B given", need, proj_bytes);
+        return SD_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const MlpLayout L = mlp_layout(mlp->d_in, mlp->d_hidden, mlp->d_out);
+    const unsigned char *blob = reinterpret_cast<const unsigned char *>(mlp->packed);
+    unsigned char *out = reinterpret_cast<unsigned char *>(proj);
+    const float *w_in_t = reinterpret_cast<const float *>(blob + L.off_w_in_t);
+    const float *w_out_t = reinterpret_cast<const float *>(blob + L.off_w_out_t);
+    const int n2 = (mlp->d_out + 15) / 16 * 16;
+    SD_CUDA_OK(cudaMemsetAsync(out, 0, PROJX_OFF_MAP, st));
+    pj::x3_weights_kernel<<<1, 128, 0, st>>>(w_in_t, w_out_t, scene->C, mlp->d_out, L.d_out_pad, n2, scene->empty_feature,
+                                             scene->learn_empty, out);
+    SD_LAUNCH_OK("x3_weights_kernel");
+    const long long n_texels = (long long)scene->Hf * scene->Wf;
+    __half *P_hi = reinterpret_cast<__half *>(out + PROJX_OFF_MAP);
+    pj::proj_x3_kernel<<<(unsigned)((n_texels + pj::X3_TEX - 1) / pj::X3_TEX), 256, 0, st>>>(
+        reinterpret_cast<const float *>(scene->feat), w_in_t, scene->C, n_texels, P_hi, P_hi + (size_t)n_texels * 128);
+    SD_LAUNCH_OK("proj_x3_kernel");
+    return SD_OK;
+}
 
 extern "C" size_t sd_field_project_bytes(const sd_scene *scene) {
     if (!scene || scene->Hf <= 0 || scene->Wf <= 0) return 0;

@@ -121,6 +121,14 @@ int make_tmap(void *tmap_out, const void *base, int elem_bytes, int rank, const 
 int make_tmap_f16(void *tmap_out, const void *base, int rank, const unsigned long long *dims,
                   const unsigned long long *strides_bytes, const unsigned int *box);
 bool bin_kernel_supported(const sd_scene *scene, const sd_mlp *mlp);
+// rel-1e-4 variant (field_bin_x3.cu; scene->feat_proj_x3 from sd_field_project_x3, mlp->precision == SD_MLP_F32_TC)
+constexpr int PROJX_OFF_WC = 0;            // 2 x 16 KB: code block of W_in (+ projected empty feature in column 39), hi and lo images
+constexpr int PROJX_OFF_W2 = 32768;        // 2 x (2 K blocks x n2 rows x 128 B): W_out hi and lo images (feature rows first, density row last)
+constexpr int PROJX_W2_BYTES = 2 * 2 * 80 * 128;
+constexpr int PROJX_OFF_MAP = PROJX_OFF_W2 + PROJX_W2_BYTES;   // P_hi [Hf*Wf][128] fp16, then P_lo
+bool bin_kernel_supported_x3(const sd_scene *scene, const sd_mlp *mlp);
+int launch_field_bin_x3(const sd_scene *scene, const FieldParams &fp, const float *xyz, long long N, const sd_mlp *mlp,
+                        const BinOrder &order, const TcOut &out, cudaStream_t st);
 int launch_field_bin(const sd_scene *scene, const FieldParams &fp, const float *xyz, long long N, const sd_mlp *mlp,
                      const BinOrder &order, const TcOut &out, cudaStream_t st);
 // ResnetFC.forward on explicit rows through the same tcgen05 pipeline (unit test of the MMA path)

@@ -15,6 +15,7 @@ from . import _abi
 from .heads import _f32c, _ptr, _stream, device_guard, on_device, require_cuda
 
 FP32, F16 = _abi.SD_MLP_FP32, _abi.SD_MLP_F16_TC
+F32TC = _abi.SD_MLP_F32_TC      # rel 1e-4 on the tensor cores: fp16 (hi, lo) operand pairs, three products per contraction
 
 
 def _dev(t, device):
@@ -83,6 +84,7 @@ class Scene:
     learn_empty: bool = False
     empty_feature: torch.Tensor | None = None
     proj: torch.Tensor | None = None    # blob of sd_field_project (tied to one head), see project()
+    proj_x3: torch.Tensor | None = None  # blob of sd_field_project_x3 (F32TC queries), see project_x3()
 
     @classmethod
     def from_arrays(cls, feat_nchw, K_f, w2c_f, rgb=None, K_c=None, w2c_c=None, device="cuda",
@@ -97,7 +99,7 @@ class Scene:
         return s
 
     def sd_tensors(self):
-        return [t for t in (self.feat, self.K_f, self.w2c_f, self.rgb, self.K_c, self.w2c_c, self.empty_feature, self.proj)
+        return [t for t in (self.feat, self.K_f, self.w2c_f, self.rgb, self.K_c, self.w2c_c, self.empty_feature, self.proj, self.proj_x3)
                 if t is not None]
 
     def with_feat_dtype(self, feat_nchw, dtype):
@@ -119,6 +121,22 @@ class Scene:
             blob = raw[off:off + nbytes]
             _abi.check(lib.sd_field_project(C.byref(sc), C.byref(m), _ptr(blob), nbytes, _stream()), "sd_field_project")
         return dataclasses.replace(self, proj=blob)
+
+    def project_x3(self, mlp: "Mlp") -> "Scene":
+        """The projection for F32TC queries (sd_field_project_x3): fp32 map -> P in fp32 -> (hi, lo) fp16 maps + (hi, lo)
+        weight images of ``mlp``.  Returns a copy of the scene."""
+        import dataclasses
+        if self.feat.dtype != torch.float32:
+            raise ValueError("project_x3() needs the fp32 channels-last map")
+        sc, m = dataclasses.replace(self, proj=None, proj_x3=None).c(), mlp.c(F32TC)
+        lib = _abi.lib()
+        nbytes = lib.sd_field_project_x3_bytes(C.byref(sc))
+        with on_device(self, mlp):
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.feat.device)
+            off = (-raw.data_ptr()) % 1024
+            blob = raw[off:off + nbytes]
+            _abi.check(lib.sd_field_project_x3(C.byref(sc), C.byref(m), _ptr(blob), nbytes, _stream()), "sd_field_project_x3")
+        return dataclasses.replace(self, proj_x3=blob)
 
     @property
     def nv_c(self) -> int:
@@ -146,6 +164,8 @@ class Scene:
             s.empty_feature = self.empty_feature.data_ptr()
         if self.proj is not None:
             s.feat_proj = self.proj.data_ptr()
+        if self.proj_x3 is not None:
+            s.feat_proj_x3 = self.proj_x3.data_ptr()
         return s
 
 
@@ -286,7 +306,7 @@ def query_points_sorted(scene: Scene, mlp: Mlp, xyz, out: dict):
 
 
 @device_guard
-def query_points_binned(scene: Scene, mlp: Mlp, xyz, out=None, reuse_sorted=False):
+def query_points_binned(scene: Scene, mlp: Mlp, xyz, out=None, reuse_sorted=False, precision=F16):
     """The point query with the 64-d features left in texel-bin order (sd_query_points_binned): dict(sigma [N],
     invalid_features [N] -- caller's order --, dino_binned [N,64], perm [N] int32: row r of dino_binned belongs to point
     perm[r]).  ``dino_binned[argsort(perm)]`` is bit-identical to ``query_points(...)["dino"]``.  ``reuse_sorted``: the
@@ -296,7 +316,7 @@ def query_points_binned(scene: Scene, mlp: Mlp, xyz, out=None, reuse_sorted=Fals
     if out is None:
         out = dict(sigma=_e((N,), xyz), dino_binned=_e((N, 64), xyz), perm=_e((N,), xyz, torch.int32),
                    invalid_features=_e((N,), xyz, torch.uint8))
-    sc, m = scene.c(), mlp.c(F16)
+    sc, m = scene.c(), mlp.c(precision)
     lib = _abi.lib()
     need = lib.sd_query_workspace_bytes(C.byref(sc), C.byref(m), N)
     ws = out.get("_workspace")
