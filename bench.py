@@ -16,6 +16,7 @@ The one JSON line carries, besides the contract's keys (value, e2e, roofline, cp
                  sigma + label back on the host; through ``BTSNet.forward(predict_segmentation=True)``
   renders        BASELINE configs 1, 3 and 4 through ``NeRFRenderer`` (sd_render_rays): Msamples/s, tensor roofline, e2e
   fp32           the rel-1e-4 mode (CUDA-core parity path) on a slab of the grid
+  fp32_tc        the rel-1e-4 mode on the tensor cores (SD_MLP_F32_TC: fp16 hi/lo operand pairs, three products) on the whole grid
   strong_scaling (N > 1) ONE grid split into x-slabs across the ranks + all-gather of sigma and mask
 
 N > 1 (torchrun, one rank per GPU): ``value`` is weak scaling -- every rank queries one full grid against its own replica
@@ -741,7 +742,46 @@ def main():
         if line is not None:
             line["fp32"] = {"what": "rel-1e-4 parity mode: fp32 channels-last map, FFMA head (field_simt_kernel), one x-slab of 262 144 voxels",
                             "voxels_per_s": n32 / (ms32 * 1e-3), "ms": ms32, "ffma_tflops": n32 * FLOP_PER_POINT / (ms32 * 1e-3) / 1e12}
-        del feat32, sc32, o32
+        # ---- the same bar ON the tensor cores: SD_MLP_F32_TC (fp16 hi/lo operand pairs, three kind::f16 products per
+        #      contraction, fp32 epilogues: field_bin_x3.cu) on the whole grid; its once-per-encode projection beside it --
+        st3 = {}
+
+        def p3():
+            st3["s"] = sc32.project_x3(mlp)
+        proj3_ms = timed_ms(p3, n=2, warm=1)
+        sc3 = st3["s"]
+        o3 = None
+
+        def q3():
+            nonlocal o3
+            o3 = ops.query_points(sc3, mlp, pts, want_rgb=False, precision=ops.F32TC, out=o3)
+        ms3 = timed_ms(q3, n=max(3, args.steps // 2), warm=2)
+        k3 = []
+        for _ in range(4):
+            ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ka.record(); kb.record()
+            _abi.check(_abi.lib().sd_profile_next_kernel(ka.cuda_event, kb.cuda_event), "sd_profile_next_kernel")
+            q3(); torch.cuda.synchronize()
+            k3.append(ka.elapsed_time(kb))
+        k3_ms = float(np.median(k3))
+        a64, b64 = o3["sigma"][:n32].double(), o32["sigma"].double()
+        d64, e64 = o3["dino"][:n32].double(), o32["dino"].double()
+        err = max(float(((a64 - b64).abs() / torch.clamp(b64.abs(), min=float(b64.pow(2).mean().sqrt()))).max()),
+                  float(((d64 - e64).abs() / torch.clamp(e64.abs(), min=float(e64.pow(2).mean().sqrt()))).max()))
+        if line is not None:
+            # executed tensor work: 3 products per contraction of the tile kernel's own algebra (interpolation K = 64 per
+            # chunk ~1.6 chunks per tile, code block K = 48, layer 2 K = 128 x N = 80)
+            line["fp32_tc"] = {"what": "rel-1e-4 mode on the tensor cores (SD_MLP_F32_TC): texel sort + field_bin_kernel (x3) on the whole "
+                                       "2 097 152-voxel grid, fp32 map projected once per encode into an fp16 (hi, lo) pair of maps",
+                               "voxels_per_s": N / (ms3 * 1e-3), "ms": ms3, "kernel_ms": k3_ms, "project_x3_ms": proj3_ms,
+                               "max_rel_err_vs_fp32_cuda_core_kernel": err,
+                               "speedup_vs_fp32_cuda_core_kernel": (N / ms3) / (n32 / ms32),
+                               "roofline": {"bound": "tensor", "achieved": N * FLOP_PER_POINT / (k3_ms * 1e-3) / 1e12,
+                                            "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                                            "frac": N * FLOP_PER_POINT / (k3_ms * 1e-3) / 1e12 / pk["tc_burst"], "traffic": None,
+                                            "note": "reference-algorithm FLOPs (92 160 per voxel) over the tile kernel's time against the "
+                                                    "fp16 dense peak; the kernel issues 3 fp16 products per contraction, so 1/3 is its ceiling"}}
+        del feat32, sc32, o32, sc3, o3, st3
         torch.cuda.empty_cache()
 
     # ---- strong scaling: ONE grid split into x-slabs (what north_star's partition names), all-gather of sigma + mask ----

@@ -17,7 +17,7 @@ from . import _abi
 from .heads import (MlpDimReduction, ResnetFC, _f32c, _ptr, _stream, device_guard, expand_precision, note_field_precision,
                     require_cuda)
 
-PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC}
+PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC, "fp32_tc": _abi.SD_MLP_F32_TC}
 
 
 class BTSNet(nn.Module):
@@ -172,7 +172,7 @@ class BTSNet(nn.Module):
         if p == "auto":
             p = "fp16" if torch.is_autocast_enabled() else "fp32"
         if p not in PRECISIONS:
-            raise ValueError(f"precision must be one of fp32|fp16|auto, got {self.precision!r}")
+            raise ValueError(f"precision must be one of fp32|fp32_tc|fp16|auto, got {self.precision!r}")
         note_field_precision(PRECISIONS[p])
         return PRECISIONS[p]
 
@@ -209,8 +209,9 @@ class BTSNet(nn.Module):
         return st
 
     def _projection(self, st, b: int, mlp: _abi.SdMlp):
-        """Blob of sd_field_project for batch element ``b`` and this head, made once per encode: the fp16 map pushed
-        through the feature columns of the head's first layer, for the projected-map tile kernel."""
+        """Blob of sd_field_project (fp16 state) / sd_field_project_x3 (fp32 state, SD_MLP_F32_TC) for batch element ``b``
+        and this head, made once per encode: the map pushed through the feature columns of the head's first layer, for the
+        projected-map tile kernel."""
         # the blob bakes in W_in[:, :C] and W_feat . empty_feature: key it on the pack generation of the head (a repack
         # can land on a recycled allocator address) and on the identity / version of empty_feature
         cache = st.setdefault("proj", {})
@@ -223,18 +224,23 @@ class BTSNet(nn.Module):
         if blob is None:
             sc = self._scene(st, b)
             lib = _abi.lib()
-            nbytes = lib.sd_field_project_bytes(C.byref(sc))
+            x3 = mlp.precision == _abi.SD_MLP_F32_TC
+            nbytes = (lib.sd_field_project_x3_bytes if x3 else lib.sd_field_project_bytes)(C.byref(sc))
             raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=st["feat"].device)
             off = (-raw.data_ptr()) % 1024
             blob = raw[off:off + nbytes]
-            _abi.check(lib.sd_field_project(C.byref(sc), C.byref(mlp), _ptr(blob), nbytes, _stream()), "sd_field_project")
+            _abi.check((lib.sd_field_project_x3 if x3 else lib.sd_field_project)(C.byref(sc), C.byref(mlp), _ptr(blob), nbytes, _stream()),
+                       "sd_field_project_x3" if x3 else "sd_field_project")
             cache[key] = blob
         return blob
 
     def _scene(self, st, b: int, proj=None) -> _abi.SdScene:
         s = _abi.SdScene()
         if proj is not None:
-            s.feat_proj = proj.data_ptr()
+            if st["dt"] == _abi.SD_F16:
+                s.feat_proj = proj.data_ptr()
+            else:                              # (the fp32 state's projection is the x3 one)
+                s.feat_proj_x3 = proj.data_ptr()
         s.feat = st["feat"][b].data_ptr()
         s.feat_dtype = st["dt"]
         s.nv_f, s.C, s.Hf, s.Wf = 1, st["C"], st["Hf"], st["Wf"]
@@ -338,7 +344,7 @@ class BTSNet(nn.Module):
             lib = _abi.lib()
             # big reduced-precision queries (SSC voxel chunks) run on the projected map: made once per encode and head
             hf, wf = st["Hf"], st["Wf"]
-            use_proj = (prec == _abi.SD_MLP_F16_TC and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
+            use_proj = (prec in (_abi.SD_MLP_F16_TC, _abi.SD_MLP_F32_TC) and st["C"] == 256 and mlp.d_hidden == 128 and D <= 64
                         and N >= 16 * ((hf + 5) // 7 + 1) * ((wf + 5) // 7 + 1))
             # predict_segmentation with the fused head: the 64-d rows only feed sd_ssc_head, which takes a permutation --
             # they stay in the tile kernel's own (texel-bin) order and leave the SM by TMA tile stores

@@ -74,3 +74,25 @@ def test_ssc_grid_full_size_x3(map_hw):
     assert torch.isfinite(q["sigma"]).all() and torch.isfinite(q["dino"]).all()
     b = ops.query_points_binned(dscp, dmlp, dp, precision=ops.F32TC)
     assert torch.equal(b["sigma"], q["sigma"]) and torch.equal(b["dino_binned"], q["dino"][b["perm"].long()])
+
+
+def test_btsnet_forward_fp32_tc(golden):
+    """BTSNet.forward with sd_precision = "fp32_tc": the reference-shaped surface on the x3 tile kernel; against the fp32
+    CUDA-core precision of the same net at 1e-4, masks bit for bit."""
+    import bench
+    import scenedino_b200 as sd
+    hold = {"map": dev(syn.make_feature_map(1, 256, 96, 320))}
+    net = bench.build_net(sd, torch, hold, DEV, "fp32_tc", with_head=False)
+    imgs = dev(syn.make_images(2, 1))[None]
+    Kc = dev(syn.kitti360_K()[None])[None]
+    c2w = dev(np.eye(4, dtype=np.float32)[None])[None]
+    net.encode(imgs * 2 - 1, Kc, c2w, ids_encoder=[0], ids_render=[0], images_alt=imgs)
+    net.set_scale(0)
+    grid = dev(syn.ssc_voxel_grid()[::3].copy())[None]
+    with torch.no_grad():
+        _, inv_a, sig_a, _, st_a = net(grid, only_density=True)
+        net.precision = "fp32"
+        _, inv_b, sig_b, _, st_b = net(grid, only_density=True)
+    assert torch.equal(inv_a, inv_b)
+    assert_close(g2n(sig_a), g2n(sig_b), TOL_FP32, "sigma, fp32_tc vs fp32")
+    assert_close(g2n(st_a["dino_features"]), g2n(st_b["dino_features"]), TOL_FP32, "dino, fp32_tc vs fp32")
