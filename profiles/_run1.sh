@@ -1,7 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_x3.py -x -q 2>&1 | grep -v "^$" | tail -15
-SD_BENCH_VERBOSE=1 python bench.py --no-render --no-cpu-baseline > gpurun_out/bench_r02d.json 2> gpurun_out/bench_r02d.err; tail -3 gpurun_out/bench_r02d.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_r02d.json'))
-print({k:d[k] for k in ('value','ms_per_step')}); print(d['fp32']); print(d['fp32_tc'])
-PY
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_surface.py tests/test_gpu_zz_next.py -x -q -k "render or pass or surface or d768 or rays" 2>&1 | tail -3
+python profiles/time_r02.py 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print({k:round(v['ms'],3) for k,v in d.items() if isinstance(v,dict) and 'ms' in v})"

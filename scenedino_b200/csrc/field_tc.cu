@@ -621,10 +621,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
             const int nv_c = P.fp.nv_c;
             // inputs of a tile row (global row index, 3-D point, sample depth), fetched one tile ahead so that the
             // dependent perm -> xyz (or ray + z) loads are off the critical path
-            struct RowIn { long long grow; float px, py, pz, zs; };
+            // (the loaded values are kept RAW -- origin, direction, depth -- and turned into the point when the tile is
+            // processed: forming o + z d here made the loop wait for these loads right where they were issued)
+            struct RowIn { long long grow; float px, py, pz, dx, dy, dz, zs; };
             auto fetch = [&](long long jj) {
                 RowIn r;
-                r.grow = -1; r.px = r.py = r.pz = r.zs = 0.0f;
+                r.grow = -1; r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.zs = 0.0f;
                 if (jj >= my_tiles) return r;
                 const long long unit = (first + jj * stride) * P.upt + row / K;
                 if (!(row_used && unit < P.n_units)) return r;
@@ -632,14 +634,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 if (!P.src.xyz) {
                     const float *ry = P.src.rays + (r.grow / P.src.K) * P.src.r_dim;
                     r.zs = __ldg(P.src.z + r.grow);
-                    r.px = ray_point(__ldg(ry + 0), __ldg(ry + 3), r.zs);
-                    r.py = ray_point(__ldg(ry + 1), __ldg(ry + 4), r.zs);
-                    r.pz = ray_point(__ldg(ry + 2), __ldg(ry + 5), r.zs);
+                    r.px = __ldg(ry + 0); r.py = __ldg(ry + 1); r.pz = __ldg(ry + 2);
+                    r.dx = __ldg(ry + 3); r.dy = __ldg(ry + 4); r.dz = __ldg(ry + 5);
                 } else {
                     r.px = __ldg(P.src.xyz + 3 * r.grow); r.py = __ldg(P.src.xyz + 3 * r.grow + 1); r.pz = __ldg(P.src.xyz + 3 * r.grow + 2);
                 }
                 return r;
             };
+            const bool from_rays = !P.src.xyz;
             RowIn nxt = fetch(0);
             for (long long j = 0; j < my_tiles; ++j) {
                 const RowIn cur = nxt;
@@ -658,7 +660,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 3 * MAX_NVC_TC; ++c) call[c] = 0.0f;
                 if (ok) {
-                    const float px = cur.px, py = cur.py, pz = cur.pz;
+                    const float px = from_rays ? ray_point(cur.px, cur.dx, zs) : cur.px, py = from_rays ? ray_point(cur.py, cur.dy, zs) : cur.py,
+                                pz = from_rays ? ray_point(cur.pz, cur.dz, zs) : cur.pz;
                     float zc;
                     bool inv;
                     project_point(s_cam, s_cam + 9, px, py, pz, x, y, zc, inv);
@@ -729,9 +732,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                         code[42 + d] = hi;
                     }
                     float s[3], c[3];
-                    sincosf(__fmul_rn(x, P.fp.enc.freq_factor), &s[0], &c[0]);
-                    sincosf(__fmul_rn(y, P.fp.enc.freq_factor), &s[1], &c[1]);
-                    sincosf(__fmul_rn(zp, P.fp.enc.freq_factor), &s[2], &c[2]);
+                    const float a0 = __fmul_rn(x, P.fp.enc.freq_factor), a1 = __fmul_rn(y, P.fp.enc.freq_factor), a2 = __fmul_rn(zp, P.fp.enc.freq_factor);
+                    if (fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(a2)) <= 3.2f) {     // the usual case: hardware sin / cos (as field_bin.cu)
+                        s[0] = __sinf(a0); c[0] = __cosf(a0); s[1] = __sinf(a1); c[1] = __cosf(a1); s[2] = __sinf(a2); c[2] = __cosf(a2);
+                    } else {                                                          // next to / behind the camera: |z'| is large
+                        sincosf(a0, &s[0], &c[0]); sincosf(a1, &s[1], &c[1]); sincosf(a2, &s[2], &c[2]);
+                    }
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
 #pragma unroll
