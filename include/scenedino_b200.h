@@ -310,6 +310,23 @@ int sd_debug_read_trace(long long *host_out);
 int sd_debug_read_trace_bin(long long *host_out);
 int sd_debug_read_cta_ns(unsigned long long *host_out);
 
+/* ---- section 8f-4: backward pass of the training step (training/base_trainer.py:223-255) ---------------------------------
+ * The fused kernels above are forward-only.  In training mode (autograd on) the Python surface runs the path unfused --
+ * sd_sample_features, the head as plain torch modules (its GEMMs and their gradients are library GEMMs), sd_composite --
+ * and these two entries supply the gradients of the two custom stages.
+ *
+ * sd_composite_bwd: gradients of sd_composite (nerf.py:376-421) for the same z / sigma / feat / rgb and render options.
+ *   g_depth [R], g_dino [R,D], g_rgb_out [R,Crgb], g_weights [R,K], g_alphas [R,K]: upstream gradients (NULL = zero);
+ *   g_sigma [R,K], g_feat [R,K,D], g_rgb [R,K,Crgb]: outputs (any may be NULL).  K <= 256.
+ * sd_sample_features_bwd: gradient of BTSNet.sample_features (bts.py:299-319) with respect to the encoder feature map:
+ *   g_feat [N, C + code] is scattered (atomic adds) into g_map [Hf,Wf,C] fp32 channels-last, which the caller zeroes;
+ *   rows the forward replaced by the learned empty feature add to g_empty [C] instead. */
+int sd_composite_bwd(const float *z, const float *sigma, const float *feat, const float *rgb, long long R, int K, int D,
+                     int Crgb, const sd_render_cfg *cfg, const float *g_depth, const float *g_dino, const float *g_rgb_out,
+                     const float *g_weights, const float *g_alphas, float *g_sigma, float *g_feat, float *g_rgb, void *stream);
+int sd_sample_features_bwd(const sd_scene *scene, const float *xyz, long long N, const float *g_feat, float *g_map,
+                           float *g_empty, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ PROTOTYPES = {
     "sd_sample_coarse_from_dist": (_I, [_LL, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "sd_sort_rows": (_I, [_P, _LL, _I, _P]),
     "sd_composite": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _RC, _P, _P, _P, _P, _P, _P]),
+    "sd_composite_bwd": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _RC, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sd_sample_features_bwd": (_I, [_SC, _P, _LL, _P, _P, _P, _P]),
     "sd_render_workspace_bytes": (_SZ, [_SC, _ML, _LL, _I]),
     "sd_render_pass": (_I, [_SC, _ML, _RC, _P, _LL, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                             _P, _SZ, _P]),

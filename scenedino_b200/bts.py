@@ -278,9 +278,45 @@ class BTSNet(nn.Module):
         require_cuda(xyz, "xyz")
         if xyz.dim() != 3 or xyz.shape[-1] != 3:
             raise ValueError(f"xyz must be [n, n_pts, 3], got {tuple(xyz.shape)}")
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError("scenedino_b200 is forward-only: call under torch.no_grad() / .eval()")
         return _f32c(xyz)
+
+    def _wants_grad(self) -> bool:
+        """Training mode with autograd on: the differentiable (unfused) path, SURVEY 8f-4."""
+        return torch.is_grad_enabled() and self.training
+
+    def _forward_train(self, xyz, only_density=False):
+        """BTSNet.forward (bts.py:476-595) with a gradient: feature gather (custom backward into the encoder map and the
+        learned empty feature), the head as torch modules, colours from the images (no gradient).  Same returns."""
+        from .autograd import SampleFeaturesFn
+        xyz = self._check_points(xyz)
+        st = self._state(_abi.SD_MLP_FP32)
+        n, N, _ = xyz.shape
+        fmap = self.grid_f_features[self._scale]                  # [n, 1, C, Hf, Wf], part of the encoder's graph
+        d_in = st["C"] + self.code_xyz.d_out
+        head = self.heads[self.final_pred_head]
+        feats, invs = [], []
+        for b in range(n):
+            sc = self._scene(st, b)
+            f, inv = SampleFeaturesFn.apply(fmap[b, 0], self.empty_feature if self.learn_empty else None, xyz[b], sc,
+                                            (st, getattr(self, "_empty_f32", None)), d_in)
+            feats.append(f); invs.append(inv)
+        feat = torch.stack(feats, 0)                              # [n, N, C + code]
+        invalid_features = torch.stack(invs, 0).view(torch.bool).unsqueeze(-1)        # [n, N, 1]
+        mlp_output = head.lin_out(head.activation(head.lin_in(feat)))                 # resnetfc.py:162-199, n_blocks = 0
+        sigma = torch.nn.functional.softplus(mlp_output[..., :1])
+        dino = mlp_output[..., 1:]
+        if only_density:
+            rgb = torch.zeros((n, N, st["rgb"].shape[1] * 3), device=xyz.device)
+            invalid = invalid_features.to(sigma.dtype)
+        else:
+            with torch.no_grad():
+                rgb, invalid_colors = self.sample_colors(xyz)     # (n, nv, N, 3), (n, nv, N, 1)
+            nv_ = rgb.shape[1]
+            rgb = rgb.permute(0, 2, 1, 3).reshape(n, N, nv_ * 3)
+            invalid_colors = invalid_colors.permute(0, 2, 1, 3).reshape(n, N, nv_)
+            invalid = (invalid_colors | torch.all(invalid_features, dim=-1)[..., None]).to(rgb.dtype)
+        state_dict = {"invalid_features": invalid_features.flatten(0, 1)[None], "dino_features": dino}
+        return rgb, invalid, sigma, None, state_dict
 
     # ---- BTSNet.sample_features (bts.py:271-328) ---------------------------------------------------
     @device_guard
@@ -326,6 +362,13 @@ class BTSNet(nn.Module):
             raise NotImplementedError("render_flow is not implemented")
         if not self.predict_dino:
             raise NotImplementedError("predict_dino=False heads are not implemented")
+        if self._wants_grad():
+            if predict_segmentation:
+                raise NotImplementedError("predict_segmentation with autograd is not implemented (the SSC head is evaluation-only)")
+            head = self.heads[self.final_pred_head]
+            if not (hasattr(head, "lin_in") and hasattr(head, "lin_out") and getattr(head, "n_blocks", 0) == 0):
+                raise NotImplementedError("the differentiable path needs a ResnetFC head with n_blocks = 0")
+            return self._forward_train(xyz, only_density=only_density)
         with torch.profiler.record_function("model_inference"):
             xyz = self._check_points(xyz)
             prec = self._precision()

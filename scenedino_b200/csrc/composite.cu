@@ -97,7 +97,129 @@ __global__ void __launch_bounds__(128) composite_kernel(const float *__restrict_
     if (rgb_out && lane < Crgb) rgb_out[r * Crgb + lane] = white_bkgd ? cacc + 1.0f - wsum : cacc;
 }
 
+// ---- backward of the composite (what autograd derives from nerf.py:376-421) ---------------------------------
+// With s_k = 1 - a_k + 1e-10, T_k = prod_{i<k} s_i, w_k = a_k T_k and the outputs depth = sum w z, dino = sum w f,
+// rgb = sum w c (+ 1 - sum w), weights = w, alphas = a:
+//   G_k      = g_weights[k] + g_depth z_k + <g_dino, f_k> + <g_rgb, c_k> - white * sum(g_rgb)        (dL/dw_k)
+//   dL/df_k  = w_k g_dino,   dL/dc_k = w_k g_rgb
+//   dL/da_k  = G_k T_k + g_alphas[k] - (sum_{j>k} G_j w_j) / s_k          (torch.cumprod's backward divides the same way)
+//   dL/dsig_k = dL/da_k |delta_k| exp(-|delta_k| sig_k)   for sigma_k > 0 and unless hard_alpha_cap pins the last alpha to 1
+// One warp per ray, K <= 32 * NCH samples held in registers (lane = sample within a chunk).
+__device__ __forceinline__ float warp_scan_add_down(float v, int lane) {   // inclusive suffix sum over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += n;
+    }
+    return v;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const float *__restrict__ z, const float *__restrict__ sigma,
+                                                            const float *__restrict__ feat, const float *__restrict__ rgb,
+                                                            long long R, int K, int D, int Crgb, int hard_alpha_cap, int white_bkgd,
+                                                            const float *__restrict__ g_depth, const float *__restrict__ g_dino,
+                                                            const float *__restrict__ g_rgb_out, const float *__restrict__ g_weights,
+                                                            const float *__restrict__ g_alphas, float *__restrict__ g_sigma,
+                                                            float *__restrict__ g_feat, float *__restrict__ g_rgb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 4 + warp;
+    if (r >= R) return;
+    const float *zr = z + r * K, *sr = sigma + r * K;
+    float a[NCH], Tk[NCH], w[NCH], G[NCH], dl[NCH];
+    float T = 1.0f;
+    const float gd = g_depth ? __ldg(g_depth + r) : 0.0f;
+    float gsum_rgb = 0.0f;                                   // sum_c g_rgb[c] (white background term)
+    const float grgb_l = (g_rgb_out && lane < Crgb) ? __ldg(g_rgb_out + r * Crgb + lane) : 0.0f;
+    if (white_bkgd) gsum_rgb = warp_sum(grgb_l);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int k = c * 32 + lane;
+        const bool act = k < K;
+        const float zk = act ? __ldg(zr + k) : 0.0f;
+        const float zn = (k + 1 < K) ? __ldg(zr + k + 1) : 0.0f;
+        dl[c] = (k + 1 < K) ? fabsf(zn - zk) : 1e10f;
+        a[c] = act ? sample_alpha(dl[c], __ldg(sr + k), k == K - 1, hard_alpha_cap) : 0.0f;
+        const float shifted = act ? (1.0f - a[c]) + 1e-10f : 1.0f;
+        const float incl = warp_scan_mul(shifted, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0f;
+        Tk[c] = T * excl;
+        w[c] = a[c] * Tk[c];
+        T = T * __shfl_sync(0xffffffffu, incl, 31);
+        G[c] = act ? ((g_weights ? __ldg(g_weights + r * K + k) : 0.0f) + gd * zk - gsum_rgb) : 0.0f;
+    }
+    // <g_dino, f_k>, <g_rgb, c_k> per sample (lanes stride the channels), and the gradients of f / c
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int n = min(32, K - c * 32);
+        for (int j = 0; j < n; ++j) {
+            const size_t row = (size_t)(r * K + c * 32 + j);
+            const float wj = __shfl_sync(0xffffffffu, w[c], j);
+            float part = 0.0f;
+            if (g_dino && feat) {
+                for (int ch = lane; ch < D; ch += 32) {
+                    const float g = __ldg(g_dino + r * D + ch);
+                    part = fmaf(g, __ldg(feat + row * D + ch), part);
+                    if (g_feat) g_feat[row * D + ch] = wj * g;
+                }
+            } else if (g_feat) {
+                for (int ch = lane; ch < D; ch += 32) g_feat[row * D + ch] = 0.0f;
+            }
+            if (lane < Crgb) {
+                if (g_rgb_out && rgb) part = fmaf(grgb_l, __ldg(rgb + row * Crgb + lane), part);
+                if (g_rgb) g_rgb[row * Crgb + lane] = wj * grgb_l;
+            }
+            part = warp_sum(part);
+            if (lane == j) G[c] += part;
+        }
+    }
+    // suffix sums of G w, last chunk first
+    float carry = 0.0f;                                       // sum over the chunks behind the current one
+#pragma unroll
+    for (int c = NCH - 1; c >= 0; --c) {
+        const int k = c * 32 + lane;
+        const bool act = k < K;
+        const float gw = act ? G[c] * w[c] : 0.0f;
+        const float incl = warp_scan_add_down(gw, lane);
+        const float S = incl - gw + carry;                    // sum_{j>k} G_j w_j
+        carry += __shfl_sync(0xffffffffu, incl, 0);
+        if (act && g_sigma) {
+            const float s_k = (1.0f - a[c]) + 1e-10f;
+            float da = G[c] * Tk[c] + (g_alphas ? __ldg(g_alphas + r * K + k) : 0.0f) - S / s_k;
+            const float sg = __ldg(sr + k);
+            const bool pinned = hard_alpha_cap && k == K - 1;
+            g_sigma[r * K + k] = (sg > 0.0f && !pinned) ? da * dl[c] * expf(-dl[c] * sg) : 0.0f;   // d/dsig (1 - exp(-|delta| sig))
+        }
+    }
+}
+
 }  // namespace sd
+
+extern "C" int sd_composite_bwd(const float *z, const float *sigma, const float *feat, const float *rgb, long long R, int K, int D,
+                                int Crgb, const sd_render_cfg *cfg, const float *g_depth, const float *g_dino,
+                                const float *g_rgb_out, const float *g_weights, const float *g_alphas, float *g_sigma,
+                                float *g_feat, float *g_rgb, void *stream) {
+    SD_REQUIRE(cfg, "sd_composite_bwd: null pointer");
+    SD_REQUIRE(R >= 0 && K > 0 && K <= 256, "sd_composite_bwd: 1 <= K <= 256 samples per ray (got %d)", K);
+    if (R == 0) return SD_OK;
+    SD_REQUIRE(z && sigma, "sd_composite_bwd: null pointer");
+    SD_REQUIRE(D >= 0 && D <= 1024 && Crgb >= 0 && Crgb <= 32, "sd_composite_bwd: D <= 1024, Crgb <= 32");
+    SD_REQUIRE(!(g_dino && D > 0) || feat, "sd_composite_bwd: g_dino without feat");
+    SD_REQUIRE(!(g_rgb_out && Crgb > 0) || rgb, "sd_composite_bwd: g_rgb_out without rgb");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((R + 3) / 4);
+#define SD_COMPOSITE_BWD(NCH)                                                                                                  \
+    sd::composite_bwd_kernel<NCH><<<grid, 128, 0, st>>>(z, sigma, feat, rgb, R, K, D, Crgb, cfg->hard_alpha_cap, cfg->white_bkgd, \
+                                                        g_depth, g_dino, g_rgb_out, g_weights, g_alphas, g_sigma, g_feat, g_rgb)
+    if (K <= 32) SD_COMPOSITE_BWD(1);
+    else if (K <= 64) SD_COMPOSITE_BWD(2);
+    else if (K <= 128) SD_COMPOSITE_BWD(4);
+    else SD_COMPOSITE_BWD(8);
+#undef SD_COMPOSITE_BWD
+    SD_LAUNCH_OK("composite_bwd_kernel");
+    return SD_OK;
+}
 
 extern "C" int sd_composite(const float *z, const float *sigma, const float *feat, const float *rgb,
                             long long R, int K, int D, int Crgb, const sd_render_cfg *cfg, float *weights,

@@ -185,7 +185,7 @@ class NeRFRenderer(torch.nn.Module):
             rays = self._rays2d(rays)
             z_samp = _f32c(z_samp)
             B, K = z_samp.shape
-            if hasattr(model, "_sd_render_pass") or hasattr(model, "_scene"):
+            if (hasattr(model, "_sd_render_pass") or hasattr(model, "_scene")) and not self._wants_grad(model):
                 out = self._composite_native(model, rays, z_samp, max(sb, 1), want_rgb_samps)
             else:
                 out = self._composite_generic(model, rays, z_samp, coarse, sb)
@@ -194,6 +194,12 @@ class NeRFRenderer(torch.nn.Module):
                 self._nan_check(depth, rgb_final, z_samp)
             ray_info = rays[:, None, 8:] if rays.shape[-1] > 8 else None
             return weights, rgb_final, depth, alphas, invalid, z_samp, rgbs, ray_info, None, state
+
+    @staticmethod
+    def _wants_grad(model) -> bool:
+        """Training with autograd on: the fused kernels are forward-only, the pass runs unfused (model(points) with a graph,
+        then the composite with its custom backward: scenedino_b200.autograd)."""
+        return torch.is_grad_enabled() and bool(getattr(model, "training", False))
 
     @staticmethod
     def _nan_check(*tensors):
@@ -330,13 +336,20 @@ class NeRFRenderer(torch.nn.Module):
             if extras is not None:
                 raise NotImplementedError("models returning extras are not implemented")
             r_all.append(rgbs); i_all.append(invalid); s_all.append(sigmas); st_all.append(sd)
-        rgbs = _f32c(torch.cat(r_all, dim=dim)).reshape(B, K, -1)
+        graph = torch.is_grad_enabled() and any(t.requires_grad for t in s_all)      # training: keep the autograd graph
+        keep = (lambda t: t.float().contiguous()) if graph else _f32c
+        rgbs = keep(torch.cat(r_all, dim=dim)).reshape(B, K, -1)
         invalid = torch.cat(i_all, dim=dim).reshape(B, K, -1)
-        sigmas = _f32c(torch.cat(s_all, dim=dim)).reshape(B, K)
+        sigmas = keep(torch.cat(s_all, dim=dim)).reshape(B, K)
         state = {k: torch.cat([s[k] for s in st_all], dim=dim) for k in st_all[0].keys()}
         state = {k: v.reshape(B, K, *v.shape[2:]) for k, v in state.items()}
-        feat = _f32c(state["dino_features"])
+        feat = keep(state["dino_features"])
         D, Crgb = feat.shape[-1], rgbs.shape[-1]
+        if torch.is_grad_enabled() and (sigmas.requires_grad or feat.requires_grad or rgbs.requires_grad):
+            from .autograd import CompositeFn          # training: the composite with its custom backward (sd_composite_bwd)
+            weights, alphas, depth, dino, rgb = CompositeFn.apply(z, sigmas, feat, rgbs, self.hard_alpha_cap, self.white_bkgd)
+            state["dino_features"] = dino
+            return weights, rgb, depth, alphas, invalid, rgbs, state
         f32 = dict(dtype=torch.float32, device=rays.device)
         weights, alphas = torch.empty((B, K), **f32), torch.empty((B, K), **f32)
         depth, dino, rgb = torch.empty((B,), **f32), torch.empty((B, D), **f32), torch.empty((B, Crgb), **f32)
@@ -359,7 +372,8 @@ class NeRFRenderer(torch.nn.Module):
             assert len(rays.shape) == 3
             sb = rays.shape[0]
             rays = rays.reshape(-1, rays.shape[-1])
-            if sample_from_dist is None and (hasattr(model, "_sd_render_pass") or hasattr(model, "_scene")):
+            if (sample_from_dist is None and (hasattr(model, "_sd_render_pass") or hasattr(model, "_scene"))
+                    and not self._wants_grad(model)):
                 passes = self._forward_native(model, rays, sb, want_rgb_samps)
                 fmt = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
                            want_rgb_samps=want_rgb_samps)
