@@ -890,7 +890,43 @@ def main():
                    expand=True)
         render_cfg("cfg3", "BASELINE configs[2]: 4 views x 192x640 rays against the view-0 ViT-B/8 map, 64 coarse + 32 fine samples "
                            "(coarse pass 64, fine pass 96), 768-d feature composite, 4 colour views", HF, WF, [0, 1, 2, 3], 64, 32, 769, 4)
+        # ---- one training step's render: forward + backward of the unfused differentiable path on
+        #      BASELINE configs[0]'s ray batch (4096 rays x 64 coarse samples): gradients to the encoder map and the head ----
+        train = None
+        try:
+            tmap = torch.randn((1, C_FEAT, HF2, WF2), device=dev, generator=g).requires_grad_()
+            tnet = build_net(sd, torch, {"map": tmap}, dev, "fp32", with_head=False, seed=0)
+            tnet.train()
+            tren = sd.NeRFRenderer.from_conf({"n_coarse": 64, "n_fine": 0, "lindisp": True, "hard_alpha_cap": False})
+            tren.nan_check = False
+            tren.train()
+            timg = torch.from_numpy(syn.make_images(2, 1)).to(dev)[None]
+            tK = torch.from_numpy(syn.kitti360_K()[None]).to(dev)[None]
+            tpose = torch.from_numpy(syn.view_pose_c2w(0)[None]).to(dev)[None]
+            tnet.encode(timg * 2 - 1, tK, tpose, ids_encoder=[0], ids_render=[0], images_alt=timg)
+            tnet.set_scale(0)
+            trays, _ = ray_sampler.sample(None, torch.from_numpy(syn.view_pose_c2w(1)[None]).to(dev)[None], tK)
+            trays = trays[:, torch.randperm(trays.shape[1], device=dev, generator=g)[:4096]].contiguous()
+            tparams = [tmap] + [p_ for p_ in tnet.heads.parameters()]
+
+            def tstep():
+                for p_ in tparams:
+                    p_.grad = None
+                o = tren(tnet, trays)["coarse"]
+                (o["depth"].sum() * 0.01 + o["dino_features"].sum() + o["rgb"].sum()).backward()
+
+            t_ms = timed_ms(tstep, n=max(3, args.steps // 4), warm=2)
+            train = {"what": "training-mode render of 4096 rays x 64 coarse samples (DINOv2-sized map), forward + backward through "
+                             "BTSNet / NeRFRenderer with autograd on: sd_sample_features, the head as torch modules (library "
+                             "GEMMs), sd_composite, sd_composite_bwd, sd_sample_features_bwd; gradients to the encoder map and "
+                             "the head weights", "ms": t_ms, "msamples_per_s": 4096 * 64 / (t_ms * 1e-3) / 1e6,
+                     "grad_map_abs_sum": float(tmap.grad.abs().sum())}
+            del tnet, tren, tmap
+        except Exception as exc:      # noqa: BLE001 -- an extra: never takes the line down
+            train = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
         if line is not None:
+            line["train_step"] = train
             line["renders"] = renders
             line["render"] = {"msamples_per_s": renders["cfg4"]["msamples_per_s"], "ms": renders["cfg4"]["ms"],
                               "tensor_frac": renders["cfg4"]["roofline"]["frac"], "workload": "see renders.cfg4"}

@@ -277,12 +277,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     }
                     tmem_st16(t_lane + b * 128 + kb * 32, pk);
                     tmem_st16(t_lane + b * 128 + kb * 32 + 16, pl);
-                    continue;
-                }
+                } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    pk[e] = pack_h2_relu(__uint_as_float(vr[2 * e]), __uint_as_float(vr[2 * e + 1]));
-                tmem_st16(t_lane + b * 128 + kb * 16, pk);
+                    for (int e = 0; e < 16; ++e)
+                        pk[e] = pack_h2_relu(__uint_as_float(vr[2 * e]), __uint_as_float(vr[2 * e + 1]));
+                    tmem_st16(t_lane + b * 128 + kb * 16, pk);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
