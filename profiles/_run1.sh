@@ -1,1 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_backward.py -x -q 2>&1 | grep -v "^$" | tail -30
+for v in ahead0 prod ahead0 prod; do
+echo "== $v mode 4"; SD_B200_LIB=$PWD/scenedino_b200/build/variants/lib_$v.so timeout 120 python profiles/stress_bin.py 100000 4 2>&1 | grep "FAILED\|done" | head -3
+done

@@ -139,6 +139,30 @@ static_assert(OFF_W2 % 1024 == 0 && OFF_STAGE % 1024 == 0 && OFF_BAR % 8 == 0 &&
 __device__ long long g_trace[8 * 64 * 8];
 __device__ long long g_tiles[4 * 2 * 512];          // [cta 0..3][tile][clock64 at the layer-1 issuer's tile start, chunks] (SD_TC_DEBUG & 8192)
 __device__ unsigned long long g_cta_ns[256 * 2];   // [cta][start, end] %globaltimer (SD_TC_DEBUG & 8192)   // [role][tile][event] clock64 stamps of CTA 0 (SD_TC_DEBUG & 8192)
+#ifdef SD_DEBUG_WAIT
+// debug build: last stage every warp reached, frozen when the first wait times out (profiles/stress_bin.py prints it)
+__device__ int g_prog[160 * 16 * 4];
+#define TB_PROG(jj, stage, a1, a2)                                                                               \
+    do {                                                                                                          \
+        if ((threadIdx.x & 31) == 0 && *reinterpret_cast<volatile unsigned int *>(&tcx::g_wait_timeout[0]) == 0) { \
+            int *pp_ = g_prog + (blockIdx.x * 16 + (threadIdx.x >> 5)) * 4;                                       \
+            pp_[0] = (int)(jj); pp_[1] = (stage); pp_[2] = (int)(a1); pp_[3] = (int)(a2);                           \
+        }                                                                                                         \
+    } while (0)
+#else
+#define TB_PROG(jj, stage, a1, a2) do {} while (0)
+#endif
+#ifdef SD_TB_JITTER
+// debug build: random delays in every role (per warp, from the clock) to shake out protocol races
+#define TB_JIT()                                                                                     \
+    do {                                                                                             \
+        unsigned int h_ = (unsigned int)clock64() * 2654435761u + (threadIdx.x >> 5) * 40503u;         \
+        h_ = __shfl_sync(0xffffffffu, h_, 0);                                                         \
+        if ((h_ & 0x30000u) == 0) __nanosleep((h_ >> 20) & 0xFFFu);                                    \
+    } while (0)
+#else
+#define TB_JIT() do {} while (0)
+#endif
 #define TB_TRACE(role, j, ev)                                                                    \
     do {                                                                                         \
         if ((P.dbg & 8192) && blockIdx.x == 0 && (j) >= TB_T0 && (j) < TB_T0 + 64 && (role) < 8 && (threadIdx.x & 31) == 0) \
@@ -286,6 +310,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             }
             tmem_st_wait();
             tc_fence_before();
+            TB_JIT();
             mbar_arrive_warp(BAR(BAR_H + b));
             if (warp == 0) TB_TRACE(0, j, 3);
         }
@@ -393,6 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                             make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                 }
                 tc_fence_before();
+                TB_JIT();
                 mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));            // (__syncwarp inside: the staged rows are visible)
                 if (wq == 0) TB_TRACE(0, j, 4);
                 if (ok && P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
@@ -452,6 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 // too: one barrier test where there were three.
                 mbar_wait_warp(BAR(BAR_FULL_A + e), ph);
                 const int m = __shfl_sync(0xffffffffu, s_minfo[e], 0);
+                TB_PROG(j, 1, m, e);
                 // the accumulator (its first 64 columns held the hidden tile of tile j-2) is free once layer 2 of j-2 has run.
                 // (Also before the closing arrival below: nobody may complete two phases of a barrier ahead of its waiter.)
                 mbar_wait_warp(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
@@ -461,6 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 TB_TRACE(1, j, 0);
                 if ((P.dbg & 8192) && blockIdx.x < 4 && j < 500 && lane == 0) { g_tiles[(blockIdx.x * 512 + j) * 2] = clock64(); g_tiles[(blockIdx.x * 512 + j) * 2 + 1] = m; }
                 for (int i = 0; i < m; ++i) {
+                    TB_PROG(j, 10 + i, m, e);
                     if (i > 0) mbar_wait_warp(BAR(BAR_FULL_A + e), ph);
                     if (i == 0) TB_TRACE(1, j, 1);
                     mbar_wait_warp(BAR(BAR_FULL_B + eb), phb);
@@ -476,6 +504,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                             umma_e(d1, umma_desc(a_h), umma_desc_mn(b_h + CHUNK, CHUNK / 2, 1024), idesc_mn, 1);
                         }
                     }
+                    TB_JIT();
                     umma_commit_e(BAR(BAR_EMPTY_A + e));
                     umma_commit_e(BAR(BAR_EMPTY_B + eb));
                     if (++e == NRA) { e = 0; ph ^= 1; }
@@ -492,6 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                         umma_e(d1, umma_desc(c_h), umma_desc(w_h + CHUNK), idesc_k, 1);
                     }
                 }
+                TB_JIT();
                 umma_commit_e(BAR(BAR_EMPTY_C + cs));
                 umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
                 TB_TRACE(1, j, 6);
@@ -536,6 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                               umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
                 umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
                 }
+                TB_JIT();
                 umma_commit_e(BAR(BAR_D2 + b));
                 umma_commit_e(BAR(BAR_D1_FREE + b));
             }
@@ -585,7 +616,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 ti.rows = __shfl_sync(0xffffffffu, tl.rows, 0);
                 v = base + bi;
             }
+            TB_PROG(slot, 1, ti.rows, ti.c0m);
+            TB_JIT();
             mbar_wait_warp(BAR(BAR_REC_EMPTY + r), (uint32_t)(((slot / NREC) & 1) ^ 1));
+            TB_PROG(slot, 2, ti.rows, v);
             if (lane == 0) {
                 s_hdr[r].c0m = ti.c0m; s_hdr[r].b01 = ti.b01; s_hdr[r].b23 = ti.b23; s_hdr[r].rows = ti.rows;
                 reinterpret_cast<volatile int *>(sm + OFF_TIDX)[r] = (int)(P.n_tiles - 1 - v);
@@ -618,6 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                                b01 = __shfl_sync(0xffffffffu, s_hdr[r].b01, 0), b23 = __shfl_sync(0xffffffffu, s_hdr[r].b23, 0);
             if (rows == 0) return false;
             const int c0 = (int)(c0m & 0xFFFFu), m = (int)(c0m >> 16);
+            TB_PROG(j, 3, rows, m);
             for (int i = 0; i < m; ++i) {
                 unsigned int b = i == 0 ? (b01 & 0xFFFFu) : i == 1 ? (b01 >> 16) : i == 2 ? (b23 & 0xFFFFu) : (b23 >> 16);
                 if (i >= 4) b = __shfl_sync(0xffffffffu, __ldg(P.cbin + c0 + i), 0);   // a tile that touches more than four bins (rare)
@@ -668,6 +703,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             RowIn cur;
             rec_wait(j);
             const int rows = (int)s_hdr[j % NREC].rows;
+            TB_PROG(j, 1, rows, e);
             if (rows == 0) {                               // no more tiles for this CTA: tell the MMA issuer (chunk count 0)
                 if ((int)(j % N_PT_GROUPS) == grp) {
                     mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
@@ -690,6 +726,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 cur.w01 = ra.w; cur.w23 = rb.x; cur.grow = (int)rb.y;
                 cur.cr = (int)(rb.z & 0xFFFFu); cur.slot = (int)((rb.z >> 16) & 0xFFu);
             }
+            TB_JIT();
             mbar_arrive_warp(BAR(BAR_REC_EMPTY + (int)(j % NREC)));
             TB_TRACE(pt_role, j, 0);
             if (!mine) {
@@ -790,8 +827,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             };
             TB_TRACE(pt_role, j, 1);
             const int m = cur.c1 - cur.c0 + 1;
+            TB_PROG(j, 5, m, (cur.c0 << 16) | (cur.c1 & 0xFFFF));
             for (int i = 0; i < m; ++i) {
                 mbar_wait(BAR(BAR_EMPTY_A + e), ph ^ 1);
+                TB_PROG(j, 20 + i, m, e);
                 if (i == 0) TB_TRACE(pt_role, j, 2);
                 unsigned char *arow = sm + OFF_A + e * XK * CHUNK + row * 128;
                 const int d = s_dirty[e * TM + row];
@@ -820,6 +859,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 }
                 if (i == 0 && row == 0) s_minfo[e] = m;           // chunks of this tile, read by the MMA issuer behind FULL_A
                 fence_proxy_async();
+                TB_JIT();
                 mbar_arrive_warp(BAR(BAR_FULL_A + e));
                 if (++e == NRA) { e = 0; ph ^= 1; }
             }
@@ -884,7 +924,19 @@ extern "C" int sd_debug_read_trace_bin(long long *host_out) {
     return SD_OK;
 }
 
+#ifdef SD_TRAP_REPORT
+extern "C" int sd_debug_set_trap_buffer(unsigned int *host_mapped) {
+    SD_CUDA_OK(cudaMemcpyToSymbol(tcx::g_trap_report, &host_mapped, sizeof(host_mapped)));
+    return SD_OK;
+}
+#endif
+#if defined(SD_DEBUG_WAIT) || defined(SD_DEBUG_LONGWAIT)
 #ifdef SD_DEBUG_WAIT
+extern "C" int sd_debug_read_progress(int *host_out) {
+    SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tb::g_prog, sizeof(int) * 160 * 16 * 4));
+    return SD_OK;
+}
+#endif
 extern "C" int sd_debug_read_timeout(unsigned int *host_out) {
     SD_CUDA_OK(cudaMemcpyFromSymbol(host_out, tcx::g_wait_timeout, sizeof(unsigned int) * 260));
     return SD_OK;

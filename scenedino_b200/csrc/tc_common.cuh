@@ -9,8 +9,8 @@ namespace tcx {
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-#ifdef SD_DEBUG_WAIT
-__device__ unsigned int g_wait_timeout[260];
+#if defined(SD_DEBUG_WAIT) || defined(SD_DEBUG_LONGWAIT)
+__device__ unsigned int g_wait_timeout[260];   // [0] count, then 60 x (bar, parity, thread, block)
 #endif
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -27,12 +27,34 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a trap (launch failure) within a second, never as a hung GPU.  Plain
-// try_wait spins: a suspend-time hint was measured and removed (slow wake-ups put the producer warps in lockstep with
-// the consumers they were supposed to run ahead of).
+// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  Plain try_wait spins: a
+// suspend-time hint was measured and removed (slow wake-ups put the producer warps in lockstep with the consumers they
+// were supposed to run ahead of).
+// KNOWN ISSUE: in a stress test (profiles/stress_bin.py) the tile kernel deadlocks about once per
+// 50 000 - 100 000 queries when a fresh texel sort precedes every launch and the rows leave in the caller's order (the
+// layer-1 issuer waits for a weight chunk the point warps believe they have delivered); with the waits unbounded the
+// kernel hangs, so it is a deadlock, not a slow start.  It has not been pinned down: builds with extra instrumentation do
+// not show it, random delays injected into every role (-DSD_TB_JITTER) do not provoke it, and the binned output path ran
+// 500 000 queries clean.  The bound below turns it into a launch failure within milliseconds.
+#ifndef SD_WAIT_SPINS
+#define SD_WAIT_SPINS 2000000u
+#endif
+// The loop is C++, not a branch inside the asm: with the polling loop hidden in an asm block the compiler lays the code
+// behind it out as if the warp could not have diverged in there, and warps that run a role in lockstep (all 32 lanes
+// poll, then one elected lane issues tcgen05 / TMA instructions) failed about once per 20 000 launches of the tile
+// kernel (profiles/stress_bin.py); as a visible loop with a per-lane exit the same code ran 240 000 launches clean.
+#ifdef SD_TRAP_REPORT
+__device__ unsigned int *g_trap_report;      // host-mapped buffer (sd_debug_set_trap_buffer): who timed out, readable after the trap
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#ifdef SD_DEBUG_WAIT
     uint32_t done = 0;
+#ifdef SD_DEBUG_LONGWAIT
+#ifndef SD_LONGWAIT_US
+#define SD_LONGWAIT_US 1000ull
+#endif
+    unsigned long long lw_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(lw_t0));
+#endif
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -41,36 +63,58 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 18)) {   // debug build: record who timed out on what and carry on (results are garbage)
-            const unsigned int k = atomicAdd(&g_wait_timeout[0], 1u);
-            if (k < 40) { g_wait_timeout[4 + 4 * k] = bar; g_wait_timeout[5 + 4 * k] = parity; g_wait_timeout[6 + 4 * k] = threadIdx.x; g_wait_timeout[7 + 4 * k] = blockIdx.x; }
+#ifdef SD_DEBUG_LONGWAIT
+        // debug build: waits that COMPLETE after more than ~1 ms are recorded with their duration (bar, parity | 0x80000000,
+        // thread, microseconds); waits that never complete (2^31 spins) are recorded with parity as is -- tells a rare
+        // long stall from a deadlock
+        if (done && spin > 1000u) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            const unsigned long long us = (t1 - lw_t0) / 1000ull;
+            if (us > SD_LONGWAIT_US && (threadIdx.x & 31) == 0) {
+                const unsigned int k = atomicAdd(&g_wait_timeout[0], 1u);
+                if (k < 60) { g_wait_timeout[4 + 4 * k] = bar; g_wait_timeout[5 + 4 * k] = parity | 0x80000000u; g_wait_timeout[6 + 4 * k] = threadIdx.x; g_wait_timeout[7 + 4 * k] = (unsigned int)us; }
+            }
+        }
+        if (!done && spin > 0x7FFFFFF0u) {
+            if ((threadIdx.x & 31) == 0) {
+                const unsigned int k = atomicAdd(&g_wait_timeout[0], 1u);
+                if (k < 60) { g_wait_timeout[4 + 4 * k] = bar; g_wait_timeout[5 + 4 * k] = parity; g_wait_timeout[6 + 4 * k] = threadIdx.x; g_wait_timeout[7 + 4 * k] = blockIdx.x; }
+            }
             return;
         }
-    }
-#else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .u32 n;\n\t"
-        "mov.u32 n, 0;\n\t"
-        "SD_WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra SD_WAIT_DONE;\n\t"
-        "add.u32 n, n, 1;\n\t"
-        "setp.lt.u32 p, n, 2000000;\n\t"
-        "@p bra SD_WAIT_LOOP;\n\t"
-        "trap;\n\t"
-        "SD_WAIT_DONE:\n\t"
-        "}"
-        ::"r"(bar), "r"(parity)
-        : "memory");
+        continue;
 #endif
+#ifdef SD_DEBUG_WAIT
+        if (!done && spin > (1u << 18)) {   // debug build: record who timed out on what and carry on (results are garbage)
+            if ((threadIdx.x & 31) == 0) {                     // one record per warp
+                const unsigned int k = atomicAdd(&g_wait_timeout[0], 1u);
+                if (k < 60) { g_wait_timeout[4 + 4 * k] = bar; g_wait_timeout[5 + 4 * k] = parity; g_wait_timeout[6 + 4 * k] = threadIdx.x; g_wait_timeout[7 + 4 * k] = blockIdx.x; }
+            }
+            return;
+        }
+#else
+#ifdef SD_TRAP_REPORT
+        if (!done && spin == 2000000u && (threadIdx.x & 31) == 0) {   // one record per stuck warp, then keep waiting so that every
+            unsigned int *r = g_trap_report;                          // stuck role gets to report before the trap
+            if (r) {
+                const unsigned int k = atomicAdd_system(r, 1u);
+                if (k < 60) { r[4 + 4 * k] = bar; r[5 + 4 * k] = parity; r[6 + 4 * k] = threadIdx.x; r[7 + 4 * k] = blockIdx.x; }
+                __threadfence_system();
+            }
+        }
+        if (!done && spin > SD_WAIT_SPINS) __trap();
+#else
+        if (!done && spin > SD_WAIT_SPINS) __trap();
+#endif
+#endif
+    }
 }
 // The wait of a role that a whole warp runs in lockstep (elected issue forms below): every lane polls, then the warp is
-// reconverged EXPLICITLY.  Lanes can leave the polling loop in different iterations; a uniform-datapath instruction
-// (tcgen05.mma / commit, TMA) reached by two halves of a diverged warp would be issued twice -- a commit that arrives
-// twice skews the barrier's phase and the pipeline deadlocks many tiles later (seen once per few thousand launches, under
-// the timing of a second GPU's peer traffic only).
+// reconverged explicitly -- lanes can leave the polling loop in different iterations, and a uniform-datapath instruction
+// (tcgen05.mma / commit, TMA) reached by two parts of a diverged warp would be issued twice.
+// (Measured alternatives: polling from one elected lane puts every tcgen05 instruction behind it back into an ELECT loop,
+// 2x slower; leaving the loop on a warp vote is as fast as this form.)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
     mbar_wait(bar, parity);
     __syncwarp();
