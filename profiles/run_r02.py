@@ -17,7 +17,7 @@ def main():
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(1)
     Kc = syn.kitti360_K()
-    if mode in ("query", "ssc", "binned"):
+    if mode in ("query", "ssc", "binned", "x3"):
         N = 1 << 21
         if mode == "ssc":
             f = torch.randn((N, 64), device=dev, generator=g) * 0.5
@@ -26,10 +26,10 @@ def main():
             for _ in range(n_iter):
                 ops.ssc_head(head, f, want_scores=False, out=o)
         else:
-            feat = ops.featmap_pack(torch.randn((1, 256, 384, 1280), device=dev, generator=g), torch.float16)
+            feat = ops.featmap_pack(torch.randn((1, 256, 384, 1280), device=dev, generator=g), torch.float32 if mode == "x3" else torch.float16)
             sc = ops.Scene(feat=feat[0], K_f=torch.from_numpy(Kc[None]).to(dev), w2c_f=torch.eye(4, device=dev)[None])
-            mlp = ops.Mlp(*syn.make_mlp(0), device=dev, precision=ops.F16)
-            sc = sc.project(mlp)
+            mlp = ops.Mlp(*syn.make_mlp(0), device=dev, precision=ops.F32TC if mode == "x3" else ops.F16)
+            sc = sc.project_x3(mlp) if mode == "x3" else sc.project(mlp)
             pts = torch.from_numpy(syn.ssc_voxel_grid()).to(dev)
             out = None
             for _ in range(n_iter):
@@ -37,6 +37,8 @@ def main():
                     r = ops.query_points_binned(sc, mlp, pts, out=out)
                     if out is None:
                         out = dict(r); out["invalid_features"] = out["invalid_features"].view(torch.uint8)
+                elif mode == "x3":
+                    out = ops.query_points(sc, mlp, pts, want_rgb=False, precision=ops.F32TC, out=out)
                 else:
                     out = ops.query_points(sc, mlp, pts, want_rgb=False, out=out)
     elif mode == "expand":

@@ -31,6 +31,9 @@ def main():
             lines.append(f"| {k} | {units[idx[k]]} | {r[idx[k]]} |")
     rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
     lines += ["", f"traffic per launch (dram read + write): {rd + wr:.1f} {units[idx['dram__bytes_read.sum']]}", ""]
+    if launches == "-":
+        open(out, "w").write("\n".join(lines) + "\n")
+        return
     lines += ["## launch list (ncu --metrics gpu__time_duration.sum, cold-cache serialised: compare shares)", ""]
     tot = collections.Counter(); cnt = collections.Counter()
     with open(launches) as f:
@@ -42,14 +45,13 @@ def main():
             continue
         v = float(x[vi].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(x[ui], 1.0)
-        name = x[ki].split("(")[0]
+        name = x[ki].split("(")[0][:90]
         tot[name] += v; cnt[name] += 1
     s = sum(tot.values())
     lines += ["| kernel | launches | total us | share |", "|---|---|---|---|"]
     for name, v in tot.most_common():
         lines.append(f"| {name} | {cnt[name]} | {v:.1f} | {100 * v / s:.1f}% |")
     open(out, "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines))
 
 
 if __name__ == "__main__":

@@ -291,6 +291,16 @@ def test_no_silent_fallback(golden):
     net = build(g)
     with pytest.raises(sd.SdError):
         net(torch.zeros(1, 4, 3))                     # CPU tensor
+    net.train()                                       # training + autograd: the differentiable (unfused) route, SURVEY 8f-4
+    pts = dev(g["points"][:64].reshape(1, -1, 3))
+    rgb, invalid, sigma, _, state = net(pts)
+    assert sigma.requires_grad and state["dino_features"].requires_grad and not rgb.requires_grad
+    net.eval()
+    with torch.no_grad():
+        rgb_e, invalid_e, sigma_e, _, state_e = net(pts)
+    assert torch.equal(rgb, rgb_e) and torch.equal(invalid, invalid_e)
+    assert_close(sigma.detach().cpu().numpy(), sigma_e.cpu().numpy(), TOL_FP32, "training-route sigma vs fused kernel")
+    assert_close(state["dino_features"].detach().cpu().numpy(), state_e["dino_features"].cpu().numpy(), TOL_FP32, "training-route dino")
     net.train()
     with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 4, 3, device=DEV))         # autograd / training is out of scope
+        net(pts, predict_segmentation=True)           # the SSC head is evaluation-only
