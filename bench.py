@@ -192,7 +192,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_sample / v * 1e3,
             "step_unit": f"one step = {n_sample} voxels (a bounded strided sample of the grid), not the whole grid",
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config("fp16"), "cpu_baseline": last,
+            "config": workload_config("fp16", binned=args.layout == "binned"), "cpu_baseline": last,   # (the native arm's config)
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
