@@ -258,10 +258,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                 if (!P.head2) {
                     mbar_wait_warp(BAR(BAR_A_FULL), (uint32_t)(j & 1));
                     tc_fence_after();
+                    if (elect_one()) {          // ONE elected thread issues: a single-thread region (tc_common.cuh)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_e(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
-                    umma_commit_e(BAR(BAR_D1_FULL));
+                        for (int k = 0; k < 4; ++k)
+                            umma(tmem_base, umma_desc(sm_u + OFF_A + k * 32), umma_desc(sm_u + OFF_W1 + k * 32), idesc, k != 0);
+                        umma_commit(BAR(BAR_D1_FULL));
+                    }
+                    __syncwarp();
                 }
                 mbar_wait_warp(BAR(BAR_H_FULL), (uint32_t)(j & 1));
                 tc_fence_after();
@@ -271,12 +274,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) expand_tc_kernel(const __grid_con
                     mbar_wait_warp(BAR(BAR_D2_FREE + b), (uint32_t)(((g >> 1) & 1) ^ 1));
                     tc_fence_after();
                     const uint32_t w2 = sm_u + OFF_W2 + slot * W2_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                        umma_ts_e(tmem_base + D2_COL + b * 128, tmem_base + k * 8, umma_desc(w2 + (k >> 2) * 16384 + (k & 3) * 32),
-                                  idesc, k != 0);
-                    umma_commit_e(BAR(BAR_W_EMPTY + slot));
-                    umma_commit_e(BAR(BAR_D2_FULL + b));
+                        for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                            umma_ts(tmem_base + D2_COL + b * 128, tmem_base + k * 8, umma_desc(w2 + (k >> 2) * 16384 + (k & 3) * 32),
+                                    idesc, k != 0);
+                        umma_commit(BAR(BAR_W_EMPTY + slot));
+                        umma_commit(BAR(BAR_D2_FULL + b));
+                    }
+                    __syncwarp();
                 }
             }
         }

@@ -27,7 +27,7 @@
 //                record block into rings, issues the TMA boxes
 //   warps 11-14  one thread per row: weights into the chunk's A operand (an undo log keeps the rest of it zero), positional
 //                code -> code operand, point index -> perm ring
-// Rings: 2 weight chunks, 4 box chunks, 2 code operands, 3 record blocks, 8 perm blocks; layer-1 and layer-2 accumulators
+// Rings: 2 weight chunks, 5 box chunks, 2 code operands, 3 record blocks, 8 perm blocks; layer-1 and layer-2 accumulators
 // double buffered in TMEM.  Protocol rules (each was a deadlock first): an mbarrier parity wait tells apart only adjacent
 // phases, so a role that skips ring positions still waits on each of them, and the closing arrivals at the end of the tile
 // stream wait for the same conditions a real tile would.  DESIGN.md section 3.3 has the measurements behind the layout.
@@ -70,10 +70,10 @@ constexpr int CHUNK = 16384;                 // A chunk [128 rows][64 slots] fp1
 #define SD_TB_NRA 2
 #endif
 #ifndef SD_TB_NRB
-#define SD_TB_NRB 4
+#define SD_TB_NRB 5
 #endif
 #ifndef SD_TB_STAGE
-#define SD_TB_STAGE 8192      // staging bytes per epilogue-2 warp (4096: binned output only, one half reused)
+#define SD_TB_STAGE 4096      // staging bytes per epilogue-2 warp: one 32-column half at a time
 #endif
 #ifndef SD_TB_ABLATE
 #define SD_TB_ABLATE 0        // timing experiments only (results are garbage): 1 no code computation, 2 no output path in epilogue 2,
@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
             if (j >= *s_ntiles) break;                    // the MMA issuer's closing arrival, not a tile
             tc_fence_after();
             if (wq == 0) TB_TRACE(0, j, 0);
+#ifdef SD_TB_SLOW_EPI2
+            __nanosleep(SD_TB_SLOW_EPI2);        // debug: sustained back-pressure from the last role of the chain
+#endif
             const int grow_keep = s_perm[(int)(j % NPERM) * TM + row];       // point this thread's row of tile j stands for
             const uint32_t t_d2 = t_lane + D2_COL + b1 * D2_STRIDE;
             const bool ok = grow_keep >= 0;
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                         mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
                     }
                     if (SD_TB_ABLATE & 2) continue;
-                    bulk_wait_read_e<(SD_TB_STAGE == 8192 ? 1 : 0)>();     // the store that last read this half (a tile ago) has left
+                    if (elect_one()) bulk_wait_read<(SD_TB_STAGE == 8192 ? 1 : 0)>();     // the store that last read this half (a tile ago) has left
                     __syncwarp();
                     unsigned char *stage = hf ? stage1 : stage0;
 #pragma unroll
@@ -393,47 +396,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                             make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
                     fence_proxy_async();
                     __syncwarp();
-                    tma_store_2d_commit_e(&P.tmap_out, smem_u32(stage), hf * 32, t * TM + wq * 32);
+                    if (elect_one()) {          // (the same lane every time: bulk groups are per thread)
+                        tma_store_2d(&P.tmap_out, smem_u32(stage), hf * 32, t * TM + wq * 32);
+                        bulk_commit();
+                    }
                 }
                 if (ok && !(SD_TB_ABLATE & 2)) {
                     if (P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
                     if (P.perm_out) P.perm_out[(long long)t * TM + row] = (unsigned int)grow_keep;
                 }
             } else if (P.dino && D == 64) {
-                // Two halves of 32 columns (registers).  Transpose through shared memory: lane = row writes its 8 chunks
-                // of a half (XOR-swizzled, conflict free), then 8 lanes read one row back and the warp stores four
-                // 128-byte row halves per request.  (One 256-byte bulk copy per row was measured instead: ~22 cycles
-                // per copy, slower.)
+                // Two halves of 32 columns (registers), one after the other through ONE 4 KB staging buffer per warp (the
+                // other 4 KB went to a fifth box slot): lane = row writes its 8 chunks of a half (XOR-swizzled, conflict
+                // free), then 8 lanes read one row back and the warp stores four 128-byte row halves per request.  (One
+                // 256-byte bulk copy per row was measured instead: ~22 cycles per copy, slower.)
                 uint32_t sr;
+                const int c8 = lane & 7;
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t vr[32];
                     tmem_ld32_issue(t_d2 + hf * 32, vr);
                     if (hf == 1) tmem_ld1_issue(t_d2 + D, sr);                   // density column sits behind the features
                     tmem_ld_wait();
-                    unsigned char *stage = hf ? stage1 : stage0;
+                    if (hf == 1) {                                               // both halves are in registers
+                        tc_fence_before();
+                        TB_JIT();
+                        mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));
+                    }
+                    __syncwarp();                   // every lane has finished reading the previous half back
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<uint4 *>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                        *reinterpret_cast<uint4 *>(stage0 + lane * 128 + ((q ^ (lane & 7)) << 4)) =
                             make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
-                }
-                tc_fence_before();
-                TB_JIT();
-                mbar_arrive_warp(BAR(BAR_D2_EMPTY + b1));            // (__syncwarp inside: the staged rows are visible)
-                if (wq == 0) TB_TRACE(0, j, 4);
-                if (ok && P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
-                if (wq == 0) TB_TRACE(0, j, 5);
-                const int c8 = lane & 7;
-                // all the shared loads of a batch first, into distinct registers (volatile asm keeps the order): a load
-                // that reuses the source registers of a store in flight waits for that store to leave the LSU
-#pragma unroll 1
-                for (int hb = 0; hb < 2; ++hb) {       // batch = 8 requests of 4 row halves = one 32-column half
+                    __syncwarp();                   // the staged rows are visible
+                    // all the shared loads of the half first, into distinct registers (volatile asm keeps the order): a load
+                    // that reuses the source registers of a store in flight waits for that store to leave the LSU
                     float4 x[8];
                     float *dp[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int hf = hb, r = 4 * i + (lane >> 3);
-                        x[i] = lds128_ordered(smem_u32(hf ? stage1 : stage0) + r * 128 + ((c8 ^ (r & 7)) << 4));
+                        const int r = 4 * i + (lane >> 3);
+                        x[i] = lds128_ordered(smem_u32(stage0) + r * 128 + ((c8 ^ (r & 7)) << 4));
                         const int dst = __shfl_sync(0xffffffffu, grow_keep, r);
                         dp[i] = dst >= 0 ? P.dino + (long long)dst * 64 + hf * 32 + c8 * 4 : nullptr;
                     }
@@ -442,6 +445,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     for (int i = 0; i < 8; ++i)
                         if (dp[i] && !(P.dbg & 1)) stg128_ordered(dp[i], x[i]);
                 }
+                if (wq == 0) TB_TRACE(0, j, 4);
+                if (ok && P.sigma && !(P.dbg & 2)) P.sigma[grow_keep] = softplus_fast(__uint_as_float(sr));
+                if (wq == 0) TB_TRACE(0, j, 5);
                 __syncwarp();
             } else {
                 uint32_t vr[64], sr;
@@ -484,7 +490,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 mbar_wait_warp(BAR(BAR_D1_FREE + (int)(j & 1)), (uint32_t)(((j >> 1) & 1) ^ 1));
                 if (m == 0) break;
                 const uint32_t d1 = tmem_base + (uint32_t)(j & 1) * 128u;
-                uint32_t acc = 0;
                 TB_TRACE(1, j, 0);
                 if ((P.dbg & 8192) && blockIdx.x < 4 && j < 500 && lane == 0) { g_tiles[(blockIdx.x * 512 + j) * 2] = clock64(); g_tiles[(blockIdx.x * 512 + j) * 2 + 1] = m; }
                 for (int i = 0; i < m; ++i) {
@@ -494,36 +499,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                     mbar_wait_warp(BAR(BAR_FULL_B + eb), phb);
                     tc_fence_after();
                     if (i == 0) TB_TRACE(1, j, 2);
-#pragma unroll
-                    for (int k = (SD_TB_ABLATE & 16) ? 4 : 0; k < 4; ++k) {    // 16 texel slots per instruction
-                        const uint32_t a_h = sm_u + OFF_A + e * XK * CHUNK + k * 32, b_h = sm_u + OFF_B + eb * XK * CHUNK + k * 2048;
-                        umma_e(d1, umma_desc(a_h), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, acc);
-                        acc = 1;
-                        if (X3) {       // + w_lo . P_hi + w_hi . P_lo
-                            umma_e(d1, umma_desc(a_h + CHUNK), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, 1);
-                            umma_e(d1, umma_desc(a_h), umma_desc_mn(b_h + CHUNK, CHUNK / 2, 1024), idesc_mn, 1);
-                        }
-                    }
                     TB_JIT();
-                    umma_commit_e(BAR(BAR_EMPTY_A + e));
-                    umma_commit_e(BAR(BAR_EMPTY_B + eb));
+                    // ONE elected thread issues (a single-thread region: even a warp that has split cannot issue twice)
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = (SD_TB_ABLATE & 16) ? 4 : 0; k < 4; ++k) {    // 16 texel slots per instruction
+                            const uint32_t a_h = sm_u + OFF_A + e * XK * CHUNK + k * 32, b_h = sm_u + OFF_B + eb * XK * CHUNK + k * 2048;
+                            umma(d1, umma_desc(a_h), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, (i | k) != 0);
+                            if (X3) {       // + w_lo . P_hi + w_hi . P_lo
+                                umma(d1, umma_desc(a_h + CHUNK), umma_desc_mn(b_h, CHUNK / 2, 1024), idesc_mn, 1);
+                                umma(d1, umma_desc(a_h), umma_desc_mn(b_h + CHUNK, CHUNK / 2, 1024), idesc_mn, 1);
+                            }
+                        }
+                        umma_commit(BAR(BAR_EMPTY_A + e));
+                        umma_commit(BAR(BAR_EMPTY_B + eb));
+                    }
+                    __syncwarp();
                     if (++e == NRA) { e = 0; ph ^= 1; }
                     if (++eb == NRB) { eb = 0; phb ^= 1; }
                 }
                 const int cs = (int)(j % NCODE);
                 TB_TRACE(1, j, 4);
-#pragma unroll
-                for (int k = 0; k < KCODE; ++k) {
-                    const uint32_t c_h = sm_u + OFF_CODE + cs * XK * CHUNK + k * 32, w_h = sm_u + OFF_WC + k * 32;
-                    umma_e(d1, umma_desc(c_h), umma_desc(w_h), idesc_k, 1);
-                    if (X3) {
-                        umma_e(d1, umma_desc(c_h + CHUNK), umma_desc(w_h), idesc_k, 1);
-                        umma_e(d1, umma_desc(c_h), umma_desc(w_h + CHUNK), idesc_k, 1);
-                    }
-                }
                 TB_JIT();
-                umma_commit_e(BAR(BAR_EMPTY_C + cs));
-                umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < KCODE; ++k) {
+                        const uint32_t c_h = sm_u + OFF_CODE + cs * XK * CHUNK + k * 32, w_h = sm_u + OFF_WC + k * 32;
+                        umma(d1, umma_desc(c_h), umma_desc(w_h), idesc_k, 1);
+                        if (X3) {
+                            umma(d1, umma_desc(c_h + CHUNK), umma_desc(w_h), idesc_k, 1);
+                            umma(d1, umma_desc(c_h), umma_desc(w_h + CHUNK), idesc_k, 1);
+                        }
+                    }
+                    umma_commit(BAR(BAR_EMPTY_C + cs));
+                    umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                }
+                __syncwarp();
                 TB_TRACE(1, j, 6);
             }
             // closing: tell everybody downstream how many tiles there were and complete the phase the first epilogue waits
@@ -547,28 +558,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bin_kernel(const __grid_con
                 if (j >= nt) { mbar_arrive_e(BAR(BAR_D2 + b)); break; }
                 tc_fence_after();
                 TB_TRACE(1, j + 1, 5);
-                if (X3) {
-                    // hidden (hi, lo) pairs sit in blocks of 16 columns per 32 units (epilogue 1): k-step k reads hi at
-                    // 32 (k / 2) + 8 (k % 2), lo 16 columns further; W_out hi image, then the lo image 2 n2 128 bytes behind
-                    const uint32_t w2l = 2u * (uint32_t)P.n2 * 128u;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t a_h = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
-                        const uint32_t w_h = sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32;
-                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h), idesc2, k != 0);
-                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h + 16, umma_desc(w_h), idesc2, 1);
-                        umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h + w2l), idesc2, 1);
-                    }
-                } else {
-#pragma unroll
-                for (int k = (SD_TB_ABLATE & 8) ? 8 : 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
-                              umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
-                umma_ts_e(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
-                }
                 TB_JIT();
-                umma_commit_e(BAR(BAR_D2 + b));
-                umma_commit_e(BAR(BAR_D1_FREE + b));
+                if (elect_one()) {
+                    if (X3) {
+                        // hidden (hi, lo) pairs sit in blocks of 16 columns per 32 units (epilogue 1): k-step k reads hi at
+                        // 32 (k / 2) + 8 (k % 2), lo 16 columns further; W_out hi image, then the lo image 2 n2 128 bytes behind
+                        const uint32_t w2l = 2u * (uint32_t)P.n2 * 128u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t a_h = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
+                            const uint32_t w_h = sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32;
+                            umma_ts(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h), idesc2, k != 0);
+                            umma_ts(tmem_base + D2_COL + b * D2_STRIDE, a_h + 16, umma_desc(w_h), idesc2, 1);
+                            umma_ts(tmem_base + D2_COL + b * D2_STRIDE, a_h, umma_desc(w_h + w2l), idesc2, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = (SD_TB_ABLATE & 8) ? 8 : 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                            umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + b * 128 + k * 8,
+                                    umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
+                        umma_ts(tmem_base + D2_COL + b * D2_STRIDE, tmem_base + ONE_COL, umma_desc(sm_u + OFF_W2 + 2 * P.n2 * 128), idesc2, 1);
+                    }
+                    umma_commit(BAR(BAR_D2 + b));
+                    umma_commit(BAR(BAR_D1_FREE + b));
+                }
+                __syncwarp();
             }
         }
     } else if (warp == WARP_TMA) {

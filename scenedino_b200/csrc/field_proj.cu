@@ -181,12 +181,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) featmap_project_kernel(const __gr
                 mbar_wait_warp(BAR(BAR_FULL + s), (uint32_t)((j >> 1) & 1));
                 mbar_wait_warp(BAR(BAR_DEMPTY + s), (uint32_t)(((j >> 1) & 1) ^ 1));
                 tc_fence_after();
+                if (elect_one()) {              // ONE elected thread issues: a single-thread region (tc_common.cuh)
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    umma_e(tmem_base + s * 128, umma_desc(sm_u + OFF_A + s * A_BYTES + (k >> 2) * CHUNK + (k & 3) * 32),
-                           umma_desc(sm_u + OFF_W + (k >> 2) * CHUNK + (k & 3) * 32), idesc, k != 0);
-                umma_commit_e(BAR(BAR_EMPTY + s));
-                umma_commit_e(BAR(BAR_DFULL + s));
+                    for (int k = 0; k < 16; ++k)
+                        umma(tmem_base + s * 128, umma_desc(sm_u + OFF_A + s * A_BYTES + (k >> 2) * CHUNK + (k & 3) * 32),
+                             umma_desc(sm_u + OFF_W + (k >> 2) * CHUNK + (k & 3) * 32), idesc, k != 0);
+                    umma_commit(BAR(BAR_EMPTY + s));
+                    umma_commit(BAR(BAR_DFULL + s));
+                }
+                __syncwarp();
             }
         }
     }

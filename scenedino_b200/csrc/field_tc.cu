@@ -499,24 +499,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                 mbar_wait_warp(BAR(BAR_H), (uint32_t)(jj & 1));
                 tc_fence_after();
                 SD_TRACE(1, jj + 1, 6);
+                if (elect_one()) {          // ONE elected thread issues: a single-thread region (tc_common.cuh)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
-                    umma_ts_e(tmem_base + D2_COL, tmem_base + h_col + k * 8,
-                            umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
-                umma_commit_e(BAR(BAR_D2));
+                    for (int k = 0; k < 8; ++k)          // K = 16 per instruction = 8 packed columns of the hidden tile
+                        umma_ts(tmem_base + D2_COL, tmem_base + h_col + k * 8,
+                                umma_desc(sm_u + OFF_W2 + (k >> 2) * P.n2 * 128 + (k & 3) * 32), idesc2, k != 0);
+                    umma_commit(BAR(BAR_D2));
+                }
+                __syncwarp();
             };
             const uint32_t idesc3f = umma_idesc(TM, P.cmma == 2 ? 128 : 64) | UMMA_B_MN_MAJOR, idesc3x = umma_idesc(TM, 16) | UMMA_B_MN_MAJOR;
             const uint32_t off_v3 = P.cmma == 2 ? OFF_V : OFF_B3;
             auto composite = [&](long long jj) {   // per-ray sums of tile jj: Wt [128 x 128 rows] . V [128 rows x (64 | 128 | 16)]
                 mbar_wait_warp(BAR(BAR_B3), (uint32_t)(jj & 1));
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t a = umma_desc(sm_u + OFF_A3 + (k >> 2) * CHUNK_BYTES + (k & 3) * 32);
-                    umma_e(tmem_base + d3f_col, a, umma_desc_mn(sm_u + off_v3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
-                    umma_e(tmem_base + d3x_col, a, umma_desc_mn(sm_u + OFF_X3 + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t a = umma_desc(sm_u + OFF_A3 + (k >> 2) * CHUNK_BYTES + (k & 3) * 32);
+                        umma(tmem_base + d3f_col, a, umma_desc_mn(sm_u + off_v3 + k * 2048, CHUNK_BYTES, 1024), idesc3f, k != 0);
+                        umma(tmem_base + d3x_col, a, umma_desc_mn(sm_u + OFF_X3 + k * 2048, CHUNK_BYTES, 1024), idesc3x, k != 0);
+                    }
+                    umma_commit(BAR(BAR_D3));
                 }
-                umma_commit_e(BAR(BAR_D3));
+                __syncwarp();
             };
             auto cm_output = [&](long long jj) {
                 const float *s_bo = reinterpret_cast<const float *>(sm + OFF_PART);
@@ -587,13 +593,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_tc_kernel(const __grid_cons
                             tc_fence_after();
                             SD_TRACE(1, j, c == 0 ? 0 : 4);
                         }
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_e(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
-                                 umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
-                        umma_commit_e(BAR(BAR_EMPTY + c));
+                            for (int k = 0; k < 4; ++k)
+                                umma(d1, umma_desc(sm_u + OFF_RING + c * CHUNK_BYTES + k * 32),
+                                     umma_desc(sm_u + OFF_W1 + c * CHUNK_BYTES + k * 32), idesc1, (c | k) != 0);
+                            umma_commit(BAR(BAR_EMPTY + c));
+                            if (c == P.nch - 1) umma_commit(BAR(BAR_D1 + (int)(j & 1)));
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_e(BAR(BAR_D1 + (int)(j & 1)));
                     SD_TRACE(1, j, 5);
                     if (P.cmma && j > 1) composite(j - 2);     // its operands were written a tile ago
                     if (j > 0) layer2(j - 1);

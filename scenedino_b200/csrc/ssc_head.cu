@@ -298,24 +298,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
                 tc_fence_after();
                 for (int l = 0; l < nl; ++l) {               // layer 1 of the expansion: A from shared memory
                     wait_epi(l);                             // operand built, accumulator drained
+                    if (elect_one()) {          // ONE elected thread issues: a single-thread region (tc_common.cuh)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_e(tmem_base + ACC_COL + l * 128, umma_desc(sm_u + OFF_A + l * 16384 + k * 32), umma_desc(ring + k * 32), id128, k != 0);
-                    umma_commit_e(BAR(BAR_MMA_DONE + l));
+                        for (int k = 0; k < 4; ++k)
+                            umma(tmem_base + ACC_COL + l * 128, umma_desc(sm_u + OFF_A + l * 16384 + k * 32), umma_desc(ring + k * 32), id128, k != 0);
+                        umma_commit(BAR(BAR_MMA_DONE + l));
+                    }
+                    __syncwarp();
                 }
                 for (int l = 0; l < nl; ++l) {               // q = G h (-> |v|) and the linear path ML h -> code accumulator
                     wait_epi(l);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
-                                umma_desc(ring + 16384 + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
-                    umma_commit_e(BAR(BAR_MMA_DONE + l));
+                        for (int k = 0; k < 8; ++k)
+                            umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
+                                    umma_desc(ring + 16384 + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
+                        umma_commit(BAR(BAR_MMA_DONE + l));
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_ts_e(tmem_base + CODE_COL + l * 64, tmem_base + HE_COL + l * 64 + k * 8,
-                                umma_desc(sm_u + OFF_ML + (k >> 2) * 8192 + (k & 3) * 32), id64, k != 0);
+                        for (int k = 0; k < 8; ++k)
+                            umma_ts(tmem_base + CODE_COL + l * 64, tmem_base + HE_COL + l * 64 + k * 8,
+                                    umma_desc(sm_u + OFF_ML + (k >> 2) * 8192 + (k & 3) * 32), id64, k != 0);
+                        if (l == nl - 1) umma_commit(BAR(BAR_RING_EMPTY + slot));
+                    }
+                    __syncwarp();
                 }
-                umma_commit_e(BAR(BAR_RING_EMPTY + slot));
                 ++g;
                 // ---- chunks 1..nch: [M1 block c | Wn2 K-slice c]
                 for (int c = 0; c < P.nch; ++c, ++g) {
@@ -326,28 +332,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) ssc_head_kernel(const __grid_cons
                     for (int l = 0; l < nl; ++l) {
                         if (c == 0) wait_epi(l);             // |v| taken: the accumulator is free (later blocks: the tensor pipe
                                                              // runs this thread's MMAs in order, behind the Wn2 slice that read it)
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
-                                    umma_desc(ring + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
-                        umma_commit_e(BAR(BAR_MMA_DONE + l));
+                            for (int k = 0; k < 8; ++k)
+                                umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8,
+                                        umma_desc(ring + (k >> 2) * 16384 + (k & 3) * 32), id128, k != 0);
+                            umma_commit(BAR(BAR_MMA_DONE + l));
+                        }
+                        __syncwarp();
                     }
                     for (int l = 0; l < nl; ++l) {
                         wait_epi(l);                         // the block's hidden units are in the accumulator's columns as fp16
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_ts_e(tmem_base + CODE_COL + l * 64, tmem_base + ACC_COL + l * 128 + k * 8,
-                                    umma_desc(ring + 32768 + (k >> 2) * 8192 + (k & 3) * 32), id64, 1);
+                            for (int k = 0; k < 8; ++k)
+                                umma_ts(tmem_base + CODE_COL + l * 64, tmem_base + ACC_COL + l * 128 + k * 8,
+                                        umma_desc(ring + 32768 + (k >> 2) * 8192 + (k & 3) * 32), id64, 1);
+                            if (l == nl - 1) {
+                                umma_commit(BAR(BAR_RING_EMPTY + slot));
+                                if (c == P.nch - 1)                        // code accumulators complete
+                                    for (int l2 = 0; l2 < nl; ++l2) umma_commit(BAR(BAR_MMA_DONE + l2));
+                            }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_e(BAR(BAR_RING_EMPTY + slot));
                 }
-                for (int l = 0; l < nl; ++l) umma_commit_e(BAR(BAR_MMA_DONE + l));     // code accumulators complete
                 for (int l = 0; l < nl; ++l) {               // cosine scores against the centres
                     wait_epi(l);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ts_e(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8, umma_desc(sm_u + OFF_CEN + k * 32), id32, k != 0);
-                    umma_commit_e(BAR(BAR_MMA_DONE + l));
+                        for (int k = 0; k < 4; ++k)
+                            umma_ts(tmem_base + ACC_COL + l * 128, tmem_base + HE_COL + l * 64 + k * 8, umma_desc(sm_u + OFF_CEN + k * 32), id32, k != 0);
+                        umma_commit(BAR(BAR_MMA_DONE + l));
+                    }
+                    __syncwarp();
                 }
             }
         }

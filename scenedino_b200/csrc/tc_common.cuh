@@ -30,12 +30,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  Plain try_wait spins: a
 // suspend-time hint was measured and removed (slow wake-ups put the producer warps in lockstep with the consumers they
 // were supposed to run ahead of).
-// KNOWN ISSUE: in a stress test (profiles/stress_bin.py) the tile kernel deadlocks about once per
-// 50 000 - 100 000 queries when a fresh texel sort precedes every launch and the rows leave in the caller's order (the
-// layer-1 issuer waits for a weight chunk the point warps believe they have delivered); with the waits unbounded the
-// kernel hangs, so it is a deadlock, not a slow start.  It has not been pinned down: builds with extra instrumentation do
-// not show it, random delays injected into every role (-DSD_TB_JITTER) do not provoke it, and the binned output path ran
-// 500 000 queries clean.  The bound below turns it into a launch failure within milliseconds.
+// (The deadlock that first showed up as this trap -- once per ~50 000 queries in profiles/stress_bin.py -- was a group of
+// tcgen05 instructions issued twice by a split warp: see the "elected forms" below and DESIGN.md section 3.3.)
 #ifndef SD_WAIT_SPINS
 #define SD_WAIT_SPINS 2000000u
 #endif
@@ -157,10 +153,15 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 // tcgen05.mma / tcgen05.commit / TMA copies are uniform-datapath instructions.  Issued under `if (lane == 0)` they sit in
 // divergent control flow and ptxas wraps EVERY one of them in an ELECT / BRA.U.ANY loop with its operands rebuilt in
 // uniform registers first (~90 cycles of dependent scalar work per instruction: a single-chunk tile's 16 MMAs and 6
-// commits were ~2 000 cycles of pure issue, the critical path of the tile kernel).  Run by all 32 lanes of a warp whose
-// index the compiler KNOWS to be uniform (warp_uniform()), with the single issuing lane chosen inside the asm by
-// elect.sync, the same instructions come out back to back.  elect.sync with a full mask always elects the same lane, so
-// MMAs and the commits that track them are issued by one thread, as tcgen05.commit requires.
+// commits were ~2 000 cycles of pure issue, the critical path of the tile kernel).  The issuing roles therefore run as
+// whole warps in lockstep -- warp index from warp_uniform() so that the compiler KNOWS it is uniform, every lane polling
+// the barriers (mbar_wait_warp) -- and every group of tcgen05 / TMA instructions sits in an `if (elect_one()) { ... }`
+// region followed by __syncwarp: the form ptxas recognises as single-threaded (clean UTCHMMA / UTCBAR / UTMALDG, back to
+// back), and the form in which a group can never be issued twice.  (An earlier version predicated the instructions on
+// elect.sync INSIDE the asm; ptxas drops that predicate -- a uniform-datapath instruction runs once per converged warp
+// anyway -- so a warp that was still split behind a polling loop issued the group once per part: a tcgen05.commit that
+// arrives twice lets the producers lap the issuer, which then waits for a phase that has gone by.  Seen as a deadlock
+// about once per 50 000 queries in profiles/stress_bin.py; 400 000 queries clean with the regions.)
 // elect.sync as a C++ predicate: `if (elect_one()) { ... }` in a converged warp is the form ptxas recognises as a
 // single-thread region for TMA / bulk copies (clean UTMALDG / UBLKCP; predicating them INSIDE the asm still loops)
 __device__ __forceinline__ bool elect_one() {
@@ -169,40 +170,15 @@ __device__ __forceinline__ bool elect_one() {
     return p != 0;
 }
 __device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
-__device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
         "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
-// tile store shared -> global + its bulk group, and the wait for the smem reads of all but the last N groups: issued,
-// committed and waited for by the SAME (elected) lane of a converged warp (bulk groups are per thread)
-__device__ __forceinline__ void tma_store_2d_commit_e(const void *tmap, uint32_t src, int c0, int c1) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-        "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
-        "@q cp.async.bulk.commit_group;\n\t}"
-        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read_e() {
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N) : "memory");
+// tile store shared -> global (TMA), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 // one arrival (elected lane) of a converged warp
 __device__ __forceinline__ void mbar_arrive_e(uint32_t bar) {
