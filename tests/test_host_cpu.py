@@ -196,3 +196,39 @@ def test_unsupported_configurations_raise():
         net._state(0)
     with pytest.raises(sd.SdError):
         net.eval()(torch.zeros(1, 4, 3))      # CPU points
+
+
+def test_header_constants_match_the_binding():
+    """ABI version, precision / dtype enums and the sd_scene layout the ctypes binding assumes, read from the header."""
+    src = open(os.path.join(ROOT, "include", "scenedino_b200.h")).read()
+    assert int(re.search(r"#define SD_ABI_VERSION (\d+)", src).group(1)) == _abi.ABI_VERSION
+    m = re.search(r"typedef enum sd_precision \{([^}]*)\}", src).group(1)
+    enum = {k.strip(): int(v) for k, v in (kv.split("=") for kv in m.split(","))}
+    assert enum == {"SD_MLP_FP32": _abi.SD_MLP_FP32, "SD_MLP_F16_TC": _abi.SD_MLP_F16_TC, "SD_MLP_F32_TC": _abi.SD_MLP_F32_TC}
+    body = re.search(r"typedef struct sd_scene \{(.*?)\} sd_scene;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
+    fields = [re.split(r"[\s\*]+", f)[-1] for f in fields]
+    assert fields == [n for n, _ in _abi.SdScene._fields_], fields
+
+
+def test_x3_projection_sizes_and_errors_without_gpu():
+    """sd_field_project_x3: host arithmetic of the blob size (two operand-image pairs + two fp16 maps) and loud argument errors."""
+    lib = _abi.lib()
+    sc = _abi.SdScene()
+    sc.Hf, sc.Wf, sc.C, sc.nv_f = 384, 1280, 256, 1
+    assert lib.sd_field_project_x3_bytes(ctypes.byref(sc)) == 32768 + 2 * 2 * 80 * 128 + 2 * 384 * 1280 * 256
+    assert lib.sd_field_project_x3_bytes(None) == 0
+    ml = _abi.SdMlp()
+    assert lib.sd_field_project_x3(ctypes.byref(sc), ctypes.byref(ml), None, 0, None) == -1
+    assert lib.sd_query_points_binned(ctypes.byref(sc), ctypes.byref(ml), None, 10, None, None, None, None, None, 0, 0, None) == -1
+    org = (ctypes.c_float * 3)(0, 0, 0)
+    T = (ctypes.c_double * 12)(*([0.0] * 12))
+    assert lib.sd_gen_voxel_grid(org, 0.2, 4, 4, 4, 3, 2, T, None, None) == -1 and "slab" in _abi.last_error()
+    assert lib.sd_gen_voxel_grid(org, 0.2, 4, 4, 4, 2, 2, T, None, None) == 0      # an empty slab is fine
+    assert lib.sd_composite_bwd(None, None, None, None, 0, 8, 4, 3, ctypes.byref(_abi.SdRenderCfg()), *([None] * 8), None) == 0
+    assert lib.sd_composite_bwd(None, None, None, None, 5, 300, 4, 3, ctypes.byref(_abi.SdRenderCfg()), *([None] * 8), None) == -1
