@@ -586,10 +586,13 @@ def main():
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    issue_ms = (time.perf_counter() - t0) * 1e3          # host time to issue the steps (no wait on the device)
     main_s.wait_stream(d2h)
     e1.record()
     e2e_fence()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_dev_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_issue_ms = max_over_ranks(issue_ms) / args.steps
     note("end-to-end done")
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
     e2e_value = world * N / (e2e_ms / args.steps * 1e-3)
@@ -644,6 +647,7 @@ def main():
                                   "frame spec (lidar->camera matrix, origin, voxel size: 128 B) from pinned host memory; the voxel "
                                   "centres are generated on the device (sd_gen_voxel_grid, bit-identical to the host grid)"),
                         "d2h_bytes_per_step": N * 5, "ms_per_step": e2e_ms / args.steps,
+                        "device_ms": e2e_dev_ms, "host_issue_ms": e2e_issue_ms,
                         "api": "scenedino_b200.BTSNet.forward(xyz, only_density=True) (models/bts.py:476-595), fresh outputs and "
                                "workspace per call, full texel sort per call",
                         "note": "every step: inputs host->device (see `input`), BTSNet.forward, density grid + frustum mask device->host "
