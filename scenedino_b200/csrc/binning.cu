@@ -11,55 +11,96 @@
 // (Sorting by the exact texel instead was measured too: no faster in the fused kernel, and the histogram
 // atomics on the few corner texels that collect all behind-camera points made the sort itself 3x slower.)
 //
-// Three launches: (1) bin id per point + histogram (shared-memory pre-aggregation), (2) exclusive scan of the
-// histogram (one block) together with a compact numbering of the non-empty bins, (3) scatter of the point
-// indices and of their compact bin number (per-block ranges reserved with one global atomic per non-empty bin,
-// ranks from shared-memory atomics).  The order inside a bin depends on atomics and is not
-// reproducible; the results per point are (the fused kernel computes each row independently).
+// Three launches over the SAME partition of the points into contiguous ranges, one per block: (1) histogram per range in
+// shared memory; its merge into the global histogram (one atomic per non-empty bin) hands back the number of points earlier
+// ranges put into the bin -- the range's offset inside the bin, kept in `bbase`; (2) exclusive scan of the histogram (one
+// block) together with a compact numbering of the non-empty bins; (3) scatter: position = start of the bin + offset of the
+// range + rank inside the range (shared-memory atomic).  The points are read twice and projected twice (the projection is
+// cheaper than carrying its result through memory).  The order inside a bin depends on atomics and is not reproducible;
+// the results per point are (the fused kernel computes each row independently).
 #include "common.cuh"
 #include "launch.h"
 #include "tc_common.cuh"
 
 namespace sd {
 
-constexpr int BIN_THREADS = 256;
-constexpr int SCAT_THREADS = 512;   // scatter: two blocks per SM by shared memory (2 x 80 KB), so bigger blocks for occupancy
-constexpr int MAX_BINS = 12288;   // the scan stages counts and compact numbers in 96 KB of shared memory
+constexpr int SCAT_THREADS = 512;
+constexpr int MAX_BINS = 12288;     // the scan stages counts and compact numbers in 96 KB of shared memory
+constexpr int BLOCKS_PER_SM = 2;    // (three per SM at 40 registers were measured: no change)
+constexpr int MAX_RANGES = 320;     // ranges (= blocks) of the count and scatter passes: BLOCKS_PER_SM per SM, at most this many
 
 struct BinGeom {
     int Hf, Wf, bw, nbx, nbins;   // bins of bw x bw texels (bw = SD_BIN unless the map is huge)
+    unsigned int bw_magic;        // ceil(2^32 / bw): v / bw == __umulhi(v, bw_magic) for v * bw < 2^32
 };
 
-__device__ __forceinline__ int point_bin(const float *cam, const BinGeom &bg, const float *__restrict__ xyz, long long i) {
+constexpr int BIN_UNROLL = 4;       // points per thread and trip, their loads issued together: both passes are chains of
+                                    // dependent latencies (load -> projection with two divisions -> shared-memory atomic
+                                    // -> store), not bandwidth
+
+__device__ __forceinline__ int point_bin(const float *cam, const BinGeom &bg, float px, float py, float pz) {
     float x, y, z;
     bool inv;
-    project_point(cam, cam + 9, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, z, inv);
+    project_point(cam, cam + 9, px, py, pz, x, y, z, inv);
     Tap t = bilinear_tap(clamp_keep_nan(x, -2.0f, 2.0f), clamp_keep_nan(y, -2.0f, 2.0f), bg.Hf, bg.Wf);
     clamp_footprint(t, bg.Hf, bg.Wf);   // the same base texel as the kernels that consume the order
-    return (t.y0 / bg.bw) * bg.nbx + t.x0 / bg.bw;
+    return (int)(__umulhi((unsigned int)t.y0, bg.bw_magic) * (unsigned int)bg.nbx + __umulhi((unsigned int)t.x0, bg.bw_magic));
 }
 
-// Histogram with shared-memory pre-aggregation per block (a warp-aggregated version with global atomics only was
-// measured: 1.7x slower, the border bins that collect the out-of-frustum points serialise in L2).
-__global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(const float *__restrict__ K, const float *__restrict__ w2c,
-                                                                BinGeom bg, const float *__restrict__ xyz, long long N,
-                                                                unsigned short *__restrict__ bins,
-                                                                unsigned int *__restrict__ hist) {
+// Histogram with shared-memory pre-aggregation per range (a warp-aggregated version with global atomics only was
+// measured: 1.7x slower, the border bins that collect the out-of-frustum points serialise in L2).  bbase[range][bin] =
+// what the global counter of the bin held when this range added its share.
+template <bool WRITE_BINS>
+__global__ void __launch_bounds__(SCAT_THREADS) bin_count_kernel(const float *__restrict__ K, const float *__restrict__ w2c,
+                                                                 BinGeom bg, const float *__restrict__ xyz, long long N,
+                                                                 unsigned short *__restrict__ bins,
+                                                                 unsigned int *__restrict__ hist,
+                                                                 unsigned int *__restrict__ bbase,
+                                                                 unsigned short *__restrict__ blist,
+                                                                 unsigned int *__restrict__ bcount) {
     extern __shared__ unsigned int sh[];
     __shared__ float cam[21];
-    for (int i = threadIdx.x; i < 21; i += BIN_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
-    for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS) sh[b] = 0;
+    __shared__ unsigned int n_list;
+    if (threadIdx.x == 0) n_list = 0;
+    for (int i = threadIdx.x; i < 21; i += SCAT_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
+    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) sh[b] = 0;
     __syncthreads();
     const long long per = (N + gridDim.x - 1) / gridDim.x;
     const long long lo = per * blockIdx.x, hi = min(N, lo + per);
-    for (long long i = lo + threadIdx.x; i < hi; i += BIN_THREADS) {
-        const int b = point_bin(cam, bg, xyz, i);
-        bins[i] = (unsigned short)b;
-        atomicAdd(&sh[b], 1u);
+    const unsigned int n = hi > lo ? (unsigned int)(hi - lo) : 0u;
+    const float *__restrict__ p = xyz + 3 * lo;
+    for (unsigned int j0 = threadIdx.x; j0 < n; j0 += BIN_UNROLL * SCAT_THREADS) {   // (32-bit indexing inside a range: N < 2^31)
+        float q[BIN_UNROLL][3];
+#pragma unroll
+        for (int u = 0; u < BIN_UNROLL; ++u) {
+            const unsigned int j = j0 + u * SCAT_THREADS;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) q[u][c] = j < n ? __ldg(p + 3u * j + c) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < BIN_UNROLL; ++u) {
+            const unsigned int j = j0 + u * SCAT_THREADS;
+            if (j < n) {
+                const int b = point_bin(cam, bg, q[u][0], q[u][1], q[u][2]);
+                if (WRITE_BINS) bins[lo + j] = (unsigned short)b;
+                atomicAdd(&sh[b], 1u);
+            }
+        }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < bg.nbins; b += BIN_THREADS)
-        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+    // a range of consecutive points touches a small part of the bins: the scatter pass gets the list of them, so that it
+    // reads (and this pass writes) only those entries of the range's row
+    unsigned int *__restrict__ row = bbase + (size_t)blockIdx.x * bg.nbins;
+    unsigned short *__restrict__ list = blist + (size_t)blockIdx.x * bg.nbins;
+    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) {
+        const unsigned int c = sh[b];
+        if (c) {
+            row[b] = atomicAdd(&hist[b], c);
+            list[atomicAdd(&n_list, 1u)] = (unsigned short)b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) bcount[blockIdx.x] = n_list;
 }
 
 // exclusive scan of hist[0..nbins) in place, one block of 1024 threads, staged through shared memory (coalesced global
@@ -129,50 +170,73 @@ struct GeoOut {
 template <bool GEO>
 __global__ void __launch_bounds__(SCAT_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
                                                                   const unsigned short *__restrict__ bins,
-                                                                  unsigned int *__restrict__ cursor,
+                                                                  const unsigned int *__restrict__ start,
+                                                                  const unsigned int *__restrict__ bbase,
+                                                                  const unsigned short *__restrict__ blist,
+                                                                  const unsigned int *__restrict__ bcount,
                                                                   const unsigned int *__restrict__ cidx,
                                                                   unsigned int *__restrict__ perm,
                                                                   unsigned short *__restrict__ pcb,
                                                                   const float *__restrict__ K, const float *__restrict__ w2c,
                                                                   const float *__restrict__ xyz, GeoOut go) {
-    extern __shared__ unsigned int sh[];          // [nbins] counts, then [nbins] bases
+    extern __shared__ unsigned int sh[];          // [nbins] next free position of this range in each bin it touches
     __shared__ float cam[21];
-    unsigned int *cnt = sh, *base = sh + bg.nbins;
-    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) cnt[b] = 0;
+    const unsigned int *__restrict__ row = bbase + (size_t)blockIdx.x * bg.nbins;
+    const unsigned short *__restrict__ list = blist + (size_t)blockIdx.x * bg.nbins;
+    const unsigned int n_list = __ldg(bcount + blockIdx.x);
+    for (unsigned int k = threadIdx.x; k < n_list; k += SCAT_THREADS) {
+        const unsigned int b = __ldg(list + k);
+        sh[b] = __ldg(start + b) + __ldg(row + b);
+    }
     if (GEO)
         for (int i = threadIdx.x; i < 21; i += SCAT_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
     __syncthreads();
-    const long long per = (N + gridDim.x - 1) / gridDim.x;
+    const long long per = (N + gridDim.x - 1) / gridDim.x;   // the partition of bin_count_kernel (same grid)
     const long long lo = per * blockIdx.x, hi = min(N, lo + per);
-    for (long long i = lo + threadIdx.x; i < hi; i += SCAT_THREADS) atomicAdd(&cnt[bins[i]], 1u);
-    __syncthreads();
-    for (int b = threadIdx.x; b < bg.nbins; b += SCAT_THREADS) {
-        const unsigned int c = cnt[b];
-        if (c) base[b] = atomicAdd(&cursor[b], c);
-        cnt[b] = 0;
-    }
-    __syncthreads();
-    for (long long i = lo + threadIdx.x; i < hi; i += SCAT_THREADS) {
-        const int b = bins[i];
-        const unsigned int pos = base[b] + atomicAdd(&cnt[b], 1u);
-        const unsigned int ci = __ldg(cidx + b);
-        if (!GEO) {
-            perm[pos] = (unsigned int)i;
-            pcb[pos] = (unsigned short)ci;
-        } else {
-            float x, y, zc;
-            bool inv;
-            project_point(cam, cam + 9, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), x, y, zc, inv);
-            x = clamp_keep_nan(x, -2.0f, 2.0f);
-            y = clamp_keep_nan(y, -2.0f, 2.0f);
-            Tap t = bilinear_tap(x, y, bg.Hf, bg.Wf);
-            clamp_footprint(t, bg.Hf, bg.Wf);
-            const int lx = t.x0 - (t.x0 / SD_BIN) * SD_BIN, ly = t.y0 - (t.y0 / SD_BIN) * SD_BIN;
-            const unsigned int slot = (go.learn_empty && inv) ? 0xFFu : (unsigned int)(ly * 8 + lx);
-            uint4 *dst = reinterpret_cast<uint4 *>(go.rec + pos);
-            dst[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(znorm(zc, go.enc)), tcx::pack_h2(t.wnw, t.wne));
-            dst[1] = make_uint4(tcx::pack_h2(t.wsw, t.wse), (unsigned int)i, ci | (slot << 16), (unsigned int)b);
-            if (go.invalid_feat) go.invalid_feat[i] = inv ? 1 : 0;
+    const unsigned int n = hi > lo ? (unsigned int)(hi - lo) : 0u;
+    if (!GEO) {
+        for (unsigned int j = threadIdx.x; j < n; j += SCAT_THREADS) {
+            const int b = bins[lo + j];
+            const unsigned int pos = atomicAdd(&sh[b], 1u);
+            perm[pos] = (unsigned int)lo + j;
+            pcb[pos] = (unsigned short)__ldg(cidx + b);
+        }
+    } else {
+        const float *__restrict__ p = xyz + 3 * lo;
+        const unsigned int i0 = (unsigned int)lo;
+        unsigned char *__restrict__ inv_out = go.invalid_feat ? go.invalid_feat + lo : nullptr;
+        // (One atomic per run of equal bins in a warp instead of one per lane was measured: no change -- the pass is bound by
+        // the ~250 instructions per point of projection, normalisation and record packing, not by the atomics.)
+        for (unsigned int j0 = threadIdx.x; j0 < n; j0 += BIN_UNROLL * SCAT_THREADS) {
+            float q[BIN_UNROLL][3];
+#pragma unroll
+            for (int u = 0; u < BIN_UNROLL; ++u) {
+                const unsigned int j = j0 + u * SCAT_THREADS;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) q[u][c] = j < n ? __ldg(p + 3u * j + c) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < BIN_UNROLL; ++u) {
+                const unsigned int j = j0 + u * SCAT_THREADS;
+                if (j >= n) continue;
+                float x, y, zc;
+                bool inv;
+                project_point(cam, cam + 9, q[u][0], q[u][1], q[u][2], x, y, zc, inv);
+                x = clamp_keep_nan(x, -2.0f, 2.0f);
+                y = clamp_keep_nan(y, -2.0f, 2.0f);
+                Tap t = bilinear_tap(x, y, bg.Hf, bg.Wf);
+                clamp_footprint(t, bg.Hf, bg.Wf);
+                const int bx = t.x0 / SD_BIN, by = t.y0 / SD_BIN;            // GEO: bg.bw == SD_BIN
+                const int b = by * bg.nbx + bx;                              // the bin bin_count_kernel counted this point in
+                const int lx = t.x0 - bx * SD_BIN, ly = t.y0 - by * SD_BIN;
+                const unsigned int pos = atomicAdd(&sh[b], 1u);
+                const unsigned int ci = __ldg(cidx + b);
+                const unsigned int slot = (go.learn_empty && inv) ? 0xFFu : (unsigned int)(ly * 8 + lx);
+                uint4 *dst = reinterpret_cast<uint4 *>(go.rec + pos);
+                dst[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(znorm(zc, go.enc)), tcx::pack_h2(t.wnw, t.wne));
+                dst[1] = make_uint4(tcx::pack_h2(t.wsw, t.wse), i0 + j, ci | (slot << 16), (unsigned int)b);
+                if (inv_out) inv_out[j] = inv ? 1 : 0;
+            }
         }
     }
 }
@@ -201,6 +265,7 @@ static BinGeom bin_geom(int Hf, int Wf) {
     for (;;) {
         g.nbx = (Wf - 1) / g.bw + 1;
         g.nbins = g.nbx * ((Hf - 1) / g.bw + 1);
+        g.bw_magic = (unsigned int)(((1ull << 32) + (unsigned)g.bw - 1) / (unsigned)g.bw);
         if (g.nbins <= MAX_BINS) return g;
         g.bw += SD_BIN;
     }
@@ -213,7 +278,9 @@ size_t bin_workspace_bytes(int Hf, int Wf, long long N) {
     const BinGeom g = bin_geom(Hf, Wf);
     return a256((size_t)N * 4) + 2 * a256((size_t)N * 2) + 3 * a256((size_t)g.nbins * 4) + 256 +
            a256((size_t)N * sizeof(GeoRec)) +               // per-point records of the tile kernel
-           a256((size_t)((N + 127) / 128 + 8) * sizeof(TileInfo));
+           a256((size_t)((N + 127) / 128 + 8) * sizeof(TileInfo)) +
+           a256((size_t)MAX_RANGES * g.nbins * 4) +         // offsets of the ranges inside the bins,
+           a256((size_t)MAX_RANGES * g.nbins * 2) + a256((size_t)MAX_RANGES * 4);   // the bins each range touches
 }
 
 // Sorts the point indices by bin.  Fills `out` with device pointers into the workspace.
@@ -236,7 +303,10 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     unsigned int *cbin = reinterpret_cast<unsigned int *>(ws);               ws += a256((size_t)g.nbins * 4);
     GeoOut go = {};
     go.rec = reinterpret_cast<GeoRec *>(ws);                                                           ws += a256((size_t)N * sizeof(GeoRec));
-    TileInfo *tiles = reinterpret_cast<TileInfo *>(ws);
+    TileInfo *tiles = reinterpret_cast<TileInfo *>(ws);                      ws += a256((size_t)((N + 127) / 128 + 8) * sizeof(TileInfo));
+    unsigned int *bbase = reinterpret_cast<unsigned int *>(ws);              ws += a256((size_t)MAX_RANGES * g.nbins * 4);
+    unsigned short *blist = reinterpret_cast<unsigned short *>(ws);          ws += a256((size_t)MAX_RANGES * g.nbins * 2);
+    unsigned int *bcount = reinterpret_cast<unsigned int *>(ws);
     go.invalid_feat = invalid_feat;
     go.enc = fp.enc;
     go.learn_empty = fp.learn_empty;
@@ -245,9 +315,10 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     bool first_use = false;
     if (int rc_dev = device_once(once, &sm_count, &first_use)) return rc_dev;
     if (first_use) {
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
     }
     if (reuse_sorted) {
@@ -259,19 +330,23 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
         out->has_geo = true; out->rec = go.rec; out->tile_ctr = meta + 1; out->tiles = tiles;
         return SD_OK;
     }
-    const long long blocks_wanted = (N + 4 * BIN_THREADS - 1) / (4 * BIN_THREADS);
-    const unsigned grid = (unsigned)(blocks_wanted < 4 * sm_count ? blocks_wanted : 4 * sm_count);
-    const unsigned grid2 = (unsigned)(blocks_wanted < 2 * sm_count ? blocks_wanted : 2 * sm_count);
+    const long long blocks_wanted = (N + 2 * SCAT_THREADS - 1) / (2 * SCAT_THREADS);
+    const long long cap = BLOCKS_PER_SM * sm_count < MAX_RANGES ? BLOCKS_PER_SM * sm_count : MAX_RANGES;
+    const unsigned grid = (unsigned)(blocks_wanted < cap ? blocks_wanted : cap);     // ranges: the same for both passes
+    const bool geo = want_geo && g.bw == SD_BIN;
     // histogram and meta (meta[1]: tile counter of the tile kernel) in one go
     SD_CUDA_OK(cudaMemsetAsync(hist, 0, a256((size_t)g.nbins * 4) + 256, st));
-    bin_count_kernel<<<grid, BIN_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist);
+    if (geo)   // the scatter recomputes the bin from the projection it needs anyway: no bin array
+        bin_count_kernel<false><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist, bbase, blist, bcount);
+    else
+        bin_count_kernel<true><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist, bbase, blist, bcount);
     SD_LAUNCH_OK("bin_count_kernel");
     bin_scan_kernel<<<1, 1024, (size_t)g.nbins * 8, st>>>(hist, g.nbins, cidx, cbin, meta);
     SD_LAUNCH_OK("bin_scan_kernel");
-    if (want_geo && g.bw == SD_BIN)
-        bin_scatter_kernel<true><<<grid2, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+    if (geo)
+        bin_scatter_kernel<true><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(g, N, bins, hist, bbase, blist, bcount, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     else
-        bin_scatter_kernel<false><<<grid2, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+        bin_scatter_kernel<false><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(g, N, bins, hist, bbase, blist, bcount, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     SD_LAUNCH_OK("bin_scatter_kernel");
     out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
     out->has_geo = want_geo && g.bw == SD_BIN;

@@ -67,7 +67,9 @@ def test_argument_validation_without_gpu():
     ml.d_in, ml.d_hidden, ml.d_out, ml.precision = 295, 128, 65, _abi.SD_MLP_F16_TC
     n = 1 << 21
     need = lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), n)
-    assert n * (4 + 2 + 2 + 32) + (n // 128) * 16 <= need <= n * 41 + (1 << 20)
+    # ... plus what does not: per range of the two passes (at most 320) a 4-byte offset and a 2-byte list entry per texel bin
+    nbins = ((384 - 1) // 7 + 1) * ((1280 - 1) // 7 + 1)
+    assert n * (4 + 2 + 2 + 32) + (n // 128) * 16 + 320 * nbins * 6 <= need <= n * 41 + (1 << 20) + 320 * nbins * 6
     assert lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), 1000) == 0        # small queries are not sorted
     ml.precision = _abi.SD_MLP_FP32
     assert lib.sd_query_workspace_bytes(ctypes.byref(sc), ctypes.byref(ml), n) == 0           # nor is the fp32 path
