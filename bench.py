@@ -209,7 +209,7 @@ def workload_config(precision, binned=False):
             "voxels_per_step": GRID[0] * GRID[1] * GRID[2], "feature_map": [C_FEAT, HF, WF],
             "mlp": [D_IN, D_HID, D_OUT],
             "l2": "working set per step (map + 25 MB points + 545 MB outputs) exceeds the 126 MB L2; no explicit flush",
-            "launch": "one CUDA-graph replay per step (memset + 4 sort kernels + field kernel)" if precision == "fp16" else "direct calls"}
+            "launch": "one CUDA-graph replay per step (memset + 3 sort kernels + field kernel)" if precision == "fp16" else "direct calls"}
 
 
 def build_net(sd, torch, feat_holder, dev, precision, d_out=D_OUT, with_head=True, seed=0):

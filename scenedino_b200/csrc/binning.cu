@@ -11,11 +11,11 @@
 // (Sorting by the exact texel instead was measured too: no faster in the fused kernel, and the histogram
 // atomics on the few corner texels that collect all behind-camera points made the sort itself 3x slower.)
 //
-// Three launches over the SAME partition of the points into contiguous ranges, one per block: (1) histogram per range in
+// Two passes over the SAME partition of the points into contiguous ranges, one per block: (1) histogram per range in
 // shared memory; its merge into the global histogram (one atomic per non-empty bin) hands back the number of points earlier
-// ranges put into the bin -- the range's offset inside the bin, kept in `bbase`; (2) exclusive scan of the histogram (one
-// block) together with a compact numbering of the non-empty bins; (3) scatter: position = start of the bin + offset of the
-// range + rank inside the range (shared-memory atomic).  The points are read twice and projected twice (the projection is
+// ranges put into the bin -- the range's offset inside the bin, kept in `bbase`; (2) scatter: every block scans the histogram
+// for itself (bin starts + a compact numbering of the non-empty bins, in shared memory), then position = start of the bin +
+// offset of the range + rank inside the range (shared-memory atomic); (3) the tile table.  The points are read twice and projected twice (the projection is
 // cheaper than carrying its result through memory).  The order inside a bin depends on atomics and is not reproducible;
 // the results per point are (the fused kernel computes each row independently).
 #include "common.cuh"
@@ -25,7 +25,7 @@
 namespace sd {
 
 constexpr int SCAT_THREADS = 512;
-constexpr int MAX_BINS = 12288;     // the scan stages counts and compact numbers in 96 KB of shared memory
+constexpr int MAX_BINS = 12288;     // the scatter pass holds bin starts and compact numbers in 96 KB of shared memory per block
 constexpr int BLOCKS_PER_SM = 2;    // (three per SM at 40 registers were measured: no change)
 constexpr int MAX_RANGES = 320;     // ranges (= blocks) of the count and scatter passes: BLOCKS_PER_SM per SM, at most this many
 
@@ -103,23 +103,23 @@ __global__ void __launch_bounds__(SCAT_THREADS) bin_count_kernel(const float *__
     if (threadIdx.x == 0) bcount[blockIdx.x] = n_list;
 }
 
-// exclusive scan of hist[0..nbins) in place, one block of 1024 threads, staged through shared memory (coalesced global
-// accesses); cidx[b] = number of non-empty bins before b (the compact number of b when it is non-empty), cbin[c] = bin
-// with compact number c, meta[0] = their count
-__global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict__ hist, int nbins,
-                                                        unsigned int *__restrict__ cidx, unsigned int *__restrict__ cbin,
-                                                        unsigned int *__restrict__ meta) {
-    extern __shared__ unsigned int sh[];            // [nbins] counts -> starts, [nbins] compact numbers
-    __shared__ unsigned int warp_tot[32], warp_ne[32];
-    unsigned int *s_cnt = sh, *s_ci = sh + nbins;
-    for (int b = threadIdx.x; b < nbins; b += 1024) s_cnt[b] = hist[b];
+// Exclusive scan of the histogram by ONE block (SCAT_THREADS threads), into shared memory: s_start[b] = first sorted position
+// of bin b, s_ci[b] = number of non-empty bins before b (the compact number of b when it is non-empty, else 0xFFFFFFFF).
+// Every block of the scatter pass does this for itself (40 KB of counts from L2, ~2 us, all blocks at once) instead of waiting
+// for a one-block kernel in between (8 us + a launch); block 0 also publishes cbin[c] = bin with compact number c and
+// meta[0] = their count.
+__device__ __forceinline__ void block_scan_bins(const unsigned int *__restrict__ hist, int nbins, unsigned int *s_start,
+                                                unsigned int *s_ci, unsigned int *__restrict__ cbin,
+                                                unsigned int *__restrict__ meta) {
+    __shared__ unsigned int warp_tot[SCAT_THREADS / 32], warp_ne[SCAT_THREADS / 32];
+    for (int i = threadIdx.x; i < nbins; i += SCAT_THREADS) s_start[i] = __ldcg(hist + i);
     __syncthreads();
-    const int per = (nbins + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(nbins, lo + per);
-    unsigned int s = 0, ne = 0;
-    for (int b = lo; b < hi; ++b) { const unsigned int c = s_cnt[b]; s += c; ne += c != 0; }
+    const int per = (nbins + SCAT_THREADS - 1) / SCAT_THREADS;
+    const int lo = min(nbins, (int)threadIdx.x * per), hi = min(nbins, lo + per);
+    unsigned int sum = 0, ne = 0;
+    for (int i = lo; i < hi; ++i) { const unsigned int c = s_start[i]; sum += c; ne += c != 0; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int incl = s, incl_ne = ne;
+    unsigned int incl = sum, incl_ne = ne;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o), m = __shfl_up_sync(0xffffffffu, incl_ne, o);
@@ -127,34 +127,18 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int *__restrict
     }
     if (lane == 31) { warp_tot[warp] = incl; warp_ne[warp] = incl_ne; }
     __syncthreads();
-    if (warp == 0) {
-        const unsigned int w = warp_tot[lane], v = warp_ne[lane];
-        unsigned int wi = w, vi = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o), m = __shfl_up_sync(0xffffffffu, vi, o);
-            if (lane >= o) { wi += n; vi += m; }
-        }
-        warp_tot[lane] = wi - w;
-        warp_ne[lane] = vi - v;
-        if (lane == 31) meta[0] = vi;
-    }
-    __syncthreads();
-    unsigned int run = warp_tot[warp] + incl - s, run_ne = warp_ne[warp] + incl_ne - ne;
-    for (int b = lo; b < hi; ++b) {
-        const unsigned int c = s_cnt[b];
-        s_cnt[b] = run;
-        s_ci[b] = c ? run_ne : 0xFFFFFFFFu;        // compact number, or "empty"
+    unsigned int run = incl - sum, run_ne = incl_ne - ne;
+    for (int w = 0; w < warp; ++w) { run += warp_tot[w]; run_ne += warp_ne[w]; }
+    for (int i = lo; i < hi; ++i) {
+        const unsigned int c = s_start[i];
+        s_start[i] = run;
+        s_ci[i] = c ? run_ne : 0xFFFFFFFFu;
+        if (c && blockIdx.x == 0) cbin[run_ne] = (unsigned int)i;
         run += c;
         run_ne += c != 0;
     }
+    if (blockIdx.x == 0 && threadIdx.x == SCAT_THREADS - 1) meta[0] = run_ne;
     __syncthreads();
-    for (int b = threadIdx.x; b < nbins; b += 1024) {
-        const unsigned int ci = s_ci[b];
-        hist[b] = s_cnt[b];
-        cidx[b] = ci;
-        if (ci != 0xFFFFFFFFu) cbin[ci] = (unsigned int)b;
-    }
 }
 
 // Per-point record of the projected-map tile kernel (field_bin.cu), written at the SORTED position of the point as
@@ -170,23 +154,26 @@ struct GeoOut {
 template <bool GEO>
 __global__ void __launch_bounds__(SCAT_THREADS) bin_scatter_kernel(BinGeom bg, long long N,
                                                                   const unsigned short *__restrict__ bins,
-                                                                  const unsigned int *__restrict__ start,
+                                                                  const unsigned int *__restrict__ hist,
                                                                   const unsigned int *__restrict__ bbase,
                                                                   const unsigned short *__restrict__ blist,
                                                                   const unsigned int *__restrict__ bcount,
-                                                                  const unsigned int *__restrict__ cidx,
+                                                                  unsigned int *__restrict__ cbin,
+                                                                  unsigned int *__restrict__ meta,
                                                                   unsigned int *__restrict__ perm,
                                                                   unsigned short *__restrict__ pcb,
                                                                   const float *__restrict__ K, const float *__restrict__ w2c,
                                                                   const float *__restrict__ xyz, GeoOut go) {
-    extern __shared__ unsigned int sh[];          // [nbins] next free position of this range in each bin it touches
-    __shared__ float cam[21];
+    extern __shared__ unsigned int sh[];          // [nbins] bin starts, then the next free position of this range in each bin
+    __shared__ float cam[21];                     // it touches; [nbins] compact bin numbers
+    unsigned int *s_ci = sh + bg.nbins;
+    block_scan_bins(hist, bg.nbins, sh, s_ci, cbin, meta);
     const unsigned int *__restrict__ row = bbase + (size_t)blockIdx.x * bg.nbins;
     const unsigned short *__restrict__ list = blist + (size_t)blockIdx.x * bg.nbins;
     const unsigned int n_list = __ldg(bcount + blockIdx.x);
     for (unsigned int k = threadIdx.x; k < n_list; k += SCAT_THREADS) {
         const unsigned int b = __ldg(list + k);
-        sh[b] = __ldg(start + b) + __ldg(row + b);
+        sh[b] += __ldg(row + b);
     }
     if (GEO)
         for (int i = threadIdx.x; i < 21; i += SCAT_THREADS) cam[i] = i < 9 ? __ldg(K + i) : __ldg(w2c + (i - 9));
@@ -199,7 +186,7 @@ __global__ void __launch_bounds__(SCAT_THREADS) bin_scatter_kernel(BinGeom bg, l
             const int b = bins[lo + j];
             const unsigned int pos = atomicAdd(&sh[b], 1u);
             perm[pos] = (unsigned int)lo + j;
-            pcb[pos] = (unsigned short)__ldg(cidx + b);
+            pcb[pos] = (unsigned short)s_ci[b];
         }
     } else {
         const float *__restrict__ p = xyz + 3 * lo;
@@ -230,7 +217,7 @@ __global__ void __launch_bounds__(SCAT_THREADS) bin_scatter_kernel(BinGeom bg, l
                 const int b = by * bg.nbx + bx;                              // the bin bin_count_kernel counted this point in
                 const int lx = t.x0 - bx * SD_BIN, ly = t.y0 - by * SD_BIN;
                 const unsigned int pos = atomicAdd(&sh[b], 1u);
-                const unsigned int ci = __ldg(cidx + b);
+                const unsigned int ci = s_ci[b];
                 const unsigned int slot = (go.learn_empty && inv) ? 0xFFu : (unsigned int)(ly * 8 + lx);
                 uint4 *dst = reinterpret_cast<uint4 *>(go.rec + pos);
                 dst[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(znorm(zc, go.enc)), tcx::pack_h2(t.wnw, t.wne));
@@ -317,9 +304,8 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     if (first_use) {
         SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
         SD_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 4));
-        SD_CUDA_OK(cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
+        SD_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BINS * 8));
     }
     if (reuse_sorted) {
         // the workspace still holds the sort of these points for these cameras (sd_query_points_sorted): only the tile
@@ -341,12 +327,10 @@ int launch_bin_points(const FieldParams &fp, const float *xyz, long long N, void
     else
         bin_count_kernel<true><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(fp.K_f, fp.w2c_f, g, xyz, N, bins, hist, bbase, blist, bcount);
     SD_LAUNCH_OK("bin_count_kernel");
-    bin_scan_kernel<<<1, 1024, (size_t)g.nbins * 8, st>>>(hist, g.nbins, cidx, cbin, meta);
-    SD_LAUNCH_OK("bin_scan_kernel");
     if (geo)
-        bin_scatter_kernel<true><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(g, N, bins, hist, bbase, blist, bcount, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+        bin_scatter_kernel<true><<<grid, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, bbase, blist, bcount, cbin, meta, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     else
-        bin_scatter_kernel<false><<<grid, SCAT_THREADS, (size_t)g.nbins * 4, st>>>(g, N, bins, hist, bbase, blist, bcount, cidx, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
+        bin_scatter_kernel<false><<<grid, SCAT_THREADS, (size_t)g.nbins * 8, st>>>(g, N, bins, hist, bbase, blist, bcount, cbin, meta, perm, pcb, fp.K_f, fp.w2c_f, xyz, go);
     SD_LAUNCH_OK("bin_scatter_kernel");
     out->perm = perm; out->pcb = pcb; out->cbin = cbin; out->bw = g.bw; out->nbx = g.nbx; out->nbins = g.nbins;
     out->has_geo = want_geo && g.bw == SD_BIN;

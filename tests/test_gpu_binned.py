@@ -90,7 +90,7 @@ def test_binned_errors_are_loud(golden):
 
 def test_btsnet_forward_segmentation_takes_the_binned_path():
     """BTSNet.forward(grid, predict_segmentation=True) (models/bts.py:584-592): with the fused head the 64-d rows stay in
-    texel-bin order between the query and sd_ssc_head (launches: 4 sort + tile kernel + head = 6, then tile + head = 2 on
+    texel-bin order between the query and sd_ssc_head (launches: 3 sort + tile kernel + head = 5, then tile + head = 2 on
     the next frame of a static grid); labels / sigma equal the caller-order route (materialize_dino_full) wherever the
     head's top-2 gap is clear -- here: bit for bit, both routes feed the head the same rows."""
     import bench
@@ -116,7 +116,7 @@ def test_btsnet_forward_segmentation_takes_the_binned_path():
         _, _, sig_c, seg_c = net(grid, predict_segmentation=True)          # static grid: the sort is reused
         n2 = _abi.launch_count()
     assert none is None and full is not None
-    assert n1 - n0 == 6 and n2 - n1 == 2, (n1 - n0, n2 - n1)
+    assert n1 - n0 == 5 and n2 - n1 == 2, (n1 - n0, n2 - n1)
     assert torch.equal(sig_a, sig_b) and torch.equal(sig_b, sig_c)
     assert torch.equal(seg_a.reshape(-1).to(torch.int64), seg_b.reshape(-1).to(torch.int64)) and torch.equal(seg_b, seg_c)
 

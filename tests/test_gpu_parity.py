@@ -151,7 +151,7 @@ def test_query_points_projected(golden, tag, learn_empty):
     pts = np.concatenate([g["points"], g["points"], syn.random_points(7, 70000 - 2 * n_g + 77)]).astype(np.float32)
     n0 = _abi.launch_count()
     q = ops.query_points(dscp, dmlp, dev(pts), precision=ops.F16)
-    assert _abi.launch_count() - n0 == 5, "expected sort (4 launches) + field_bin_kernel"
+    assert _abi.launch_count() - n0 == 4, "expected sort (3 launches) + field_bin_kernel"
     o = O.query_points(osc, omlp, pts)
     for lo in (0, n_g):   # both copies of the golden points against the reference
         sl = slice(lo, lo + n_g)
@@ -188,7 +188,7 @@ def test_tile_kernel_vs_reference_big(golden, tag, learn_empty):
     pts, sub = big_query_points(g)
     n0 = _abi.launch_count()
     q = ops.query_points(dscp, dmlp, dev(pts), want_rgb=False, precision=ops.F16)
-    assert _abi.launch_count() - n0 == 5
+    assert _abi.launch_count() - n0 == 4
     inv = np.unpackbits(g["invalid_features" + tag])[:len(pts)].astype(bool)
     assert np.array_equal(g2n(q["invalid_features"]), inv)
     assert_close(g2n(q["sigma"])[sub], g["sigma" + tag], TOL_F16, "sigma vs reference")
@@ -230,7 +230,7 @@ def test_query_graph_replay_matches_direct_calls(golden):
     out = dict(sigma=torch.empty_like(ref["sigma"]), dino=torch.empty_like(ref["dino"]),
                invalid_features=torch.empty(len(pts), dtype=torch.uint8, device=DEV))
     qg = ops.QueryGraph(dscp, dmlp, pts, out, precision=ops.F16)
-    assert qg.launches == 5
+    assert qg.launches == 4
     for k in out:
         if not k.startswith("_"):
             out[k].zero_()
@@ -270,7 +270,7 @@ def test_tile_kernel_shapes(Hf, Wf, d_out, nv_c):
     dscp = dsc.project(dmlp)
     n0 = _abi.launch_count()
     q = ops.query_points(dscp, dmlp, dev(pts), precision=ops.F16, want_rgb=nv_c > 0)
-    assert _abi.launch_count() - n0 == 5, "expected the texel sort + the tile kernel"
+    assert _abi.launch_count() - n0 == 4, "expected the texel sort + the tile kernel"
     o = O.query_points(osc, O.Mlp(*mlp_w), pts, want_rgb=nv_c > 0)
     assert q["dino"].shape == (len(pts), d_out - 1)
     assert np.array_equal(g2n(q["invalid_features"]), o["invalid_features"])

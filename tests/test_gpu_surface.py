@@ -216,7 +216,7 @@ def test_btsnet_forward_large_fp16_uses_projected_map(golden):
         second = _abi.launch_count() - n0
     projs = [st["proj"] for st in net._packed.values() if "proj" in st]
     assert len(projs) == 1 and len(projs[0]) == 1, "one projection per encode, batch element and head"
-    assert 5 <= second <= 8, "sort (4 launches) + tile kernel (+ expand_dim), no second projection"
+    assert 4 <= second <= 7, "sort (3 launches) + tile kernel (+ expand_dim), no second projection"
     assert torch.equal(st16["invalid_features"], st32["invalid_features"])
     assert_close(sigma16[0, :, 0].cpu().numpy(), sigma32[0, :, 0].cpu().numpy(), TOL_F16, "sigma fp16 vs fp32")
     assert_close(st16["dino_features"][0].cpu().numpy(), st32["dino_features"][0].cpu().numpy(), TOL_F16, "dino fp16 vs fp32")

@@ -32,7 +32,7 @@ def test_projection_x3_matches_fp32_matmul(golden):
 @pytest.mark.parametrize("tag,learn_empty", [("", False), ("_le", True)])
 def test_tile_kernel_x3_vs_reference_big(golden, tag, learn_empty):
     """The reference's own outputs on the 70 001-point query (fixture query_big): masks bit-exact, densities / features of
-    the stored subset within 1e-4 -- on the tensor cores; launches: 4 sort + tile kernel."""
+    the stored subset within 1e-4 -- on the tensor cores; launches: 3 sort + tile kernel."""
     g = golden("query_big")
     kw = dict(learn_empty=learn_empty, empty_feature=g["empty_feature"] if learn_empty else None)
     _, dsc, _, dmlp = scenes_from_golden(g, **kw)
@@ -40,7 +40,7 @@ def test_tile_kernel_x3_vs_reference_big(golden, tag, learn_empty):
     pts, sub = big_query_points(g)
     n0 = _abi.launch_count()
     q = ops.query_points(dscp, dmlp, dev(pts), want_rgb=False, precision=ops.F32TC)
-    assert _abi.launch_count() - n0 == 5
+    assert _abi.launch_count() - n0 == 4
     inv = np.unpackbits(g["invalid_features" + tag])[:len(pts)].astype(bool)
     assert np.array_equal(g2n(q["invalid_features"]), inv)
     assert_close(g2n(q["sigma"])[sub], g["sigma" + tag], TOL_FP32, "sigma vs reference")
