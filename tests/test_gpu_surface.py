@@ -304,3 +304,19 @@ def test_no_silent_fallback(golden):
     net.train()
     with pytest.raises(NotImplementedError):
         net(pts, predict_segmentation=True)           # the SSC head is evaluation-only
+
+
+def test_launch_stream_follows_torch_current_stream():
+    """Every C-ABI launch goes to torch's CURRENT stream of the tensors' device (heads._stream hands the raw handle over):
+    the default stream outside, a side stream inside ``torch.cuda.stream`` -- and work queued there is ordered with it."""
+    from scenedino_b200 import heads
+    assert (heads._stream().value or 0) == torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        assert (heads._stream().value or 0) == side.cuda_stream
+        x = torch.randn(1000, 3, device=DEV)
+        code = sd.PositionalEncoding(num_freqs=6, d_in=3, freq_factor=1.5, include_input=True)(x)
+        ev = torch.cuda.Event(); ev.record()
+    assert (heads._stream().value or 0) == torch.cuda.current_stream().cuda_stream
+    ev.synchronize()
+    assert code.shape == (1000, 39) and torch.equal(code[:, :3], x)
