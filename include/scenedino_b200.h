@@ -305,10 +305,13 @@ int sd_gen_voxel_grid(const float *origin, float voxel_size, int nx, int ny, int
  * With the environment variable SD_TC_DEBUG & 8192 set when the library is loaded, CTA 0 of the tensor-core kernels
  * records clock64 stamps per warp role and tile; these calls copy the trace of the last launch to HOST buffers:
  * sd_debug_read_trace: field_tc_kernel, [4 roles][64 tiles][8 events] long long; sd_debug_read_trace_bin: field_bin_kernel,
- * [8][64][8] long long; sd_debug_read_cta_ns: field_bin_kernel, [256 CTAs][start, end] %globaltimer. */
+ * [8][64][8] long long; sd_debug_read_cta_ns: field_bin_kernel, [256 CTAs][start, end] %globaltimer;
+ * sd_debug_read_tiles_bin: field_bin_kernel, [4 CTAs][512 tiles][clock64 at the layer-1 issuer's tile start, operand chunks of
+ * the tile] long long (entries 510 / 511 of a CTA: kernel start / end). */
 int sd_debug_read_trace(long long *host_out);
 int sd_debug_read_trace_bin(long long *host_out);
 int sd_debug_read_cta_ns(unsigned long long *host_out);
+int sd_debug_read_tiles_bin(long long *host_out);
 
 /* ---- section 8f-4: backward pass of the training step (training/base_trainer.py:223-255) ---------------------------------
  * The fused kernels above are forward-only.  In training mode (autograd on) the Python surface runs the path unfused --

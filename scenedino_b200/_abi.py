@@ -102,6 +102,7 @@ PROTOTYPES = {
     "sd_debug_read_trace": (_I, [_P]),
     "sd_debug_read_trace_bin": (_I, [_P]),
     "sd_debug_read_cta_ns": (_I, [_P]),
+    "sd_debug_read_tiles_bin": (_I, [_P]),
 }
 
 _lib = None

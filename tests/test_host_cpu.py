@@ -32,6 +32,14 @@ def test_library_exports_every_declared_symbol():
     assert _abi.lib().sd_abi_version() == _abi.ABI_VERSION == 4
 
 
+def test_library_exports_nothing_the_header_does_not_declare():
+    """the other direction: every dynamic `sd_*` symbol of the built library (diagnostics included) is in the header"""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("sd_")})
+    assert exported == header_symbols()
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_gpu_means_error_not_fallback():
     lib = _abi.lib()
