@@ -20,6 +20,47 @@ from .heads import (MlpDimReduction, ResnetFC, _f32c, _ptr, _stream, device_guar
 PRECISIONS = {"fp32": _abi.SD_MLP_FP32, "fp16": _abi.SD_MLP_F16_TC, "fp32_tc": _abi.SD_MLP_F32_TC}
 
 
+class _PoseInverse:
+    """``torch.linalg.inv_ex(poses).inverse`` for the [n, v, 4, 4] poses of ``BTSNet.encode`` (bts.py:125-126), replayed
+    from a CUDA graph from the second call with a given shape on.  The solver path behind the 4 x 4 inverse is eleven small
+    kernels and 0.9 ms of host time per call -- half of a 1.9 ms SSC frame; a replay issues the very same kernels (the same
+    bits) in ~20 us.  Anything unusual -- poses that require grad, an enclosing capture, a capture that fails -- takes the
+    eager call."""
+
+    def __init__(self):
+        self._by_shape = {}
+
+    @staticmethod
+    def _eager(poses):
+        return torch.linalg.inv_ex(poses).inverse
+
+    def __call__(self, poses: torch.Tensor) -> torch.Tensor:
+        if (not poses.is_cuda or poses.requires_grad or poses.dtype != torch.float32 or poses.numel() == 0
+                or poses.device.index != torch.cuda.current_device() or torch.cuda.is_current_stream_capturing()):
+            return self._eager(poses)
+        key = (tuple(poses.shape), poses.device)
+        ent = self._by_shape.get(key)
+        if ent is None:                   # first call with this shape: eager (it also creates the solver handles)
+            self._by_shape[key] = "seen"
+            return self._eager(poses)
+        if ent == "seen":
+            try:
+                static_in = poses.detach().clone()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    static_out = self._eager(static_in)
+                ent = (graph, static_in, static_out)
+            except Exception:             # noqa: BLE001 -- a solver path that cannot be captured: stay eager, same results
+                ent = "eager"
+            self._by_shape[key] = ent
+        if ent == "eager":
+            return self._eager(poses)
+        graph, static_in, static_out = ent
+        static_in.copy_(poses)
+        graph.replay()
+        return static_out.clone()
+
+
 class BTSNet(nn.Module):
     def __init__(self, conf, encoder: nn.Module, code_xyz, heads: dict, final_pred_head: str | None = None,
                  uncertainty_predictor: nn.Module | None = None, ren_nc=None,
@@ -90,6 +131,11 @@ class BTSNet(nn.Module):
         #: caller on the camera too; "check" compares the encoder camera at every encode (one small device->host read-back).
         self.static_query = False
         self._static_cache = {}
+        #: the pose inverse of encode() replayed from a CUDA graph (same kernels, same bits, no 0.9 ms of host time per
+        #: frame); False calls torch.linalg.inv_ex every time
+        self.graph_pose_inverse = True
+        self._pose_inverse = _PoseInverse()
+        self._ids_cache = {}
         self._packed = {}
         self._head_packed = None
         self.grid_f_features = None
@@ -108,6 +154,18 @@ class BTSNet(nn.Module):
         """Drops the point sorts kept under ``static_query``."""
         self._static_cache.clear()
 
+    def _take_views(self, x: torch.Tensor, ids):
+        """``x[:, ids]`` for a list of view ids, with the index tensor kept on the device of ``x``"""
+        if torch.is_tensor(ids) or not x.is_cuda:
+            return x[:, ids]
+        key = (tuple(int(i) for i in ids), x.device)
+        idx = self._ids_cache.get(key)
+        if idx is None:
+            if len(self._ids_cache) >= 64:
+                self._ids_cache.clear()
+            idx = self._ids_cache[key] = torch.tensor(key[0], dtype=torch.long, device=x.device)
+        return x[:, idx]
+
     # ---- encode (bts.py:112-259) -----------------------------------------------------------------
     def encode(self, images, Ks, poses_c2w, ids_encoder=None, ids_render=None, ids_loss=None, images_alt=None,
                combine_ids=None, color_frame_filter=None, loss_feature_grid_shift=None):
@@ -118,21 +176,26 @@ class BTSNet(nn.Module):
         if self.flip_augmentation and self.training:
             raise NotImplementedError("flip_augmentation is a training-time option; not implemented")
         with torch.autocast(device_type=images.device.type, enabled=False):
-            # bts.py:125-126 calls torch.inverse, which reads the LU status back (a device sync per encode: 0.9 ms of a
-            # 1.9 ms SSC frame spent waiting for the previous frame's kernels).  inv_ex is the same routine -- the same
-            # bits -- without the read-back; rigid poses are never singular.
-            poses_w2c = torch.linalg.inv_ex(poses_c2w.float()).inverse
+            # bts.py:125-126 calls torch.inverse, which reads the LU status back (a device sync per encode).  inv_ex is the
+            # same routine -- the same bits -- without the read-back; rigid poses are never singular.  From the second
+            # encode with the same batch shape on, the call is replayed from a CUDA graph (_PoseInverse).
+            poses_f = poses_c2w.float()
+            poses_w2c = self._pose_inverse(poses_f) if self.graph_pose_inverse else torch.linalg.inv_ex(poses_f).inverse
 
+        # the reference indexes with the Python lists themselves (bts.py:128-141): each such index is a host -> device copy
+        # of the list followed by a stream synchronisation -- six per encode, and the host then waits for the previous
+        # frame's kernels.  The same index tensors, made once per (ids, device), give the same copies without the wait.
+        take = self._take_views
         if ids_encoder is None:
             images_encoder, Ks_encoder, poses_w2c_encoder = images, Ks, poses_w2c
         else:
-            images_encoder, Ks_encoder, poses_w2c_encoder = images[:, ids_encoder], Ks[:, ids_encoder], poses_w2c[:, ids_encoder]
-        images_loss = images if ids_loss is None else images[:, ids_loss]
+            images_encoder, Ks_encoder, poses_w2c_encoder = take(images, ids_encoder), take(Ks, ids_encoder), take(poses_w2c, ids_encoder)
+        images_loss = images if ids_loss is None else take(images, ids_loss)
         images = images_alt if images_alt is not None else images * 0.5 + 0.5
         if ids_render is None:
             images_render, Ks_render, poses_w2c_render = images, Ks, poses_w2c
         else:
-            images_render, Ks_render, poses_w2c_render = images[:, ids_render], Ks[:, ids_render], poses_w2c[:, ids_render]
+            images_render, Ks_render, poses_w2c_render = take(images, ids_render), take(Ks, ids_render), take(poses_w2c, ids_render)
 
         n_, nv_, c_, h_, w_ = images_encoder.shape
         image_latents_ms = self.encoder(images_encoder.reshape(n_ * nv_, c_, h_, w_))

@@ -320,3 +320,37 @@ def test_launch_stream_follows_torch_current_stream():
     assert (heads._stream().value or 0) == torch.cuda.current_stream().cuda_stream
     ev.synchronize()
     assert code.shape == (1000, 39) and torch.equal(code[:, :3], x)
+
+
+def test_encode_pose_inverse_replayed_from_a_graph_is_bit_identical(golden):
+    """BTSNet.encode inverts the poses with torch's own solver (bts.py:125-126); from the second encode with the same batch
+    shape on, that call is replayed from a CUDA graph: the same kernels, so the same bits as the eager call -- for new pose
+    values, after a change of shape, and with the switch off."""
+    g = golden("query")
+    net = build(g)                                           # encode no. 1 (eager)
+    nv = g["K"].shape[0]
+    K = dev(g["K"][None]); imgs = torch.zeros(1, nv, 3, 8, 8, device=DEV)
+    rs = np.random.RandomState(5)
+
+    def pose_batch(n_views):
+        out = []
+        for _ in range(n_views):
+            q, _ = np.linalg.qr(rs.randn(3, 3))
+            m = np.eye(4, dtype=np.float32); m[:3, :3] = q.astype(np.float32); m[:3, 3] = rs.uniform(-3, 3, 3)
+            out.append(m)
+        return dev(np.stack(out)[None])
+
+    for i in range(4):                                       # no. 2 captures, 3.. replay
+        c2w = pose_batch(nv)
+        net.encode(imgs, K, c2w, ids_encoder=[0], ids_render=list(range(nv)))
+        want = torch.linalg.inv_ex(c2w).inverse
+        assert torch.equal(net.grid_c_poses_w2c, want) and torch.equal(net.grid_f_poses_w2c, want[:, [0]]), f"encode {i + 2}"
+    kinds = {type(v).__name__ for v in net._pose_inverse._by_shape.values()}
+    assert kinds == {"tuple"}, f"the solver path was not captured: {net._pose_inverse._by_shape}"
+    c2w1 = pose_batch(1)                                     # another shape: eager first, its own graph afterwards
+    for _ in range(3):
+        net.encode(imgs[:, :1], K[:, :1], c2w1, ids_encoder=[0], ids_render=[0])
+        assert torch.equal(net.grid_c_poses_w2c, torch.linalg.inv_ex(c2w1).inverse)
+    net.graph_pose_inverse = False
+    net.encode(imgs[:, :1], K[:, :1], c2w1, ids_encoder=[0], ids_render=[0])
+    assert torch.equal(net.grid_c_poses_w2c, torch.linalg.inv_ex(c2w1).inverse)
