@@ -242,3 +242,27 @@ def test_x3_projection_sizes_and_errors_without_gpu():
     assert lib.sd_gen_voxel_grid(org, 0.2, 4, 4, 4, 2, 2, T, None, None) == 0      # an empty slab is fine
     assert lib.sd_composite_bwd(None, None, None, None, 0, 8, 4, 3, ctypes.byref(_abi.SdRenderCfg()), *([None] * 8), None) == 0
     assert lib.sd_composite_bwd(None, None, None, None, 5, 300, 4, 3, ctypes.byref(_abi.SdRenderCfg()), *([None] * 8), None) == -1
+
+
+def test_encode_stash_on_the_host_matches_the_reference_indexing():
+    """BTSNet.encode (bts.py:112-259) with host tensors: the stash (views picked by ids_encoder / ids_render, inverted
+    poses, colour images rescaled to [0, 1]) is what the reference keeps; the device-side shortcuts of encode (index
+    tensors kept on the GPU, the pose inverse replayed from a CUDA graph) leave host tensors to the plain torch calls."""
+    net = _net()
+    rs = np.random.RandomState(0)
+    n, nv = 2, 3
+    images = torch.from_numpy(rs.uniform(-1, 1, (n, nv, 3, 8, 8)).astype(np.float32))
+    Ks = torch.from_numpy(rs.uniform(0.5, 1.5, (n, nv, 3, 3)).astype(np.float32))
+    poses = torch.eye(4).repeat(n, nv, 1, 1)
+    poses[..., :3, 3] = torch.from_numpy(rs.uniform(-2, 2, (n, nv, 3)).astype(np.float32))
+    net.encode(images, Ks, poses, ids_encoder=[0], ids_render=[2, 1])
+    w2c = torch.inverse(poses)
+    assert torch.equal(net.grid_f_poses_w2c, w2c[:, [0]]) and torch.equal(net.grid_c_poses_w2c, w2c[:, [2, 1]])
+    assert torch.equal(net.grid_f_Ks, Ks[:, [0]]) and torch.equal(net.grid_c_Ks, Ks[:, [2, 1]])
+    assert torch.equal(net.grid_c_imgs, (images * 0.5 + 0.5)[:, [2, 1]])
+    assert net.grid_f_features[0].shape == (n, 1, 256, 4, 4)
+    assert net._pose_inverse._by_shape == {} and net._ids_cache == {}      # nothing device-side was set up
+    net.encode(images, Ks, poses)                                          # no ids: everything, no copies
+    assert net.grid_c_Ks is Ks and torch.equal(net.grid_c_poses_w2c, w2c)
+    with pytest.raises(NotImplementedError):
+        net.encode(images, Ks, poses, combine_ids=[[0, 1]])
