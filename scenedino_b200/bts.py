@@ -45,7 +45,9 @@ class _PoseInverse:
             return self._eager(poses)
         if ent == "seen":
             try:
-                static_in = poses.detach().clone()
+                with torch.inference_mode(False):     # a plain tensor: later encodes may run in or outside inference mode
+                    static_in = torch.empty(poses.shape, dtype=poses.dtype, device=poses.device)
+                static_in.copy_(poses)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     static_out = self._eager(static_in)
@@ -56,9 +58,13 @@ class _PoseInverse:
         if ent == "eager":
             return self._eager(poses)
         graph, static_in, static_out = ent
-        static_in.copy_(poses)
-        graph.replay()
-        return static_out.clone()
+        try:
+            static_in.copy_(poses)
+            graph.replay()
+            return static_out.clone()
+        except RuntimeError:              # (e.g. autograd-mode restrictions on the static buffers): same results, eagerly
+            self._by_shape[key] = "eager"
+            return self._eager(poses)
 
 
 class BTSNet(nn.Module):
