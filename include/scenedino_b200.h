@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 4
+#define SD_ABI_VERSION 5
 
 typedef enum sd_status {
     SD_OK = 0,
@@ -295,10 +295,12 @@ int sd_gen_rays(const float *c2w, const float *proj, const float *frame_ids, int
  * once (generate_point_grid, sscbench/point_utils.py:46-67) and uploads -- 25 MB for 256 x 256 x 32 -- made on the device
  * instead.  origin [3] (voxel (0,0,0) corner, lidar frame) and T [3][4] (row-major float64 lidar -> camera, the
  * calibration's T_velo_2_cam) are HOST pointers read before the call returns.  xyz [(x1-x0)*ny*nz, 3] fp32, flattened
- * 'ij' order (x slowest); [x0, x1) selects a slab of x indices (voxel-slab sharding).  centre = origin + size*idx + size/2
- * in fp32 (TSDFVolume.vox2world, sscbench/fusion.py:205-219), then the rigid transform as a float64 dot product rounded
- * once (rigid_transform, fusion.py:407-411): bit-identical to scenedino_b200.synthetic.ssc_voxel_grid. */
-int sd_gen_voxel_grid(const float *origin, float voxel_size, int nx, int ny, int nz, int x0, int x1,
+ * 'ij' order (x slowest); [x0, x1) selects a slab of x indices (voxel-slab sharding).  centre = origin + size*idx + size*0.5
+ * with the fp32 origin and index but the size as the double it is in the reference (a Python float inside the numba-compiled
+ * TSDFVolume.vox2world, sscbench/fusion.py:205-219): evaluated in double, rounded to fp32 once; then the rigid transform as a
+ * float64 dot product rounded once (rigid_transform, fusion.py:407-411; .float() at evaluate_model_sscbench.py:277).
+ * Bit-identical to the reference's own grid (tests/golden/voxel_grid.npz, made by running the reference's functions). */
+int sd_gen_voxel_grid(const float *origin, double voxel_size, int nx, int ny, int nz, int x0, int x1,
                       const double *T, float *xyz, void *stream);
 
 /* ---- diagnostics (timing experiments; not part of the data path) ----------------------------------------------------

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SD_B200_LIB") or os.path.join(HERE, "libscenedino_b20
 
 SD_F32, SD_F16 = 0, 1
 SD_MLP_FP32, SD_MLP_F16_TC, SD_MLP_F32_TC = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SdError(RuntimeError):
@@ -53,7 +53,7 @@ class SdSampling(C.Structure):
     _fields_ = [("n_coarse", C.c_int), ("n_fine", C.c_int), ("n_fine_depth", C.c_int), ("depth_std", C.c_float)]
 
 
-_P, _LL, _I, _F, _SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
+_P, _LL, _I, _F, _D, _SZ = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double, C.c_size_t
 _SC, _ML, _RC = C.POINTER(SdScene), C.POINTER(SdMlp), C.POINTER(SdRenderCfg)
 
 # name -> (restype, argtypes); must list EVERY symbol declared in include/scenedino_b200.h
@@ -94,7 +94,7 @@ PROTOTYPES = {
                             C.POINTER(SdRenderOut), _P, _SZ, _P]),
     "sd_expand_dim": (_I, [_ML, _P, _LL, _P, _P]),
     "sd_gen_rays": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _F, _F, _P, _P]),
-    "sd_gen_voxel_grid": (_I, [_P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "sd_gen_voxel_grid": (_I, [_P, _D, _I, _I, _I, _I, _I, _P, _P, _P]),
     "sd_ssc_head_pack_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
     "sd_ssc_head_pack": (_I, [_P] * 12 + [_I] * 6 + [_P, _P]),
     "sd_ssc_head": (_I, [_P, _I, _I, _P, _P, _LL, _P, _P, _P, _P]),

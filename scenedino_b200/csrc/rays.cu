@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(RAYS_PER_BLOCK) gen_rays_kernel(RayGrid g, con
 // left to right, as scenedino_b200.synthetic.ssc_voxel_grid does), then rigid_transform (fusion.py:407-411) with the
 // calibration's float64 matrix: a double-precision dot product rounded once to fp32.  Flattened 'ij' order (x slowest).
 struct VoxGrid {
-    float ox, oy, oz, vs;
+    float ox, oy, oz;
+    double vs;
     int ny, nz, x0;
     long long n;
     double T[12];
@@ -91,10 +92,13 @@ __global__ void __launch_bounds__(256) gen_voxel_grid_kernel(VoxGrid g, float *_
     const int iz = (int)(i % g.nz);
     const long long t = i / g.nz;
     const int iy = (int)(t % g.ny), ix = (int)(t / g.ny) + g.x0;
-    const float half = __fmul_rn(g.vs, 0.5f);
-    const float px = __fadd_rn(__fadd_rn(g.ox, __fmul_rn(g.vs, (float)ix)), half);
-    const float py = __fadd_rn(__fadd_rn(g.oy, __fmul_rn(g.vs, (float)iy)), half);
-    const float pz = __fadd_rn(__fadd_rn(g.oz, __fmul_rn(g.vs, (float)iz)), half);
+    // TSDFVolume.vox2world (sscbench/fusion.py:205-219) is compiled by numba: fp32 origin and fp32 voxel index, but the voxel
+    // size and the 0.5 offset are Python floats, so  origin + size * idx + size * 0.5  is evaluated in DOUBLE, left to right,
+    // and rounded to fp32 once when it is stored
+    const double half = __dmul_rn(g.vs, 0.5);
+    const float px = __double2float_rn(__dadd_rn(__dadd_rn((double)g.ox, __dmul_rn(g.vs, (double)ix)), half));
+    const float py = __double2float_rn(__dadd_rn(__dadd_rn((double)g.oy, __dmul_rn(g.vs, (double)iy)), half));
+    const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)g.oz, __dmul_rn(g.vs, (double)iz)), half));
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const double v = fma(g.T[4 * r], (double)px, fma(g.T[4 * r + 1], (double)py, fma(g.T[4 * r + 2], (double)pz, g.T[4 * r + 3])));
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(256) gen_voxel_grid_kernel(VoxGrid g, float *_
 
 using namespace sd;
 
-extern "C" int sd_gen_voxel_grid(const float *origin, float voxel_size, int nx, int ny, int nz, int x0, int x1,
+extern "C" int sd_gen_voxel_grid(const float *origin, double voxel_size, int nx, int ny, int nz, int x0, int x1,
                                  const double *T_host, float *xyz, void *stream) {
     SD_REQUIRE(origin && T_host, "sd_gen_voxel_grid: origin / T are host pointers and must not be NULL");
     SD_REQUIRE(nx > 0 && ny > 0 && nz > 0 && 0 <= x0 && x0 <= x1 && x1 <= nx, "sd_gen_voxel_grid: bad grid (%d x %d x %d, slab %d..%d)", nx, ny, nz, x0, x1);

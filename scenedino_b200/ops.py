@@ -239,7 +239,8 @@ def gen_rays(c2w, proj, H: int, W: int, z_near: float, z_far: float, frame_ids=N
 
 def gen_voxel_grid(T, dims=(256, 256, 32), voxel_size=0.2, origin=(0.0, -25.6, -2.0), x_range=None, device="cuda", out=None):
     """Voxel centres of an SSC grid in the camera frame, made on the device (sd_gen_voxel_grid): [N,3] fp32, bit-identical
-    to ``synthetic.ssc_voxel_grid``.  ``T``: [3..4, 4] float64 lidar -> camera (host array)."""
+    to ``synthetic.ssc_voxel_grid`` and through it to the reference's grid (tests/golden/voxel_grid.npz).  ``T``: [3..4, 4]
+    float64 lidar -> camera (host array); ``voxel_size`` is used as a double, as in the reference."""
     import numpy as np
     x0, x1 = (0, dims[0]) if x_range is None else x_range
     Th = np.ascontiguousarray(np.asarray(T, np.float64)[:3, :4])

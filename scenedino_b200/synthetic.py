@@ -114,15 +114,17 @@ def ssc_voxel_grid(dims=(256, 256, 32), voxel_size: float = 0.2, origin=(0.0, -2
     """Voxel centres of the SSCBench grid in the camera frame, flattened 'ij' order, [N,3] fp32.
     ``x_range`` selects a slab of x indices (used for multi-GPU voxel-slab sharding)."""
     x0, x1 = (0, dims[0]) if x_range is None else x_range
-    org = np.asarray(origin, np.float32)
-    vs = np.float32(voxel_size)
-    ix = np.arange(x0, x1, dtype=np.float32)
-    iy = np.arange(dims[1], dtype=np.float32)
-    iz = np.arange(dims[2], dtype=np.float32)
-    # vox2world (sscbench/fusion.py:203-219): origin + size*idx + size*0.5 in fp32
-    px = org[0] + vs * ix + vs * np.float32(0.5)
-    py = org[1] + vs * iy + vs * np.float32(0.5)
-    pz = org[2] + vs * iz + vs * np.float32(0.5)
+    org = np.asarray(origin, np.float32).astype(np.float64)      # vol_origin.astype(np.float32), fusion.py:207
+    vs = float(voxel_size)                                        # a Python float in the reference: a double inside numba
+
+    def centres(o, idx):
+        # vox2world (sscbench/fusion.py:205-219, numba): vol_origin[j] + (vox_size * vox_coords[i, j]) + vox_size * offsets[j]
+        # with fp32 origin / index and double size / offset -> double arithmetic, ONE rounding when stored to the fp32 array
+        return ((o + vs * idx.astype(np.float32).astype(np.float64)) + vs * 0.5).astype(np.float32)
+
+    px = centres(org[0], np.arange(x0, x1))
+    py = centres(org[1], np.arange(dims[1]))
+    pz = centres(org[2], np.arange(dims[2]))
     P = np.stack(np.meshgrid(px, py, pz, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
     T = velo_to_cam()
     Ph = np.hstack([P, np.ones((len(P), 1), np.float32)])  # rigid_transform (fusion.py:407-411)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, n), f"{n} is declared in include/scenedino_b200.h but not exported"
         assert n in _abi.PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(_abi.PROTOTYPES) == names
-    assert _abi.lib().sd_abi_version() == _abi.ABI_VERSION == 4
+    assert _abi.lib().sd_abi_version() == _abi.ABI_VERSION == 5
 
 
 def test_library_exports_nothing_the_header_does_not_declare():

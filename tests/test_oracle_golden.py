@@ -253,3 +253,23 @@ def test_ssc_head(golden):
     assert np.array_equal(seg, w["lut"][pseudo])
     # scaled copies of a row get the row's label (the head normalises its input); the all-zero row is finite
     assert np.array_equal(pseudo[512:576], pseudo[:64]) and np.isfinite(ip[-1]).all()
+
+
+def test_voxel_grid_is_the_references_grid():
+    """synthetic.ssc_voxel_grid (the host construction sd_gen_voxel_grid is tested against, tests/test_gpu_binned.py) equals
+    the grid the reference builds (sscbench/evaluate_model_sscbench.py:270-278) bit for bit: SHA-256 of all 2 097 152 fp32
+    centres, a strided sample, a slab, and a second grid with odd dimensions, size and origin.  The fixture was made by
+    running the reference's own functions (oracle/make_golden_grid.py)."""
+    import hashlib
+    import os
+    from scenedino_b200 import synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxel_grid.npz"))
+    assert np.array_equal(syn.velo_to_cam(), g["T"])
+    full = syn.ssc_voxel_grid()
+    assert full.dtype == np.float32 and full.shape == (256 * 256 * 32, 3)
+    assert hashlib.sha256(np.ascontiguousarray(full).tobytes()).digest() == g["sha256_f32"].tobytes()
+    assert np.array_equal(full[g["sample_idx"]], g["sample"])
+    assert np.array_equal(syn.ssc_voxel_grid(x_range=(37, 101))[:64], g["slab_37_101"])
+    odd = syn.ssc_voxel_grid(dims=tuple(int(d) for d in g["odd_dims"]), voxel_size=float(g["odd_voxel_size"]),
+                             origin=tuple(float(o) for o in g["odd_origin"]))
+    assert np.array_equal(odd, g["odd"])
