@@ -130,3 +130,12 @@ def test_gen_voxel_grid_bit_identical_to_the_host_grid(x_range):
     assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
     odd = ops.gen_voxel_grid(syn.velo_to_cam(), dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1))
     assert np.array_equal(odd.cpu().numpy(), syn.ssc_voxel_grid(dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1)))
+    # ... and what the reference's own generate_point_grid + .float() produced (oracle/make_golden_grid.py)
+    import hashlib
+    import os
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxel_grid.npz"))
+    assert np.array_equal(odd.cpu().numpy(), ref["odd"])
+    if x_range is None:
+        host = np.ascontiguousarray(got.cpu().numpy())
+        assert hashlib.sha256(host.tobytes()).digest() == ref["sha256_f32"].tobytes()
+        assert np.array_equal(host[ref["sample_idx"]], ref["sample"])
