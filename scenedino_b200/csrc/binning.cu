@@ -15,8 +15,8 @@
 // shared memory; its merge into the global histogram (one atomic per non-empty bin) hands back the number of points earlier
 // ranges put into the bin -- the range's offset inside the bin, kept in `bbase`; (2) scatter: every block scans the histogram
 // for itself (bin starts + a compact numbering of the non-empty bins, in shared memory), then position = start of the bin +
-// offset of the range + rank inside the range (shared-memory atomic); (3) the tile table.  The points are read twice and projected twice (the projection is
-// cheaper than carrying its result through memory).  The order inside a bin depends on atomics and is not reproducible;
+// offset of the range + rank inside the range (shared-memory atomic); (3) the tile table.  The points are read twice and
+// projected twice (carrying the projection through memory would cost about what the second projection does).  The order inside a bin depends on atomics and is not reproducible;
 // the results per point are (the fused kernel computes each row independently).
 #include "common.cuh"
 #include "launch.h"
@@ -34,9 +34,9 @@ struct BinGeom {
     unsigned int bw_magic;        // ceil(2^32 / bw): v / bw == __umulhi(v, bw_magic) for v * bw < 2^32
 };
 
-constexpr int BIN_UNROLL = 4;       // points per thread and trip, their loads issued together: both passes are chains of
-                                    // dependent latencies (load -> projection with two divisions -> shared-memory atomic
-                                    // -> store), not bandwidth
+constexpr int BIN_UNROLL = 4;       // points per thread and trip, their 12 coordinate loads issued together (count pass -2 us;
+                                    // beyond that both passes are bound by the instructions of the projection itself:
+                                    // profiles/r02_sort_passes.md)
 
 __device__ __forceinline__ int point_bin(const float *cam, const BinGeom &bg, float px, float py, float pz) {
     float x, y, z;
