@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(RAYS_PER_BLOCK) gen_rays_kernel(RayGrid g, con
 }
 
 // ---- voxel centres of an SSC grid in the camera frame (sscbench/point_utils.py:46-67 generate_point_grid) ---------------
-// centre = origin + size * idx + size * 0.5 per axis (TSDFVolume.vox2world, sscbench/fusion.py:205-219; evaluated in fp32,
-// left to right, as scenedino_b200.synthetic.ssc_voxel_grid does), then rigid_transform (fusion.py:407-411) with the
+// centre = origin + size * idx + size * 0.5 per axis (TSDFVolume.vox2world, sscbench/fusion.py:205-219; evaluated in double,
+// left to right, rounded to fp32 once -- see the kernel), then rigid_transform (fusion.py:407-411) with the
 // calibration's float64 matrix: a double-precision dot product rounded once to fp32.  Flattened 'ij' order (x slowest).
 struct VoxGrid {
     float ox, oy, oz;
