@@ -119,23 +119,3 @@ def test_btsnet_forward_segmentation_takes_the_binned_path():
     assert n1 - n0 == 5 and n2 - n1 == 2, (n1 - n0, n2 - n1)
     assert torch.equal(sig_a, sig_b) and torch.equal(sig_b, sig_c)
     assert torch.equal(seg_a.reshape(-1).to(torch.int64), seg_b.reshape(-1).to(torch.int64)) and torch.equal(seg_b, seg_c)
-
-
-@pytest.mark.parametrize("x_range", [None, (0, 1), (37, 101), (255, 256)])
-def test_gen_voxel_grid_bit_identical_to_the_host_grid(x_range):
-    """sd_gen_voxel_grid: the SSC grid of sscbench/evaluate_model_sscbench.py:270-278 made on the device, whole and in
-    x-slabs, bit for bit what synthetic.ssc_voxel_grid (the host construction) gives."""
-    want = syn.ssc_voxel_grid(x_range=x_range)
-    got = ops.gen_voxel_grid(syn.velo_to_cam(), x_range=x_range)
-    assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
-    odd = ops.gen_voxel_grid(syn.velo_to_cam(), dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1))
-    assert np.array_equal(odd.cpu().numpy(), syn.ssc_voxel_grid(dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1)))
-    # ... and what the reference's own generate_point_grid + .float() produced (oracle/make_golden_grid.py)
-    import hashlib
-    import os
-    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxel_grid.npz"))
-    assert np.array_equal(odd.cpu().numpy(), ref["odd"])
-    if x_range is None:
-        host = np.ascontiguousarray(got.cpu().numpy())
-        assert hashlib.sha256(host.tobytes()).digest() == ref["sha256_f32"].tobytes()
-        assert np.array_equal(host[ref["sample_idx"]], ref["sample"])

@@ -256,7 +256,7 @@ def test_ssc_head(golden):
 
 
 def test_voxel_grid_is_the_references_grid():
-    """synthetic.ssc_voxel_grid (the host construction sd_gen_voxel_grid is tested against, tests/test_gpu_binned.py) equals
+    """synthetic.ssc_voxel_grid (the host construction sd_gen_voxel_grid is tested against, tests/test_gpu_zzz_voxel_grid.py) equals
     the grid the reference builds (sscbench/evaluate_model_sscbench.py:270-278) bit for bit: SHA-256 of all 2 097 152 fp32
     centres, a strided sample, a slab, and a second grid with odd dimensions, size and origin.  The fixture was made by
     running the reference's own functions (oracle/make_golden_grid.py)."""
