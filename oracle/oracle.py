@@ -19,11 +19,20 @@ _LIB_PATH = os.path.join(_HERE, "build", "libsd_oracle.so")
 _lib = None
 
 
+ORACLE_VERSION = 2          # sdo_version() of sd_oracle.c
+
+
 def build(force: bool = False) -> str:
-    """Compiles the oracle with the recipe in oracle/Makefile (gcc, a second or two)."""
+    """Compiles the oracle with the recipe in oracle/Makefile (gcc, a second or two).  Rebuilt when the source is newer than
+    the library or the library was built from another version of the source (stamp file: copied trees lose timestamps)."""
     src = os.path.join(_HERE, "sd_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    stamp = os.path.join(os.path.dirname(_LIB_PATH), ".version")
+    fresh = (os.path.exists(_LIB_PATH) and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src) and os.path.exists(stamp)
+             and open(stamp).read().strip() == str(ORACLE_VERSION))
+    if force or not fresh:
+        subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+        with open(stamp, "w") as f:
+            f.write(str(ORACLE_VERSION))
     return _LIB_PATH
 
 
@@ -50,6 +59,9 @@ def lib():
         build()
         _lib = C.CDLL(_LIB_PATH)
         _lib.sdo_version.restype = C.c_int
+        if _lib.sdo_version() != ORACLE_VERSION:
+            raise RuntimeError(f"oracle library version {_lib.sdo_version()}, oracle.py expects {ORACLE_VERSION}: "
+                               "delete oracle/build/ and run again")
         _lib.sdo_num_threads.restype = C.c_int
         _lib.sdo_code_dim.restype = C.c_int
         _lib.sdo_query_points.restype = C.c_int
@@ -351,3 +363,15 @@ def ssc_head(x, wl, bl, wn1, bn1, wn2, bn2, centres, lut):
     if rc:
         raise MemoryError("sdo_ssc_head")
     return seg, pseudo, ip
+
+
+def voxel_grid(T, dims=(256, 256, 32), voxel_size=0.2, origin=(0.0, -25.6, -2.0), x_range=None):
+    """The SSC voxel grid in the camera frame as the reference builds it (sscbench/evaluate_model_sscbench.py:270-278,
+    point_utils.py:46-67, fusion.py:205-219, 407-411): [N, 3] fp32, 'ij' order.  ``T``: [3..4, 4] float64 lidar -> camera."""
+    x0, x1 = (0, dims[0]) if x_range is None else x_range
+    Th = np.ascontiguousarray(np.asarray(T, np.float64)[:3, :4])
+    org = np.ascontiguousarray(np.asarray(origin, np.float32))
+    out = np.empty(((x1 - x0) * dims[1] * dims[2], 3), np.float32)
+    lib().sdo_voxel_grid(_p(org), C.c_double(float(voxel_size)), int(dims[0]), int(dims[1]), int(dims[2]), int(x0), int(x1),
+                         Th.ctypes.data_as(C.c_void_p), _p(out))
+    return out

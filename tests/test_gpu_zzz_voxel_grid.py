@@ -5,6 +5,7 @@ spent -- checked by a CPU emulation of the same IEEE operations -- and this is i
 import numpy as np
 import pytest
 
+from oracle import oracle as O
 from scenedino_b200 import ops
 from scenedino_b200 import synthetic as syn
 
@@ -18,6 +19,7 @@ def test_gen_voxel_grid_bit_identical_to_the_host_grid(x_range):
     want = syn.ssc_voxel_grid(x_range=x_range)
     got = ops.gen_voxel_grid(syn.velo_to_cam(), x_range=x_range)
     assert got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(got.cpu().numpy(), O.voxel_grid(syn.velo_to_cam(), x_range=x_range))      # the C oracle
     odd = ops.gen_voxel_grid(syn.velo_to_cam(), dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1))
     assert np.array_equal(odd.cpu().numpy(), syn.ssc_voxel_grid(dims=(5, 3, 7), voxel_size=0.35, origin=(1.5, -2.25, 0.1)))
     # ... and what the reference's own generate_point_grid + .float() produced (oracle/make_golden_grid.py)

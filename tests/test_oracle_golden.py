@@ -270,6 +270,12 @@ def test_voxel_grid_is_the_references_grid():
     assert hashlib.sha256(np.ascontiguousarray(full).tobytes()).digest() == g["sha256_f32"].tobytes()
     assert np.array_equal(full[g["sample_idx"]], g["sample"])
     assert np.array_equal(syn.ssc_voxel_grid(x_range=(37, 101))[:64], g["slab_37_101"])
-    odd = syn.ssc_voxel_grid(dims=tuple(int(d) for d in g["odd_dims"]), voxel_size=float(g["odd_voxel_size"]),
-                             origin=tuple(float(o) for o in g["odd_origin"]))
-    assert np.array_equal(odd, g["odd"])
+    kw = dict(dims=tuple(int(d) for d in g["odd_dims"]), voxel_size=float(g["odd_voxel_size"]),
+              origin=tuple(float(o) for o in g["odd_origin"]))
+    assert np.array_equal(syn.ssc_voxel_grid(**kw), g["odd"])
+    # the C oracle's restatement of the same construction (the expression the CUDA kernel evaluates)
+    ofull = O.voxel_grid(g["T"])
+    assert hashlib.sha256(np.ascontiguousarray(ofull).tobytes()).digest() == g["sha256_f32"].tobytes()
+    assert np.array_equal(O.voxel_grid(g["T"], x_range=(37, 101))[:64], g["slab_37_101"])
+    assert np.array_equal(O.voxel_grid(g["T"], x_range=(255, 256)), full[255 * 256 * 32:])
+    assert np.array_equal(O.voxel_grid(g["T"], **kw), g["odd"])
