@@ -97,3 +97,18 @@ def test_sharded_wrappers_gloo(world, n_rays, grid):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_voxel_slabs_of_the_grid_concatenate_to_the_whole_grid():
+    """Voxel-slab sharding (one x-slab of the SSC grid per rank): the slabs every rank builds for itself -- host restatement
+    and C oracle alike -- laid end to end are the whole grid, for even and ragged splits."""
+    from oracle import oracle as O
+    from scenedino_b200 import synthetic as syn
+    dims = (24, 8, 4)
+    T = syn.velo_to_cam()
+    whole = syn.ssc_voxel_grid(dims=dims)
+    assert np.array_equal(whole, O.voxel_grid(T, dims=dims))
+    for w in (1, 2, 3, 5, 8):
+        slabs = sh.shard_bounds(dims[0], w)
+        assert np.array_equal(np.concatenate([syn.ssc_voxel_grid(dims=dims, x_range=b) for b in slabs]), whole)
+        assert np.array_equal(np.concatenate([O.voxel_grid(T, dims=dims, x_range=b) for b in slabs]), whole)
